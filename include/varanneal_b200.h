@@ -1,0 +1,185 @@
+/*
+ * varanneal_b200 -- C ABI of libvarannealb200.so
+ *
+ * The reference (paulrozdeba/varanneal) is pure Python and has no FFI of its own; its seams are
+ * Python methods.  This header declares the native entry points that replace the numeric body of
+ * those seams, and for each one cites the reference interface it stands in for
+ * (paths relative to the reference tree, varanneal/...).  The Python classes in
+ * varanneal_b200/va_ode.py and varanneal_b200/va_nnet.py keep the reference's method names and
+ * argument order and call these functions through ctypes (see INTEGRATION.md for the stub a
+ * maintainer of the reference would add).
+ *
+ * Conventions
+ *   - plain C: pointers, sizes, ints, doubles.  No torch / C++ types cross this boundary.
+ *   - every function returns int: 0 = ok, <0 = vab_status error.  vab_last_error() gives text.
+ *   - pointers named *_dev are DEVICE pointers owned by the caller (PyTorch allocates them);
+ *     pointers named *_host are host pointers read during the call only.  The library never
+ *     frees caller memory.  Internal workspaces belong to the context.
+ *   - all work is enqueued on the context's CUDA stream.  Only vab_sync, vab_*_minimize and
+ *     vab_*_anneal block the host (they poll a pinned completion flag).
+ *   - a context is bound to one device and is not thread-safe; distinct contexts are independent
+ *     (no global state -- unlike the reference's process-global ADOL-C tape ids).
+ *   - batches: B independent paths ("annealing initialisations") share the problem data.
+ *     Path b lives at XP_dev + b*ldxp (doubles), laid out exactly like the reference's flat
+ *     XP = X.flatten() ++ P[Pidx]   (va_ode.py:715-732, va_nnet.py:468-473).
+ *     ldxp must be even (16-byte aligned paths).
+ */
+#ifndef VARANNEAL_B200_H
+#define VARANNEAL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VAB_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define VAB_API __attribute__((visibility("default")))
+#else
+#define VAB_API
+#endif
+
+typedef struct vab_ctx vab_ctx;
+
+typedef enum {
+  VAB_OK = 0,
+  VAB_ERR_INVALID = -1,   /* bad argument / unsupported combination */
+  VAB_ERR_CUDA = -2,      /* CUDA runtime error (text in vab_last_error) */
+  VAB_ERR_STATE = -3,     /* call order (e.g. action before problem_set) */
+  VAB_ERR_NOMEM = -4
+} vab_status;
+
+/* Device vector fields selectable through set_model (replaces the arbitrary Python callable of
+ * va_ode.py:56-67; equations: examples/Lorenz96_D20/Lorenz96_anneal.py:15-16, tutorial
+ * notebook cell 36 for NaKL; Lorenz63 is an extension named by BASELINE.json). */
+typedef enum { VAB_MODEL_LORENZ96 = 0, VAB_MODEL_LORENZ63 = 1, VAB_MODEL_NAKL = 2 } vab_model;
+
+/* Time discretisations: va_ode.py:341-356 (euler), :358-380 (trapezoid), :404-437
+ * (SimpsonHermite, needs odd N_model), :439-454 (forwardmap); rk4 is an extension following the
+ * commented-out intent at :382-402 (static parameters, no stimulus). */
+typedef enum {
+  VAB_DISC_EULER = 0, VAB_DISC_TRAPEZOID = 1, VAB_DISC_SIMPSON_HERMITE = 2,
+  VAB_DISC_FORWARDMAP = 3, VAB_DISC_RK4 = 4
+} vab_disc;
+
+typedef enum { VAB_ACT_SIGMOID = 0, VAB_ACT_TANH = 1, VAB_ACT_LINEAR = 2 } vab_activation;
+
+/* ---- context ------------------------------------------------------------------------------ */
+VAB_API int vab_abi_version(void);
+/* stream: a cudaStream_t passed as void* (NULL = the device's default stream). */
+VAB_API int vab_ctx_create(int device, void* stream, vab_ctx** out);
+VAB_API int vab_ctx_destroy(vab_ctx* ctx);
+VAB_API int vab_sync(vab_ctx* ctx);
+/* Text of the last error on this context (ctx may be NULL: last error of a failed create). */
+VAB_API const char* vab_last_error(const vab_ctx* ctx);
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+VAB_API long long vab_launch_count(const vab_ctx* ctx);
+
+/* ---- ODE problem -------------------------------------------------------------------------- */
+/* Everything va_ode.Annealer.anneal_init fixes for a run (va_ode.py:531-705). */
+typedef struct {
+  int32_t model;        /* vab_model */
+  int32_t disc;         /* vab_disc */
+  int32_t D;            /* state dimension (set_model, va_ode.py:56-67) */
+  int32_t N_model;      /* (N_data-1)*nskip+1 (va_ode.py:557) */
+  int32_t N_data;       /* rows of Y (va_ode.py:104-107) */
+  int32_t nskip;        /* merr_nskip (va_ode.py:556) */
+  int32_t L;            /* len(Lidx) (va_ode.py:577-578) */
+  int32_t NP;           /* len(P0) (va_ode.py:564-570); must equal the model's parameter count */
+  int32_t NPest;        /* len(Pidx) (va_ode.py:573-574) */
+  int32_t n_stim;       /* columns of the stimulus (0 = none) (va_ode.py:113-124) */
+  double dt_model;      /* va_ode.py:549-555 */
+} vab_ode_desc;
+
+/* Lidx_host[L], Pidx_host[NPest]: index lists as passed to anneal().
+ * Y_dev: (N_data, L) row-major observations (va_ode.py:112,120).
+ * stim_dev: (N_model, n_stim) row-major or NULL.
+ * The arrays behind Y_dev / stim_dev must stay alive while the problem is set. */
+VAB_API int vab_ode_problem_set(vab_ctx* ctx, const vab_ode_desc* desc,
+                        const int32_t* Lidx_host, const int32_t* Pidx_host,
+                        const double* Y_dev, const double* stim_dev);
+
+/* RM / RF0 exactly as anneal_init normalises them (va_ode.py:612-640): a scalar, or a per-entry
+ * array already broadcast to (N_data, L) / (N_model-1, D).  rm_dev / rf0_dev NULL = scalar.
+ * The (.,L,L)/(.,D,D) matrix forms are unsupported (the reference's own branch is broken,
+ * va_ode.py:222). */
+VAB_API int vab_ode_set_weights(vab_ctx* ctx, double rm_scalar, const double* rm_dev,
+                        double rf0_scalar, const double* rf0_dev);
+
+/* Values of the parameters that are NOT estimated (va_ode.py:178-181): pfix_dev is (NP) shared by
+ * all paths (pfix_stride = 0) or (B, NP) (pfix_stride = NP).  Estimated entries are ignored. */
+VAB_API int vab_ode_set_fixed_params(vab_ctx* ctx, const double* pfix_dev, int64_t pfix_stride);
+
+/* Replaces ADmin.A_gradA_taped (_autodiffmin.py:57-58) -- and tape_A (:32-49), which has no
+ * analogue -- for B paths at once, with RF = RF0 * rf_scale (rf_scale = alpha**beta,
+ * va_ode.py:650,782).  Outputs (any may be NULL): A_dev[B] action, me_dev[B] measurement error
+ * (va_ode.py:138-158), fe_dev[B] RF-weighted model error (:160-234), G_dev gradient with the same
+ * layout / leading dimension convention as XP (ldg doubles between paths). */
+VAB_API int vab_ode_action_grad(vab_ctx* ctx, int32_t B, const double* XP_dev, int64_t ldxp,
+                        double rf_scale, double* A_dev, double* me_dev, double* fe_dev,
+                        double* G_dev, int64_t ldg);
+
+/* ---- neural-network problem ---------------------------------------------------------------- */
+/* va_nnet.Annealer.set_structure / set_activation / set_input_data / set_output_data
+ * (va_nnet.py:59-106) + the parts of anneal_init that fix the problem (:288-457).
+ * structure_host[n_layers]; Lin_host[n_Lin] / Lout_host[n_Lout] = Lidx[0] / Lidx[1];
+ * data_in_dev (M, n_Lin), data_out_dev (M, n_Lout) row-major; Pidx_host[NPest] indexes the flat
+ * parameter vector [W_0 (d_1 x d_0 row-major), b_0, W_1, b_1, ...] (va_nnet.py:194-207). */
+VAB_API int vab_nn_problem_set(vab_ctx* ctx, int32_t n_layers, const int32_t* structure_host, int32_t M,
+                       int32_t activation,
+                       int32_t n_Lin, const int32_t* Lin_host,
+                       int32_t n_Lout, const int32_t* Lout_host,
+                       const double* data_in_dev, const double* data_out_dev,
+                       int32_t NPest, const int32_t* Pidx_host);
+/* RM scalar or (2,) (va_nnet.py:131-144): pass rm_in == rm_out for the scalar form. RF0 scalar. */
+VAB_API int vab_nn_set_weights(vab_ctx* ctx, double rm_in, double rm_out, double rf0);
+VAB_API int vab_nn_set_fixed_params(vab_ctx* ctx, const double* pfix_dev, int64_t pfix_stride);
+/* Replaces A_gradA_taped for va_nnet.A_gaussian (va_nnet.py:111-255). Same conventions. */
+VAB_API int vab_nn_action_grad(vab_ctx* ctx, int32_t B, const double* XP_dev, int64_t ldxp,
+                       double rf_scale, double* A_dev, double* me_dev, double* fe_dev,
+                       double* G_dev, int64_t ldg);
+
+/* ---- minimiser + ladder -------------------------------------------------------------------- */
+/* Options forwarded from opt_args to scipy.optimize.minimize(method='L-BFGS-B')
+ * (_autodiffmin.py:85-86): gtol -> pgtol, ftol -> ftol (factr = ftol/eps), maxfun, maxiter,
+ * maxcor -> m, maxls. */
+typedef struct {
+  int32_t m;          /* history size, SciPy default 10 */
+  int32_t maxls;      /* line-search steps per iteration, SciPy default 20 */
+  int64_t maxfun;     /* SciPy default 15000 */
+  int64_t maxiter;    /* SciPy default 15000 */
+  double ftol;        /* stop when (f_k - f_{k+1})/max(|f_k|,|f_{k+1}|,1) <= ftol */
+  double pgtol;       /* stop when max|proj g| <= pgtol */
+  int32_t poll_every; /* evaluations enqueued between host polls of the done flag (>=1) */
+  int32_t reserved;
+} vab_lbfgs_opts;
+
+/* Replaces ADmin.min_lbfgs_scipy (_autodiffmin.py:72-95) for whichever problem (ODE or NN) was
+ * set last on this context: minimise A(.; RF0*rf_scale) from XP_dev (overwritten by the
+ * minimiser) for B paths concurrently, entirely on the device (batched L-BFGS-B with per-path
+ * convergence masks).  lo_dev / hi_dev: (n) bounds shared by all paths or NULL (= unbounded),
+ * with +-inf for one-sided (va_ode.py:582-605, _autodiffmin.py:86).
+ * Outputs [B] each (device, may be NULL): A/me/fe at the minimiser, status (SciPy warnflag:
+ * 0 converged, 1 maxfun/maxiter, 2 abnormal), nit iterations, nfev evaluations. */
+VAB_API int vab_minimize(vab_ctx* ctx, int32_t B, double* XP_dev, int64_t ldxp, double rf_scale,
+                 const vab_lbfgs_opts* opts, const double* lo_dev, const double* hi_dev,
+                 double* A_dev, double* me_dev, double* fe_dev,
+                 int32_t* status_dev, int32_t* nit_dev, int32_t* nfev_dev);
+
+/* Replaces the beta loop of Annealer.anneal + anneal_step (va_ode.py:473-490, 707-789;
+ * va_nnet.py:281-286, 459-523): for i in range(Nbeta): minimise at RF0*alpha**beta[i] warm-started
+ * from the previous minimiser.  table_dev: (B, Nbeta, 5) rows [beta, A, me, fe, fe/(alpha**beta)]
+ * -- the caller divides column 4 by RF0 (va_ode.py:847-873).  minpaths_dev: (B, Nbeta, ldxp) or
+ * NULL; status/nit/nfev: (B, Nbeta) or NULL. */
+VAB_API int vab_anneal(vab_ctx* ctx, int32_t B, double* XP_dev, int64_t ldxp, double alpha,
+               const double* beta_host, int32_t Nbeta, const vab_lbfgs_opts* opts,
+               const double* lo_dev, const double* hi_dev,
+               double* table_dev, double* minpaths_dev,
+               int32_t* status_dev, int32_t* nit_dev, int32_t* nfev_dev);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VARANNEAL_B200_H */

@@ -1,0 +1,172 @@
+"""Device-side stand-in for the reference's ``ADmin`` base class (_autodiffmin.py:16-168).
+
+The reference tapes ``self.A`` with ADOL-C once per beta and hands ``A_gradA_taped`` to
+``scipy.optimize.minimize``.  Here both halves live in libvarannealb200.so: the fused analytic
+action+gradient kernels replace the tape, and a batched, device-resident L-BFGS-B replaces the
+SciPy driver.  The method names of the two seams are kept (``A_gradA_taped``,
+``min_lbfgs_scipy``) so code written against the reference keeps working; ``tape_A`` is a no-op
+because RF is a kernel argument, not a tape constant.
+"""
+import ctypes as ct
+
+import numpy as np
+
+from . import _lib
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("varanneal_b200 needs a CUDA device (B200); there is no CPU fallback")
+    return torch
+
+
+def ptr(t):
+    return ct.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def round_up(n, k):
+    return (n + k - 1) // k * k
+
+
+class DeviceMin(object):
+    """State shared by the ODE and NN annealers: native context, device buffers for the batch of
+    paths, and the eval / minimise seams."""
+
+    _ctx = None
+    _B = 1
+    _n = 0          # unknowns per path
+    _ld = 0         # leading dimension (doubles) of the path buffers
+    opt_args = None
+    bounds = None
+    RF0_scalar = None
+    verbose = False
+
+    # ------------------------------------------------------------------ plumbing
+    def _open_context(self, device=None):
+        torch = _torch()
+        if device is None:
+            device = torch.cuda.current_device()
+        self._device = torch.device("cuda", int(device))
+        if self._ctx is not None:
+            self._ctx.close()
+        stream = torch.cuda.current_stream(self._device).cuda_stream
+        self._ctx = _lib.Context(self._device.index, stream)
+        return self._ctx
+
+    def _to_dev(self, a, dtype=np.float64):
+        torch = _torch()
+        return torch.from_numpy(np.ascontiguousarray(a, dtype=dtype)).to(self._device)
+
+    def _alloc_paths(self, B, n):
+        torch = _torch()
+        self._B, self._n, self._ld = int(B), int(n), round_up(int(n), 16)
+        z = lambda *s, **k: torch.zeros(*s, dtype=k.get("dtype", torch.float64), device=self._device)  # noqa: E731
+        self._XP = z(self._B, self._ld)
+        self._G = z(self._B, self._ld)
+        self._A = z(self._B)
+        self._me = z(self._B)
+        self._fe = z(self._B)
+        self._status = z(self._B, dtype=torch.int32)
+        self._nit = z(self._B, dtype=torch.int32)
+        self._nfev = z(self._B, dtype=torch.int32)
+
+    def _upload_paths(self, XP):
+        torch = _torch()
+        XP = np.ascontiguousarray(np.atleast_2d(XP), dtype=np.float64)
+        if XP.shape != (self._B, self._n):
+            raise ValueError("XP has shape %s, expected (%d, %d)" % (XP.shape, self._B, self._n))
+        self._XP[:, :self._n].copy_(torch.from_numpy(XP))
+
+    def _action_grad_native(self, rf_scale):
+        raise NotImplementedError
+
+    # ------------------------------------------------------------------ eval seam
+    def _rf_scale(self):
+        return float(self.alpha) ** float(self.beta)
+
+    def A_gradA(self, XP):
+        """(A, grad A) at XP for the current RF.  XP flat (n,) -> (float, (n,) array); a batch
+        (B, n) -> ((B,), (B, n)).  Replaces ADmin.A_gradA_taped (_autodiffmin.py:57-58)."""
+        XP = np.asarray(XP, dtype=np.float64)
+        single = XP.ndim == 1
+        if single and self._B != 1:
+            raise ValueError("this Annealer was initialised with a batch of %d paths" % self._B)
+        self._upload_paths(XP)
+        self._action_grad_native(self._rf_scale())
+        A = self._A.cpu().numpy()
+        G = self._G[:, :self._n].cpu().numpy()
+        if single:
+            return float(A[0]), G[0]
+        return A, G
+
+    def A_gradA_taped(self, XP):
+        return self.A_gradA(XP)
+
+    def A_taped(self, XP):
+        return self.A_gradA(XP)[0]
+
+    def gradA_taped(self, XP):
+        return self.A_gradA(XP)[1]
+
+    def tape_A(self, xtrace=None):
+        """No-op: nothing is taped (kept for API compatibility, _autodiffmin.py:32-49)."""
+        self.taped = True
+
+    # ------------------------------------------------------------------ minimise seam
+    def _lbfgs_opts(self):
+        o = dict(self.opt_args or {})
+        known = {"gtol", "ftol", "maxfun", "maxiter", "maxcor", "maxls", "poll_every",
+                 "disp", "iprint", "eps", "maxiter_per_beta"}
+        bad = set(o) - known
+        if bad:
+            raise ValueError("unsupported opt_args keys for the device L-BFGS-B: %s" % sorted(bad))
+        opts = _lib.LbfgsOpts()
+        opts.m = int(o.get("maxcor", 10))
+        opts.maxls = int(o.get("maxls", 20))
+        opts.maxfun = int(min(float(o.get("maxfun", 15000)), 2 ** 62))
+        opts.maxiter = int(min(float(o.get("maxiter", 15000)), 2 ** 62))
+        opts.ftol = float(o.get("ftol", 2.220446049250313e-09))
+        opts.pgtol = float(o.get("gtol", 1e-5))
+        opts.poll_every = int(o.get("poll_every", 0))
+        opts.reserved = 0
+        return opts
+
+    def _minimize_device(self, rf_scale):
+        """Runs the device L-BFGS-B on the paths currently in self._XP (in place)."""
+        opts = self._lbfgs_opts()
+        lo = ptr(getattr(self, "_lo_dev", None))
+        hi = ptr(getattr(self, "_hi_dev", None))
+        _lib.check(self._ctx.lib.vab_minimize(
+            self._ctx.h, self._B, ptr(self._XP), self._ld, float(rf_scale), ct.byref(opts),
+            lo, hi, ptr(self._A), ptr(self._me), ptr(self._fe), ptr(self._status),
+            ptr(self._nit), ptr(self._nfev)), self._ctx.h)
+
+    def min_lbfgs_scipy(self, XP0, xtrace=None):
+        """Same contract as ADmin.min_lbfgs_scipy (_autodiffmin.py:72-95): returns
+        (XPmin, Amin, status) -- but the whole minimisation runs on the device.  With a batch,
+        the three are arrays over the paths."""
+        XP0 = np.asarray(XP0, dtype=np.float64)
+        single = XP0.ndim == 1
+        self._upload_paths(XP0)
+        self._minimize_device(self._rf_scale())
+        XPmin = self._XP[:, :self._n].cpu().numpy()
+        A = self._A.cpu().numpy()
+        st = self._status.cpu().numpy()
+        self.last_nit = self._nit.cpu().numpy()
+        self.last_nfev = self._nfev.cpu().numpy()
+        if single:
+            return XPmin[0], float(A[0]), int(st[0])
+        return XPmin, A, st
+
+    min_lbfgs = min_lbfgs_scipy
+
+    def min_cg_scipy(self, XP0, xtrace=None):
+        raise NotImplementedError("method='NCG' (SURVEY.md 8(f2)) is not built yet on the device")
+
+    def min_tnc_scipy(self, XP0, xtrace=None):
+        raise NotImplementedError("method='TNC' (SURVEY.md 8(f2)) is not built yet on the device")
+
+    @property
+    def gpu_launches(self):
+        return self._ctx.launches if self._ctx is not None else 0

@@ -1,0 +1,59 @@
+// Internal context layout of libvarannealb200.so (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/varanneal_b200.h"
+#include "ode_plan.h"
+#include "ode_walk.cuh"
+
+struct NnProblem;   // nn_action.h
+struct LbfgsWork;   // lbfgs.h
+
+enum { VAB_PROBLEM_NONE = 0, VAB_PROBLEM_ODE = 1, VAB_PROBLEM_NN = 2 };
+
+struct vab_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int num_sms = 148;
+  std::string err;
+  long long launches = 0;
+  int problem = VAB_PROBLEM_NONE;
+
+  // ---- ODE problem (vab_ode_problem_set / set_weights / set_fixed_params)
+  vab_ode_desc od{};
+  int* obs_slot_dev = nullptr;      // (D)
+  int* pmap_dev = nullptr;          // (NP)
+  const double* Y_dev = nullptr;
+  const double* stim_dev = nullptr;
+  double rm_scalar = 1.0;
+  const double* rm_dev = nullptr;
+  double rf0_scalar = 1.0;
+  const double* rf0_dev = nullptr;
+  const double* pfix_dev = nullptr;
+  long long pfix_stride = 0;
+  double* pfix_zero = nullptr;      // default fixed-parameter block (zeros)
+  int tseg_override = 0;            // tuning knob (env VAB_TSEG)
+
+  // ---- NN problem
+  NnProblem* nn = nullptr;
+
+  // ---- workspaces
+  double* partials = nullptr;
+  size_t partials_cap = 0;          // doubles
+  LbfgsWork* lb = nullptr;
+
+  long long n_unknowns() const;     // per path, for the problem currently set
+};
+
+int vab_fail(vab_ctx* ctx, int code, const std::string& msg);
+int vab_cuda_fail(vab_ctx* ctx, cudaError_t e, const char* where);
+// grow-only device buffer
+int vab_reserve(vab_ctx* ctx, double** buf, size_t* cap, size_t need);
+
+// objective evaluation for the problem currently set (ODE or NN); used by the minimiser.
+// active_dev: (B) int mask or nullptr.
+int vab_eval(vab_ctx* ctx, int B, const double* XP, long long ldxp, double rf_scale,
+             const int* active_dev, double* A, double* me, double* fe, double* G, long long ldg);
