@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""bench.py -- action+gradient evals/s of the annealing hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1], SURVEY.md 8(d) "C2"): Lorenz96 D=100, N=5001 model points
+(Simpson-Hermite needs an odd N), L=40 observed components, a batch of 64
+independent paths per GPU, synthetic twin-experiment data.  One *step* = one fused
+action+gradient evaluation of the whole batch = 64 evals.  Under torchrun every rank owns its
+own batch of 64 paths (weak scaling, no collective on the data path); time = max over ranks.
+
+JSON keys: see the contract in the task statement.  ``value`` = device-resident evals/s,
+``e2e`` = the same through ``va_ode.Annealer.A_gradA`` with pinned host buffers (H2D of XP and
+D2H of A and grad inside the timed region), ``roofline`` = algorithmic bytes / kernel time
+against MEASURED_PEAKS.json, ``cpu_baseline`` = the NumPy oracle port on one host core.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+D, N_MODEL, DT, K_FORCING = 100, 5001, 0.025, 8.17
+PATHS_PER_GPU = 64
+RM, RF0, ALPHA, BETA_EVAL = 4.0, 4e-6, 2.5, 10
+LIDX = [i for i in range(D) if i % 5 in (0, 2)]
+METRIC = "action+gradient evals/sec (Lorenz96 D=100 N=5001 SimpsonHermite, 64 paths/GPU)"
+UNIT = "evals/s"
+
+
+def l96(x, k):
+    return np.roll(x, 1, -1) * (np.roll(x, -1, -1) - np.roll(x, 2, -1)) - x + k
+
+
+def twin_data(seed=100):
+    """SURVEY.md 8(d) C2 recipe: RK4-integrate L96, drop a transient, add N(0, 0.5^2) noise."""
+    rng = np.random.RandomState(seed)
+    x = K_FORCING + rng.randn(D)
+    rows = []
+    for n in range(1000 + N_MODEL):
+        k1 = l96(x, K_FORCING)
+        k2 = l96(x + 0.5 * DT * k1, K_FORCING)
+        k3 = l96(x + 0.5 * DT * k2, K_FORCING)
+        k4 = l96(x + DT * k3, K_FORCING)
+        x = x + DT / 6.0 * (k1 + 2 * k2 + 2 * k3 + k4)
+        if n >= 1000:
+            rows.append(x.copy())
+    truth = np.array(rows)
+    Y = truth[:, LIDX] + 0.5 * np.random.RandomState(seed + 1).randn(N_MODEL, len(LIDX))
+    return truth, Y
+
+
+def initial_paths(B, first_seed):
+    X0 = np.empty((B, N_MODEL, D))
+    P0 = np.empty((B, 1))
+    for b in range(B):
+        rng = np.random.RandomState(first_seed + b)
+        X0[b] = 20.0 * rng.rand(N_MODEL, D) - 10.0
+        P0[b, 0] = 4.0 * rng.rand() + 6.0
+    return X0, P0
+
+
+def algorithmic_bytes(B):
+    """read X once + write grad once + read Y once, per path."""
+    return B * (16 * N_MODEL * D + 8 * N_MODEL * len(LIDX))
+
+
+# ------------------------------------------------------------------------------------ clocks
+class ClockSampler(object):
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for nm, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------ CPU arms
+def _oracle_problem(Y):
+    from oracle.ode_port import OdeProblem      # the checker, used here as the CPU baseline only
+    return OdeProblem("lorenz96", D, Y, LIDX, DT, "SimpsonHermite", np.array([K_FORCING]), [0], RM)
+
+
+def _cpu_worker(args):
+    Y, seed, reps = args
+    os.environ["OMP_NUM_THREADS"] = "1"
+    prob = _oracle_problem(Y)
+    X0, P0 = initial_paths(1, seed)
+    XP = np.append(X0[0].ravel(), P0[0])
+    rf = RF0 * ALPHA ** BETA_EVAL
+    for _ in range(reps):
+        prob.action_grad(XP, rf)
+    return reps
+
+
+def cpu_baseline_single_core(Y, budget_s=12.0):
+    prob = _oracle_problem(Y)
+    X0, P0 = initial_paths(1, 1000)
+    XP = np.append(X0[0].ravel(), P0[0])
+    rf = RF0 * ALPHA ** BETA_EVAL
+    prob.action_grad(XP, rf)
+    t0 = time.perf_counter()
+    reps = 0
+    while time.perf_counter() - t0 < budget_s and reps < 400:
+        prob.action_grad(XP, rf)
+        reps += 1
+    dt = time.perf_counter() - t0
+    return {"value": reps / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": "%d evals of one C2 path (NumPy oracle port of va_ode.A_gaussian + analytic "
+                      "adjoint, stand-in for pyadolc which is not installable), %.1f s" % (reps, dt)}
+
+
+def run_reference(args):
+    """--impl reference: the CPU path (oracle port; pyadolc/python2 are absent so the reference
+    itself cannot run) on all host cores, one path per process like the reference's SGE array."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    _, Y = twin_data()
+    cores = os.cpu_count() or 1
+    reps = 2
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        jobs = [(Y, 1000 + c, reps) for c in range(cores)]
+        for _ in range(args.warmup):
+            pool.map(_cpu_worker, jobs)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            pool.map(_cpu_worker, jobs)
+        dt = time.perf_counter() - t0
+    evals = cores * reps * args.steps
+    val = evals / dt
+    sample = ("each step = %d processes x %d evals of one C2 path each (NumPy oracle port, "
+              "stand-in for pyadolc)" % (cores, reps))
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": workload_config(args.gpus),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def workload_config(n_gpus):
+    return {"workload": "C2: Lorenz96 D=100, N_model=5001, L=40 observed, SimpsonHermite, "
+                        "RF=RF0*alpha**beta at beta=%d, twin-experiment data" % BETA_EVAL,
+            "paths_per_gpu": PATHS_PER_GPU, "global_paths": PATHS_PER_GPU * n_gpus,
+            "unknowns_per_path": N_MODEL * D + 1, "parallelism": "paths sharded over GPUs, no collective",
+            "l2_policy": "inputs larger than L2 (XP + grad = 512 MB per step per GPU vs 126 MB L2)"}
+
+
+# ------------------------------------------------------------------------------------ GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from varanneal_b200 import va_ode
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    B = PATHS_PER_GPU
+    _, Y = twin_data()
+    X0, P0 = initial_paths(B, 1000 + rank * B)
+    an = va_ode.Annealer(device=local)
+    an.set_model("lorenz96", D)
+    an.set_data(Y, t=DT * np.arange(N_MODEL))
+    an.anneal_init(X0, P0, ALPHA, [BETA_EVAL], RM, RF0, LIDX, [0], disc="SimpsonHermite",
+                   init_to_data=True, opt_args={"gtol": 1e-8, "ftol": 1e-8})
+    n = an._n
+    XP_host = torch.empty(B, n, dtype=torch.float64, pin_memory=True)
+    XP_host[:, :N_MODEL * D] = torch.from_numpy(X0.reshape(B, -1))
+    XP_host[:, N_MODEL * D:] = torch.from_numpy(P0)
+    an._XP[:, :n].copy_(XP_host)
+    scale = an._rf_scale()
+    stream = torch.cuda.current_stream()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident evals/s
+    for _ in range(args.warmup):
+        an._action_grad_native(scale)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = an.gpu_launches
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    barrier()
+    ev[0].record(stream)
+    for i in range(args.steps):
+        an._action_grad_native(scale)
+        ev[i + 1].record(stream)
+    barrier()
+    launches = an.gpu_launches - l0
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = ev[0].elapsed_time(ev[-1])
+    per_step = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t.item())
+    value = world * B * args.steps / (total_ms_max * 1e-3)
+
+    # ---- end to end through the public eval seam, pinned host buffers
+    for _ in range(2):
+        an.A_gradA(XP_host)
+    barrier()
+    t0 = time.perf_counter()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(e2e_steps):
+        A_h, G_h = an.A_gradA(XP_host)
+    e1.record(stream)
+    barrier()
+    e2e_ms = max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t0) * 0.0)
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_val = world * B * e2e_steps / (float(t.item()) * 1e-3)
+
+    if rank == 0:
+        peaks = {}
+        pk_src = "fallback"
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+                peaks = json.load(fh)
+            pk_src = "measured"
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        kern_ms = float(np.mean(per_step))
+        achieved = algorithmic_bytes(B) / (kern_ms * 1e-3) / 1e9
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+                traffic = json.load(fh).get("ode_walk_bytes_per_launch")
+        except Exception:
+            pass
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": workload_config(world),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": pk_src,
+                         "kernel": "ode_walk_kernel<ModelL96<4>, SimpsonHermite> (+3 us finalize)",
+                         "algorithmic_bytes_per_launch": algorithmic_bytes(B),
+                         "kernel_ms": kern_ms},
+            "e2e": {"value": e2e_val, "unit": UNIT,
+                    "h2d_bytes_per_step": int(XP_host.numel() * 8),
+                    "d2h_bytes_per_step": int(G_h.numel() * 8 + A_h.numel() * 8),
+                    "api": "va_ode.Annealer.A_gradA(pinned XP) -> (A, grad) pinned"},
+            "gpu_launches": int(launches), "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_baseline_single_core(Y)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -85,9 +85,32 @@ class DeviceMin(object):
     def _rf_scale(self):
         return float(self.alpha) ** float(self.beta)
 
+    def _pinned(self):
+        """Pinned host staging buffers for the eval seam (allocated on first use)."""
+        torch = _torch()
+        if getattr(self, "_XP_pin", None) is None or self._XP_pin.shape != (self._B, self._n):
+            self._XP_pin = torch.empty(self._B, self._n, dtype=torch.float64, pin_memory=True)
+            self._G_pin = torch.empty(self._B, self._n, dtype=torch.float64, pin_memory=True)
+            self._A_pin = torch.empty(self._B, dtype=torch.float64, pin_memory=True)
+        return self._XP_pin, self._G_pin, self._A_pin
+
     def A_gradA(self, XP):
         """(A, grad A) at XP for the current RF.  XP flat (n,) -> (float, (n,) array); a batch
-        (B, n) -> ((B,), (B, n)).  Replaces ADmin.A_gradA_taped (_autodiffmin.py:57-58)."""
+        (B, n) -> ((B,), (B, n)).  Replaces ADmin.A_gradA_taped (_autodiffmin.py:57-58).
+        A pinned host ``torch.Tensor`` (B, n) is copied to the device without staging and the
+        results come back as pinned host tensors (valid until the next call)."""
+        torch = _torch()
+        if isinstance(XP, torch.Tensor):
+            if XP.shape != (self._B, self._n) or XP.dtype != torch.float64:
+                raise ValueError("XP tensor must be float64 of shape (%d, %d)" % (self._B, self._n))
+            _, G_pin, A_pin = self._pinned()
+            self._XP[:, :self._n].copy_(XP, non_blocking=True)
+            self._dev_paths_current = False
+            self._action_grad_native(self._rf_scale())
+            G_pin.copy_(self._G[:, :self._n], non_blocking=True)
+            A_pin.copy_(self._A, non_blocking=True)
+            torch.cuda.current_stream(self._device).synchronize()
+            return A_pin, G_pin
         XP = np.asarray(XP, dtype=np.float64)
         single = XP.ndim == 1
         if single and self._B != 1:
