@@ -96,13 +96,16 @@ typedef struct {
 /* Lidx_host[L], Pidx_host[NPest]: index lists as passed to anneal().
  * Y_dev: (N_data, L) row-major observations (va_ode.py:112,120).
  * stim_dev: (N_model, n_stim) row-major or NULL.
- * The arrays behind Y_dev / stim_dev must stay alive while the problem is set. */
+ * Y is copied into a library-owned buffer during the call (padded rows, columns sorted by
+ * state component, the layout the kernels stream); the array behind stim_dev must stay alive
+ * while the problem is set. */
 VAB_API int vab_ode_problem_set(vab_ctx* ctx, const vab_ode_desc* desc,
                         const int32_t* Lidx_host, const int32_t* Pidx_host,
                         const double* Y_dev, const double* stim_dev);
 
 /* RM / RF0 exactly as anneal_init normalises them (va_ode.py:612-640): a scalar, or a per-entry
  * array already broadcast to (N_data, L) / (N_model-1, D).  rm_dev / rf0_dev NULL = scalar.
+ * An RM array is copied by the call; the array behind rf0_dev must stay alive.
  * The (.,L,L)/(.,D,D) matrix forms are unsupported (the reference's own branch is broken,
  * va_ode.py:222). */
 VAB_API int vab_ode_set_weights(vab_ctx* ctx, double rm_scalar, const double* rm_dev,

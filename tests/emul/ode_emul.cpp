@@ -70,6 +70,8 @@ extern "C" int emul_ode_action_grad(
   P.pfix = pfix; P.pfix_stride = pfix_stride;
   P.Tseg = pl.Tseg; P.nseg = pl.nseg; P.TPR = pl.TPR; P.RG = pl.RG; P.nunits = pl.nunits;
   P.K = 2 + NP;
+  P.upp = pl.nseg;
+  P.Lp = L;
   std::vector<double> partials((size_t)pl.nunits * P.K, 0.0);
   P.partials = partials.data();
   P.active = active;

@@ -3,6 +3,10 @@
 
 #include "ode_action.h"
 #include "ode_dispatch.h"
+#include "ode_sweep.cuh"
+#include "ode_stream.cuh"
+
+#include <cstdlib>
 
 namespace {
 
@@ -89,6 +93,211 @@ int ode_launch_action(const OdeParams& P, const OdePlan& pl, int model, int disc
   }
   ode_finalize_kernel<<<P.B, 32, 0, st>>>(P, A, me, fe);
   cudaError_t e = cudaGetLastError();
+  if (cerr) *cerr = e;
+  return e == cudaSuccess ? 0 : -2;
+}
+
+// ============================================================================================
+// sweep kernels: plan + dispatch
+// ============================================================================================
+#ifndef VAB_SW_PD2
+#define VAB_SW_PD2 2     // prefetch distance (rows) of the two-point kernels
+#endif
+#ifndef VAB_SW_PDS
+#define VAB_SW_PDS 1     // prefetch distance (pairs) of the Simpson kernel
+#endif
+#ifndef VAB_SW_PDR
+#define VAB_SW_PDR 1     // prefetch distance (rows) of the RK4 kernel
+#endif
+#ifndef VAB_SW_MINB
+#define VAB_SW_MINB 4    // resident CTAs per SM the register allocator must allow
+#endif
+
+namespace {
+
+typedef void (*SweepKernel)(const OdeParams);
+
+template <class M, int MINB>
+SweepKernel sweep_kernel_for(int disc) {
+  switch (disc) {
+    case DISC_EULER: return sweep_twopoint_kernel<M, DISC_EULER, VAB_SW_PD2, MINB>;
+    case DISC_TRAPEZOID: return sweep_twopoint_kernel<M, DISC_TRAPEZOID, VAB_SW_PD2, MINB>;
+    case DISC_FORWARDMAP: return sweep_twopoint_kernel<M, DISC_FORWARDMAP, VAB_SW_PD2, MINB>;
+    case DISC_SIMPSON: return sweep_simpson_kernel<M, VAB_SW_PDS, MINB>;
+    case DISC_RK4: return sweep_rk4_kernel<M, VAB_SW_PDR, MINB>;
+  }
+  return nullptr;
+}
+
+SweepKernel sweep_kernel(int model, int C, int disc) {
+  if (model == 0) {
+    if (C == 4) {
+      if (disc == DISC_SIMPSON) {                 // tuning variants of the flagship kernel
+        static int variant = -1;
+        if (variant < 0) {
+          const char* v = getenv("VAB_SIMPSON_VARIANT");
+          variant = v ? atoi(v) : 0;
+        }
+        switch (variant) {
+          case 1: return sweep_simpson_kernel<ModelL96<4>, 1, 3>;
+          case 2: return sweep_simpson_kernel<ModelL96<4>, 2, 3>;
+          case 3: return sweep_simpson_kernel<ModelL96<4>, 2, 2>;
+          default: return sweep_simpson_kernel<ModelL96<4>, 1, 4>;
+        }
+      }
+      return sweep_kernel_for<ModelL96<4>, VAB_SW_MINB>(disc);
+    }
+    if (C == 2) return sweep_kernel_for<ModelL96<2>, VAB_SW_MINB>(disc);
+    if (C == 1) return sweep_kernel_for<ModelL96<1>, VAB_SW_MINB>(disc);
+    return nullptr;
+  }
+  if (model == 1) return sweep_kernel_for<ModelL63, VAB_SW_MINB>(disc);
+  if (model == 2) return sweep_kernel_for<ModelNaKL, 2>(disc);
+  return nullptr;
+}
+
+#ifndef VAB_ST_NS
+#define VAB_ST_NS 4      // ring stages per warp of the stream kernels (prefetch = NS-2 stages)
+#endif
+#ifndef VAB_ST_MINB
+#define VAB_ST_MINB 4
+#endif
+
+template <class M, bool FAST>
+SweepKernel stream_kernel_for(int disc) {
+  switch (disc) {
+    case DISC_EULER: return stream_twopoint_kernel<M, DISC_EULER, VAB_ST_NS, VAB_ST_MINB, FAST>;
+    case DISC_TRAPEZOID: return stream_twopoint_kernel<M, DISC_TRAPEZOID, VAB_ST_NS, VAB_ST_MINB, FAST>;
+    case DISC_FORWARDMAP: return stream_twopoint_kernel<M, DISC_FORWARDMAP, VAB_ST_NS, VAB_ST_MINB, FAST>;
+    case DISC_SIMPSON: return stream_simpson_kernel<M, VAB_ST_NS, VAB_ST_MINB, FAST>;
+  }
+  return nullptr;
+}
+int stream_variant() {
+  static int variant = -1;
+  if (variant < 0) {
+    const char* v = getenv("VAB_STREAM_VARIANT");
+    variant = v ? atoi(v) : 0;
+  }
+  return variant;
+}
+int stream_ns(int C, int disc, bool fast) {
+  if (fast && C == 4 && disc == DISC_SIMPSON) {
+    switch (stream_variant()) {
+      case 2: return 6;
+      case 3: return 3;
+      default: return 4;
+    }
+  }
+  return VAB_ST_NS;
+}
+SweepKernel stream_kernel(int C, int disc, bool fast) {
+  if (fast && C == 4 && disc == DISC_SIMPSON) {       // tuning variants of the flagship kernel
+    switch (stream_variant()) {
+      case 1: return stream_simpson_kernel<ModelL96<4>, 4, 3, true>;
+      case 2: return stream_simpson_kernel<ModelL96<4>, 6, 3, true>;
+      case 3: return stream_simpson_kernel<ModelL96<4>, 3, 4, true>;
+      default: return stream_simpson_kernel<ModelL96<4>, 4, 4, true>;
+    }
+  }
+  if (C == 4) return fast ? stream_kernel_for<ModelL96<4>, true>(disc) : stream_kernel_for<ModelL96<4>, false>(disc);
+  if (C == 2) return fast ? stream_kernel_for<ModelL96<2>, true>(disc) : stream_kernel_for<ModelL96<2>, false>(disc);
+  return nullptr;
+}
+
+// resident CTAs per SM of each kernel at a given dynamic shared memory size (queried once)
+int blocks_per_sm(SweepKernel k, size_t smem, cudaError_t* cerr) {
+  struct Entry { SweepKernel k; size_t smem; int nb; };
+  static Entry seen[128];
+  static int nseen = 0;
+  for (int i = 0; i < nseen; ++i)
+    if (seen[i].k == k && seen[i].smem == smem) return seen[i].nb;
+  cudaError_t e = cudaSuccess;
+  if (smem > 48 * 1024) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  int nb = 0;
+  if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k, 128, smem);
+  if (e != cudaSuccess) {
+    if (cerr) *cerr = e;
+    return -1;
+  }
+  if (nb < 1) return 0;
+  if (nseen < 128) seen[nseen++] = Entry{k, smem, nb};
+  return nb;
+}
+
+}  // namespace
+
+int ode_sweep_prepare(int model, int disc, int D, int N, int B, int num_sms, int tseg_override,
+                      bool allow_stream, OdeParams* P, SweepLaunch* sl, cudaError_t* cerr) {
+  OdeGeo g;
+  if (ode_geometry(model, disc, D, &g) != 0) return -1;
+  const int K = 2 + ode_model_npm(model);
+  P->TPR = g.TPR; P->GW = g.GW; P->GPW = g.GPW; P->WS = g.WS; P->nwin = g.nwin; P->NHL = g.NHL;
+  P->K = K;
+  sl->C = g.C;
+  sl->stream = false;
+  sl->smem = (size_t)128 * K * sizeof(double);
+  SweepKernel k = nullptr;
+  int nb = 0;
+  if (allow_stream && ode_stream_supported(model, disc, g)) {
+    const size_t stage_d = (size_t)g.GPW * (2 * (size_t)g.GW * g.C + 2 * (size_t)P->Lw);
+    const bool fast = (P->nskip == 1 && P->rm_arr == nullptr && P->rf_arr == nullptr);
+    const int ns = stream_ns(g.C, disc, fast);
+    const size_t smem = ((size_t)4 * ns * stage_d + 4 * ns + (size_t)128 * K) * sizeof(double);
+    if (smem <= 200 * 1024) {
+      k = stream_kernel(g.C, disc, fast);
+      nb = k ? blocks_per_sm(k, smem, cerr) : 0;
+      if (nb < 0) return -2;
+      if (nb > 0) { sl->stream = true; sl->smem = smem; }
+    }
+  }
+  if (!sl->stream) {
+    k = sweep_kernel(model, g.C, disc);
+    if (!k) return -1;
+    nb = blocks_per_sm(k, sl->smem, cerr);
+    if (nb < 0) return -2;
+    if (nb == 0) nb = 1;
+  }
+  // one wave of resident warps, every warp walking an equally long segment
+  const int lead = (disc == DISC_SIMPSON) ? 3 : 2;
+  long long target_warps = (long long)num_sms * nb * 4;
+  if (const char* w = getenv("VAB_WAVES")) target_warps *= (atoi(w) > 0 ? atoi(w) : 1);
+  const long long wpb = ((long long)B + g.GPW - 1) / g.GPW;      // warps per (segment, window)
+  long long per_seg = wpb * g.nwin;
+  long long nseg = (target_warps + per_seg / 2) / per_seg;
+  if (nseg < 1) nseg = 1;
+  long long tseg = (N + nseg - 1) / nseg;
+  const int tmin = 8 * lead;                              // keep the lead-in rows under ~12 %
+  if (tseg < tmin) tseg = tmin;
+  if (tseg > N) tseg = N;
+  if (tseg_override > 0) tseg = tseg_override;
+  if (tseg % 2) tseg += 1;
+  P->Tseg = (int)tseg;
+  P->nseg = (N + P->Tseg - 1) / P->Tseg;
+  P->upp = P->nseg * g.nwin;
+  P->nunits = B * P->upp;
+  P->wpb = (int)wpb;
+  long long warps;
+  if (sl->stream) {
+    warps = wpb * P->nseg * g.nwin;
+  } else {
+    warps = ((long long)P->nunits + g.GPW - 1) / g.GPW;
+  }
+  sl->grid = (int)((warps + 3) / 4);
+  return 0;
+}
+
+int ode_sweep_launch(const OdeParams& P, const SweepLaunch& sl, int model, int disc,
+                     cudaStream_t st, double* A, double* me, double* fe, cudaError_t* cerr) {
+  const bool fast = (P.nskip == 1 && P.rm_arr == nullptr && P.rf_arr == nullptr);
+  SweepKernel k = sl.stream ? stream_kernel(sl.C, disc, fast) : sweep_kernel(model, sl.C, disc);
+  if (!k) return -1;
+  k<<<sl.grid, 128, sl.smem, st>>>(P);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) {
+    ode_finalize_kernel<<<P.B, 32, 0, st>>>(P, A, me, fe);
+    e = cudaGetLastError();
+  }
   if (cerr) *cerr = e;
   return e == cudaSuccess ? 0 : -2;
 }

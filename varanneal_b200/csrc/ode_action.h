@@ -4,8 +4,22 @@
 #include "ode_plan.h"
 #include "ode_walk.cuh"
 
-// Launches the strip-walk kernel selected by (model, plan.C, disc) followed by the per-path
-// finalize kernel (2 launches).  Returns 0, -1 (unsupported combination) or -2 (CUDA error, code
-// in *cerr).  A / me / fe may be nullptr.
+// Legacy strip-walk kernels (shared-memory halo exchange, one __syncthreads per phase); kept as the
+// A/B reference for the sweep kernels (env VAB_KERNEL=walk).  Returns 0, -1 (unsupported
+// combination) or -2 (CUDA error, code in *cerr).  A / me / fe may be nullptr.
 int ode_launch_action(const OdeParams& P, const OdePlan& pl, int model, int disc,
                       cudaStream_t st, double* A, double* me, double* fe, cudaError_t* cerr);
+
+// Register-sweep kernels (ode_sweep.cuh).  ode_sweep_prepare fills the mapping fields of P
+// (TPR, GW, GPW, WS, nwin, NHL, Tseg, nseg, nunits, upp) and the launch shape; the caller then
+// sizes P.partials (nunits * K doubles) and calls ode_sweep_launch (walk kernel + finalize).
+struct SweepLaunch {
+  int C;         // strip width
+  int grid;      // CTAs of 128 threads
+  bool stream;   // TMA stream kernel (ode_stream.cuh) instead of the register sweep
+  size_t smem;   // dynamic shared memory per CTA
+};
+int ode_sweep_prepare(int model, int disc, int D, int N, int B, int num_sms, int tseg_override,
+                      bool allow_stream, OdeParams* P, SweepLaunch* sl, cudaError_t* cerr);
+int ode_sweep_launch(const OdeParams& P, const SweepLaunch& sl, int model, int disc,
+                     cudaStream_t st, double* A, double* me, double* fe, cudaError_t* cerr);

@@ -36,6 +36,6 @@ int ode_dispatch(int model, int C, int disc, F& fn) {
 // Sum of one partial slot over the segments of path b, in segment order (deterministic).
 VAB_HD double ode_partial_sum(const OdeParams& P, int b, int k) {
   double acc = 0.0;
-  for (int sg = 0; sg < P.nseg; ++sg) acc += P.partials[((long long)b * P.nseg + sg) * P.K + k];
+  for (int u = 0; u < P.upp; ++u) acc += P.partials[((long long)b * P.upp + u) * P.K + k];
   return acc;
 }

@@ -39,6 +39,18 @@ struct ModelL96 {
       pacc[0] += vh[c];
     }
   }
+  // the same without the diagonal term:  t_j = (J^T v)_j + v_j  (callers fold v into the store)
+  VAB_HD static void adj_t(const double* xh, const double* vh, const double* /*p*/, double* t,
+                           double* pacc) {
+#pragma unroll
+    for (int j = 0; j < C; ++j) {
+      const int c = j + H;
+      double u = vh[c + 1] * (xh[c + 2] - xh[c - 1]);
+      u = fma(vh[c - 1], xh[c - 2], u);
+      t[j] = fma(-vh[c + 2], xh[c + 1], u);
+      pacc[0] += vh[c];
+    }
+  }
 };
 
 struct ModelL63 {

@@ -54,3 +54,50 @@ inline int ode_make_plan(int model, int disc, int D, int N, int B, int num_sms, 
   pl->grid = (pl->nunits + pl->RG - 1) / pl->RG;
   return 0;
 }
+
+// ---- lane geometry shared by the sweep and stream kernels (see ode_sweep.cuh / ode_stream.cuh)
+struct OdeGeo {
+  int C, H;      // strip width, stencil halo (components)
+  int TPR;       // strips per row
+  int GW, GPW;   // lanes per group, groups per warp
+  int WS, nwin;  // output strips per window, windows per row
+  int NHL;       // halo lanes either side of a window (0: whole row in one group, periodic wrap)
+};
+
+inline int ode_geometry(int model, int disc, int D, OdeGeo* g) {
+  if (model == 0) {
+    if (D < 4) return -1;
+    g->C = (D % 4 == 0) ? 4 : ((D % 2 == 0) ? 2 : 1);
+    g->H = 2;
+  } else if (model == 1) {
+    if (D != 3) return -1;
+    g->C = 3; g->H = 0;
+  } else if (model == 2) {
+    if (D != 4) return -1;
+    g->C = 4; g->H = 0;
+  } else {
+    return -1;
+  }
+  g->TPR = D / g->C;
+  if (g->H == 0) {
+    g->GW = 1; g->WS = 1; g->nwin = 1; g->NHL = 0;
+  } else if (g->TPR <= 32) {
+    g->GW = g->TPR; g->WS = g->TPR; g->nwin = 1; g->NHL = 0;
+  } else {
+    const int need = (disc == 4) ? 12 : 3;     // components of validity lost per side (rk4 : others)
+    g->NHL = (need + g->C - 1) / g->C;
+    const int usable = 32 - 2 * g->NHL;
+    if (usable < 1) return -1;
+    g->nwin = (g->TPR + usable - 1) / usable;
+    g->WS = (g->TPR + g->nwin - 1) / g->nwin;
+    g->GW = g->WS + 2 * g->NHL;
+  }
+  g->GPW = 32 / g->GW;
+  return 0;
+}
+
+// the TMA stream kernels exist for the Lorenz96 stencil with 16-byte strips and the one/two-row
+// discretisations
+inline bool ode_stream_supported(int model, int disc, const OdeGeo& g) {
+  return model == 0 && (g.C == 4 || g.C == 2) && disc != 4;
+}

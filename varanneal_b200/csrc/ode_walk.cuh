@@ -33,10 +33,13 @@ struct OdeParams {
   long long ldg;
   int B, D, N, N_data, nskip, L;
   double dt;
-  const int* obs_slot;    // (D) -> column of Y, or -1
-  const double* Y;        // (N_data, L)
+  const int* obs_slot;    // (D) -> column of Y (library layout: columns sorted by component), or -1
+  const double* Y;        // (N_data, Lp) library copy of the observations, row pitch Lp (even)
+  int Lp;
   double rm_scalar;
-  const double* rm_arr;   // (N_data, L) or nullptr
+  const double* rm_arr;   // (N_data, Lp) same layout as Y, or nullptr
+  const int* win_y0;      // (nwin) first Y column (even) a window's stage copies; stream kernels
+  int Lw;                 // Y columns copied per row and window (even)
   double rf_scalar;       // RF0*scale when rf_arr == nullptr
   const double* rf_arr;   // RF0 (N-1, D) or nullptr
   double rf_scale;
@@ -48,7 +51,11 @@ struct OdeParams {
   long long pfix_stride;  // 0 (shared) or NP
   int Tseg, nseg;         // rows per segment, segments per path
   int TPR, RG;            // threads per row-group, row-groups per CTA
-  int nunits;             // B*nseg
+  int nunits;             // units in the launch
+  int upp;                // units per path (their partials are contiguous and summed in order)
+  int wpb;                // stream kernels: warps per (segment, window) = ceil(B / GPW)
+  int GW, GPW, WS, nwin, NHL;   // sweep kernels: lanes per group, groups per warp, output strips
+                                // per window, windows per row, halo lanes either side (0 = wrap)
   int K;                  // partial slots per unit = 2 + NPM
   double* partials;       // (nunits, K)
   const int* active;      // (B) or nullptr: skip paths with active[b] == 0
@@ -155,7 +162,7 @@ struct WalkBase {
 #pragma unroll
     for (int j = 0; j < C; ++j) {
       if (slot[j] >= 0) {
-        const long long o = nd * Pp->L + slot[j];
+        const long long o = nd * Pp->Lp + slot[j];
         const double rm = Pp->rm_arr ? vab_ldg(Pp->rm_arr + o) : Pp->rm_scalar;
         const double diff = xown[j] - vab_ldg(Pp->Y + o);
         me_acc = fma(rm * diff, diff, me_acc);

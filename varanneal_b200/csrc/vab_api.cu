@@ -37,6 +37,32 @@ int vab_reserve(vab_ctx* ctx, double** buf, size_t* cap, size_t need) {
   return VAB_OK;
 }
 
+// dst (rows, Lp) <- src (rows, L) with column l going to perm[l] (padding zeroed beforehand)
+__global__ void vab_pack_obs_scatter(const double* __restrict__ src, double* __restrict__ dst,
+                                     const int* __restrict__ perm, long long rows, int L, int Lp) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * L) return;
+  const long long r = i / L;
+  const int l = (int)(i - r * L);
+  dst[r * Lp + perm[l]] = src[i];
+}
+
+static int vab_pack_obs(vab_ctx* ctx, const double* src, double** dst, size_t* cap) {
+  const vab_ode_desc& d = ctx->od;
+  const size_t need = (size_t)d.N_data * ctx->Lp + ctx->Lw + 2;
+  int rc = vab_reserve(ctx, dst, cap, need);
+  if (rc != VAB_OK) return rc;
+  cudaError_t e = cudaMemsetAsync(*dst, 0, need * sizeof(double), ctx->stream);
+  if (e != cudaSuccess) return vab_cuda_fail(ctx, e, "pack observations (memset)");
+  const long long n = (long long)d.N_data * d.L;
+  if (n > 0)
+    vab_pack_obs_scatter<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(src, *dst, ctx->lperm_dev, d.N_data, d.L, ctx->Lp);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return vab_cuda_fail(ctx, e, "pack observations");
+  ctx->launches += 1;
+  return VAB_OK;
+}
+
 long long vab_ctx::n_unknowns() const {
   if (problem == VAB_PROBLEM_ODE) return (long long)od.N_model * od.D + od.NPest;
   if (problem == VAB_PROBLEM_NN) return nn_unknowns(this);
@@ -78,6 +104,10 @@ int vab_ctx_create(int device, void* stream, vab_ctx** out) {
   c->stream = (cudaStream_t)stream;
   c->num_sms = prop.multiProcessorCount;
   if (const char* t = getenv("VAB_TSEG")) c->tseg_override = atoi(t);
+  if (const char* t = getenv("VAB_KERNEL")) {
+    c->use_walk = (strcmp(t, "walk") == 0);
+    c->use_sweep = (strcmp(t, "sweep") == 0);
+  }
   e = cudaMalloc((void**)&c->pfix_zero, 64 * sizeof(double));
   if (e == cudaSuccess) e = cudaMemsetAsync(c->pfix_zero, 0, 64 * sizeof(double), c->stream);
   if (e != cudaSuccess) {
@@ -96,6 +126,10 @@ int vab_ctx_destroy(vab_ctx* ctx) {
   lbfgs_destroy(ctx);
   cudaFree(ctx->obs_slot_dev);
   cudaFree(ctx->pmap_dev);
+  cudaFree(ctx->Y_pad);
+  cudaFree(ctx->rm_pad);
+  cudaFree(ctx->lperm_dev);
+  cudaFree(ctx->win_y0_dev);
   cudaFree(ctx->pfix_zero);
   cudaFree(ctx->partials);
   delete ctx;
@@ -135,41 +169,86 @@ int vab_ode_problem_set(vab_ctx* ctx, const vab_ode_desc* d, const int32_t* Lidx
     return vab_fail(ctx, VAB_ERR_INVALID, "ode_problem_set: rk4 (extension) takes no stimulus");
   if (d->L > 0 && (!Lidx_host || !Y_dev))
     return vab_fail(ctx, VAB_ERR_INVALID, "ode_problem_set: Lidx/Y missing");
-  OdePlan pl;
-  int prc = ode_make_plan(d->model, d->disc, d->D, d->N_model, 1, ctx->num_sms, 0, &pl);
-  if (prc == -2)
-    return vab_fail(ctx, VAB_ERR_INVALID, "ode_problem_set: D too large for one CTA row "
-                                          "(D/strip > 256); column tiling not built yet");
-  if (prc != 0)
+  if (ctx->use_walk) {
+    OdePlan pl;
+    int prc = ode_make_plan(d->model, d->disc, d->D, d->N_model, 1, ctx->num_sms, 0, &pl);
+    if (prc != 0)
+      return vab_fail(ctx, VAB_ERR_INVALID, "ode_problem_set: D not supported by the legacy walk kernels");
+  }
+  if ((d->model == VAB_MODEL_LORENZ96 && d->D < 4) || (d->model == VAB_MODEL_LORENZ63 && d->D != 3) ||
+      (d->model == VAB_MODEL_NAKL && d->D != 4))
     return vab_fail(ctx, VAB_ERR_INVALID, "ode_problem_set: D not valid for this model");
 
-  std::vector<int> obs(d->D, -1), pmap(d->NP, -1);
+  std::vector<int> obs(d->D, -1), pmap(d->NP, -1), lperm(d->L > 0 ? d->L : 1, 0);
   for (int l = 0; l < d->L; ++l) {
     const int i = Lidx_host[l];
     if (i < 0 || i >= d->D) return vab_fail(ctx, VAB_ERR_INVALID, "ode_problem_set: Lidx out of range");
     if (obs[i] >= 0) return vab_fail(ctx, VAB_ERR_INVALID, "ode_problem_set: duplicate Lidx entry");
     obs[i] = l;
   }
+  // library layout of Y / RM: columns sorted by state component (rank), row pitch Lp (even)
+  std::vector<int> sorted_comp;
+  for (int i = 0, rank = 0; i < d->D; ++i)
+    if (obs[i] >= 0) {
+      lperm[obs[i]] = rank;
+      obs[i] = rank++;
+      sorted_comp.push_back(i);
+    }
   for (int e = 0; e < d->NPest; ++e) {
     const int k = Pidx_host[e];
     if (k < 0 || k >= d->NP) return vab_fail(ctx, VAB_ERR_INVALID, "ode_problem_set: Pidx out of range");
     if (pmap[k] >= 0) return vab_fail(ctx, VAB_ERR_INVALID, "ode_problem_set: duplicate Pidx entry");
     pmap[k] = e;
   }
+  // per-window Y column ranges of the stream kernels
+  OdeGeo geo;
+  if (ode_geometry(d->model, d->disc, d->D, &geo) != 0)
+    return vab_fail(ctx, VAB_ERR_INVALID, "ode_problem_set: D not valid for this model");
+  const int Lp = (d->L + 1) & ~1;
+  std::vector<int> wy0(geo.nwin, 0);
+  int Lw = 2;
+  for (int w = 0; w < geo.nwin; ++w) {
+    const int c_lo = w * geo.WS * geo.C;
+    int c_hi = (w + 1) * geo.WS * geo.C;
+    if (c_hi > d->D) c_hi = d->D;
+    int s0 = 0, s1 = 0;
+    for (int c : sorted_comp) { if (c < c_lo) ++s0; if (c < c_hi) ++s1; }
+    const int y0 = s0 & ~1;
+    int len = (s1 - y0 + 1) & ~1;
+    if (geo.nwin == 1) len = Lp;
+    wy0[w] = y0;
+    if (len > Lw) Lw = len;
+  }
   cudaStreamSynchronize(ctx->stream);
   cudaFree(ctx->obs_slot_dev);
   cudaFree(ctx->pmap_dev);
+  cudaFree(ctx->lperm_dev);
+  cudaFree(ctx->win_y0_dev);
   ctx->obs_slot_dev = nullptr;
   ctx->pmap_dev = nullptr;
+  ctx->lperm_dev = nullptr;
+  ctx->win_y0_dev = nullptr;
   cudaError_t e = cudaMalloc((void**)&ctx->obs_slot_dev, sizeof(int) * d->D);
   if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->pmap_dev, sizeof(int) * (d->NP > 0 ? d->NP : 1));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->lperm_dev, sizeof(int) * lperm.size());
+  if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->win_y0_dev, sizeof(int) * wy0.size());
   if (e == cudaSuccess)
     e = cudaMemcpy(ctx->obs_slot_dev, obs.data(), sizeof(int) * d->D, cudaMemcpyHostToDevice);
   if (e == cudaSuccess && d->NP > 0)
     e = cudaMemcpy(ctx->pmap_dev, pmap.data(), sizeof(int) * d->NP, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess)
+    e = cudaMemcpy(ctx->lperm_dev, lperm.data(), sizeof(int) * lperm.size(), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess)
+    e = cudaMemcpy(ctx->win_y0_dev, wy0.data(), sizeof(int) * wy0.size(), cudaMemcpyHostToDevice);
   if (e != cudaSuccess) return vab_cuda_fail(ctx, e, "ode_problem_set");
   ctx->od = *d;
-  ctx->Y_dev = Y_dev;
+  ctx->Lp = Lp;
+  ctx->Lw = Lw;
+  {
+    int rc = vab_pack_obs(ctx, Y_dev, &ctx->Y_pad, &ctx->Y_cap);
+    if (rc != VAB_OK) return rc;
+  }
+  ctx->Y_dev = ctx->Y_pad;
   ctx->stim_dev = (d->n_stim > 0) ? stim_dev : nullptr;
   ctx->pfix_dev = ctx->pfix_zero;
   ctx->pfix_stride = 0;
@@ -183,7 +262,13 @@ int vab_ode_set_weights(vab_ctx* ctx, double rm_scalar, const double* rm_dev, do
                         const double* rf0_dev) {
   if (!ctx) return VAB_ERR_INVALID;
   if (ctx->problem != VAB_PROBLEM_ODE) return vab_fail(ctx, VAB_ERR_STATE, "set_weights: no ODE problem set");
-  ctx->rm_scalar = rm_scalar; ctx->rm_dev = rm_dev;
+  ctx->rm_scalar = rm_scalar; ctx->rm_dev = nullptr;
+  if (rm_dev) {
+    cudaSetDevice(ctx->device);
+    int rc = vab_pack_obs(ctx, rm_dev, &ctx->rm_pad, &ctx->rm_cap);
+    if (rc != VAB_OK) return rc;
+    ctx->rm_dev = ctx->rm_pad;
+  }
   ctx->rf0_scalar = rf0_scalar; ctx->rf0_dev = rf0_dev;
   return VAB_OK;
 }
@@ -211,30 +296,45 @@ static int ode_eval(vab_ctx* ctx, int B, const double* XP, long long ldxp, doubl
   if (G && (ldg < n || (ldg & 1))) return vab_fail(ctx, VAB_ERR_INVALID, "ode_action_grad: ldg must be even and >= n");
   if (((uintptr_t)XP & 15) || ((uintptr_t)G & 15))
     return vab_fail(ctx, VAB_ERR_INVALID, "ode_action_grad: XP/G must be 16-byte aligned");
-  OdePlan pl;
-  if (ode_make_plan(d.model, d.disc, d.D, d.N_model, B, ctx->num_sms, ctx->tseg_override, &pl) != 0)
-    return vab_fail(ctx, VAB_ERR_INVALID, "ode_action_grad: unsupported shape");
   OdeParams P;
   memset(&P, 0, sizeof(P));
   P.XP = XP; P.ldxp = ldxp; P.G = G; P.ldg = ldg;
   P.B = B; P.D = d.D; P.N = d.N_model; P.N_data = d.N_data; P.nskip = d.nskip; P.L = d.L;
   P.dt = d.dt_model;
-  P.obs_slot = ctx->obs_slot_dev; P.Y = ctx->Y_dev;
+  P.obs_slot = ctx->obs_slot_dev; P.Y = ctx->Y_dev; P.Lp = ctx->Lp; P.Lw = ctx->Lw;
+  P.win_y0 = ctx->win_y0_dev;
   P.rm_scalar = ctx->rm_scalar; P.rm_arr = ctx->rm_dev;
   P.rf_scalar = ctx->rf0_scalar * rf_scale; P.rf_arr = ctx->rf0_dev; P.rf_scale = rf_scale;
   P.stim = ctx->stim_dev; P.S = d.n_stim;
   P.NP = d.NP; P.NPest = d.NPest; P.pmap = ctx->pmap_dev;
   P.pfix = ctx->pfix_dev; P.pfix_stride = ctx->pfix_stride;
-  P.Tseg = pl.Tseg; P.nseg = pl.nseg; P.TPR = pl.TPR; P.RG = pl.RG; P.nunits = pl.nunits;
   P.K = 2 + d.NP;
   P.active = active_dev;
   P.cm = d.L > 0 ? 1.0 / ((double)d.L * d.N_data) : 0.0;
   P.cf = 1.0 / ((double)d.D * (d.N_model - 1));
-  int rc = vab_reserve(ctx, &ctx->partials, &ctx->partials_cap, (size_t)pl.nunits * P.K);
-  if (rc != VAB_OK) return rc;
-  P.partials = ctx->partials;
   cudaError_t cerr = cudaSuccess;
-  rc = ode_launch_action(P, pl, d.model, d.disc, ctx->stream, A, me, fe, &cerr);
+  int rc;
+  if (ctx->use_walk) {
+    OdePlan pl;
+    if (ode_make_plan(d.model, d.disc, d.D, d.N_model, B, ctx->num_sms, ctx->tseg_override, &pl) != 0)
+      return vab_fail(ctx, VAB_ERR_INVALID, "ode_action_grad: unsupported shape");
+    P.Tseg = pl.Tseg; P.nseg = pl.nseg; P.TPR = pl.TPR; P.RG = pl.RG; P.nunits = pl.nunits;
+    P.upp = pl.nseg;
+    rc = vab_reserve(ctx, &ctx->partials, &ctx->partials_cap, (size_t)pl.nunits * P.K);
+    if (rc != VAB_OK) return rc;
+    P.partials = ctx->partials;
+    rc = ode_launch_action(P, pl, d.model, d.disc, ctx->stream, A, me, fe, &cerr);
+  } else {
+    SweepLaunch sl;
+    rc = ode_sweep_prepare(d.model, d.disc, d.D, d.N_model, B, ctx->num_sms, ctx->tseg_override,
+                           !ctx->use_sweep, &P, &sl, &cerr);
+    if (rc == -1) return vab_fail(ctx, VAB_ERR_INVALID, "ode_action_grad: unsupported shape");
+    if (rc != 0) return vab_cuda_fail(ctx, cerr, "ode_action_grad occupancy query");
+    rc = vab_reserve(ctx, &ctx->partials, &ctx->partials_cap, (size_t)P.nunits * P.K);
+    if (rc != VAB_OK) return rc;
+    P.partials = ctx->partials;
+    rc = ode_sweep_launch(P, sl, d.model, d.disc, ctx->stream, A, me, fe, &cerr);
+  }
   if (rc == -1) return vab_fail(ctx, VAB_ERR_INVALID, "ode_action_grad: no kernel for this model/disc");
   if (rc != 0) return vab_cuda_fail(ctx, cerr, "ode_action_grad launch");
   ctx->launches += 2;

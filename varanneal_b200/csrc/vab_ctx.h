@@ -26,7 +26,13 @@ struct vab_ctx {
   vab_ode_desc od{};
   int* obs_slot_dev = nullptr;      // (D)
   int* pmap_dev = nullptr;          // (NP)
-  const double* Y_dev = nullptr;
+  const double* Y_dev = nullptr;    // library copy: (N_data, Lp), columns sorted by component
+  double* Y_pad = nullptr;
+  double* rm_pad = nullptr;         // same layout, when RM is an array
+  size_t Y_cap = 0, rm_cap = 0;     // doubles
+  int Lp = 0, Lw = 0;
+  int* lperm_dev = nullptr;         // (L) column of the library layout for each caller column
+  int* win_y0_dev = nullptr;        // (nwin)
   const double* stim_dev = nullptr;
   double rm_scalar = 1.0;
   const double* rm_dev = nullptr;
@@ -36,6 +42,8 @@ struct vab_ctx {
   long long pfix_stride = 0;
   double* pfix_zero = nullptr;      // default fixed-parameter block (zeros)
   int tseg_override = 0;            // tuning knob (env VAB_TSEG)
+  bool use_walk = false;            // env VAB_KERNEL=walk: legacy strip-walk kernels
+  bool use_sweep = false;           // env VAB_KERNEL=sweep: register sweep kernels even where the stream kernels apply
 
   // ---- NN problem
   NnProblem* nn = nullptr;
