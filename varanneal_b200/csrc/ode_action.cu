@@ -1,48 +1,23 @@
-// Kernel wrappers and launcher for the fused ODE action+gradient (see ode_walk.cuh for the design).
+// Launch planning and dispatch of the fused ODE action+gradient kernels
+// (register sweep: ode_sweep.cuh; TMA stream: ode_stream.cuh).
 #include <cuda_runtime.h>
-
-#include "ode_action.h"
-#include "ode_dispatch.h"
-#include "ode_sweep.cuh"
-#include "ode_stream.cuh"
 
 #include <cstdlib>
 
+#include "ode_action.h"
+#include "ode_stream.cuh"
+#include "ode_sweep.cuh"
+
 namespace {
 
-template <class WK, int U, int PH>
-__device__ __forceinline__ void dev_phases(WK& w, int step) {
-  w.template phase<U, PH>(step);
-  if constexpr (WK::H > 0) __syncthreads();
-  if constexpr (PH + 1 < WK::NPH) dev_phases<WK, U, PH + 1>(w, step);
-}
-template <class WK, int U>
-__device__ __forceinline__ void dev_steps(WK& w, int s0) {
-  dev_phases<WK, U, 0>(w, s0 + U);
-  if constexpr (U + 1 < WK::PD) dev_steps<WK, U + 1>(w, s0);
-}
-
-template <class WK, int MAXT>
-__global__ void __launch_bounds__(MAXT) ode_walk_kernel(const __grid_constant__ OdeParams P) {
-  extern __shared__ double smem[];
-  WK w;
-  w.init(P, blockIdx.x, threadIdx.x, smem);
-  w.prologue();
-  if constexpr (WK::H > 0) __syncthreads();
-  const int ns = WK::nsteps(P);
-  for (int s0 = 0; s0 < ns; s0 += WK::PD) dev_steps<WK, 0>(w, s0);
-  __syncthreads();                       // exchange rows are dead; reuse smem for the reduction
-  w.finish_write(threadIdx.x, WK::PSIGN);
-  __syncthreads();
-  walk_reduce(P, blockIdx.x, threadIdx.x, blockDim.x, smem);
-}
-
-// one warp per path: lane k sums partial slot k over the path's segments in segment order
+// one warp per path: lane k sums partial slot k over the path's units in unit order
 __global__ void ode_finalize_kernel(const __grid_constant__ OdeParams P, double* A, double* me,
                                     double* fe) {
   const int b = blockIdx.x, k = threadIdx.x;
   if (P.active != nullptr && P.active[b] == 0) return;
-  double v = (k < P.K) ? ode_partial_sum(P, b, k) : 0.0;
+  double v = 0.0;
+  if (k < P.K)
+    for (int u = 0; u < P.upp; ++u) v += P.partials[((long long)b * P.upp + u) * P.K + k];
   const double m = __shfl_sync(0xffffffffu, v, 0), f = __shfl_sync(0xffffffffu, v, 1);
   if (k == 0) {
     if (me) me[b] = m;
@@ -55,47 +30,7 @@ __global__ void ode_finalize_kernel(const __grid_constant__ OdeParams P, double*
   }
 }
 
-struct DevRun {
-  const OdeParams* P;
-  const OdePlan* pl;
-  cudaStream_t st;
-  cudaError_t err = cudaSuccess;
-  template <class WK>
-  int run() {
-    const size_t smem = (size_t)walk_smem_doubles<WK>(*P, pl->NT) * sizeof(double);
-    if (pl->NT <= 128) {
-      return launch<WK, 128>(smem);
-    }
-    return launch<WK, 256>(smem);
-  }
-  template <class WK, int MAXT>
-  int launch(size_t smem) {
-    auto kern = ode_walk_kernel<WK, MAXT>;
-    if (smem > 48 * 1024) {
-      err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (err != cudaSuccess) return -2;
-    }
-    kern<<<pl->grid, pl->NT, smem, st>>>(*P);
-    err = cudaGetLastError();
-    return err == cudaSuccess ? 0 : -2;
-  }
-};
-
 }  // namespace
-
-int ode_launch_action(const OdeParams& P, const OdePlan& pl, int model, int disc,
-                      cudaStream_t st, double* A, double* me, double* fe, cudaError_t* cerr) {
-  DevRun dr{&P, &pl, st};
-  int rc = ode_dispatch(model, pl.C, disc, dr);
-  if (rc != 0) {
-    if (cerr) *cerr = dr.err;
-    return rc;
-  }
-  ode_finalize_kernel<<<P.B, 32, 0, st>>>(P, A, me, fe);
-  cudaError_t e = cudaGetLastError();
-  if (cerr) *cerr = e;
-  return e == cudaSuccess ? 0 : -2;
-}
 
 // ============================================================================================
 // sweep kernels: plan + dispatch
@@ -184,7 +119,7 @@ int stream_variant() {
 int stream_ns(int C, int disc, bool fast) {
   if (fast && C == 4 && disc == DISC_SIMPSON) {
     switch (stream_variant()) {
-      case 2: return 6;
+      case 2: return 3;
       case 3: return 3;
       default: return 4;
     }
@@ -194,8 +129,8 @@ int stream_ns(int C, int disc, bool fast) {
 SweepKernel stream_kernel(int C, int disc, bool fast) {
   if (fast && C == 4 && disc == DISC_SIMPSON) {       // tuning variants of the flagship kernel
     switch (stream_variant()) {
-      case 1: return stream_simpson_kernel<ModelL96<4>, 4, 3, true>;
-      case 2: return stream_simpson_kernel<ModelL96<4>, 6, 3, true>;
+      case 1: return stream_simpson_kernel<ModelL96<4>, 4, 5, true>;
+      case 2: return stream_simpson_kernel<ModelL96<4>, 3, 5, true>;
       case 3: return stream_simpson_kernel<ModelL96<4>, 3, 4, true>;
       default: return stream_simpson_kernel<ModelL96<4>, 4, 4, true>;
     }
@@ -212,8 +147,9 @@ int blocks_per_sm(SweepKernel k, size_t smem, cudaError_t* cerr) {
   static int nseen = 0;
   for (int i = 0; i < nseen; ++i)
     if (seen[i].k == k && seen[i].smem == smem) return seen[i].nb;
-  cudaError_t e = cudaSuccess;
-  if (smem > 48 * 1024) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  // opt in to the largest dynamic shared memory size once per kernel (a later, smaller request
+  // must not lower the limit of an earlier one)
+  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   int nb = 0;
   if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k, 128, smem);
   if (e != cudaSuccess) {
@@ -240,10 +176,10 @@ int ode_sweep_prepare(int model, int disc, int D, int N, int B, int num_sms, int
   SweepKernel k = nullptr;
   int nb = 0;
   if (allow_stream && ode_stream_supported(model, disc, g)) {
-    const size_t stage_d = (size_t)g.GPW * (2 * (size_t)g.GW * g.C + 2 * (size_t)P->Lw);
-    const bool fast = (P->nskip == 1 && P->rm_arr == nullptr && P->rf_arr == nullptr);
+    const size_t stage_b = (size_t)g.GPW * 4 * (size_t)g.GW * g.C * sizeof(double);
+    const bool fast = (P->nskip == 1 && P->rmd == nullptr && P->rf_arr == nullptr && P->L > 0);
     const int ns = stream_ns(g.C, disc, fast);
-    const size_t smem = ((size_t)4 * ns * stage_d + 4 * ns + (size_t)128 * K) * sizeof(double);
+    const size_t smem = (size_t)4 * ns * stage_b + ((size_t)4 * ns + (size_t)128 * K) * sizeof(double);
     if (smem <= 200 * 1024) {
       k = stream_kernel(g.C, disc, fast);
       nb = k ? blocks_per_sm(k, smem, cerr) : 0;
@@ -289,7 +225,7 @@ int ode_sweep_prepare(int model, int disc, int D, int N, int B, int num_sms, int
 
 int ode_sweep_launch(const OdeParams& P, const SweepLaunch& sl, int model, int disc,
                      cudaStream_t st, double* A, double* me, double* fe, cudaError_t* cerr) {
-  const bool fast = (P.nskip == 1 && P.rm_arr == nullptr && P.rf_arr == nullptr);
+  const bool fast = (P.nskip == 1 && P.rmd == nullptr && P.rf_arr == nullptr && P.L > 0);
   SweepKernel k = sl.stream ? stream_kernel(sl.C, disc, fast) : sweep_kernel(model, sl.C, disc);
   if (!k) return -1;
   k<<<sl.grid, 128, sl.smem, st>>>(P);

@@ -1,14 +1,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include "ode_params.h"
 #include "ode_plan.h"
-#include "ode_walk.cuh"
-
-// Legacy strip-walk kernels (shared-memory halo exchange, one __syncthreads per phase); kept as the
-// A/B reference for the sweep kernels (env VAB_KERNEL=walk).  Returns 0, -1 (unsupported
-// combination) or -2 (CUDA error, code in *cerr).  A / me / fe may be nullptr.
-int ode_launch_action(const OdeParams& P, const OdePlan& pl, int model, int disc,
-                      cudaStream_t st, double* A, double* me, double* fe, cudaError_t* cerr);
 
 // Register-sweep kernels (ode_sweep.cuh).  ode_sweep_prepare fills the mapping fields of P
 // (TPR, GW, GPW, WS, nwin, NHL, Tseg, nseg, nunits, upp) and the launch shape; the caller then

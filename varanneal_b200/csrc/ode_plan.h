@@ -1,59 +1,10 @@
-// Launch planning for the strip-walk kernels: strip width, CTA shape, segment length.
-// Shared by the product (ode_action.cu) and the test-only host emulator (tests/emul/).
+// Launch geometry of the fused ODE kernels, shared by the plan (ode_action.cu) and the problem
+// set-up (vab_api.cu).
 #pragma once
-
-struct OdePlan {
-  int C;        // strip width (components per thread)
-  int NT;       // threads per CTA (128 or 256)
-  int TPR;      // threads per row-group = D / C
-  int RG;       // row-groups per CTA
-  int Tseg;     // time rows per segment (even)
-  int nseg;     // segments per path
-  int nunits;   // B * nseg
-  int grid;     // CTAs
-};
 
 // model ids as in include/varanneal_b200.h
 inline int ode_model_npm(int model) { return model == 0 ? 1 : (model == 1 ? 3 : (model == 2 ? 18 : -1)); }
 inline int ode_model_nstim(int model) { return model == 2 ? 1 : 0; }
-
-// returns 0 on success; <0: unsupported shape
-inline int ode_make_plan(int model, int disc, int D, int N, int B, int num_sms, int tseg_override,
-                         OdePlan* pl) {
-  if (model == 0) {
-    if (D < 4) return -1;
-    pl->C = (D % 4 == 0) ? 4 : ((D % 2 == 0) ? 2 : 1);
-    pl->TPR = D / pl->C;
-  } else if (model == 1) {
-    if (D != 3) return -1;
-    pl->C = 3;
-    pl->TPR = 1;
-  } else if (model == 2) {
-    if (D != 4) return -1;
-    pl->C = 4;
-    pl->TPR = 1;
-  } else {
-    return -1;
-  }
-  if (pl->TPR > 256) return -2;                 // wider rows need column tiling (not built yet)
-  pl->NT = (pl->TPR <= 128) ? 128 : 256;
-  pl->RG = pl->NT / pl->TPR;
-  const int lead = (disc == 2) ? 8 : 3;         // redundant lead-in/out rows per segment
-  int tmin = 16 * lead;                         // keep the redundant work under ~6 %
-  if (tmin > N) tmin = N;
-  long long target_units = (long long)num_sms * 6 * pl->RG;
-  long long nseg = (target_units + B - 1) / B;
-  if (nseg < 1) nseg = 1;
-  long long tseg = (N + nseg - 1) / nseg;
-  if (tseg < tmin) tseg = tmin;
-  if (tseg_override > 0) tseg = tseg_override;
-  if (tseg % 2) tseg += 1;
-  pl->Tseg = (int)tseg;
-  pl->nseg = (N + pl->Tseg - 1) / pl->Tseg;
-  pl->nunits = B * pl->nseg;
-  pl->grid = (pl->nunits + pl->RG - 1) / pl->RG;
-  return 0;
-}
 
 // ---- lane geometry shared by the sweep and stream kernels (see ode_sweep.cuh / ode_stream.cuh)
 struct OdeGeo {

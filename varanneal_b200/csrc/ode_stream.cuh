@@ -5,16 +5,16 @@
 // engine:
 //   * every warp owns a private ring of NS stages in shared memory.  A stage holds two
 //     consecutive time rows of the warp's window of X (for each of the GPW paths the warp works
-//     on) plus the matching rows of the observations Y.  One lane per path issues
+//     on) and the same two rows of the dense observation matrix Y.  One lane per path issues
 //     `cp.async.bulk` (TMA, 1-D) copies global -> shared that complete on the stage's mbarrier;
-//     the other lanes only wait on the barrier.  No registers are spent on prefetching, loads are
+//     the other lanes only wait on the barrier.  No registers are spent on prefetching, loads run
 //     NS-2 stages (2(NS-2) rows) ahead of the compute, and the measurement data arrives with the
 //     state instead of stalling the gradient on an L2 round trip.
 //   * lanes read their own strip and its two-component halo straight from the staged row
-//     (4 x LDS.128); only the adjoint seed v is exchanged between lanes, with warp shuffles.
-//   * all warps of a (segment, window) share row validity, so the time loop is uniform: the
-//     steady state runs without any per-lane predicate except the store mask; ragged ends are
-//     peeled into separate code.
+//     (LDS.128 at precomputed 32-bit shared addresses); only the adjoint seed v is exchanged
+//     between lanes, with warp shuffles.
+//   * all paths of a warp share (segment, window), so row validity is warp-uniform: the steady
+//     state runs without per-lane predicates except the store mask; ragged ends are peeled.
 //   * there is no __syncthreads anywhere; warps run decoupled.
 // Gradient rows are written once with streaming 16-byte stores; per-unit partial sums are reduced
 // in a fixed order (bit-reproducible).  Reference semantics: va_ode.py:130-234 (action),
@@ -25,7 +25,8 @@
 #include <type_traits>
 
 #include "ode_models.cuh"
-#include "ode_walk.cuh"
+#include "ode_params.h"
+#include "vab_hd.h"
 
 #ifndef VAB_FULL
 #define VAB_FULL 0xffffffffu
@@ -64,6 +65,9 @@ __device__ __forceinline__ void tma_load(uint32_t dst, const void* src, uint32_t
       ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
       : "memory");
 }
+__device__ __forceinline__ void lds2(uint32_t addr, double& a, double& b) {
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "r"(addr));
+}
 
 // FAST: nskip == 1, scalar RM, scalar RF (the common case); otherwise every weight / row test is
 // looked up at run time.
@@ -73,25 +77,25 @@ struct Stream {
   static_assert(H == 2 && (C == 4 || C == 2), "stream kernels: Lorenz96-type stencil, strips of 4 or 2");
   const OdeParams& P;
   // warp-uniform
-  int lane, sg, w, r0, r1, N, D, Wd, Lw, nact, rowbase, qmax, y0w;
-  bool wrap, has_obs;
-  uint32_t full_bytes;         // bytes a full stage (two valid rows) brings in, all paths of the warp
-  int st0, n1;                 // window mode: first strip of the window, strips before the wrap
-  double* ring;                // this warp's stages
-  uint32_t bar0;               // shared address of this warp's first barrier
-  int stage_d, grp_d;
+  int sg, w, r0, r1, N, rowbase, qmax;
+  bool wrap;
+  uint32_t ring0, bar0;        // shared addresses: this warp's first stage / first barrier
+  uint32_t stage_b, row_b;     // bytes per stage (all paths of the warp) / per staged window row
+  uint32_t full_bytes;         // bytes a full stage brings in, all paths of the warp
   // per lane
-  int g, j, b, bidx, i0;
+  int g, j, bidx, i0, D;
   bool pact, out, leader, bvalid;
-  double wfs;                  // 2 cf RF (scalar RF)
-  int o_own, o_l, o_r;         // offsets (doubles) inside a staged window row
+  bool swz;                    // lanes 4..7 of every quarter-warp read their 16-byte pieces in the
+                               // opposite order: conflict-free LDS.128 at a 32-byte lane stride
+  uint32_t a_o1, a_o2;         // shared addresses (stage 0, row 0) of the two halves of the own strip
+  uint32_t a_h1, a_h2;         // ... of the left / right halo pair (swapped when sw)
   int srcM1, srcP1;
-  const double* xpath;
-  double* gpath;
+  const double* xsrc;          // leader: first global element of this path's window
+  const double* ysrc;
+  double* grow;                // &G[b][0][i0]
   double p[NPM];
-  int ys[C];                   // Y column inside the staged Y row (0 if unobserved)
-  int slot[C];                 // Y column in the library layout, -1 if unobserved
-  double wobs[C];              // 2 cm RM for observed components (scalar RM), else 0
+  double wob[C];               // 2 cm RM of the own components (0 = unobserved)
+  double wfs;                  // 2 cf RF (scalar RF)
   double me_acc, fe_acc, pacc[NPM];
 
   __device__ __forceinline__ Stream(const OdeParams& P_) : P(P_) {}
@@ -99,7 +103,7 @@ struct Stream {
   // returns false if this warp has no work
   __device__ __forceinline__ bool init(double* smem) {
     const int warp = __shfl_sync(VAB_FULL, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform
-    lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31;
     const int gwarp = blockIdx.x * 4 + warp;
     const int sw = gwarp / P.wpb, bgrp = gwarp - sw * P.wpb;
     if (sw >= P.nseg * P.nwin) return false;
@@ -110,58 +114,58 @@ struct Stream {
     r0 = sg * P.Tseg;
     r1 = min(r0 + P.Tseg, N);
     wrap = (P.NHL == 0);
-    Wd = P.GW * C;
-    Lw = P.Lw;
-    grp_d = 2 * Wd + 2 * Lw;
-    stage_d = P.GPW * grp_d;
-    ring = smem + (size_t)warp * NS * stage_d;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)4 * NS * stage_d) + warp * NS;
-    bar0 = s32(bars);
-    y0w = __ldg(P.win_y0 + w);
-    g = lane / P.GW;
-    j = lane - g * P.GW;
-    const bool ingroup = g < P.GPW;
-    b = bgrp * P.GPW + g;
+    const int Wd = P.GW * C;                               // doubles per staged window row
+    row_b = (uint32_t)Wd * 8u;
+    const uint32_t grp_b = 4u * row_b;                     // X rows a, b then Y rows a, b
+    stage_b = (uint32_t)P.GPW * grp_b;
+    ring0 = s32(smem) + (uint32_t)warp * NS * stage_b;
+    bar0 = s32(smem) + 4u * NS * stage_b + (uint32_t)warp * NS * 8u;
+    int gg = lane / P.GW;
+    j = lane - gg * P.GW;
+    const bool ingroup = gg < P.GPW;
+    int b = bgrp * P.GPW + gg;
     bidx = b;
     bvalid = ingroup && b < P.B;
-    wfs = 2.0 * P.cf * P.rf_scalar;
-    pact = ingroup && b < P.B && (P.active == nullptr || __ldg(P.active + b) != 0);
-    if (!ingroup || b >= P.B) b = 0;
-    if (!ingroup) g = 0;
+    pact = bvalid && (P.active == nullptr || __ldg(P.active + b) != 0);
+    if (!bvalid) b = 0;
+    if (!ingroup) gg = 0;
+    g = gg;
     leader = pact && j == 0;
-    nact = __popc(__ballot_sync(VAB_FULL, leader));
-    has_obs = P.L > 0;
-    full_bytes = (uint32_t)nact * (uint32_t)(2 * Wd + (has_obs ? 2 * Lw : 0)) * 8u;
+    const int nact = __popc(__ballot_sync(VAB_FULL, leader));
+    full_bytes = (uint32_t)nact * grp_b;
     const int TPR = P.TPR;
-    int st;
+    int st, st0 = 0, jo = j * C;
+    uint32_t o_l, o_r;
     if (wrap) {
       st = j;
       out = pact;
-      o_own = j * C;
-      o_l = (j * C - 2 + Wd) % Wd;
-      o_r = (j * C + C) % Wd;
-      const int gb = g * P.GW;
-      srcM1 = gb + (j + P.GW - 1) % P.GW;
-      srcP1 = gb + (j + 1) % P.GW;
-      st0 = 0;
-      n1 = P.GW;
+      o_l = (uint32_t)((jo - 2 + Wd) % Wd);
+      o_r = (uint32_t)((jo + C) % Wd);
+      srcM1 = gg * P.GW + (j + P.GW - 1) % P.GW;
+      srcP1 = gg * P.GW + (j + 1) % P.GW;
     } else {
       const int rel = w * P.WS - P.NHL;
       st0 = ((rel % TPR) + TPR) % TPR;
-      n1 = min(P.GW, TPR - st0);
       st = (st0 + j) % TPR;
       out = pact && j >= P.NHL && j < P.NHL + P.WS && (w * P.WS + j - P.NHL) < TPR;
-      o_own = j * C;
-      o_l = max(j * C - 2, 0);
-      o_r = min(j * C + C, Wd - 2);
-      const int gb = g * P.GW;
-      srcM1 = gb + max(j - 1, 0);
-      srcP1 = gb + min(j + 1, P.GW - 1);
+      o_l = (uint32_t)max(jo - 2, 0);
+      o_r = (uint32_t)min(jo + C, Wd - 2);
+      srcM1 = gg * P.GW + max(j - 1, 0);
+      srcP1 = gg * P.GW + min(j + 1, P.GW - 1);
     }
-    if (!ingroup) { srcM1 = srcP1 = lane; o_own = o_l = o_r = 0; }
+    if (!ingroup) { srcM1 = srcP1 = lane; jo = 0; o_l = o_r = 0; }
+    const uint32_t gbase = ring0 + (uint32_t)gg * grp_b;
+    swz = (C == 4) && ((lane >> 2) & 1);
+    const uint32_t a_own = gbase + (uint32_t)jo * 8u, a_l = gbase + o_l * 8u, a_r = gbase + o_r * 8u;
+    a_o1 = a_own + (swz ? 16u : 0u);
+    a_o2 = a_own + (swz ? 0u : 16u);
+    a_h1 = swz ? a_r : a_l;
+    a_h2 = swz ? a_l : a_r;
     i0 = st * C;
-    xpath = P.XP + (long long)b * P.ldxp;
-    gpath = P.G ? P.G + (long long)b * P.ldg + (long long)st * C : nullptr;
+    const double* xpath = P.XP + (long long)b * P.ldxp;
+    xsrc = xpath + st0 * C;
+    ysrc = P.Y + st0 * C;
+    grow = (out && P.G != nullptr) ? P.G + (long long)b * P.ldg + i0 : nullptr;
     const long long nX = (long long)N * D;
 #pragma unroll
     for (int k = 0; k < NPM; ++k) {
@@ -174,24 +178,25 @@ struct Stream {
       pacc[k] = 0.0;
     }
 #pragma unroll
-    for (int c = 0; c < C; ++c) {
-      const int s = out ? __ldg(P.obs_slot + st * C + c) : -1;
-      slot[c] = s;
-      ys[c] = (s >= 0) ? s - y0w : 0;
-      wobs[c] = (s >= 0) ? 2.0 * P.cm * P.rm_scalar : 0.0;
-    }
+    for (int c = 0; c < C; ++c) wob[c] = out ? __ldg(P.wobs + i0 + c) : 0.0;
+    wfs = 2.0 * P.cf * P.rf_scalar;
     me_acc = 0.0;
     fe_acc = 0.0;
+    // zero this warp's ring: rows that are never copied (path ends, rows without observations)
+    // must read as finite numbers
+    for (uint32_t o = lane * 16u; o < NS * stage_b; o += 32u * 16u)
+      asm volatile("st.shared.v2.f64 [%0], {%1, %1};" ::"r"(ring0 + o), "d"(0.0) : "memory");
     if (lane == 0) {
 #pragma unroll
-      for (int s = 0; s < NS; ++s) mbar_init(bar0 + 8 * s, 1);
+      for (int s = 0; s < NS; ++s) mbar_init(bar0 + 8u * s, 1);
       mbar_fence_init();
     }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // zero fill before TMA writes
     __syncwarp();
     return true;
   }
 
-  __device__ __forceinline__ double* stage(int q) const { return ring + (size_t)(q % NS) * stage_d + g * grp_d; }
+  __device__ __forceinline__ uint32_t slot_off(int q) const { return (uint32_t)(q % NS) * stage_b; }
   __device__ __forceinline__ bool obs_row(int r) const { return FAST || P.nskip == 1 || (r % P.nskip) == 0; }
   __device__ __forceinline__ int obs_index(int r) const { return FAST ? r : r / P.nskip; }
 
@@ -199,63 +204,74 @@ struct Stream {
   __device__ __forceinline__ void issue(int q) {
     if (q > qmax) return;
     const int ra = rowbase + 2 * q, rb = ra + 1;
-    const uint32_t bar = bar0 + 8 * (q % NS);
-    if (FAST && wrap && ra >= 0 && rb < N) {       // steady state: two valid rows, rows contiguous
-      if (lane == 0) mbar_expect_tx(bar, full_bytes);
+    const uint32_t bar = bar0 + 8u * (q % NS);
+    const uint32_t so = slot_off(q);
+    if (FAST && wrap && ra >= 0 && rb < N) {       // steady state: two valid, contiguous rows
+      if ((threadIdx.x & 31) == 0) mbar_expect_tx(bar, full_bytes);
       __syncwarp();
       if (leader) {
-        double* dst = stage(q);
-        tma_load(s32(dst), xpath + (long long)ra * D, 2u * Wd * 8u, bar);
-        if (has_obs) tma_load(s32(dst + 2 * Wd), P.Y + (long long)ra * P.Lp, 2u * Lw * 8u, bar);
+        const uint32_t dst = ring0 + (uint32_t)g * 4u * row_b + so;   // the path's stage base
+        const long long off = (long long)ra * D;
+        tma_load(dst, xsrc + off, 2u * row_b, bar);
+        tma_load(dst + 2u * row_b, ysrc + off, 2u * row_b, bar);
       }
       return;
     }
     const bool va = ra >= 0 && ra < N, vb = rb >= 0 && rb < N;
-    const bool ya = va && has_obs && obs_row(ra), yb = vb && has_obs && obs_row(rb);
-    const uint32_t per = (uint32_t)((va ? 1 : 0) + (vb ? 1 : 0)) * Wd * 8u +
-                         (uint32_t)((ya ? 1 : 0) + (yb ? 1 : 0)) * Lw * 8u;
-    if (lane == 0) mbar_expect_tx(bar, per * (uint32_t)nact);
+    const bool ya = va && P.L > 0 && obs_row(ra), yb = vb && P.L > 0 && obs_row(rb);
+    const uint32_t per = (uint32_t)((va ? 1 : 0) + (vb ? 1 : 0) + (ya ? 1 : 0) + (yb ? 1 : 0)) * row_b;
+    const int nact = (int)(full_bytes / (4u * row_b));
+    if ((threadIdx.x & 31) == 0) mbar_expect_tx(bar, per * (uint32_t)nact);
     __syncwarp();
     if (leader) {
-      double* dst = stage(q);
-      if (wrap) {
-        if (va && vb) {
-          tma_load(s32(dst), xpath + (long long)ra * D, 2u * Wd * 8u, bar);
-        } else if (va) {
-          tma_load(s32(dst), xpath + (long long)ra * D, Wd * 8u, bar);
-        } else if (vb) {
-          tma_load(s32(dst + Wd), xpath + (long long)rb * D, Wd * 8u, bar);
-        }
-      } else {
+      const uint32_t dst = ring0 + (uint32_t)g * 4u * row_b + so;
+      // a window that runs past the end of the row continues at its beginning (periodic model)
+      const int st0 = (int)((xsrc - (P.XP + (long long)bidx * P.ldxp)) / C);
+      const int n1 = wrap ? P.GW : min(P.GW, P.TPR - st0);
+      const uint32_t b1 = (uint32_t)n1 * C * 8u, b2 = row_b - b1;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          if (h == 0 ? va : vb) {
-            const double* src = xpath + (long long)(ra + h) * D;
-            tma_load(s32(dst + h * Wd), src + st0 * C, (uint32_t)n1 * C * 8u, bar);
-            if (n1 < P.GW) tma_load(s32(dst + h * Wd + n1 * C), src, (uint32_t)(P.GW - n1) * C * 8u, bar);
-          }
+      for (int h = 0; h < 2; ++h) {
+        const int r = ra + h;
+        if (h == 0 ? va : vb) {
+          const double* src = xsrc + (long long)r * D;
+          tma_load(dst + h * row_b, src, b1, bar);
+          if (b2) tma_load(dst + h * row_b + b1, src - st0 * C, b2, bar);
+        }
+        if (h == 0 ? ya : yb) {
+          const double* src = ysrc + (long long)obs_index(r) * D;
+          tma_load(dst + (2 + h) * row_b, src, b1, bar);
+          if (b2) tma_load(dst + (2 + h) * row_b + b1, src - st0 * C, b2, bar);
         }
       }
-      if (ya) tma_load(s32(dst + 2 * Wd), P.Y + (long long)obs_index(ra) * P.Lp + y0w, Lw * 8u, bar);
-      if (yb) tma_load(s32(dst + 2 * Wd + Lw), P.Y + (long long)obs_index(rb) * P.Lp + y0w, Lw * 8u, bar);
     }
   }
   __device__ __forceinline__ void wait(int q) const {
     if (q > qmax) return;
-    mbar_wait(bar0 + 8 * (q % NS), (uint32_t)((q / NS) & 1));
+    mbar_wait(bar0 + 8u * (q % NS), (uint32_t)((q / NS) & 1));
   }
 
-  // staged row -> own strip with halo
-  __device__ __forceinline__ void read_row(const double* row, double* X) const {
-    const double2 l = *reinterpret_cast<const double2*>(row + o_l);
-    const double2 r = *reinterpret_cast<const double2*>(row + o_r);
-    X[0] = l.x; X[1] = l.y;
-    X[H + C] = r.x; X[H + C + 1] = r.y;
-#pragma unroll
-    for (int c = 0; c < C; c += 2) {
-      const double2 o = *reinterpret_cast<const double2*>(row + o_own + c);
-      X[H + c] = o.x; X[H + c + 1] = o.y;
+  // staged row (byte offset `off` from stage 0 / row 0) -> own strip with halo
+  __device__ __forceinline__ void read_own(uint32_t off, double* x) const {
+    if constexpr (C == 4) {
+      double o0, o1, o2, o3;
+      lds2(a_o1 + off, o0, o1);
+      lds2(a_o2 + off, o2, o3);
+      x[0] = swz ? o2 : o0; x[1] = swz ? o3 : o1;
+      x[2] = swz ? o0 : o2; x[3] = swz ? o1 : o3;
+    } else {
+      lds2(a_o1 + off, x[0], x[1]);
     }
+  }
+  __device__ __forceinline__ void read_halo(uint32_t off, double* X) const {
+    double h0, h1, h2, h3;
+    lds2(a_h1 + off, h0, h1);
+    lds2(a_h2 + off, h2, h3);
+    X[0] = swz ? h2 : h0; X[1] = swz ? h3 : h1;
+    X[H + C] = swz ? h0 : h2; X[H + C + 1] = swz ? h1 : h3;
+  }
+  __device__ __forceinline__ void read_row(uint32_t off, double* X) const {
+    read_halo(off, X);
+    read_own(off, X + H);
   }
   // own values in V[H..H+C): fetch the halo from the neighbour lanes (all lanes must call)
   __device__ __forceinline__ void halo(double* V) const {
@@ -268,25 +284,29 @@ struct Stream {
     if (FAST) return wfs;
     return P.rf_arr ? 2.0 * P.cf * P.rf_scale * __ldg(P.rf_arr + (long long)row * D + i0 + c) : wfs;
   }
-  // measurement term of row r (va_ode.py:138-158) from the staged Y row: d += 2 cm RM (x - y)
-  __device__ __forceinline__ void measure(int r, const double* yrow, const double* xown, double* d) {
-    if (!has_obs || !obs_row(r)) return;                       // warp-uniform
+  // measurement term of row r (va_ode.py:138-158), y staged at byte offset yoff:
+  // d += 2 cm RM (x - y);  me_acc += 2 cm RM (x - y)^2.  Branch-free: unobserved components have
+  // weight 0 and a zero y.
+  __device__ __forceinline__ void measure(int r, uint32_t yoff, const double* xown, double* d) {
+    if (!FAST) {
+      if (P.L == 0 || !obs_row(r)) return;                    // warp-uniform
+    }
+    double y[C];
+    read_own(yoff, y);
 #pragma unroll
     for (int c = 0; c < C; ++c) {
-      double wo = wobs[c];
+      double wo = wob[c];
       if (!FAST) {
-        if (P.rm_arr != nullptr && slot[c] >= 0)
-          wo = 2.0 * P.cm * __ldg(P.rm_arr + (long long)obs_index(r) * P.Lp + slot[c]);
+        if (P.rmd != nullptr) wo = out ? __ldg(P.rmd + (long long)obs_index(r) * D + i0 + c) : 0.0;
       }
-      const double diff = xown[c] - yrow[ys[c]];
+      const double diff = xown[c] - y[c];
       const double wd = wo * diff;
       me_acc = fma(wd, diff, me_acc);
       d[c] += wd;
     }
   }
-  // g = d + v - t  (t = adjoint product without its -v term); streaming 16-byte stores
-  __device__ __forceinline__ void store(int r, const double* g) const {
-    if (out && gpath != nullptr) vab_store_strip<C>(gpath + (long long)r * D, g);
+  __device__ __forceinline__ void store(int r, const double* gr) const {
+    if (grow != nullptr) vab_store_strip<C>(grow + (long long)r * D, gr);
   }
   __device__ __forceinline__ void finish(double* red) {
     if (!out) {
@@ -319,7 +339,8 @@ struct Stream {
 // Simpson-Hermite (va_ode.py:404-437 + :192-195).  Pair k = rows (a, b, c) = (2k, 2k+1, 2k+2):
 //   e1 = x_c - x_a - dt/3 (f_a + 4 f_b + f_c),  e2 = x_b - (x_a + x_c)/2 - dt/4 (f_a - f_c)
 // One step per pair = one ring stage (rows b, c).  Rows a and b get their gradient in the step of
-// their pair; row c's partial seed is carried into the next pair, where it is row a.
+// their pair; row c's partial seed is carried into the next pair, where it is row a.  Row a itself
+// is re-read from the previous stage (kept resident one step longer) instead of being carried.
 template <class M, int NS, int MINB, bool FAST>
 __global__ void __launch_bounds__(128, MINB) stream_simpson_kernel(const __grid_constant__ OdeParams P) {
   using ST = vabs::Stream<M, NS, FAST>;
@@ -327,9 +348,10 @@ __global__ void __launch_bounds__(128, MINB) stream_simpson_kernel(const __grid_
   extern __shared__ __align__(16) double smem[];
   ST S(P);
   if (!S.init(smem)) return;
-  double* red = smem + (size_t)4 * NS * S.stage_d + 4 * NS;
+  double* red = smem + ((size_t)4 * NS * S.stage_b) / 8 + 4 * NS;
   const double dt = P.dt, dt3 = dt / 3.0, dt4 = dt / 4.0, dt43 = 4.0 * dt / 3.0;
-  const int r0 = S.r0, N = S.N, Wd = S.Wd, Lw = S.Lw;
+  const int r0 = S.r0, N = S.N;
+  const uint32_t rb = S.row_b;
   const bool last = (S.r1 == N);
   const int nfull = last ? (N - 1 - r0) / 2 : P.Tseg / 2;
   S.rowbase = r0 - 3;                       // stage q holds rows (r0 - 3 + 2q, r0 - 2 + 2q)
@@ -337,51 +359,57 @@ __global__ void __launch_bounds__(128, MINB) stream_simpson_kernel(const __grid_
 #pragma unroll
   for (int q = 0; q < NS; ++q) S.issue(q);
 
-  double Xa[W], Fa[C], vcp[C], dcp[C];
-  // one pair; STORE = false for the lead-in pair (only the carried c-part is wanted)
-  auto pair = [&](int a, const double* stq, const double* yarow, auto store_tag) {
+  double xa[C], Fa[C], vcp[C], dcp[C];
+  // one pair: sq = slot offset of its stage (rows b, c), sp = slot offset of the previous stage
+  // (whose second row is row a).  STORE = false for the lead-in pair.
+  auto pair = [&](int a, uint32_t sq, uint32_t sp, auto store_tag) {
     constexpr bool STORE = decltype(store_tag)::value;
-    double Xb[W], Xc[W], Fb[C], Fc[C], l1[C], l2[C];
-    S.read_row(stq, Xb);
-    S.read_row(stq + Wd, Xc);
-    M::f(Xb, S.p, nullptr, Fb);
-    M::f(Xc, S.p, nullptr, Fc);
+    double Xb[W], l1[C], l2[C], Fc[C], xc[C];
+    {
+      double Xc[W], Fb[C];
+      S.read_row(sq, Xb);
+      S.read_row(sq + rb, Xc);
+      M::f(Xb, S.p, nullptr, Fb);
+      M::f(Xc, S.p, nullptr, Fc);
 #pragma unroll
-    for (int c = 0; c < C; ++c) {
-      const double s = fma(4.0, Fb[c], Fa[c]) + Fc[c];
-      const double e1 = fma(-dt3, s, Xc[H + c] - Xa[H + c]);
-      const double e2 = fma(-dt4, Fa[c] - Fc[c], fma(-0.5, Xa[H + c] + Xc[H + c], Xb[H + c]));
-      l1[c] = S.wgt(a, c) * e1;
-      l2[c] = S.wgt(a + 1, c) * e2;
-      if (STORE) S.fe_acc = fma(l1[c], e1, fma(l2[c], e2, S.fe_acc));
+      for (int c = 0; c < C; ++c) {
+        xc[c] = Xc[H + c];
+        const double s = fma(4.0, Fb[c], Fa[c]) + Fc[c];
+        const double e1 = fma(-dt3, s, xc[c] - xa[c]);
+        const double e2 = fma(-dt4, Fa[c] - Fc[c], fma(-0.5, xa[c] + xc[c], Xb[H + c]));
+        l1[c] = S.wgt(a, c) * e1;
+        l2[c] = S.wgt(a + 1, c) * e2;
+        if (STORE) S.fe_acc = fma(l1[c], e1, fma(l2[c], e2, S.fe_acc));
+      }
     }
     if (STORE) {
       {   // row b:  v = 4dt/3 l1,  d = l2
-        double V[W], g[C];
+        double V[W], gr[C], t[C];
 #pragma unroll
-        for (int c = 0; c < C; ++c) { V[H + c] = dt43 * l1[c]; g[c] = l2[c]; }
+        for (int c = 0; c < C; ++c) { V[H + c] = dt43 * l1[c]; gr[c] = l2[c]; }
         S.halo(V);
-        S.measure(a + 1, stq + 2 * Wd, Xb + H, g);
-        double t[C];
+        S.measure(a + 1, sq + 2u * rb, Xb + H, gr);
         M::adj_t(Xb, V, S.p, t, S.pacc);
 #pragma unroll
-        for (int c = 0; c < C; ++c) g[c] = (g[c] + V[H + c]) - t[c];
-        S.store(a + 1, g);
+        for (int c = 0; c < C; ++c) gr[c] = (gr[c] + V[H + c]) - t[c];
+        S.store(a + 1, gr);
       }
       {   // row a:  v = carried c-part + dt/3 l1 + dt/4 l2,  d = carried - l1 - l2/2
-        double V[W], g[C];
+        double Xa[W], V[W], gr[C], t[C];
 #pragma unroll
         for (int c = 0; c < C; ++c) {
           V[H + c] = fma(dt4, l2[c], fma(dt3, l1[c], vcp[c]));
-          g[c] = fma(-0.5, l2[c], dcp[c] - l1[c]);
+          gr[c] = fma(-0.5, l2[c], dcp[c] - l1[c]);
         }
         S.halo(V);
-        S.measure(a, yarow, Xa + H, g);
-        double t[C];
+        S.read_halo(sp + rb, Xa);
+#pragma unroll
+        for (int c = 0; c < C; ++c) Xa[H + c] = xa[c];
+        S.measure(a, sp + 3u * rb, xa, gr);
         M::adj_t(Xa, V, S.p, t, S.pacc);
 #pragma unroll
-        for (int c = 0; c < C; ++c) g[c] = (g[c] + V[H + c]) - t[c];
-        S.store(a, g);
+        for (int c = 0; c < C; ++c) gr[c] = (gr[c] + V[H + c]) - t[c];
+        S.store(a, gr);
       }
     }
 #pragma unroll
@@ -389,25 +417,26 @@ __global__ void __launch_bounds__(128, MINB) stream_simpson_kernel(const __grid_
       vcp[c] = fma(-dt4, l2[c], dt3 * l1[c]);
       dcp[c] = fma(-0.5, l2[c], l1[c]);
       Fa[c] = Fc[c];
+      xa[c] = xc[c];
     }
-#pragma unroll
-    for (int c = 0; c < W; ++c) Xa[c] = Xc[c];
   };
 
   // ---- lead-in: pair (r0-2, r0-1, r0), or just row 0 when the segment starts the path
   S.wait(0);
   S.wait(1);
   {
-    const double* st1 = S.stage(1);
+    double Xa[W];
     if (r0 >= 2) {
-      S.read_row(S.stage(0) + Wd, Xa);
-      M::f(Xa, S.p, nullptr, Fa);
-      pair(r0 - 2, st1, nullptr, std::false_type{});
-    } else {
-      S.read_row(st1 + Wd, Xa);
+      S.read_row(S.slot_off(0) + rb, Xa);
       M::f(Xa, S.p, nullptr, Fa);
 #pragma unroll
-      for (int c = 0; c < C; ++c) { vcp[c] = 0.0; dcp[c] = 0.0; }
+      for (int c = 0; c < C; ++c) { xa[c] = Xa[H + c]; vcp[c] = 0.0; dcp[c] = 0.0; }
+      pair(r0 - 2, S.slot_off(1), S.slot_off(0), std::false_type{});
+    } else {
+      S.read_row(S.slot_off(1) + rb, Xa);
+      M::f(Xa, S.p, nullptr, Fa);
+#pragma unroll
+      for (int c = 0; c < C; ++c) { xa[c] = Xa[H + c]; vcp[c] = 0.0; dcp[c] = 0.0; }
     }
   }
   __syncwarp();
@@ -416,21 +445,25 @@ __global__ void __launch_bounds__(128, MINB) stream_simpson_kernel(const __grid_
   for (int t = 1; t <= nfull; ++t) {
     const int q = t + 1;
     S.wait(q);
-    pair(r0 + 2 * (t - 1), S.stage(q), S.stage(q - 1) + 2 * Wd + Lw, std::true_type{});
+    pair(r0 + 2 * (t - 1), S.slot_off(q), S.slot_off(q - 1), std::true_type{});
     __syncwarp();
     S.issue(q - 1 + NS);
   }
   // ---- the last row of the path (even, only the c-part of the last pair and its measurement)
   if (last) {
-    double V[W], g[C], t[C];
+    double Xa[W], V[W], gr[C], t[C];
 #pragma unroll
-    for (int c = 0; c < C; ++c) { V[H + c] = vcp[c]; g[c] = dcp[c]; }
+    for (int c = 0; c < C; ++c) { V[H + c] = vcp[c]; gr[c] = dcp[c]; }
     S.halo(V);
-    S.measure(N - 1, S.stage(nfull + 1) + 2 * Wd + Lw, Xa + H, g);
+    const uint32_t sl = S.slot_off(nfull + 1);
+    S.read_halo(sl + rb, Xa);
+#pragma unroll
+    for (int c = 0; c < C; ++c) Xa[H + c] = xa[c];
+    S.measure(N - 1, sl + 3u * rb, xa, gr);
     M::adj_t(Xa, V, S.p, t, S.pacc);
 #pragma unroll
-    for (int c = 0; c < C; ++c) g[c] = (g[c] + V[H + c]) - t[c];
-    S.store(N - 1, g);
+    for (int c = 0; c < C; ++c) gr[c] = (gr[c] + V[H + c]) - t[c];
+    S.store(N - 1, gr);
   }
   S.finish(red);
 }
@@ -447,12 +480,13 @@ __global__ void __launch_bounds__(128, MINB) stream_twopoint_kernel(const __grid
   extern __shared__ __align__(16) double smem[];
   ST S(P);
   if (!S.init(smem)) return;
-  double* red = smem + (size_t)4 * NS * S.stage_d + 4 * NS;
+  double* red = smem + ((size_t)4 * NS * S.stage_b) / 8 + 4 * NS;
   const double dt = P.dt;
   const double ca = (DISC == DISC_EULER) ? dt : (DISC == DISC_TRAPEZOID ? 0.5 * dt : 1.0);
   const double cb = (DISC == DISC_TRAPEZOID) ? 0.5 * dt : 0.0;
   const double al = (DISC == DISC_FORWARDMAP) ? 0.0 : 1.0;
-  const int r0 = S.r0, r1 = S.r1, N = S.N, Wd = S.Wd, Lw = S.Lw;
+  const int r0 = S.r0, r1 = S.r1, N = S.N;
+  const uint32_t rb = S.row_b;
   S.rowbase = r0 - 2;                       // stage q holds rows (r0 - 2 + 2q, r0 - 1 + 2q)
   S.qmax = (min(r1, N - 1) - r0 + 2) / 2;
 #pragma unroll
@@ -460,11 +494,11 @@ __global__ void __launch_bounds__(128, MINB) stream_twopoint_kernel(const __grid
 
   double X1[W], F1[C], lamp[C];
   bool valid1;
-  // row m arrives (staged at xrow); finalises row m-1 (its Y row at yrow) when fin
-  auto sub = [&](int m, const double* xrow, const double* yrow, bool vm, bool fin) {
+  // row m arrives (staged at byte offset xoff); finalises row m-1 (its Y row at yoff) when fin
+  auto sub = [&](int m, uint32_t xoff, uint32_t yoff, bool vm, bool fin) {
     double Xm[W], Fm[C], lam[C];
     if (vm) {
-      S.read_row(xrow, Xm);
+      S.read_row(xoff, Xm);
       M::f(Xm, S.p, nullptr, Fm);
     } else {
 #pragma unroll
@@ -473,29 +507,30 @@ __global__ void __launch_bounds__(128, MINB) stream_twopoint_kernel(const __grid
       for (int c = 0; c < C; ++c) Fm[c] = 0.0;
     }
     const bool ve = vm && valid1;
+    const bool own = (m - 1 >= r0) && (m - 1 < r1);
 #pragma unroll
     for (int c = 0; c < C; ++c) {
       double l = 0.0;
       if (ve) {
         const double e = Xm[H + c] - al * X1[H + c] - fma(ca, F1[c], cb * Fm[c]);
         l = S.wgt(m - 1, c) * e;
-        if (m - 1 >= r0 && m - 1 < r1) S.fe_acc = fma(l, e, S.fe_acc);
+        if (own) S.fe_acc = fma(l, e, S.fe_acc);
       }
       lam[c] = l;
     }
     if (fin) {
-      double V[W], g[C], t[C];
+      double V[W], gr[C], t[C];
 #pragma unroll
       for (int c = 0; c < C; ++c) {
         V[H + c] = fma(cb, lamp[c], ca * lam[c]);
-        g[c] = lamp[c] - al * lam[c];
+        gr[c] = lamp[c] - al * lam[c];
       }
       S.halo(V);
-      S.measure(m - 1, yrow, X1 + H, g);
+      S.measure(m - 1, yoff, X1 + H, gr);
       M::adj_t(X1, V, S.p, t, S.pacc);
 #pragma unroll
-      for (int c = 0; c < C; ++c) g[c] = (g[c] + V[H + c]) - t[c];
-      S.store(m - 1, g);
+      for (int c = 0; c < C; ++c) gr[c] = (gr[c] + V[H + c]) - t[c];
+      S.store(m - 1, gr);
     }
 #pragma unroll
     for (int c = 0; c < W; ++c) X1[c] = Xm[c];
@@ -508,7 +543,7 @@ __global__ void __launch_bounds__(128, MINB) stream_twopoint_kernel(const __grid
   S.wait(0);
   valid1 = (r0 >= 1);
   if (valid1) {
-    S.read_row(S.stage(0) + Wd, X1);
+    S.read_row(S.slot_off(0) + rb, X1);
     M::f(X1, S.p, nullptr, F1);
   } else {
 #pragma unroll
@@ -525,14 +560,13 @@ __global__ void __launch_bounds__(128, MINB) stream_twopoint_kernel(const __grid
   for (int t = 0; t <= tmax; ++t) {
     const int q = t + 1, m1 = r0 + 2 * t;
     S.wait(q);
-    const double* st = S.stage(q);
-    const double* stp = S.stage(q - 1);
+    const uint32_t sq = S.slot_off(q), sp = S.slot_off(q - 1);
     if (t >= 1 && t <= tfull) {
-      sub(m1, st, stp + 2 * Wd + Lw, true, true);
-      sub(m1 + 1, st + Wd, st + 2 * Wd, true, true);
+      sub(m1, sq, sp + 3u * rb, true, true);
+      sub(m1 + 1, sq + rb, sq + 2u * rb, true, true);
     } else {
-      sub(m1, st, stp + 2 * Wd + Lw, m1 < N, t >= 1);
-      if (m1 + 1 <= r1) sub(m1 + 1, st + Wd, st + 2 * Wd, m1 + 1 < N, true);
+      sub(m1, sq, sp + 3u * rb, m1 < N, t >= 1);
+      if (m1 + 1 <= r1) sub(m1 + 1, sq + rb, sq + 2u * rb, m1 + 1 < N, true);
     }
     __syncwarp();
     S.issue(q - 1 + NS);

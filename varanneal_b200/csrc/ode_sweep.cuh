@@ -21,6 +21,7 @@
 //   partials buffer that ode_finalize reduces in a fixed order: bit-reproducible, no atomics.
 #pragma once
 #include "ode_models.cuh"
+#include "ode_params.h"
 #include "vab_hd.h"
 
 #define VAB_FULL 0xffffffffu
@@ -34,7 +35,7 @@ struct SLane {
   const double* xpath;
   double* gpath;
   double p[NPM];
-  int slot[C];
+  double wob[C];                       // 2 cm RM of the own components (0 = unobserved)
   double me_acc, fe_acc, pacc[NPM];
 
   __device__ __forceinline__ void init(const OdeParams& P) {
@@ -95,7 +96,7 @@ struct SLane {
       pacc[k] = 0.0;
     }
 #pragma unroll
-    for (int c = 0; c < C; ++c) slot[c] = act ? __ldg(P.obs_slot + i0 + c) : -1;
+    for (int c = 0; c < C; ++c) wob[c] = act ? __ldg(P.wobs + i0 + c) : 0.0;
     me_acc = 0.0;
     fe_acc = 0.0;
   }
@@ -136,17 +137,18 @@ struct SLane {
     return P.rf_arr ? __ldg(P.rf_arr + (long long)row * D + i0 + c) * P.rf_scale : P.rf_scalar;
   }
   // measurement term of row r (va_ode.py:138-158): adds to the direct gradient and to me_acc
+  // (me_acc collects sum 2 cm RM diff^2 = 2 me)
   __device__ __forceinline__ void measure(const OdeParams& P, int r, const double* xown, double* dir) {
-    if (P.nskip != 1 && (r % P.nskip) != 0) return;
-    const long long nd = (P.nskip == 1) ? r : r / P.nskip;
+    if (P.L == 0 || (P.nskip != 1 && (r % P.nskip) != 0)) return;
+    const long long o = (long long)((P.nskip == 1) ? r : r / P.nskip) * D + i0;
 #pragma unroll
     for (int c = 0; c < C; ++c) {
-      if (slot[c] >= 0) {
-        const long long o = nd * P.Lp + slot[c];
-        const double rm = P.rm_arr ? __ldg(P.rm_arr + o) : P.rm_scalar;
-        const double diff = xown[c] - __ldg(P.Y + o);
-        me_acc = fma(rm * diff, diff, me_acc);
-        dir[c] = fma(2.0 * P.cm * rm, diff, dir[c]);
+      const double w = P.rmd ? __ldg(P.rmd + o + c) : wob[c];
+      if (w != 0.0) {
+        const double diff = xown[c] - __ldg(P.Y + o + c);
+        const double wd = w * diff;
+        me_acc = fma(wd, diff, me_acc);
+        dir[c] += wd;
       }
     }
   }
@@ -160,7 +162,7 @@ struct SLane {
   // per-unit partials: lane partials -> shared memory -> fixed-order sum by the group's lanes
   __device__ __forceinline__ void finish(const OdeParams& P, double* smem, double psign) const {
     double* mine = smem + (long long)threadIdx.x * P.K;
-    mine[0] = me_acc * P.cm;
+    mine[0] = 0.5 * me_acc;
     mine[1] = fe_acc * P.cf;
 #pragma unroll
     for (int k = 0; k < NPM; ++k) mine[2 + k] = psign * pacc[k];

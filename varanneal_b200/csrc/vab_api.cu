@@ -37,29 +37,35 @@ int vab_reserve(vab_ctx* ctx, double** buf, size_t* cap, size_t need) {
   return VAB_OK;
 }
 
-// dst (rows, Lp) <- src (rows, L) with column l going to perm[l] (padding zeroed beforehand)
-__global__ void vab_pack_obs_scatter(const double* __restrict__ src, double* __restrict__ dst,
-                                     const int* __restrict__ perm, long long rows, int L, int Lp) {
+// dense (rows, D) <- compact (rows, L): column l goes to state component comp[l], times `scale`
+// (padding zeroed beforehand)
+__global__ void vab_scatter_obs_kernel(const double* __restrict__ src, double* __restrict__ dst,
+                                       const int* __restrict__ comp, long long rows, int L, int D,
+                                       double scale) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * L) return;
   const long long r = i / L;
   const int l = (int)(i - r * L);
-  dst[r * Lp + perm[l]] = src[i];
+  dst[r * D + comp[l]] = scale * src[i];
 }
 
-static int vab_pack_obs(vab_ctx* ctx, const double* src, double** dst, size_t* cap) {
+// src == nullptr: fill one row with `scale` at the observed components (the scalar-RM weights)
+static int vab_scatter_obs(vab_ctx* ctx, const double* src, long long rows, double scale,
+                           double** dst, size_t* cap) {
   const vab_ode_desc& d = ctx->od;
-  const size_t need = (size_t)d.N_data * ctx->Lp + ctx->Lw + 2;
+  const size_t need = (size_t)rows * d.D + 2;
   int rc = vab_reserve(ctx, dst, cap, need);
   if (rc != VAB_OK) return rc;
   cudaError_t e = cudaMemsetAsync(*dst, 0, need * sizeof(double), ctx->stream);
-  if (e != cudaSuccess) return vab_cuda_fail(ctx, e, "pack observations (memset)");
-  const long long n = (long long)d.N_data * d.L;
-  if (n > 0)
-    vab_pack_obs_scatter<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(src, *dst, ctx->lperm_dev, d.N_data, d.L, ctx->Lp);
-  e = cudaGetLastError();
-  if (e != cudaSuccess) return vab_cuda_fail(ctx, e, "pack observations");
-  ctx->launches += 1;
+  if (e != cudaSuccess) return vab_cuda_fail(ctx, e, "dense observation layout (memset)");
+  const long long n = rows * d.L;
+  if (n > 0 && src != nullptr) {
+    vab_scatter_obs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(
+        src, *dst, ctx->lcomp_dev, rows, d.L, d.D, scale);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return vab_cuda_fail(ctx, e, "dense observation layout");
+    ctx->launches += 1;
+  }
   return VAB_OK;
 }
 
@@ -104,10 +110,7 @@ int vab_ctx_create(int device, void* stream, vab_ctx** out) {
   c->stream = (cudaStream_t)stream;
   c->num_sms = prop.multiProcessorCount;
   if (const char* t = getenv("VAB_TSEG")) c->tseg_override = atoi(t);
-  if (const char* t = getenv("VAB_KERNEL")) {
-    c->use_walk = (strcmp(t, "walk") == 0);
-    c->use_sweep = (strcmp(t, "sweep") == 0);
-  }
+  if (const char* t = getenv("VAB_KERNEL")) c->use_sweep = (strcmp(t, "sweep") == 0);
   e = cudaMalloc((void**)&c->pfix_zero, 64 * sizeof(double));
   if (e == cudaSuccess) e = cudaMemsetAsync(c->pfix_zero, 0, 64 * sizeof(double), c->stream);
   if (e != cudaSuccess) {
@@ -124,12 +127,11 @@ int vab_ctx_destroy(vab_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   nn_destroy(ctx);
   lbfgs_destroy(ctx);
-  cudaFree(ctx->obs_slot_dev);
   cudaFree(ctx->pmap_dev);
-  cudaFree(ctx->Y_pad);
-  cudaFree(ctx->rm_pad);
-  cudaFree(ctx->lperm_dev);
-  cudaFree(ctx->win_y0_dev);
+  cudaFree(ctx->lcomp_dev);
+  cudaFree(ctx->Y_dense);
+  cudaFree(ctx->rm_dense);
+  cudaFree(ctx->wobs_dev);
   cudaFree(ctx->pfix_zero);
   cudaFree(ctx->partials);
   delete ctx;
@@ -169,105 +171,80 @@ int vab_ode_problem_set(vab_ctx* ctx, const vab_ode_desc* d, const int32_t* Lidx
     return vab_fail(ctx, VAB_ERR_INVALID, "ode_problem_set: rk4 (extension) takes no stimulus");
   if (d->L > 0 && (!Lidx_host || !Y_dev))
     return vab_fail(ctx, VAB_ERR_INVALID, "ode_problem_set: Lidx/Y missing");
-  if (ctx->use_walk) {
-    OdePlan pl;
-    int prc = ode_make_plan(d->model, d->disc, d->D, d->N_model, 1, ctx->num_sms, 0, &pl);
-    if (prc != 0)
-      return vab_fail(ctx, VAB_ERR_INVALID, "ode_problem_set: D not supported by the legacy walk kernels");
-  }
-  if ((d->model == VAB_MODEL_LORENZ96 && d->D < 4) || (d->model == VAB_MODEL_LORENZ63 && d->D != 3) ||
-      (d->model == VAB_MODEL_NAKL && d->D != 4))
+  OdeGeo geo;
+  if (ode_geometry(d->model, d->disc, d->D, &geo) != 0)
     return vab_fail(ctx, VAB_ERR_INVALID, "ode_problem_set: D not valid for this model");
-
-  std::vector<int> obs(d->D, -1), pmap(d->NP, -1), lperm(d->L > 0 ? d->L : 1, 0);
+  std::vector<int> seen(d->D, 0), pmap(d->NP, -1), lcomp(d->L > 0 ? d->L : 1, 0);
   for (int l = 0; l < d->L; ++l) {
     const int i = Lidx_host[l];
     if (i < 0 || i >= d->D) return vab_fail(ctx, VAB_ERR_INVALID, "ode_problem_set: Lidx out of range");
-    if (obs[i] >= 0) return vab_fail(ctx, VAB_ERR_INVALID, "ode_problem_set: duplicate Lidx entry");
-    obs[i] = l;
+    if (seen[i]) return vab_fail(ctx, VAB_ERR_INVALID, "ode_problem_set: duplicate Lidx entry");
+    seen[i] = 1;
+    lcomp[l] = i;
   }
-  // library layout of Y / RM: columns sorted by state component (rank), row pitch Lp (even)
-  std::vector<int> sorted_comp;
-  for (int i = 0, rank = 0; i < d->D; ++i)
-    if (obs[i] >= 0) {
-      lperm[obs[i]] = rank;
-      obs[i] = rank++;
-      sorted_comp.push_back(i);
-    }
   for (int e = 0; e < d->NPest; ++e) {
     const int k = Pidx_host[e];
     if (k < 0 || k >= d->NP) return vab_fail(ctx, VAB_ERR_INVALID, "ode_problem_set: Pidx out of range");
     if (pmap[k] >= 0) return vab_fail(ctx, VAB_ERR_INVALID, "ode_problem_set: duplicate Pidx entry");
     pmap[k] = e;
   }
-  // per-window Y column ranges of the stream kernels
-  OdeGeo geo;
-  if (ode_geometry(d->model, d->disc, d->D, &geo) != 0)
-    return vab_fail(ctx, VAB_ERR_INVALID, "ode_problem_set: D not valid for this model");
-  const int Lp = (d->L + 1) & ~1;
-  std::vector<int> wy0(geo.nwin, 0);
-  int Lw = 2;
-  for (int w = 0; w < geo.nwin; ++w) {
-    const int c_lo = w * geo.WS * geo.C;
-    int c_hi = (w + 1) * geo.WS * geo.C;
-    if (c_hi > d->D) c_hi = d->D;
-    int s0 = 0, s1 = 0;
-    for (int c : sorted_comp) { if (c < c_lo) ++s0; if (c < c_hi) ++s1; }
-    const int y0 = s0 & ~1;
-    int len = (s1 - y0 + 1) & ~1;
-    if (geo.nwin == 1) len = Lp;
-    wy0[w] = y0;
-    if (len > Lw) Lw = len;
-  }
   cudaStreamSynchronize(ctx->stream);
-  cudaFree(ctx->obs_slot_dev);
   cudaFree(ctx->pmap_dev);
-  cudaFree(ctx->lperm_dev);
-  cudaFree(ctx->win_y0_dev);
-  ctx->obs_slot_dev = nullptr;
+  cudaFree(ctx->lcomp_dev);
+  cudaFree(ctx->wobs_dev);
   ctx->pmap_dev = nullptr;
-  ctx->lperm_dev = nullptr;
-  ctx->win_y0_dev = nullptr;
-  cudaError_t e = cudaMalloc((void**)&ctx->obs_slot_dev, sizeof(int) * d->D);
-  if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->pmap_dev, sizeof(int) * (d->NP > 0 ? d->NP : 1));
-  if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->lperm_dev, sizeof(int) * lperm.size());
-  if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->win_y0_dev, sizeof(int) * wy0.size());
-  if (e == cudaSuccess)
-    e = cudaMemcpy(ctx->obs_slot_dev, obs.data(), sizeof(int) * d->D, cudaMemcpyHostToDevice);
+  ctx->lcomp_dev = nullptr;
+  ctx->wobs_dev = nullptr;
+  cudaError_t e = cudaMalloc((void**)&ctx->pmap_dev, sizeof(int) * (d->NP > 0 ? d->NP : 1));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->lcomp_dev, sizeof(int) * lcomp.size());
+  if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->wobs_dev, sizeof(double) * (d->D + 2));
   if (e == cudaSuccess && d->NP > 0)
     e = cudaMemcpy(ctx->pmap_dev, pmap.data(), sizeof(int) * d->NP, cudaMemcpyHostToDevice);
   if (e == cudaSuccess)
-    e = cudaMemcpy(ctx->lperm_dev, lperm.data(), sizeof(int) * lperm.size(), cudaMemcpyHostToDevice);
-  if (e == cudaSuccess)
-    e = cudaMemcpy(ctx->win_y0_dev, wy0.data(), sizeof(int) * wy0.size(), cudaMemcpyHostToDevice);
+    e = cudaMemcpy(ctx->lcomp_dev, lcomp.data(), sizeof(int) * lcomp.size(), cudaMemcpyHostToDevice);
   if (e != cudaSuccess) return vab_cuda_fail(ctx, e, "ode_problem_set");
   ctx->od = *d;
-  ctx->Lp = Lp;
-  ctx->Lw = Lw;
+  // dense copy of the observations: the layout the kernels stream (same columns as X)
   {
-    int rc = vab_pack_obs(ctx, Y_dev, &ctx->Y_pad, &ctx->Y_cap);
+    int rc = vab_scatter_obs(ctx, Y_dev, d->N_data, 1.0, &ctx->Y_dense, &ctx->Y_cap);
     if (rc != VAB_OK) return rc;
   }
-  ctx->Y_dev = ctx->Y_pad;
   ctx->stim_dev = (d->n_stim > 0) ? stim_dev : nullptr;
   ctx->pfix_dev = ctx->pfix_zero;
   ctx->pfix_stride = 0;
-  ctx->rm_scalar = 1.0; ctx->rm_dev = nullptr;
   ctx->rf0_scalar = 1.0; ctx->rf0_dev = nullptr;
   ctx->problem = VAB_PROBLEM_ODE;
-  return VAB_OK;
+  return vab_ode_set_weights(ctx, 1.0, nullptr, 1.0, nullptr);
 }
 
 int vab_ode_set_weights(vab_ctx* ctx, double rm_scalar, const double* rm_dev, double rf0_scalar,
                         const double* rf0_dev) {
   if (!ctx) return VAB_ERR_INVALID;
   if (ctx->problem != VAB_PROBLEM_ODE) return vab_fail(ctx, VAB_ERR_STATE, "set_weights: no ODE problem set");
+  cudaSetDevice(ctx->device);
+  const vab_ode_desc& d = ctx->od;
+  const double cm2 = d.L > 0 ? 2.0 / ((double)d.L * d.N_data) : 0.0;
   ctx->rm_scalar = rm_scalar; ctx->rm_dev = nullptr;
-  if (rm_dev) {
-    cudaSetDevice(ctx->device);
-    int rc = vab_pack_obs(ctx, rm_dev, &ctx->rm_pad, &ctx->rm_cap);
+  {  // weights of the measurement term in the dense layout: 2 cm RM at the observed components
+    size_t cap = (size_t)d.D + 2;
+    int rc = vab_scatter_obs(ctx, nullptr, 1, 0.0, &ctx->wobs_dev, &cap);   // zero fill
     if (rc != VAB_OK) return rc;
-    ctx->rm_dev = ctx->rm_pad;
+    if (d.L > 0) {
+      std::vector<double> ones(d.L, cm2 * rm_scalar);
+      double* tmp = nullptr;
+      cudaError_t e = cudaMalloc((void**)&tmp, sizeof(double) * d.L);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(tmp, ones.data(), sizeof(double) * d.L, cudaMemcpyHostToDevice, ctx->stream);
+      if (e != cudaSuccess) { cudaFree(tmp); return vab_cuda_fail(ctx, e, "set_weights"); }
+      rc = vab_scatter_obs(ctx, tmp, 1, 1.0, &ctx->wobs_dev, &cap);
+      cudaStreamSynchronize(ctx->stream);
+      cudaFree(tmp);
+      if (rc != VAB_OK) return rc;
+    }
+  }
+  if (rm_dev) {
+    int rc = vab_scatter_obs(ctx, rm_dev, d.N_data, cm2, &ctx->rm_dense, &ctx->rm_cap);
+    if (rc != VAB_OK) return rc;
+    ctx->rm_dev = ctx->rm_dense;
   }
   ctx->rf0_scalar = rf0_scalar; ctx->rf0_dev = rf0_dev;
   return VAB_OK;
@@ -301,9 +278,7 @@ static int ode_eval(vab_ctx* ctx, int B, const double* XP, long long ldxp, doubl
   P.XP = XP; P.ldxp = ldxp; P.G = G; P.ldg = ldg;
   P.B = B; P.D = d.D; P.N = d.N_model; P.N_data = d.N_data; P.nskip = d.nskip; P.L = d.L;
   P.dt = d.dt_model;
-  P.obs_slot = ctx->obs_slot_dev; P.Y = ctx->Y_dev; P.Lp = ctx->Lp; P.Lw = ctx->Lw;
-  P.win_y0 = ctx->win_y0_dev;
-  P.rm_scalar = ctx->rm_scalar; P.rm_arr = ctx->rm_dev;
+  P.Y = ctx->Y_dense; P.wobs = ctx->wobs_dev; P.rmd = ctx->rm_dev;
   P.rf_scalar = ctx->rf0_scalar * rf_scale; P.rf_arr = ctx->rf0_dev; P.rf_scale = rf_scale;
   P.stim = ctx->stim_dev; P.S = d.n_stim;
   P.NP = d.NP; P.NPest = d.NPest; P.pmap = ctx->pmap_dev;
@@ -314,17 +289,7 @@ static int ode_eval(vab_ctx* ctx, int B, const double* XP, long long ldxp, doubl
   P.cf = 1.0 / ((double)d.D * (d.N_model - 1));
   cudaError_t cerr = cudaSuccess;
   int rc;
-  if (ctx->use_walk) {
-    OdePlan pl;
-    if (ode_make_plan(d.model, d.disc, d.D, d.N_model, B, ctx->num_sms, ctx->tseg_override, &pl) != 0)
-      return vab_fail(ctx, VAB_ERR_INVALID, "ode_action_grad: unsupported shape");
-    P.Tseg = pl.Tseg; P.nseg = pl.nseg; P.TPR = pl.TPR; P.RG = pl.RG; P.nunits = pl.nunits;
-    P.upp = pl.nseg;
-    rc = vab_reserve(ctx, &ctx->partials, &ctx->partials_cap, (size_t)pl.nunits * P.K);
-    if (rc != VAB_OK) return rc;
-    P.partials = ctx->partials;
-    rc = ode_launch_action(P, pl, d.model, d.disc, ctx->stream, A, me, fe, &cerr);
-  } else {
+  {
     SweepLaunch sl;
     rc = ode_sweep_prepare(d.model, d.disc, d.D, d.N_model, B, ctx->num_sms, ctx->tseg_override,
                            !ctx->use_sweep, &P, &sl, &cerr);

@@ -6,8 +6,8 @@
 #include <vector>
 
 #include "../../include/varanneal_b200.h"
+#include "ode_params.h"
 #include "ode_plan.h"
-#include "ode_walk.cuh"
 
 struct NnProblem;   // nn_action.h
 struct LbfgsWork;   // lbfgs.h
@@ -24,25 +24,22 @@ struct vab_ctx {
 
   // ---- ODE problem (vab_ode_problem_set / set_weights / set_fixed_params)
   vab_ode_desc od{};
-  int* obs_slot_dev = nullptr;      // (D)
   int* pmap_dev = nullptr;          // (NP)
-  const double* Y_dev = nullptr;    // library copy: (N_data, Lp), columns sorted by component
-  double* Y_pad = nullptr;
-  double* rm_pad = nullptr;         // same layout, when RM is an array
+  int* lcomp_dev = nullptr;         // (L) state component of each observed column
+  const double* Y_src = nullptr;    // caller's (N_data, L) observations (read during set-up only)
+  double* Y_dense = nullptr;        // (N_data, D) library copy, zero where unobserved
+  double* rm_dense = nullptr;       // (N_data, D) 2 cm RM[n, l] when RM is an array
+  double* wobs_dev = nullptr;       // (D) 2 cm RM for observed components (scalar RM)
   size_t Y_cap = 0, rm_cap = 0;     // doubles
-  int Lp = 0, Lw = 0;
-  int* lperm_dev = nullptr;         // (L) column of the library layout for each caller column
-  int* win_y0_dev = nullptr;        // (nwin)
   const double* stim_dev = nullptr;
   double rm_scalar = 1.0;
-  const double* rm_dev = nullptr;
+  const double* rm_dev = nullptr;   // = rm_dense when RM is an array
   double rf0_scalar = 1.0;
   const double* rf0_dev = nullptr;
   const double* pfix_dev = nullptr;
   long long pfix_stride = 0;
   double* pfix_zero = nullptr;      // default fixed-parameter block (zeros)
   int tseg_override = 0;            // tuning knob (env VAB_TSEG)
-  bool use_walk = false;            // env VAB_KERNEL=walk: legacy strip-walk kernels
   bool use_sweep = false;           // env VAB_KERNEL=sweep: register sweep kernels even where the stream kernels apply
 
   // ---- NN problem
