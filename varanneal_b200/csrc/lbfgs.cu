@@ -1,15 +1,882 @@
-// placeholder until the device-resident minimiser lands (next milestone)
+// Device-resident, batched L-BFGS-B: replaces ADmin.min_lbfgs_scipy (_autodiffmin.py:72-95), i.e.
+// scipy.optimize.minimize(method='L-BFGS-B', jac=True) driving A_gradA_taped, for B independent
+// paths at once -- and the beta loop around it (va_ode.py:473-490, 707-789).
+//
+// What is mirrored from L-BFGS-B 3.0 / SciPy: limited-memory BFGS direction
+// with H0 = I/theta, theta = y'y / s'y, m = maxcor pairs; More'-Thuente line search (dcsrch /
+// dcstep, ftol 1e-3, gtol 0.9, xtol 0.1) with first step 1/||d|| at iteration 0 and 1 afterwards;
+// the update is skipped when s'y <= eps * (-g'd * stp); at most maxls evaluations per line search,
+// after which the memory is dropped and the iteration restarted (abnormal termination if it was
+// already empty); stopping tests max|proj g| <= pgtol and
+// (f_k - f_{k+1}) <= ftol * max(|f_k|, |f_{k+1}|, 1); maxiter / maxfun checked after each
+// iteration; status = SciPy's warnflag (0 converged, 1 limit reached, 2 abnormal).
+// Bounds: active-set projection (variables sitting on a bound with the gradient pushing outward
+// are frozen for the iteration, the step is limited to the largest feasible one) instead of the
+// generalised Cauchy point + subspace minimisation -- same minimisers, different iterates.
+//
+// Execution model: nothing per-iteration ever reaches the host.  Every decision (line search
+// state machine, convergence tests, history management, the two-loop recursion carried out in
+// coefficient space on a small Gram matrix) is taken by single-CTA kernels on per-path state in
+// device memory; the n-vector work is three fused passes per iteration:
+//     trial      xt = x + stp d
+//     [f, g](xt) the fused action kernel (ode_stream.cuh / ode_sweep.cuh / nn_action.cu)
+//     gd         g(xt).d and max |proj g|                               (2 vector reads)
+//     update     s, y into the history, x <- xt, g <- gt, and every dot product the
+//                Gram matrix needs, in one sweep                         (2m+4 reads, 4 writes)
+//     direction  d = -H g as a linear combination of the history + d'd, g'd, max feasible step
+//                                                                        (2m+1 reads, 1 write)
+// The host only enqueues fixed "cycles" of these kernels and polls a counter of running paths
+// every few cycles; finished paths are masked out inside the kernels.  All reductions are
+// fixed-order (bit-reproducible runs).
+#include <cuda_runtime.h>
+
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include <string>
+
 #include "vab_ctx.h"
-void lbfgs_destroy(vab_ctx*) {}
+
+namespace {
+
+constexpr int MMAX = 10;          // largest history size (SciPy's default maxcor)
+constexpr int NT = 256;           // threads per CTA of the vector kernels
+constexpr int NACC_U = 5 * MMAX + 4;
+constexpr double EPSMCH = 2.220446049250313e-16;
+constexpr double BIG = 1.0e10;    // stpmx of an unconstrained line search (lnsrlb)
+
+struct LbPath {
+  // control flags (written by the single-CTA kernels, read by everything)
+  int done, need_eval, accepted, do_update, redo_dir, first;
+  int iter, nfev, col, head, pslot, ifun, iback, nskip, status;
+  double f, fold, me, fe;
+  double stp, gd, gdold, dnorm, stpmx, theta, sbgnrm, dr;
+  // dcsrch
+  int brackt, stage;
+  double ginit, gtest, gx, gy, finit, fx, fy, stx, sty, stmin, stmax, width, width1;
+  // Gram blocks over the history slots and the coefficients of the direction
+  double SY[MMAX * MMAX];   // SY[i][j] = s_i . y_j
+  double YY[MMAX * MMAX];   // y_i . y_j
+  double gS[MMAX], gY[MMAX], gg;
+  double cs[MMAX], cy[MMAX], cg;
+};
+
+struct LbOpts {
+  int m, maxls;
+  long long maxfun, maxiter;
+  double ftol, pgtol;
+};
+
+}  // namespace
+
+struct LbfgsWork {
+  int B = 0;
+  long long ld = 0;
+  int m = 0;
+  double* vec = nullptr;        // XT, GT, G, Dv, S[m], Y[m]  each (B, ld)
+  size_t vec_cap = 0;
+  LbPath* st = nullptr;
+  int st_cap = 0;
+  int* act_eval = nullptr;      // (B) mask handed to the action kernel
+  double* ft = nullptr;         // (B) trial f / me / fe
+  double* met = nullptr;
+  double* fet = nullptr;
+  double* part = nullptr;       // partial sums of the vector kernels
+  size_t part_cap = 0;
+  int* n_running_dev = nullptr;
+  int* n_running_host = nullptr;   // pinned
+  cudaEvent_t ev = nullptr;
+};
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// More'-Thuente step (MINPACK-2 dcstep)
+__device__ void dcstep(double& stx, double& fx, double& dx, double& sty, double& fy, double& dy,
+                       double& stp, double fp, double dp, int& brackt, double stpmin, double stpmax) {
+  const double sgnd = dp * (dx / fabs(dx));
+  double stpf, stpc, stpq, theta, s, gamma, p, q, r;
+  if (fp > fx) {
+    theta = 3.0 * (fx - fp) / (stp - stx) + dx + dp;
+    s = fmax(fabs(theta), fmax(fabs(dx), fabs(dp)));
+    gamma = s * sqrt((theta / s) * (theta / s) - (dx / s) * (dp / s));
+    if (stp < stx) gamma = -gamma;
+    p = (gamma - dx) + theta;
+    q = ((gamma - dx) + gamma) + dp;
+    r = p / q;
+    stpc = stx + r * (stp - stx);
+    stpq = stx + ((dx / ((fx - fp) / (stp - stx) + dx)) / 2.0) * (stp - stx);
+    if (fabs(stpc - stx) < fabs(stpq - stx)) stpf = stpc;
+    else stpf = stpc + (stpq - stpc) / 2.0;
+    brackt = 1;
+  } else if (sgnd < 0.0) {
+    theta = 3.0 * (fx - fp) / (stp - stx) + dx + dp;
+    s = fmax(fabs(theta), fmax(fabs(dx), fabs(dp)));
+    gamma = s * sqrt((theta / s) * (theta / s) - (dx / s) * (dp / s));
+    if (stp > stx) gamma = -gamma;
+    p = (gamma - dp) + theta;
+    q = ((gamma - dp) + gamma) + dx;
+    r = p / q;
+    stpc = stp + r * (stx - stp);
+    stpq = stp + (dp / (dp - dx)) * (stx - stp);
+    if (fabs(stpc - stp) > fabs(stpq - stp)) stpf = stpc;
+    else stpf = stpq;
+    brackt = 1;
+  } else if (fabs(dp) < fabs(dx)) {
+    theta = 3.0 * (fx - fp) / (stp - stx) + dx + dp;
+    s = fmax(fabs(theta), fmax(fabs(dx), fabs(dp)));
+    gamma = s * sqrt(fmax(0.0, (theta / s) * (theta / s) - (dx / s) * (dp / s)));
+    if (stp > stx) gamma = -gamma;
+    p = (gamma - dp) + theta;
+    q = (gamma + (dx - dp)) + gamma;
+    r = p / q;
+    if (r < 0.0 && gamma != 0.0) stpc = stp + r * (stx - stp);
+    else if (stp > stx) stpc = stpmax;
+    else stpc = stpmin;
+    stpq = stp + (dp / (dp - dx)) * (stx - stp);
+    if (brackt) {
+      if (fabs(stpc - stp) < fabs(stpq - stp)) stpf = stpc;
+      else stpf = stpq;
+      if (stp > stx) stpf = fmin(stp + 0.66 * (sty - stp), stpf);
+      else stpf = fmax(stp + 0.66 * (sty - stp), stpf);
+    } else {
+      if (fabs(stpc - stp) > fabs(stpq - stp)) stpf = stpc;
+      else stpf = stpq;
+      stpf = fmin(stpmax, stpf);
+      stpf = fmax(stpmin, stpf);
+    }
+  } else {
+    if (brackt) {
+      theta = 3.0 * (fp - fy) / (sty - stp) + dy + dp;
+      s = fmax(fabs(theta), fmax(fabs(dy), fabs(dp)));
+      gamma = s * sqrt((theta / s) * (theta / s) - (dy / s) * (dp / s));
+      if (stp > sty) gamma = -gamma;
+      p = (gamma - dp) + theta;
+      q = ((gamma - dp) + gamma) + dy;
+      r = p / q;
+      stpc = stp + r * (sty - stp);
+      stpf = stpc;
+    } else if (stp > stx) {
+      stpf = stpmax;
+    } else {
+      stpf = stpmin;
+    }
+  }
+  if (fp > fx) {
+    sty = stp; fy = fp; dy = dp;
+  } else {
+    if (sgnd < 0.0) { sty = stx; fy = fx; dy = dx; }
+    stx = stp; fx = fp; dx = dp;
+  }
+  stp = stpf;
+}
+
+// dcsrch with task = 'START': initialise the search for the step already stored in s.stp
+__device__ void dcsrch_start(LbPath& s, double f, double g, double stpmax) {
+  s.brackt = 0;
+  s.stage = 1;
+  s.finit = f;
+  s.ginit = g;
+  s.gtest = 1e-3 * g;
+  s.width = stpmax - 0.0;
+  s.width1 = s.width / 0.5;
+  s.stx = 0.0; s.fx = f; s.gx = g;
+  s.sty = 0.0; s.fy = f; s.gy = g;
+  s.stmin = 0.0;
+  s.stmax = s.stp + 4.0 * s.stp;
+}
+
+// dcsrch with task = 'FG': returns 0 = evaluate again at the new s.stp, 1 = convergence / warning
+__device__ int dcsrch_step(LbPath& s, double f, double g, double stpmin, double stpmax) {
+  const double ftol = 1e-3, gtol = 0.9, xtol = 0.1;
+  const double ftest = s.finit + s.stp * s.gtest;
+  if (s.stage == 1 && f <= ftest && g >= 0.0) s.stage = 2;
+  int stop = 0;
+  if (s.brackt && (s.stp <= s.stmin || s.stp >= s.stmax)) stop = 1;           // rounding errors
+  if (s.brackt && s.stmax - s.stmin <= xtol * s.stmax) stop = 1;               // xtol test
+  if (s.stp == stpmax && f <= ftest && g <= s.gtest) stop = 1;                 // stp = stpmax
+  if (s.stp == stpmin && (f > ftest || g >= s.gtest)) stop = 1;                // stp = stpmin
+  if (f <= ftest && fabs(g) <= gtol * (-s.ginit)) stop = 1;                    // convergence
+  if (stop) return 1;
+  (void)ftol;
+  if (s.stage == 1 && f <= s.fx && f > ftest) {
+    const double fm = f - s.stp * s.gtest;
+    double fxm = s.fx - s.stx * s.gtest, fym = s.fy - s.sty * s.gtest;
+    const double gm = g - s.gtest;
+    double gxm = s.gx - s.gtest, gym = s.gy - s.gtest;
+    dcstep(s.stx, fxm, gxm, s.sty, fym, gym, s.stp, fm, gm, s.brackt, s.stmin, s.stmax);
+    s.fx = fxm + s.stx * s.gtest;
+    s.fy = fym + s.sty * s.gtest;
+    s.gx = gxm + s.gtest;
+    s.gy = gym + s.gtest;
+  } else {
+    dcstep(s.stx, s.fx, s.gx, s.sty, s.fy, s.gy, s.stp, f, g, s.brackt, s.stmin, s.stmax);
+  }
+  if (s.brackt) {
+    if (fabs(s.sty - s.stx) >= 0.66 * s.width1) s.stp = s.stx + 0.5 * (s.sty - s.stx);
+    s.width1 = s.width;
+    s.width = fabs(s.sty - s.stx);
+  }
+  if (s.brackt) {
+    s.stmin = fmin(s.stx, s.sty);
+    s.stmax = fmax(s.stx, s.sty);
+  } else {
+    s.stmin = s.stp + 1.1 * (s.stp - s.stx);
+    s.stmax = s.stp + 4.0 * (s.stp - s.stx);
+  }
+  s.stp = fmax(s.stp, stpmin);
+  s.stp = fmin(s.stp, stpmax);
+  if ((s.brackt && (s.stp <= s.stmin || s.stp >= s.stmax)) ||
+      (s.brackt && s.stmax - s.stmin <= xtol * s.stmax))
+    s.stp = s.stx;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// helpers of the vector kernels
+
+// projected gradient component (L-BFGS-B projgr)
+__device__ __forceinline__ double proj_g(double x, double g, double lo, double hi) {
+  if (g < 0.0) return fmax(x - hi, g);
+  return fmin(x - lo, g);
+}
+// variable frozen for this iteration: on a bound with the gradient pushing outward
+__device__ __forceinline__ bool frozen(double x, double g, double lo, double hi) {
+  return (x <= lo && g > 0.0) || (x >= hi && g < 0.0);
+}
+
+struct Range { long long i0, i1; };
+__device__ __forceinline__ Range chunk_range(long long n, int nchunk, int c) {
+  long long len = (n + nchunk - 1) / nchunk;
+  len = (len + 1) & ~1LL;
+  Range r;
+  r.i0 = (long long)c * len;
+  r.i1 = r.i0 + len;
+  if (r.i1 > n) r.i1 = n;
+  if (r.i0 > n) r.i0 = n;
+  return r;
+}
+
+// block reduction of NV per-thread values (sum, or max / min per entry), fixed order; result valid in thread 0..NV-1? no:
+// every value k ends up in out[k] (written by one thread).  scratch: 8 * NT doubles.
+enum { RED_SUM = 0, RED_MAX = 1, RED_MIN = 2 };
+template <int NV>
+__device__ void block_reduce(const double* v, const int* op, double* out, double* scratch) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int base = 0; base < NV; base += 8) {
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (base + k < NV) scratch[k * NT + tid] = v[base + k];
+    __syncthreads();
+    const int k = warp;                       // NT / 32 == 8 warps: warp k reduces entry base + k
+    if (base + k < NV) {
+      const int o = op[base + k];
+      double acc = scratch[k * NT + lane];
+      for (int t = lane + 32; t < NT; t += 32) {
+        const double u = scratch[k * NT + t];
+        acc = (o == RED_SUM) ? acc + u : (o == RED_MAX ? fmax(acc, u) : fmin(acc, u));
+      }
+      for (int sft = 16; sft > 0; sft >>= 1) {
+        const double u = __shfl_down_sync(0xffffffffu, acc, sft);
+        acc = (o == RED_SUM) ? acc + u : (o == RED_MAX ? fmax(acc, u) : fmin(acc, u));
+      }
+      if (lane == 0) out[base + k] = acc;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void lb_init_kernel(LbPath* st, int* act_eval, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  LbPath& s = st[b];
+  s.done = 0; s.need_eval = 1; s.accepted = 0; s.do_update = 0; s.redo_dir = 0; s.first = 1;
+  s.iter = 0; s.nfev = 0; s.col = 0; s.head = 0; s.pslot = 0; s.ifun = 0; s.iback = 0; s.nskip = 0;
+  s.status = 2;
+  s.f = 0.0; s.fold = 0.0; s.me = 0.0; s.fe = 0.0;
+  s.stp = 0.0; s.gd = 0.0; s.gdold = 0.0; s.dnorm = 0.0; s.stpmx = BIG; s.theta = 1.0;
+  s.sbgnrm = 0.0; s.dr = 0.0;
+  s.cg = 1.0;
+  for (int j = 0; j < MMAX; ++j) { s.cs[j] = 0.0; s.cy[j] = 0.0; s.gS[j] = 0.0; s.gY[j] = 0.0; }
+  act_eval[b] = 1;
+}
+
+// clip the start point into the bounds (SciPy does this before the first evaluation)
+__global__ void lb_clip_kernel(double* X, long long ld, long long n, const double* lo, const double* hi) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double* x = X + (long long)blockIdx.y * ld;
+  x[i] = fmin(fmax(x[i], lo[i]), hi[i]);
+}
+
+// xt = x + stp d
+__global__ void __launch_bounds__(NT) lb_trial_kernel(double* __restrict__ XT, const double* __restrict__ X,
+                                                      const double* __restrict__ Dv, long long ld, long long n,
+                                                      const LbPath* __restrict__ st, int nchunk) {
+  const int b = blockIdx.y;
+  const LbPath& s = st[b];
+  if (s.done || !s.need_eval || s.first) return;
+  const double stp = s.stp;
+  const Range r = chunk_range(n, nchunk, blockIdx.x);
+  const double* x = X + (long long)b * ld;
+  const double* d = Dv + (long long)b * ld;
+  double* xt = XT + (long long)b * ld;
+  for (long long i = r.i0 + 2LL * threadIdx.x; i < r.i1; i += 2LL * NT) {
+    if (i + 1 < r.i1) {
+      const double2 xv = *reinterpret_cast<const double2*>(x + i);
+      const double2 dv = *reinterpret_cast<const double2*>(d + i);
+      *reinterpret_cast<double2*>(xt + i) = make_double2(fma(stp, dv.x, xv.x), fma(stp, dv.y, xv.y));
+    } else {
+      xt[i] = fma(stp, d[i], x[i]);
+    }
+  }
+}
+
+// partials [gd, max |proj g|] of the trial point
+template <bool BOUNDED>
+__global__ void __launch_bounds__(NT) lb_gd_kernel(const double* __restrict__ XT, const double* __restrict__ GT,
+                                                   const double* __restrict__ Dv, long long ld, long long n,
+                                                   const double* __restrict__ lo, const double* __restrict__ hi,
+                                                   const LbPath* __restrict__ st, int nchunk,
+                                                   double* __restrict__ part) {
+  __shared__ double scratch[8 * NT];
+  __shared__ double res[2];
+  const int b = blockIdx.y;
+  const LbPath& s = st[b];
+  if (s.done || !s.need_eval) return;
+  const Range r = chunk_range(n, nchunk, blockIdx.x);
+  const double* g = GT + (long long)b * ld;
+  const double* d = Dv + (long long)b * ld;
+  const double* x = XT + (long long)b * ld;
+  double v[2] = {0.0, 0.0};
+  const bool first = s.first != 0;
+  for (long long i = r.i0 + threadIdx.x; i < r.i1; i += NT) {
+    const double gi = g[i];
+    if (!first) v[0] = fma(gi, d[i], v[0]);
+    const double pg = BOUNDED ? proj_g(x[i], gi, lo[i], hi[i]) : gi;
+    v[1] = fmax(v[1], fabs(pg));
+  }
+  const int op[2] = {RED_SUM, RED_MAX};
+  block_reduce<2>(v, op, res, scratch);
+  __syncthreads();
+  if (threadIdx.x < 2) part[((long long)b * nchunk + blockIdx.x) * 2 + threadIdx.x] = res[threadIdx.x];
+}
+
+// line-search state machine + stopping tests; one warp per path
+__global__ void lb_linesearch_kernel(LbPath* st, int* act_eval, const double* ft, const double* met,
+                                     const double* fet, const double* part, int nchunk, LbOpts o,
+                                     int bounded) {
+  const int b = blockIdx.x;
+  LbPath& s = st[b];
+  if (s.done || !s.need_eval) return;
+  double gd = 0.0, sbg = 0.0;
+  if (threadIdx.x == 0) {
+    for (int c = 0; c < nchunk; ++c) {
+      gd += part[((long long)b * nchunk + c) * 2 + 0];
+      sbg = fmax(sbg, part[((long long)b * nchunk + c) * 2 + 1]);
+    }
+  } else {
+    return;
+  }
+  s.nfev += 1;
+  const double f = ft[b];
+  if (s.first) {
+    s.first = 0;
+    s.f = f; s.me = met[b]; s.fe = fet[b];
+    s.sbgnrm = sbg;
+    s.need_eval = 0;
+    s.accepted = 1; s.do_update = 0;
+    if (sbg <= o.pgtol) { s.done = 1; s.status = 0; act_eval[b] = 0; }
+    return;
+  }
+  // an evaluation that produced a NaN / Inf cannot be used by the search: treat as a failed step
+  const bool finite = isfinite(f) && isfinite(gd);
+  int conv = 0;
+  if (finite) conv = dcsrch_step(s, f, gd, 0.0, s.stpmx);
+  else s.iback = o.maxls;      // force the restart branch below
+  if (finite && conv) {
+    // NEW_X
+    s.f = f; s.me = met[b]; s.fe = fet[b];
+    s.gd = gd;
+    s.iter += 1;
+    s.sbgnrm = sbg;
+    s.need_eval = 0;
+    s.accepted = 1;
+    s.do_update = 0;
+    if (s.iter >= o.maxiter) { s.done = 1; s.status = 1; }
+    else if (s.nfev > o.maxfun) { s.done = 1; s.status = 1; }
+    else if (sbg <= o.pgtol) { s.done = 1; s.status = 0; }
+    else {
+      const double ddum = fmax(fabs(s.fold), fmax(fabs(f), 1.0));
+      if ((s.fold - f) <= o.ftol * ddum) { s.done = 1; s.status = 0; }
+    }
+    if (!s.done) {
+      double dr, dd;
+      if (s.stp == 1.0) { dr = gd - s.gdold; dd = -s.gdold; }
+      else { dr = (gd - s.gdold) * s.stp; dd = -s.gdold * s.stp; }
+      s.dr = dr;
+      if (dr <= EPSMCH * dd) { s.nskip += 1; s.do_update = 0; }
+      else {
+        s.do_update = 1;
+        s.pslot = (s.col < o.m) ? (s.head + s.col) % o.m : s.head;
+      }
+    }
+    if (s.done) act_eval[b] = 0;
+    return;
+  }
+  if (finite) {
+    s.ifun += 1;
+    s.iback = s.ifun - 1;
+  }
+  if (s.iback >= o.maxls) {
+    // line search failed: x, g, f still hold the start of the search
+    s.need_eval = 0;
+    if (s.col == 0) {
+      s.done = 1; s.status = 2; act_eval[b] = 0;      // ABNORMAL_TERMINATION_IN_LNSRCH
+    } else {
+      s.col = 0; s.head = 0; s.theta = 1.0;
+      s.redo_dir = 1;                                  // RESTART_FROM_LNSRCH
+    }
+  }
+  (void)bounded;
+}
+
+// accepted step: x <- xt, g <- gt; if the pair is kept, s = stp d and y = gt - g go to slot p;
+// partial dot products (NACC_U per chunk):
+//   [0..M)    ghat . S_j      [M..2M)  ghat . Y_j     [2M..3M)  s . Y_j
+//   [3M..4M)  y . S_j         [4M..5M) y . Y_j        5M: y.y   5M+1: ghat.s   5M+2: ghat.y  5M+3: ghat.ghat
+// (ghat = new gradient with the frozen components zeroed; entries of slot p refer to its old
+// contents and are ignored by lb_gram_kernel).
+template <bool BOUNDED>
+__global__ void __launch_bounds__(NT, 1) lb_update_kernel(
+    double* __restrict__ X, double* __restrict__ G, const double* __restrict__ XT,
+    const double* __restrict__ GT, const double* __restrict__ Dv, double* __restrict__ S,
+    double* __restrict__ Y, long long ld, long long n, long long hstride, const double* __restrict__ lo,
+    const double* __restrict__ hi, const LbPath* __restrict__ st, int m, int nchunk,
+    double* __restrict__ part) {
+  __shared__ double scratch[8 * NT];
+  __shared__ double res[NACC_U];
+  const int b = blockIdx.y;
+  const LbPath& s = st[b];
+  if (!s.accepted) return;
+  const bool upd = s.do_update != 0;
+  const int p = s.pslot;
+  const double stp = s.stp;
+  const int col = s.col;
+  const Range r = chunk_range(n, nchunk, blockIdx.x);
+  const long long off = (long long)b * ld;
+  double acc[NACC_U];
+#pragma unroll
+  for (int k = 0; k < NACC_U; ++k) acc[k] = 0.0;
+  for (long long i = r.i0 + threadIdx.x; i < r.i1; i += NT) {
+    const double xt = XT[off + i], gt = GT[off + i];
+    const double gold = G[off + i];
+    double sv = 0.0, yv = 0.0;
+    if (upd) {
+      sv = stp * Dv[off + i];
+      yv = gt - gold;
+    }
+    double gh = gt;
+    if (BOUNDED) {
+      if (frozen(xt, gt, lo[i], hi[i])) gh = 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < MMAX; ++j) {
+      if (j < m && (j < col || col == m)) {
+        const double sj = S[(long long)j * hstride + off + i];
+        const double yj = Y[(long long)j * hstride + off + i];
+        acc[j] = fma(gh, sj, acc[j]);
+        acc[MMAX + j] = fma(gh, yj, acc[MMAX + j]);
+        acc[2 * MMAX + j] = fma(sv, yj, acc[2 * MMAX + j]);
+        acc[3 * MMAX + j] = fma(yv, sj, acc[3 * MMAX + j]);
+        acc[4 * MMAX + j] = fma(yv, yj, acc[4 * MMAX + j]);
+      }
+    }
+    acc[5 * MMAX] = fma(yv, yv, acc[5 * MMAX]);
+    acc[5 * MMAX + 1] = fma(gh, sv, acc[5 * MMAX + 1]);
+    acc[5 * MMAX + 2] = fma(gh, yv, acc[5 * MMAX + 2]);
+    acc[5 * MMAX + 3] = fma(gh, gh, acc[5 * MMAX + 3]);
+    X[off + i] = xt;
+    G[off + i] = gt;
+    if (upd) {
+      S[(long long)p * hstride + off + i] = sv;
+      Y[(long long)p * hstride + off + i] = yv;
+    }
+  }
+  __shared__ int op[NACC_U];
+  for (int k = threadIdx.x; k < NACC_U; k += NT) op[k] = RED_SUM;
+  block_reduce<NACC_U>(acc, op, res, scratch);
+  __syncthreads();
+  for (int k = threadIdx.x; k < NACC_U; k += NT)
+    part[((long long)b * nchunk + blockIdx.x) * NACC_U + k] = res[k];
+}
+
+// history bookkeeping + the two-loop recursion in coefficient space; one thread per path
+__global__ void lb_gram_kernel(LbPath* st, const double* part, int nchunk, int m) {
+  const int b = blockIdx.x;
+  LbPath& s = st[b];
+  if (!(s.accepted || s.redo_dir) || s.done) return;
+  __shared__ double sum[NACC_U];
+  if (s.accepted) {
+    for (int k = threadIdx.x; k < NACC_U; k += blockDim.x) {
+      double a = 0.0;
+      for (int c = 0; c < nchunk; ++c) a += part[((long long)b * nchunk + c) * NACC_U + k];
+      sum[k] = a;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  if (s.accepted) {
+    if (s.do_update) {
+      const int p = s.pslot;
+      for (int j = 0; j < m; ++j) {
+        if (j == p) continue;
+        s.SY[p * MMAX + j] = sum[2 * MMAX + j];      // s_p . y_j
+        s.SY[j * MMAX + p] = sum[3 * MMAX + j];      // s_j . y_p
+        s.YY[p * MMAX + j] = sum[4 * MMAX + j];
+        s.YY[j * MMAX + p] = sum[4 * MMAX + j];
+      }
+      s.SY[p * MMAX + p] = s.dr;                     // s'y from the line search, as L-BFGS-B does
+      s.YY[p * MMAX + p] = sum[5 * MMAX];
+      s.theta = sum[5 * MMAX] / s.dr;
+      if (s.col < m) s.col += 1;
+      else s.head = (s.head + 1) % m;
+      for (int j = 0; j < m; ++j) { s.gS[j] = sum[j]; s.gY[j] = sum[MMAX + j]; }
+      s.gS[p] = sum[5 * MMAX + 1];
+      s.gY[p] = sum[5 * MMAX + 2];
+    } else {
+      for (int j = 0; j < m; ++j) { s.gS[j] = sum[j]; s.gY[j] = sum[MMAX + j]; }
+    }
+    s.gg = sum[5 * MMAX + 3];
+  }
+  // r = H ghat  as  cg * ghat + sum_j cs_j s_j + cy_j y_j   (d = -r)
+  double cg = 1.0, cs[MMAX], cy[MMAX], alpha[MMAX];
+  for (int j = 0; j < MMAX; ++j) { cs[j] = 0.0; cy[j] = 0.0; alpha[j] = 0.0; }
+  const int col = s.col, head = s.head;
+  for (int k = col - 1; k >= 0; --k) {               // newest -> oldest
+    const int i = (head + k) % m;
+    double sq = s.gS[i] * cg;
+    for (int j = 0; j < m; ++j) sq += cy[j] * s.SY[i * MMAX + j];
+    alpha[i] = sq / s.SY[i * MMAX + i];
+    cy[i] -= alpha[i];
+  }
+  const double gamma = (col > 0) ? 1.0 / s.theta : 1.0;
+  cg *= gamma;
+  for (int j = 0; j < m; ++j) cy[j] *= gamma;
+  for (int k = 0; k < col; ++k) {                    // oldest -> newest
+    const int i = (head + k) % m;
+    double yr = s.gY[i] * cg;
+    for (int j = 0; j < m; ++j) yr += cy[j] * s.YY[i * MMAX + j] + cs[j] * s.SY[j * MMAX + i];
+    const double beta = yr / s.SY[i * MMAX + i];
+    cs[i] += alpha[i] - beta;
+  }
+  s.cg = cg;
+  for (int j = 0; j < MMAX; ++j) { s.cs[j] = cs[j]; s.cy[j] = cy[j]; }
+}
+
+// d = -(cg ghat + sum_j cs_j S_j + cy_j Y_j), frozen components zero; partials [d.d, g.d, stpmx]
+template <bool BOUNDED>
+__global__ void __launch_bounds__(NT) lb_direction_kernel(
+    const double* __restrict__ X, const double* __restrict__ G, double* __restrict__ Dv,
+    const double* __restrict__ S, const double* __restrict__ Y, long long ld, long long n,
+    long long hstride, const double* __restrict__ lo, const double* __restrict__ hi,
+    const LbPath* __restrict__ st, int m, int nchunk, double* __restrict__ part) {
+  __shared__ double scratch[8 * NT];
+  __shared__ double res[3];
+  const int b = blockIdx.y;
+  const LbPath& s = st[b];
+  if (!(s.accepted || s.redo_dir) || s.done) return;
+  const Range r = chunk_range(n, nchunk, blockIdx.x);
+  const long long off = (long long)b * ld;
+  const int col = s.col;
+  double cs[MMAX], cy[MMAX];
+#pragma unroll
+  for (int j = 0; j < MMAX; ++j) { cs[j] = s.cs[j]; cy[j] = s.cy[j]; }
+  const double cg = s.cg;
+  double v[3] = {0.0, 0.0, BIG};
+  for (long long i = r.i0 + threadIdx.x; i < r.i1; i += NT) {
+    const double g = G[off + i];
+    bool fr = false;
+    double x = 0.0, l = 0.0, h = 0.0;
+    if (BOUNDED) {
+      x = X[off + i]; l = lo[i]; h = hi[i];
+      fr = frozen(x, g, l, h);
+    }
+    double rr = fr ? 0.0 : cg * g;
+#pragma unroll
+    for (int j = 0; j < MMAX; ++j) {
+      if (j < m && (j < col || col == m)) {
+        rr = fma(cs[j], S[(long long)j * hstride + off + i], rr);
+        rr = fma(cy[j], Y[(long long)j * hstride + off + i], rr);
+      }
+    }
+    double d = fr ? 0.0 : -rr;
+    if (BOUNDED) {
+      // keep x + stp d feasible: largest step before a bound is hit (lnsrlb)
+      if (d < 0.0 && l > -DBL_MAX) {
+        const double a2 = l - x;
+        if (a2 >= 0.0) d = 0.0;
+        else if (d * v[2] < a2) v[2] = a2 / d;
+      } else if (d > 0.0 && h < DBL_MAX) {
+        const double a2 = h - x;
+        if (a2 <= 0.0) d = 0.0;
+        else if (d * v[2] > a2) v[2] = a2 / d;
+      }
+    }
+    Dv[off + i] = d;
+    v[0] = fma(d, d, v[0]);
+    v[1] = fma(g, d, v[1]);
+  }
+  const int op[3] = {RED_SUM, RED_SUM, RED_MIN};
+  block_reduce<3>(v, op, res, scratch);
+  __syncthreads();
+  if (threadIdx.x < 3) part[((long long)b * nchunk + blockIdx.x) * 3 + threadIdx.x] = res[threadIdx.x];
+}
+
+// start of a line search (lnsrlb, task = START)
+__global__ void lb_start_kernel(LbPath* st, int* act_eval, const double* part, int nchunk, LbOpts o,
+                                int bounded) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= (int)gridDim.x * (int)blockDim.x) return;
+  LbPath& s = st[b];
+  if (!(s.accepted || s.redo_dir) || s.done) { if (s.done) { s.accepted = 0; s.redo_dir = 0; } return; }
+  double dd = 0.0, gd = 0.0, stpmx = BIG;
+  for (int c = 0; c < nchunk; ++c) {
+    dd += part[((long long)b * nchunk + c) * 3 + 0];
+    gd += part[((long long)b * nchunk + c) * 3 + 1];
+    stpmx = fmin(stpmx, part[((long long)b * nchunk + c) * 3 + 2]);
+  }
+  s.accepted = 0;
+  s.redo_dir = 0;
+  s.do_update = 0;
+  s.dnorm = sqrt(dd);
+  s.gdold = gd;
+  if (!(gd < 0.0) || !(dd > 0.0)) {
+    // not a descent direction (info = -4): drop the memory and restart, or give up
+    if (s.col == 0) { s.done = 1; s.status = (dd == 0.0) ? 0 : 2; act_eval[b] = 0; }
+    else { s.col = 0; s.head = 0; s.theta = 1.0; s.redo_dir = 1; }
+    return;
+  }
+  if (bounded && s.iter == 0) stpmx = fmin(stpmx, 1.0);
+  if (!(stpmx > 0.0)) { s.done = 1; s.status = 2; act_eval[b] = 0; return; }
+  s.stpmx = stpmx;
+  if (s.iter == 0 && !bounded) s.stp = fmin(1.0 / s.dnorm, stpmx);
+  else s.stp = fmin(1.0, stpmx);
+  s.fold = s.f;
+  s.ifun = 1;
+  s.iback = 0;
+  dcsrch_start(s, s.f, gd, stpmx);
+  s.need_eval = 1;
+  act_eval[b] = 1;
+}
+
+__global__ void lb_count_kernel(const LbPath* st, int B, int* n_running) {
+  int c = 0;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) c += st[b].done ? 0 : 1;
+  for (int sft = 16; sft > 0; sft >>= 1) c += __shfl_down_sync(0xffffffffu, c, sft);
+  __shared__ int w[8];
+  if ((threadIdx.x & 31) == 0) w[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int k = 0; k < (int)blockDim.x / 32; ++k) t += w[k];
+    *n_running = t;
+  }
+}
+
+__global__ void lb_export_kernel(const LbPath* st, int B, double* A, double* me, double* fe,
+                                 int* status, int* nit, int* nfev, double* table, int Nbeta, int ib,
+                                 double beta, double rf_scale, int* st2, int* nit2, int* nfev2) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const LbPath& s = st[b];
+  if (A) A[b] = s.f;
+  if (me) me[b] = s.me;
+  if (fe) fe[b] = s.fe;
+  if (status) status[b] = s.status;
+  if (nit) nit[b] = s.iter;
+  if (nfev) nfev[b] = s.nfev;
+  if (table) {
+    double* row = table + ((long long)b * Nbeta + ib) * 5;
+    row[0] = beta; row[1] = s.f; row[2] = s.me; row[3] = s.fe; row[4] = s.fe / rf_scale;
+  }
+  if (st2) st2[(long long)b * Nbeta + ib] = s.status;
+  if (nit2) nit2[(long long)b * Nbeta + ib] = s.iter;
+  if (nfev2) nfev2[(long long)b * Nbeta + ib] = s.nfev;
+}
+
+int lb_nchunk(long long n) {
+  long long c = (n + 8191) / 8192;
+  if (c < 1) c = 1;
+  if (c > 4096) c = 4096;
+  return (int)c;
+}
+
+#define LB_CUDA(call)                                                         \
+  do {                                                                        \
+    cudaError_t e_ = (call);                                                  \
+    if (e_ != cudaSuccess) return vab_cuda_fail(ctx, e_, #call);              \
+  } while (0)
+
+int lb_reserve(vab_ctx* ctx, int B, long long ld, int m) {
+  if (!ctx->lb) ctx->lb = new LbfgsWork();
+  LbfgsWork* w = ctx->lb;
+  const size_t nvec = (size_t)(2 * m + 4);
+  const size_t need = nvec * (size_t)B * (size_t)ld;
+  int rc = vab_reserve(ctx, &w->vec, &w->vec_cap, need);
+  if (rc != VAB_OK) return rc;
+  if (B > w->st_cap) {
+    cudaFree(w->st); cudaFree(w->act_eval); cudaFree(w->ft); cudaFree(w->met); cudaFree(w->fet);
+    w->st = nullptr; w->act_eval = nullptr; w->ft = w->met = w->fet = nullptr;
+    LB_CUDA(cudaMalloc((void**)&w->st, sizeof(LbPath) * B));
+    LB_CUDA(cudaMalloc((void**)&w->act_eval, sizeof(int) * B));
+    LB_CUDA(cudaMalloc((void**)&w->ft, sizeof(double) * B));
+    LB_CUDA(cudaMalloc((void**)&w->met, sizeof(double) * B));
+    LB_CUDA(cudaMalloc((void**)&w->fet, sizeof(double) * B));
+    w->st_cap = B;
+  }
+  const int nchunk = lb_nchunk(ctx->n_unknowns());
+  rc = vab_reserve(ctx, &w->part, &w->part_cap, (size_t)B * nchunk * NACC_U);
+  if (rc != VAB_OK) return rc;
+  if (!w->n_running_dev) LB_CUDA(cudaMalloc((void**)&w->n_running_dev, sizeof(int)));
+  if (!w->n_running_host) LB_CUDA(cudaMallocHost((void**)&w->n_running_host, sizeof(int)));
+  if (!w->ev) LB_CUDA(cudaEventCreateWithFlags(&w->ev, cudaEventDisableTiming));
+  w->B = B; w->ld = ld; w->m = m;
+  return VAB_OK;
+}
+
+// minimise from XP (in place) at the given rf_scale; leaves the per-path results in w->st
+int lb_minimize_core(vab_ctx* ctx, int B, double* XP, long long ld, double rf_scale,
+                     const vab_lbfgs_opts* uo, const double* lo, const double* hi) {
+  const long long n = ctx->n_unknowns();
+  if (n <= 0) return vab_fail(ctx, VAB_ERR_STATE, "minimize: no problem set on this context");
+  if (B < 1 || !XP || ld < n || (ld & 1)) return vab_fail(ctx, VAB_ERR_INVALID, "minimize: bad batch / XP / ldxp");
+  if ((lo == nullptr) != (hi == nullptr)) return vab_fail(ctx, VAB_ERR_INVALID, "minimize: give both bounds or none");
+  LbOpts o;
+  o.m = uo && uo->m > 0 ? uo->m : 10;
+  if (o.m > MMAX) return vab_fail(ctx, VAB_ERR_INVALID, "minimize: maxcor > 10 is not supported");
+  o.maxls = uo && uo->maxls > 0 ? uo->maxls : 20;
+  o.maxfun = uo && uo->maxfun > 0 ? uo->maxfun : 15000;
+  o.maxiter = uo && uo->maxiter > 0 ? uo->maxiter : 15000;
+  o.ftol = uo ? uo->ftol : 2.220446049250313e-09;
+  o.pgtol = uo ? uo->pgtol : 1e-5;
+  int poll = uo && uo->poll_every > 0 ? uo->poll_every : 0;
+  int rc = lb_reserve(ctx, B, ld, o.m);
+  if (rc != VAB_OK) return rc;
+  LbfgsWork* w = ctx->lb;
+  cudaStream_t st = ctx->stream;
+  const size_t vs = (size_t)B * (size_t)ld;
+  double* XT = w->vec;
+  double* GT = w->vec + vs;
+  double* G = w->vec + 2 * vs;
+  double* Dv = w->vec + 3 * vs;
+  double* S = w->vec + 4 * vs;
+  double* Y = w->vec + (4 + (size_t)o.m) * vs;
+  const long long hstride = (long long)vs;
+  const int nchunk = lb_nchunk(n);
+  const bool bounded = lo != nullptr;
+  const dim3 vgrid(nchunk, B);
+
+  lb_init_kernel<<<(B + 127) / 128, 128, 0, st>>>(w->st, w->act_eval, B);
+  if (bounded) lb_clip_kernel<<<dim3((unsigned)((n + 255) / 256), B), 256, 0, st>>>(XP, ld, n, lo, hi);
+  LB_CUDA(cudaMemcpyAsync(XT, XP, vs * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  LB_CUDA(cudaMemsetAsync(Dv, 0, vs * sizeof(double), st));
+  LB_CUDA(cudaMemsetAsync(G, 0, vs * sizeof(double), st));
+  ctx->launches += 2;
+
+  if (poll <= 0) {
+    // small problems are launch-bound (a cycle is ~30 us): poll rarely; large ones take ms per cycle
+    poll = (n * (long long)B < (1LL << 22)) ? 64 : 8;
+  }
+  long long cycles = 0;
+  const long long max_cycles = o.maxfun + o.maxiter + 64;
+  while (true) {
+    for (int c = 0; c < poll; ++c) {
+      lb_trial_kernel<<<vgrid, NT, 0, st>>>(XT, XP, Dv, ld, n, w->st, nchunk);
+      rc = vab_eval(ctx, B, XT, ld, rf_scale, w->act_eval, w->ft, w->met, w->fet, GT, ld);
+      if (rc != VAB_OK) return rc;
+      if (bounded) lb_gd_kernel<true><<<vgrid, NT, 0, st>>>(XT, GT, Dv, ld, n, lo, hi, w->st, nchunk, w->part);
+      else lb_gd_kernel<false><<<vgrid, NT, 0, st>>>(XT, GT, Dv, ld, n, lo, hi, w->st, nchunk, w->part);
+      lb_linesearch_kernel<<<B, 32, 0, st>>>(w->st, w->act_eval, w->ft, w->met, w->fet, w->part, nchunk, o, bounded ? 1 : 0);
+      if (bounded) lb_update_kernel<true><<<vgrid, NT, 0, st>>>(XP, G, XT, GT, Dv, S, Y, ld, n, hstride, lo, hi, w->st, o.m, nchunk, w->part);
+      else lb_update_kernel<false><<<vgrid, NT, 0, st>>>(XP, G, XT, GT, Dv, S, Y, ld, n, hstride, lo, hi, w->st, o.m, nchunk, w->part);
+      lb_gram_kernel<<<B, 64, 0, st>>>(w->st, w->part, nchunk, o.m);
+      if (bounded) lb_direction_kernel<true><<<vgrid, NT, 0, st>>>(XP, G, Dv, S, Y, ld, n, hstride, lo, hi, w->st, o.m, nchunk, w->part);
+      else lb_direction_kernel<false><<<vgrid, NT, 0, st>>>(XP, G, Dv, S, Y, ld, n, hstride, lo, hi, w->st, o.m, nchunk, w->part);
+      lb_start_kernel<<<B, 1, 0, st>>>(w->st, w->act_eval, w->part, nchunk, o, bounded ? 1 : 0);
+      ctx->launches += 7;
+    }
+    cycles += poll;
+    lb_count_kernel<<<1, 256, 0, st>>>(w->st, B, w->n_running_dev);
+    ctx->launches += 1;
+    LB_CUDA(cudaMemcpyAsync(w->n_running_host, w->n_running_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
+    LB_CUDA(cudaEventRecord(w->ev, st));
+    LB_CUDA(cudaEventSynchronize(w->ev));
+    LB_CUDA(cudaGetLastError());
+    if (*w->n_running_host == 0) break;
+    if (cycles > max_cycles) return vab_fail(ctx, VAB_ERR_STATE, "minimize: cycle limit exceeded (internal error)");
+  }
+  return VAB_OK;
+}
+
+}  // namespace
+
+void lbfgs_destroy(vab_ctx* ctx) {
+  LbfgsWork* w = ctx->lb;
+  if (!w) return;
+  cudaFree(w->vec); cudaFree(w->st); cudaFree(w->act_eval); cudaFree(w->ft); cudaFree(w->met);
+  cudaFree(w->fet); cudaFree(w->part); cudaFree(w->n_running_dev);
+  if (w->n_running_host) cudaFreeHost(w->n_running_host);
+  if (w->ev) cudaEventDestroy(w->ev);
+  delete w;
+  ctx->lb = nullptr;
+}
+
 extern "C" {
-int vab_minimize(vab_ctx* ctx, int32_t, double*, int64_t, double, const vab_lbfgs_opts*,
-                 const double*, const double*, double*, double*, double*, int32_t*, int32_t*,
-                 int32_t*) {
-  return vab_fail(ctx, VAB_ERR_STATE, "minimiser not built yet");
+
+int vab_minimize(vab_ctx* ctx, int32_t B, double* XP_dev, int64_t ldxp, double rf_scale,
+                 const vab_lbfgs_opts* opts, const double* lo_dev, const double* hi_dev,
+                 double* A_dev, double* me_dev, double* fe_dev, int32_t* status_dev,
+                 int32_t* nit_dev, int32_t* nfev_dev) {
+  if (!ctx) return VAB_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  int rc = lb_minimize_core(ctx, B, XP_dev, ldxp, rf_scale, opts, lo_dev, hi_dev);
+  if (rc != VAB_OK) return rc;
+  lb_export_kernel<<<(B + 127) / 128, 128, 0, ctx->stream>>>(
+      ctx->lb->st, B, A_dev, me_dev, fe_dev, status_dev, nit_dev, nfev_dev, nullptr, 0, 0, 0.0, 1.0,
+      nullptr, nullptr, nullptr);
+  ctx->launches += 1;
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) return vab_cuda_fail(ctx, e, "vab_minimize");
+  return VAB_OK;
 }
-int vab_anneal(vab_ctx* ctx, int32_t, double*, int64_t, double, const double*, int32_t,
-               const vab_lbfgs_opts*, const double*, const double*, double*, double*, int32_t*,
-               int32_t*, int32_t*) {
-  return vab_fail(ctx, VAB_ERR_STATE, "minimiser not built yet");
+
+int vab_anneal(vab_ctx* ctx, int32_t B, double* XP_dev, int64_t ldxp, double alpha,
+               const double* beta_host, int32_t Nbeta, const vab_lbfgs_opts* opts,
+               const double* lo_dev, const double* hi_dev, double* table_dev, double* minpaths_dev,
+               int32_t* status_dev, int32_t* nit_dev, int32_t* nfev_dev) {
+  if (!ctx) return VAB_ERR_INVALID;
+  if (!beta_host || Nbeta < 1) return vab_fail(ctx, VAB_ERR_INVALID, "anneal: empty beta ladder");
+  cudaSetDevice(ctx->device);
+  for (int ib = 0; ib < Nbeta; ++ib) {
+    const double scale = pow(alpha, beta_host[ib]);
+    int rc = lb_minimize_core(ctx, B, XP_dev, ldxp, scale, opts, lo_dev, hi_dev);
+    if (rc != VAB_OK) return rc;
+    lb_export_kernel<<<(B + 127) / 128, 128, 0, ctx->stream>>>(
+        ctx->lb->st, B, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, table_dev, Nbeta, ib,
+        beta_host[ib], scale, status_dev, nit_dev, nfev_dev);
+    ctx->launches += 1;
+    if (minpaths_dev) {
+      cudaError_t e = cudaMemcpy2DAsync(minpaths_dev + (size_t)ib * ldxp, (size_t)Nbeta * ldxp * sizeof(double),
+                                        XP_dev, (size_t)ldxp * sizeof(double), (size_t)ldxp * sizeof(double),
+                                        B, cudaMemcpyDeviceToDevice, ctx->stream);
+      if (e != cudaSuccess) return vab_cuda_fail(ctx, e, "anneal: minpaths copy");
+    }
+  }
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) return vab_cuda_fail(ctx, e, "vab_anneal");
+  return VAB_OK;
 }
-}
+
+}  // extern "C"
