@@ -1,0 +1,42 @@
+"""Loader for tests/golden/*.npz (written by tests/golden/make_golden.py from the reference)."""
+import os
+
+import numpy as np
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load(name):
+    return np.load(os.path.join(GOLDEN, name), allow_pickle=False)
+
+
+def ode_case(z, n):
+    """Dict of one ODE action case of ode_action_golden.npz."""
+    alpha, beta, dtm = z[n + "/meta"]
+    model, disc = [str(s) for s in z[n + "/model_disc"]]
+    RM = z[n + "/RM"]
+    RF0 = z[n + "/RF0"]
+    stim = z[n + "/stim"]
+    return dict(name=n, model=model, disc=disc, X0=z[n + "/X0"], P0=z[n + "/P0"], t=z[n + "/t"], Y=z[n + "/Y"],
+                stim=None if stim.size == 0 else stim, Lidx=z[n + "/Lidx"], Pidx=z[n + "/Pidx"],
+                RM=float(RM) if RM.ndim == 0 else RM, RF0=float(RF0) if RF0.ndim == 0 else RF0,
+                alpha=float(alpha), beta=int(beta), dt_model=None if dtm < 0 else float(dtm),
+                A=z[n + "/A"], grad=z[n + "/grad"])
+
+
+def ode_cases():
+    z = load("ode_action_golden.npz")
+    return [ode_case(z, str(n)) for n in z["names"]]
+
+
+def nnet_cases():
+    z = load("nnet_action_golden.npz")
+    out = []
+    for n in z["names"]:
+        n = str(n)
+        RM, RF0, alpha, beta = z[n + "/meta"]
+        out.append(dict(name=n, structure=z[n + "/structure"], data_in=z[n + "/data_in"],
+                        data_out=z[n + "/data_out"], X0=z[n + "/X0"], P0=z[n + "/P0"], Pidx=z[n + "/Pidx"],
+                        RM=float(RM), RF0=float(RF0), alpha=float(alpha), beta=float(beta),
+                        A=z[n + "/A"], grad=z[n + "/grad"]))
+    return out
