@@ -30,7 +30,7 @@ if ROOT not in sys.path:
 
 D, N_MODEL, DT, K_FORCING = 100, 5001, 0.025, 8.17
 PATHS_PER_GPU = 64
-RM, RF0, ALPHA, BETA_EVAL = 4.0, 4e-6, 2.5, 10
+RM, RF0, ALPHA, BETA_EVAL, N_BETA = 4.0, 4e-6, 2.5, 10, 20
 LIDX = [i for i in range(D) if i % 5 in (0, 2)]
 METRIC = "action+gradient evals/sec (Lorenz96 D=100 N=5001 SimpsonHermite, 64 paths/GPU)"
 UNIT = "evals/s"
@@ -69,8 +69,10 @@ def initial_paths(B, first_seed):
 
 
 def algorithmic_bytes(B):
-    """read X once + write grad once + read Y once, per path."""
-    return B * (16 * N_MODEL * D + 8 * N_MODEL * len(LIDX))
+    """Bytes one launch must move: read X once and write the gradient once per path
+    (16 N D) plus the observations, which the B paths of a batch share, once
+    (8 N_data L).  DESIGN.md section 4."""
+    return B * 16 * N_MODEL * D + 8 * N_MODEL * len(LIDX)
 
 
 # ------------------------------------------------------------------------------------ clocks
@@ -279,6 +281,36 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_val = world * B * e2e_steps / (float(t.item()) * 1e-3)
 
+    # ---- full ladder: 20 rungs, every rank its own 64 initial paths, one gather at the end
+    ladder = None
+    if not args.no_ladder:
+        from varanneal_b200 import parallel
+        X0l, P0l = initial_paths(B, 1000 + rank * B)
+        anl = va_ode.Annealer(device=local)
+        anl.set_model("lorenz96", D)
+        anl.set_data(Y, t=DT * np.arange(N_MODEL))
+        barrier()
+        t0 = time.perf_counter()
+        anl.anneal(X0l, P0l, ALPHA, np.arange(N_BETA), RM, RF0, LIDX, [0], disc="SimpsonHermite",
+                   init_to_data=True, opt_args={"gtol": 1e-8, "ftol": 1e-8, "maxfun": 1000000, "maxiter": 1000000})
+        tables = np.stack([anl.action_errors_table(init=i) for i in range(B)])
+        tables = parallel.gather_blocks(tables, B * world)          # the design's only collective
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        tt = torch.tensor([wall, float(anl.nfev_array.sum())], dtype=torch.float64, device="cuda")
+        if world > 1:
+            tw = tt.clone()
+            dist.all_reduce(tw[:1], op=dist.ReduceOp.MAX)
+            dist.all_reduce(tt[1:], op=dist.ReduceOp.SUM)
+            tt[0] = tw[0]
+        ladder = {"wall_s": float(tt[0].item()), "paths": B * world, "betas": N_BETA,
+                  "alpha": ALPHA, "opt_args": "gtol=ftol=1e-8 (examples/Lorenz96_D20)",
+                  "nfev_total": int(tt[1].item()), "evals_per_s_incl_optimizer": float(tt[1].item() / tt[0].item()),
+                  "converged_fraction": float(np.mean(anl.exitflags == 0)),
+                  "A_last_rung_mean": float(tables[:, -1, 1].mean()),
+                  "gathered_table_shape": list(tables.shape)}
+        del anl
+
     if rank == 0:
         peaks = {}
         pk_src = "fallback"
@@ -304,14 +336,14 @@ def run_ours(args):
             "data": "synthetic", "config": workload_config(world),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": pk_src,
-                         "kernel": "ode_walk_kernel<ModelL96<4>, SimpsonHermite> (+3 us finalize)",
+                         "kernel": "stream_simpson_kernel<ModelL96<4>> (TMA ring, + ~3 us finalize)",
                          "algorithmic_bytes_per_launch": algorithmic_bytes(B),
                          "kernel_ms": kern_ms},
             "e2e": {"value": e2e_val, "unit": UNIT,
                     "h2d_bytes_per_step": int(XP_host.numel() * 8),
                     "d2h_bytes_per_step": int(G_h.numel() * 8 + A_h.numel() * 8),
                     "api": "va_ode.Annealer.A_gradA(pinned XP) -> (A, grad) pinned"},
-            "gpu_launches": int(launches), "clocks": clocks,
+            "gpu_launches": int(launches), "clocks": clocks, "ladder": ladder,
         }
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline_single_core(Y)
@@ -327,6 +359,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-ladder", action="store_true", help="skip the full-ladder leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
