@@ -95,3 +95,63 @@ def test_minimize_seam_contract():
     assert an.last_nit[0] == 5
     A0 = an.A_gaussian(XP0)
     assert Amin < A0
+
+
+def test_saved_layouts_match_reference(tmp_path):
+    """va_ode.py:794-889: save_paths (Nbeta, N_model, 1+D) with t in column 0; save_params
+    (Nbeta, NP); save_action_errors (Nbeta, 5) = [beta, A, me, fe, fe/RF]; track_* dicts re-save
+    after every rung; minAone text file rows [beta, exitflag, A, path...]."""
+    from varanneal_b200 import va_ode
+    rng = np.random.RandomState(2)
+    D, N = 20, 21
+    Lidx = [0, 4, 9, 13]
+    Y = rng.randn(N, len(Lidx))
+    t = 0.025 * np.arange(N)
+    an = va_ode.Annealer()
+    an.set_model("lorenz96", D)
+    an.set_data(np.column_stack([t, Y]))                 # time in column 0 (va_ode.py:109-112)
+    X0 = rng.randn(N, D)
+    betas = [0, 1, 2.7, 5]                               # 2.7 truncates to 2 (uint16, App. B1)
+    track = {"filename": str(tmp_path / "track.npy")}
+    an.anneal(X0, np.array([8.0]), 1.5, betas, 4.0, 4e-6, Lidx, [0], disc="trapezoid",
+              opt_args={"maxiter": 30}, track_action_errors=track)
+    assert np.array_equal(X0[:, Lidx], Y)                # init_to_data wrote into the caller's X0
+    assert list(an.beta_array) == [0, 1, 2, 5]
+    an.save_paths(str(tmp_path / "paths.npy"))
+    an.save_params(str(tmp_path / "params.npy"))
+    an.save_action_errors(str(tmp_path / "ae.npy"))
+    an.save_action_errors(str(tmp_path / "ae.txt"))
+    an.save_as_minAone(str(tmp_path))
+    paths = np.load(tmp_path / "paths.npy")
+    assert paths.shape == (4, N, 1 + D) and np.allclose(paths[:, :, 0], t)
+    assert np.array_equal(paths[2, :, 1:].ravel(), an.minpaths[2, :N * D])
+    assert np.load(tmp_path / "params.npy").shape == (4, 1)
+    ae = np.load(tmp_path / "ae.npy")
+    assert ae.shape == (4, 5) and np.allclose(ae[:, 4], ae[:, 3] / (4e-6 * 1.5 ** ae[:, 0]))
+    assert np.allclose(np.loadtxt(tmp_path / "ae.txt"), ae, rtol=1e-7)
+    assert np.allclose(np.load(track["filename"]), ae)
+    m1 = np.loadtxt(tmp_path / ("D%d_M%d_PATH0.dat" % (D, len(Lidx))))
+    assert m1.shape == (4, 3 + N * D + 1) and np.allclose(m1[:, 2], an.A_array)
+
+
+def test_bounds_are_respected_nakl():
+    """Box bounds (va_ode.py:582-605; the NaKL tutorial uses them): every iterate and the
+    minimiser stay inside the box, and the bounded minimum is not above the start."""
+    from varanneal_b200 import va_ode
+    c = [c for c in golden_util.ode_cases() if c["name"] == "nakl_trapezoid_18p"][0]
+    an = va_ode.Annealer()
+    an.set_model("nakl", 4)
+    an.set_data(c["Y"], stim=c["stim"], t=c["t"])
+    P0 = c["P0"].copy()
+    bounds = [[-100.0, 50.0], [0.0, 1.0], [0.0, 1.0], [0.0, 1.0]]
+    for v in P0:
+        bounds.append([min(0.7 * v, 1.3 * v), max(0.7 * v, 1.3 * v)])
+    X0 = c["X0"].copy()
+    an.anneal(X0, P0, 1.1, [40, 60], 1.0, [1e-8, 1e-4, 1e-4, 1e-4], [0], list(range(18)),
+              disc="trapezoid", bounds=bounds, opt_args={"maxiter": 200, "gtol": 1e-8, "ftol": 1e-12})
+    X = an.minpaths[:, :101 * 4].reshape(2, 101, 4)
+    P = an.minpaths[:, 101 * 4:]
+    b = np.array(bounds)
+    assert np.all(X >= b[:4, 0] - 1e-12) and np.all(X <= b[:4, 1] + 1e-12)
+    assert np.all(P >= b[4:, 0] - 1e-12) and np.all(P <= b[4:, 1] + 1e-12)
+    assert np.all(np.isfinite(an.A_array)) and np.all(an.exitflags <= 1)

@@ -1,0 +1,110 @@
+"""GPU parity of the neural-network action+gradient (C ABI: vab_nn_action_grad through
+va_nnet.Annealer) against the reference-generated golden vectors (tests/golden/
+nnet_action_golden.npz: value by the reference's own loops, gradient by complex step through
+them) and against the NumPy oracle on larger seeded cases; plus a short device ladder against
+SciPy L-BFGS-B on the oracle action.  Tolerance 1e-10 relative."""
+import numpy as np
+import pytest
+import scipy.optimize as opt
+
+import golden_util
+from oracle import nnet_port
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+NN_CASES = golden_util.nnet_cases()
+
+
+def _annealer(structure, data_in, data_out, X0, P0, alpha, beta, RM, RF0, Pidx, act="sigmoid", opt_args=None,
+              Lidx=None):
+    from varanneal_b200 import va_nnet
+    an = va_nnet.Annealer()
+    an.set_structure(structure)
+    an.set_activation(act)
+    an.set_input_data(data_in)
+    an.set_output_data(data_out)
+    an.anneal_init(X0, P0, alpha, beta, RM, RF0, Pidx, Lidx=Lidx, init_to_data=False, opt_args=opt_args)
+    return an
+
+
+@pytest.mark.parametrize("c", NN_CASES, ids=[c["name"] for c in NN_CASES])
+def test_nn_action_grad_vs_reference_golden(c):
+    an = _annealer(c["structure"], c["data_in"], c["data_out"], c["X0"].copy(), c["P0"].copy(), c["alpha"],
+                   [c["beta"]], c["RM"], c["RF0"], c["Pidx"])
+    XP = np.append(c["X0"], c["P0"][c["Pidx"]])
+    A, g = an.A_gradA_taped(XP)
+    assert abs(A - c["A"][0]) <= TOL * abs(c["A"][0])
+    assert np.max(np.abs(g - c["grad"])) <= TOL * np.max(np.abs(c["grad"]))
+    assert abs(an.me_gaussian(XP) - c["A"][1]) <= TOL * abs(c["A"][1])
+    assert abs(an.fe_gaussian(XP) - c["A"][2]) <= TOL * abs(c["A"][2])
+
+
+@pytest.mark.parametrize("structure,M,act,RM,partial,B", [
+    ([25, 30, 4], 1000, "sigmoid", 1.0, False, 2),          # bar-images shape, many example tiles
+    ([100, 100, 100, 100], 130, "sigmoid", [3.0, 0.5], False, 2),   # nnet_twin widths ~100, RM (2,)
+    ([300, 17, 5], 7, "tanh", 2.0, True, 3),                # wide first layer -> chunked weights
+    ([6, 9, 9, 3], 40, "linear", 1.5, True, 1),
+])
+def test_nn_action_grad_vs_oracle(structure, M, act, RM, partial, B):
+    rng = np.random.RandomState(3)
+    st = np.array(structure)
+    NDnet = int(st.sum())
+    NP = int(sum(st[n] * st[n + 1] + st[n + 1] for n in range(len(st) - 1)))
+    Lidx = [np.arange(st[0])[::2], np.arange(st[-1])]
+    data_in = rng.rand(M, len(Lidx[0]))
+    data_out = rng.rand(M, len(Lidx[1]))
+    X0 = rng.rand(B, M * NDnet)
+    P0 = 0.3 * rng.randn(B, NP)
+    Pidx = np.arange(0, NP, 3) if partial else np.arange(NP)
+    alpha, beta, RF0 = 1.1, 30.0, 1e-2
+    an = _annealer(st, data_in, data_out, X0.copy(), P0.copy(), alpha, [beta], RM, RF0, Pidx, act=act, Lidx=Lidx)
+    XP = np.concatenate([X0, P0[:, Pidx]], axis=1)
+    A, G = an.A_gradA(XP)
+    for b in range(B):
+        prob = nnet_port.NnetProblem(st, data_in, data_out, Lidx, P0[b], Pidx, RM, act=act)
+        Ar, gr = prob.action_grad(XP[b], RF0 * alpha ** beta)
+        assert abs(A[b] - Ar) <= TOL * abs(Ar)
+        assert np.max(np.abs(G[b] - gr)) <= TOL * np.max(np.abs(gr))
+
+
+def test_nn_ladder_vs_scipy():
+    """Short annealing ladder over the neuron states of a small twin network with the weights held
+    at (perturbed) teacher values, at RF values where the model error shapes the minimum.  (With
+    the weights free, or at small RF, the net fits anything: A -> 0 along a flat valley, SciPy
+    itself runs into maxfun = 2e5 without converging, and two correct optimisers stop anywhere on
+    it -- measured while writing this test.)  Per-beta minimum action vs SciPy L-BFGS-B on the
+    oracle action to 1e-6 relative; and SciPy started at the device's minimiser has nothing left
+    to do."""
+    rng = np.random.RandomState(8)
+    st = np.array([4, 6, 3])
+    M = 12
+    NDnet, NP = int(st.sum()), int(4 * 6 + 6 + 6 * 3 + 3)
+    Wt = [rng.randn(6, 4), rng.randn(3, 6)]
+    xin = rng.rand(M, 4)
+    h = 1 / (1 + np.exp(-(xin @ Wt[0].T)))
+    yout = 1 / (1 + np.exp(-(h @ Wt[1].T))) + 0.05 * rng.randn(M, 3)
+    X0 = rng.rand(M * NDnet)
+    P0 = np.concatenate([Wt[0].ravel(), np.zeros(6), Wt[1].ravel(), np.zeros(3)]) * (1 + 0.05 * rng.randn(NP))
+    Pidx = np.arange(0)
+    alpha, betas, RM, RF0 = 2.0, np.arange(0.0, 12.0, 2.0), 400.0, 1.0
+    opts = {"gtol": 1e-11, "ftol": 1e-15, "maxfun": 200000, "maxiter": 200000}
+    from varanneal_b200 import va_nnet
+    an = va_nnet.Annealer()
+    an.set_structure(st); an.set_activation(va_nnet.sigmoid)
+    an.set_input_data(xin); an.set_output_data(yout)
+    X0d = X0.copy()
+    an.anneal(X0d, P0.copy(), alpha, betas, RM, RF0, Pidx, opt_args=opts)
+    prob = nnet_port.NnetProblem(st, xin, yout, None, P0, Pidx, RM)
+    xp = X0d.copy()                        # X0d carries the init_to_data overwrite
+    for i, beta in enumerate(betas):
+        rf = RF0 * alpha ** beta
+        res = opt.minimize(lambda z: prob.action_grad(z, rf), xp, method="L-BFGS-B", jac=True, options=opts)
+        xp = res.x
+        print("beta %4.1f scipy %.10e (nit %d) device %.10e (nit %d)" % (beta, res.fun, res.nit, an.A_array[i], an.nit_array[i]))
+        assert abs(an.A_array[i] - res.fun) <= 1e-6 * abs(res.fun), (i, an.A_array[i], res.fun)
+        # secondary acceptance: SciPy, started at the device's minimiser, has nothing left to do
+        res2 = opt.minimize(lambda z: prob.action_grad(z, rf), an.minpaths[i][:M * NDnet], method="L-BFGS-B", jac=True,
+                            options={"gtol": 1e-9, "ftol": 1e-13})
+        assert res2.nit <= 2 and abs(res2.fun - an.A_array[i]) <= 1e-9 * abs(res2.fun)
+    assert an.minpaths.shape == (len(betas), M * NDnet + NP)
+    assert np.all(an.exitflags == 0)

@@ -7,5 +7,6 @@ include/varanneal_b200.h); there is no CPU fallback.
 """
 from . import models  # noqa: F401
 from . import va_ode  # noqa: F401
+from . import va_nnet  # noqa: F401
 
 __version__ = "0.1.0"

@@ -104,12 +104,8 @@ class DeviceMin(object):
             if XP.shape != (self._B, self._n) or XP.dtype != torch.float64:
                 raise ValueError("XP tensor must be float64 of shape (%d, %d)" % (self._B, self._n))
             _, G_pin, A_pin = self._pinned()
-            self._XP[:, :self._n].copy_(XP, non_blocking=True)
             self._dev_paths_current = False
-            self._action_grad_native(self._rf_scale())
-            G_pin.copy_(self._G[:, :self._n], non_blocking=True)
-            A_pin.copy_(self._A, non_blocking=True)
-            torch.cuda.current_stream(self._device).synchronize()
+            self._pipelined_eval(XP, G_pin, A_pin)
             return A_pin, G_pin
         XP = np.asarray(XP, dtype=np.float64)
         single = XP.ndim == 1
@@ -122,6 +118,40 @@ class DeviceMin(object):
         if single:
             return float(A[0]), G[0]
         return A, G
+
+    def _pipelined_eval(self, XP_pin, G_pin, A_pin, chunks=8):
+        """Host -> device -> host evaluation of a pinned batch, software-pipelined over groups of
+        paths: the upload of group i+1 and the download of group i-1 overlap the kernel of group i
+        (both PCIe directions busy)."""
+        torch = _torch()
+        main = torch.cuda.current_stream(self._device)
+        if getattr(self, "_s_h2d", None) is None:
+            self._s_h2d = torch.cuda.Stream(self._device)
+            self._s_d2h = torch.cuda.Stream(self._device)
+        B, n = self._B, self._n
+        nch = max(1, min(chunks, B))
+        per = -(-B // nch)
+        spans = [(lo, min(lo + per, B)) for lo in range(0, B, per)]
+        scale = self._rf_scale()
+        self._s_h2d.wait_stream(main)
+        ev_in = []
+        for lo, hi in spans:
+            with torch.cuda.stream(self._s_h2d):
+                self._XP[lo:hi, :n].copy_(XP_pin[lo:hi], non_blocking=True)
+                e = torch.cuda.Event()
+                e.record(self._s_h2d)
+                ev_in.append(e)
+        for (lo, hi), e in zip(spans, ev_in):
+            main.wait_event(e)
+            self._action_grad_native(scale, lo, hi - lo)
+            eo = torch.cuda.Event()
+            eo.record(main)
+            with torch.cuda.stream(self._s_d2h):
+                self._s_d2h.wait_event(eo)
+                G_pin[lo:hi].copy_(self._G[lo:hi, :n], non_blocking=True)
+                A_pin[lo:hi].copy_(self._A[lo:hi], non_blocking=True)
+        main.wait_stream(self._s_d2h)
+        main.synchronize()
 
     def A_gradA_taped(self, XP):
         return self.A_gradA(XP)

@@ -1,21 +1,420 @@
-// placeholder until the NN kernels land (next milestone)
+// Neural-network action + gradient: replaces the ADOL-C tape of va_nnet.Annealer.A_gaussian
+// (va_nnet.py:111-255: me_gaussian :117-173, fe_gaussian :175-255, disc_forwardmap :260-264).
+//
+// Layout (reference): X flat = for each example m the layers concatenated (va_nnet.py:149-152),
+// i.e. X.reshape(M, NDnet); P flat = [W_0 (d_1 x d_0 row-major), b_0, W_1, b_1, ...]
+// (va_nnet.py:194-207); XP = X ++ P[Pidx] (va_nnet.py:468-473).
+//
+// One CTA owns a tile of TM examples of one path and walks all layers: the examples of a tile are
+// independent across layers, so the three contractions of a layer
+//     Z  = X_n W_n^T + b_n              -> S = act(Z), E = X_{n+1} - S, fe += sum E^2
+//     GX_n += Delta W_n                    Delta = -2 cf E act'(Z)
+//     GW_n  = Delta^T X_n  (contraction over the examples), Gb_n = sum_m Delta
+// are done on shared-memory tiles without leaving the CTA; every gradient row of X is written
+// once.  Weight gradients are per-tile partials reduced in a fixed order by nn_reduce_kernel
+// (bit-reproducible, no atomics).  fp64 on the CUDA cores: tcgen05 has no f64 kind, and parity is
+// 1e-10.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
 #include "vab_ctx.h"
-void nn_destroy(vab_ctx*) {}
-long long nn_unknowns(const vab_ctx*) { return 0; }
-int nn_eval(vab_ctx* ctx, int, const double*, long long, double, const int*, double*, double*,
-            double*, double*, long long) {
-  return vab_fail(ctx, VAB_ERR_STATE, "NN path not built yet");
+
+namespace {
+
+constexpr int NT = 256;
+constexpr int WCAP = 8192;         // doubles of W staged per chunk of output neurons
+
+struct NnParams {
+  const double* XP; long long ldxp;
+  double* G; long long ldg;
+  int B, M, NL, NDnet, NP, NPest, act, TM, ntiles, dpitch;
+  long long NDens;
+  const int* structure;   // (NL)
+  const int* xoff;        // (NL+1) offsets of the layers inside an example
+  const int* woff;        // (NL-1)
+  const int* boff;        // (NL-1)
+  const int* pmap;        // (NP) -> estimated index or -1
+  const double* pfix; long long pfix_stride;
+  const int* slot_in;     // (d_0) column of data_in or -1
+  const int* slot_out;    // (d_last)
+  int n_Lin, n_Lout;
+  const double* data_in;  // (M, n_Lin)
+  const double* data_out; // (M, n_Lout)
+  double wm_in, wm_out;   // 2 cm RM_in, 2 cm RM_out
+  double cf2;             // 2 RF / ((NDnet - d_0) M)
+  const int* active;
+  double* partials;       // (B, ntiles, 2): me, fe
+  double* gwpart;         // (B, ntiles, NP)
+};
+
+__device__ __forceinline__ double act_f(int act, double z) {
+  if (act == VAB_ACT_SIGMOID) return 1.0 / (1.0 + exp(-z));
+  if (act == VAB_ACT_TANH) return tanh(z);
+  return z;
 }
+__device__ __forceinline__ double act_d(int act, double s) {   // derivative through the output s
+  if (act == VAB_ACT_SIGMOID) return s * (1.0 - s);
+  if (act == VAB_ACT_TANH) return 1.0 - s * s;
+  return 1.0;
+}
+
+__global__ void __launch_bounds__(NT) nn_fused_kernel(const __grid_constant__ NnParams P) {
+  extern __shared__ double sm[];
+  const int b = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
+  if (P.active != nullptr && P.active[b] == 0) return;
+  const int TM = P.TM, dp = P.dpitch;
+  double* Xs = sm;                       // [TM][dp] states of layer n
+  double* Xn = Xs + TM * dp;             // layer n+1
+  double* GXc = Xn + TM * dp;            // gradient rows of layer n
+  double* GXn = GXc + TM * dp;           // gradient rows of layer n+1
+  double* Ds = GXn + TM * dp;            // Delta chunk [TM][dp]
+  double* Ws = Ds + TM * dp;             // [JB][dnp]
+  double* bs = Ws + WCAP + 64;           // [JB]
+  __shared__ double red[2][NT / 32];
+
+  const int m0 = tile * TM;
+  const int rows = min(TM, P.M - m0);
+  const double* xp = P.XP + (long long)b * P.ldxp;
+  double* gp = P.G ? P.G + (long long)b * P.ldg : nullptr;
+  const double* pfix = P.pfix + (long long)b * P.pfix_stride;
+  double* gw = P.gwpart + ((long long)b * P.ntiles + tile) * P.NP;
+  auto param = [&](int k) -> double {
+    const int e = P.pmap[k];
+    return e >= 0 ? xp[P.NDens + e] : pfix[k];
+  };
+  double me_acc = 0.0, fe_acc = 0.0;
+
+  // layer 0 states + measurement term of the input layer
+  {
+    const int d0 = P.structure[0];
+    for (int idx = tid; idx < TM * d0; idx += NT) {
+      const int m = idx / d0, i = idx - m * d0;
+      double x = 0.0, gx = 0.0;
+      if (m < rows) {
+        x = xp[(long long)(m0 + m) * P.NDnet + i];
+        const int s = P.slot_in[i];
+        if (s >= 0) {
+          const double diff = x - P.data_in[(long long)(m0 + m) * P.n_Lin + s];
+          me_acc = fma(P.wm_in * diff, diff, me_acc);
+          gx = P.wm_in * diff;
+        }
+      }
+      Xs[m * dp + i] = x;
+      GXc[m * dp + i] = gx;
+    }
+  }
+  for (int n = 0; n < P.NL - 1; ++n) {
+    const int dn = P.structure[n], dn1 = P.structure[n + 1];
+    const int dnp = dn | 1;                               // odd pitch: conflict-free column walks
+    const int xo1 = P.xoff[n + 1];
+    const bool lastl = (n + 1 == P.NL - 1);
+    __syncthreads();
+    for (int idx = tid; idx < TM * dn1; idx += NT) {
+      const int m = idx / dn1, j = idx - m * dn1;
+      Xn[m * dp + j] = (m < rows) ? xp[(long long)(m0 + m) * P.NDnet + xo1 + j] : 0.0;
+    }
+    int JB = WCAP / dnp;
+    if (JB > dn1) JB = dn1;
+    for (int j0 = 0; j0 < dn1; j0 += JB) {
+      const int jb = min(JB, dn1 - j0);
+      __syncthreads();
+      for (int idx = tid; idx < jb * dn; idx += NT) {
+        const int j = idx / dn, k = idx - j * dn;
+        Ws[j * dnp + k] = param(P.woff[n] + (j0 + j) * dn + k);
+      }
+      for (int j = tid; j < jb; j += NT) bs[j] = param(P.boff[n] + j0 + j);
+      __syncthreads();
+      // (1) forward, residual, Delta
+      for (int idx = tid; idx < TM * jb; idx += NT) {
+        const int m = idx / jb, j = idx - m * jb;
+        double z = bs[j];
+        const double* xr = Xs + m * dp;
+        const double* wr = Ws + j * dnp;
+        for (int k = 0; k < dn; ++k) z = fma(xr[k], wr[k], z);
+        double lam = 0.0, dl = 0.0;
+        if (m < rows) {
+          const double s = act_f(P.act, z);
+          const double e = Xn[m * dp + j0 + j] - s;
+          lam = P.cf2 * e;
+          fe_acc = fma(lam, e, fe_acc);
+          dl = -lam * act_d(P.act, s);
+        }
+        double gx = lam;
+        if (lastl && m < rows) {
+          const int so = P.slot_out[j0 + j];
+          if (so >= 0) {
+            const double diff = Xn[m * dp + j0 + j] - P.data_out[(long long)(m0 + m) * P.n_Lout + so];
+            me_acc = fma(P.wm_out * diff, diff, me_acc);
+            gx += P.wm_out * diff;
+          }
+        }
+        GXn[m * dp + j0 + j] = gx;
+        Ds[m * dp + j] = dl;
+      }
+      __syncthreads();
+      // (2) GX_n += Delta W
+      for (int idx = tid; idx < TM * dn; idx += NT) {
+        const int m = idx / dn, k = idx - m * dn;
+        double acc = 0.0;
+        const double* dr = Ds + m * dp;
+        for (int j = 0; j < jb; ++j) acc = fma(dr[j], Ws[j * dnp + k], acc);
+        GXc[m * dp + k] += acc;
+      }
+      // (3) per-tile weight / bias gradient partials
+      for (int idx = tid; idx < jb * dn; idx += NT) {
+        const int j = idx / dn, k = idx - j * dn;
+        double acc = 0.0;
+        for (int m = 0; m < TM; ++m) acc = fma(Ds[m * dp + j], Xs[m * dp + k], acc);
+        gw[P.woff[n] + (j0 + j) * dn + k] = acc;
+      }
+      for (int j = tid; j < jb; j += NT) {
+        double acc = 0.0;
+        for (int m = 0; m < TM; ++m) acc += Ds[m * dp + j];
+        gw[P.boff[n] + j0 + j] = acc;
+      }
+    }
+    __syncthreads();
+    // gradient rows of layer n are complete
+    if (gp) {
+      const int xo = P.xoff[n];
+      for (int idx = tid; idx < rows * dn; idx += NT) {
+        const int m = idx / dn, k = idx - m * dn;
+        gp[(long long)(m0 + m) * P.NDnet + xo + k] = GXc[m * dp + k];
+      }
+    }
+    __syncthreads();
+    double* t = Xs; Xs = Xn; Xn = t;
+    t = GXc; GXc = GXn; GXn = t;
+  }
+  if (gp) {
+    const int dl = P.structure[P.NL - 1], xo = P.xoff[P.NL - 1];
+    for (int idx = tid; idx < rows * dl; idx += NT) {
+      const int m = idx / dl, k = idx - m * dl;
+      gp[(long long)(m0 + m) * P.NDnet + xo + k] = GXc[m * dp + k];
+    }
+  }
+  // per-tile me / fe (fixed-order block reduction)
+  for (int sft = 16; sft > 0; sft >>= 1) {
+    me_acc += __shfl_down_sync(0xffffffffu, me_acc, sft);
+    fe_acc += __shfl_down_sync(0xffffffffu, fe_acc, sft);
+  }
+  if ((tid & 31) == 0) { red[0][tid >> 5] = me_acc; red[1][tid >> 5] = fe_acc; }
+  __syncthreads();
+  if (tid == 0) {
+    double a = 0.0, c = 0.0;
+    for (int w = 0; w < NT / 32; ++w) { a += red[0][w]; c += red[1][w]; }
+    P.partials[((long long)b * P.ntiles + tile) * 2 + 0] = 0.5 * a;
+    P.partials[((long long)b * P.ntiles + tile) * 2 + 1] = 0.5 * c;
+  }
+}
+
+// sums the per-tile partials in tile order: A / me / fe and the gradient of the estimated params
+__global__ void nn_reduce_kernel(const __grid_constant__ NnParams P, double* A, double* me, double* fe) {
+  const int b = blockIdx.y;
+  if (P.active != nullptr && P.active[b] == 0) return;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < P.NP && P.G != nullptr) {
+    const int e = P.pmap[k];
+    if (e >= 0) {
+      double acc = 0.0;
+      const double* src = P.gwpart + (long long)b * P.ntiles * P.NP + k;
+      for (int t = 0; t < P.ntiles; ++t) acc += src[(long long)t * P.NP];
+      P.G[(long long)b * P.ldg + P.NDens + e] = acc;
+    }
+  }
+  if (k == 0) {
+    double m = 0.0, f = 0.0;
+    for (int t = 0; t < P.ntiles; ++t) {
+      m += P.partials[((long long)b * P.ntiles + t) * 2 + 0];
+      f += P.partials[((long long)b * P.ntiles + t) * 2 + 1];
+    }
+    if (me) me[b] = m;
+    if (fe) fe[b] = f;
+    if (A) A[b] = m + f;
+  }
+}
+
+}  // namespace
+
+struct NnProblem {
+  int NL = 0, M = 0, NDnet = 0, NP = 0, NPest = 0, act = 0, n_Lin = 0, n_Lout = 0, dmax = 0, d0 = 0;
+  long long NDens = 0;
+  int Ltot = 0;
+  int* ints = nullptr;            // structure | xoff | woff | boff | pmap | slot_in | slot_out
+  int *structure = nullptr, *xoff = nullptr, *woff = nullptr, *boff = nullptr, *pmap = nullptr,
+      *slot_in = nullptr, *slot_out = nullptr;
+  const double* data_in = nullptr;
+  const double* data_out = nullptr;
+  double rm_in = 1.0, rm_out = 1.0, rf0 = 1.0;
+  const double* pfix = nullptr;
+  long long pfix_stride = 0;
+  double* pfix_zero = nullptr;
+  double* gwpart = nullptr;
+  size_t gwpart_cap = 0;
+};
+
+void nn_destroy(vab_ctx* ctx) {
+  NnProblem* p = ctx->nn;
+  if (!p) return;
+  cudaFree(p->ints);
+  cudaFree(p->pfix_zero);
+  cudaFree(p->gwpart);
+  delete p;
+  ctx->nn = nullptr;
+}
+
+long long nn_unknowns(const vab_ctx* ctx) { return ctx->nn ? ctx->nn->NDens + ctx->nn->NPest : 0; }
+
+int nn_eval(vab_ctx* ctx, int B, const double* XP, long long ldxp, double rf_scale,
+            const int* active_dev, double* A, double* me, double* fe, double* G, long long ldg) {
+  NnProblem* p = ctx->nn;
+  if (!p) return vab_fail(ctx, VAB_ERR_STATE, "nn_action_grad: no NN problem set");
+  const long long n = p->NDens + p->NPest;
+  if (B < 1 || !XP || ldxp < n) return vab_fail(ctx, VAB_ERR_INVALID, "nn_action_grad: bad batch / XP / ldxp");
+  if (G && ldg < n) return vab_fail(ctx, VAB_ERR_INVALID, "nn_action_grad: ldg < n");
+  NnParams P;
+  memset(&P, 0, sizeof(P));
+  P.XP = XP; P.ldxp = ldxp; P.G = G; P.ldg = ldg;
+  P.B = B; P.M = p->M; P.NL = p->NL; P.NDnet = p->NDnet; P.NP = p->NP; P.NPest = p->NPest;
+  P.act = p->act; P.NDens = p->NDens;
+  P.structure = p->structure; P.xoff = p->xoff; P.woff = p->woff; P.boff = p->boff; P.pmap = p->pmap;
+  P.pfix = p->pfix; P.pfix_stride = p->pfix_stride;
+  P.slot_in = p->slot_in; P.slot_out = p->slot_out; P.n_Lin = p->n_Lin; P.n_Lout = p->n_Lout;
+  P.data_in = p->data_in; P.data_out = p->data_out;
+  const double cm = p->Ltot > 0 ? 1.0 / ((double)p->Ltot * p->M) : 0.0;
+  P.wm_in = 2.0 * cm * p->rm_in;
+  P.wm_out = 2.0 * cm * p->rm_out;
+  P.cf2 = 2.0 * p->rf0 * rf_scale / ((double)(p->NDnet - p->d0) * p->M);
+  P.active = active_dev;
+  // tile height from the shared-memory budget: 5 [TM][dpitch] tiles + the staged weights
+  const int dpitch = p->dmax | 1;
+  const size_t budget = 200 * 1024;
+  const size_t wbytes = ((size_t)WCAP + 64 + (size_t)dpitch + 8) * sizeof(double);   // Ws + bs
+  int TM = (int)((budget - wbytes) / ((size_t)5 * dpitch * sizeof(double)));
+  if (TM > 32) TM = 32;
+  if (TM > p->M) TM = p->M;
+  if (TM < 1) return vab_fail(ctx, VAB_ERR_INVALID, "nn_action_grad: layer too wide for the shared-memory tiles");
+  if (dpitch > WCAP) return vab_fail(ctx, VAB_ERR_INVALID, "nn_action_grad: layer wider than 8191 neurons is not supported");
+  P.TM = TM;
+  P.dpitch = dpitch;
+  P.ntiles = (p->M + TM - 1) / TM;
+  const size_t smem = (size_t)5 * TM * dpitch * sizeof(double) + wbytes;
+  int rc = vab_reserve(ctx, &ctx->partials, &ctx->partials_cap, (size_t)B * P.ntiles * 2);
+  if (rc != VAB_OK) return rc;
+  rc = vab_reserve(ctx, &p->gwpart, &p->gwpart_cap, (size_t)B * P.ntiles * p->NP);
+  if (rc != VAB_OK) return rc;
+  P.partials = ctx->partials;
+  P.gwpart = p->gwpart;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(nn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    if (e != cudaSuccess) return vab_cuda_fail(ctx, e, "nn_action_grad smem opt-in");
+    attr_set = true;
+  }
+  nn_fused_kernel<<<dim3(P.ntiles, B), NT, smem, ctx->stream>>>(P);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return vab_cuda_fail(ctx, e, "nn_fused_kernel launch");
+  const int nk = p->NP > 1 ? p->NP : 1;
+  nn_reduce_kernel<<<dim3((nk + 255) / 256, B), 256, 0, ctx->stream>>>(P, A, me, fe);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return vab_cuda_fail(ctx, e, "nn_reduce_kernel launch");
+  ctx->launches += 2;
+  return VAB_OK;
+}
+
 extern "C" {
-int vab_nn_problem_set(vab_ctx* ctx, int32_t, const int32_t*, int32_t, int32_t, int32_t,
-                       const int32_t*, int32_t, const int32_t*, const double*, const double*,
-                       int32_t, const int32_t*) {
-  return vab_fail(ctx, VAB_ERR_STATE, "NN path not built yet");
+
+int vab_nn_problem_set(vab_ctx* ctx, int32_t n_layers, const int32_t* structure_host, int32_t M,
+                       int32_t activation, int32_t n_Lin, const int32_t* Lin_host, int32_t n_Lout,
+                       const int32_t* Lout_host, const double* data_in_dev, const double* data_out_dev,
+                       int32_t NPest, const int32_t* Pidx_host) {
+  if (!ctx) return VAB_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  if (n_layers < 2 || !structure_host || M < 1) return vab_fail(ctx, VAB_ERR_INVALID, "nn_problem_set: bad structure / M");
+  if (activation < VAB_ACT_SIGMOID || activation > VAB_ACT_LINEAR)
+    return vab_fail(ctx, VAB_ERR_INVALID, "nn_problem_set: unknown activation");
+  if ((n_Lin > 0 && (!Lin_host || !data_in_dev)) || (n_Lout > 0 && (!Lout_host || !data_out_dev)))
+    return vab_fail(ctx, VAB_ERR_INVALID, "nn_problem_set: Lidx / data missing");
+  cudaStreamSynchronize(ctx->stream);
+  nn_destroy(ctx);
+  NnProblem* p = new NnProblem();
+  ctx->nn = p;
+  p->NL = n_layers; p->M = M; p->act = activation; p->n_Lin = n_Lin; p->n_Lout = n_Lout;
+  p->Ltot = n_Lin + n_Lout;
+  std::vector<int> st(structure_host, structure_host + n_layers), xoff(n_layers + 1, 0), woff(n_layers - 1),
+      boff(n_layers - 1);
+  int np = 0;
+  for (int n = 0; n < n_layers; ++n) {
+    if (st[n] < 1) return vab_fail(ctx, VAB_ERR_INVALID, "nn_problem_set: empty layer");
+    xoff[n + 1] = xoff[n] + st[n];
+    if (st[n] > p->dmax) p->dmax = st[n];
+  }
+  for (int n = 0; n + 1 < n_layers; ++n) {
+    woff[n] = np; np += st[n] * st[n + 1];
+    boff[n] = np; np += st[n + 1];
+  }
+  p->NDnet = xoff[n_layers]; p->NDens = (long long)p->NDnet * M; p->NP = np; p->d0 = st[0];
+  if (NPest < 0 || NPest > np) return vab_fail(ctx, VAB_ERR_INVALID, "nn_problem_set: bad NPest");
+  p->NPest = NPest;
+  std::vector<int> pmap(np > 0 ? np : 1, -1), sin(st[0], -1), sout(st[n_layers - 1], -1);
+  for (int e = 0; e < NPest; ++e) {
+    const int k = Pidx_host[e];
+    if (k < 0 || k >= np || pmap[k] >= 0) return vab_fail(ctx, VAB_ERR_INVALID, "nn_problem_set: bad Pidx");
+    pmap[k] = e;
+  }
+  for (int l = 0; l < n_Lin; ++l) {
+    const int i = Lin_host[l];
+    if (i < 0 || i >= st[0] || sin[i] >= 0) return vab_fail(ctx, VAB_ERR_INVALID, "nn_problem_set: bad Lidx[0]");
+    sin[i] = l;
+  }
+  for (int l = 0; l < n_Lout; ++l) {
+    const int i = Lout_host[l];
+    if (i < 0 || i >= st[n_layers - 1] || sout[i] >= 0) return vab_fail(ctx, VAB_ERR_INVALID, "nn_problem_set: bad Lidx[1]");
+    sout[i] = l;
+  }
+  std::vector<int> all;
+  auto push = [&](const std::vector<int>& v) { size_t o = all.size(); all.insert(all.end(), v.begin(), v.end()); return o; };
+  const size_t o_st = push(st), o_x = push(xoff), o_w = push(woff), o_b = push(boff), o_p = push(pmap),
+               o_si = push(sin), o_so = push(sout);
+  cudaError_t e = cudaMalloc((void**)&p->ints, all.size() * sizeof(int));
+  if (e == cudaSuccess) e = cudaMemcpy(p->ints, all.data(), all.size() * sizeof(int), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&p->pfix_zero, (size_t)(np > 0 ? np : 1) * sizeof(double));
+  if (e == cudaSuccess) e = cudaMemset(p->pfix_zero, 0, (size_t)(np > 0 ? np : 1) * sizeof(double));
+  if (e != cudaSuccess) return vab_cuda_fail(ctx, e, "nn_problem_set");
+  p->structure = p->ints + o_st; p->xoff = p->ints + o_x; p->woff = p->ints + o_w; p->boff = p->ints + o_b;
+  p->pmap = p->ints + o_p; p->slot_in = p->ints + o_si; p->slot_out = p->ints + o_so;
+  p->data_in = data_in_dev; p->data_out = data_out_dev;
+  p->pfix = p->pfix_zero; p->pfix_stride = 0;
+  ctx->problem = VAB_PROBLEM_NN;
+  return VAB_OK;
 }
-int vab_nn_set_weights(vab_ctx* ctx, double, double, double) { return vab_fail(ctx, VAB_ERR_STATE, "NN path not built yet"); }
-int vab_nn_set_fixed_params(vab_ctx* ctx, const double*, int64_t) { return vab_fail(ctx, VAB_ERR_STATE, "NN path not built yet"); }
-int vab_nn_action_grad(vab_ctx* ctx, int32_t, const double*, int64_t, double, double*, double*,
-                       double*, double*, int64_t) {
-  return vab_fail(ctx, VAB_ERR_STATE, "NN path not built yet");
+
+int vab_nn_set_weights(vab_ctx* ctx, double rm_in, double rm_out, double rf0) {
+  if (!ctx) return VAB_ERR_INVALID;
+  if (!ctx->nn) return vab_fail(ctx, VAB_ERR_STATE, "nn_set_weights: no NN problem set");
+  ctx->nn->rm_in = rm_in; ctx->nn->rm_out = rm_out; ctx->nn->rf0 = rf0;
+  return VAB_OK;
 }
+
+int vab_nn_set_fixed_params(vab_ctx* ctx, const double* pfix_dev, int64_t pfix_stride) {
+  if (!ctx) return VAB_ERR_INVALID;
+  if (!ctx->nn) return vab_fail(ctx, VAB_ERR_STATE, "nn_set_fixed_params: no NN problem set");
+  if (!pfix_dev || (pfix_stride != 0 && pfix_stride != ctx->nn->NP))
+    return vab_fail(ctx, VAB_ERR_INVALID, "nn_set_fixed_params: NULL or stride not 0 / NP");
+  ctx->nn->pfix = pfix_dev; ctx->nn->pfix_stride = pfix_stride;
+  return VAB_OK;
 }
+
+int vab_nn_action_grad(vab_ctx* ctx, int32_t B, const double* XP_dev, int64_t ldxp, double rf_scale,
+                       double* A_dev, double* me_dev, double* fe_dev, double* G_dev, int64_t ldg) {
+  if (!ctx) return VAB_ERR_INVALID;
+  if (ctx->problem != VAB_PROBLEM_NN) return vab_fail(ctx, VAB_ERR_STATE, "nn_action_grad: no NN problem set");
+  cudaSetDevice(ctx->device);
+  return nn_eval(ctx, B, XP_dev, ldxp, rf_scale, nullptr, A_dev, me_dev, fe_dev, G_dev, ldg);
+}
+
+}  // extern "C"

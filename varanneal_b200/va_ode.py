@@ -18,6 +18,7 @@ Differences from the reference, all deliberate:
     reference's shapes the results have exactly the reference's shapes.
   * time-dependent parameters (``P0.ndim == 2`` with a 2-D ``X0``) are a 'next' row (8(f4)).
 """
+import ctypes as ct
 import time
 
 import numpy as np
@@ -279,11 +280,27 @@ class Annealer(DeviceMin):
         self._dev_paths_current = False
         self.initalized = True               # sic (va_ode.py:705)
 
-    def _action_grad_native(self, rf_scale):
+    def _action_grad_native(self, rf_scale, b0=0, nb=None):
+        """Evaluates paths [b0, b0 + nb) of the device batch (default: all)."""
         ctx = self._ctx
-        _lib.check(ctx.lib.vab_ode_action_grad(
-            ctx.h, self._B, ptr(self._XP), self._ld, float(rf_scale), ptr(self._A),
-            ptr(self._me), ptr(self._fe), ptr(self._G), self._ld), ctx.h)
+        nb = self._B - b0 if nb is None else nb
+        sub = (b0 != 0 or nb != self._B)
+        off = b0 * self._ld * 8
+
+        def at(t, per_path):
+            return ct.c_void_p(t.data_ptr() + b0 * per_path)
+
+        if sub:
+            _lib.check(ctx.lib.vab_ode_set_fixed_params(
+                ctx.h, ct.c_void_p(self._pfix_dev.data_ptr() + b0 * self.NP * 8), self.NP), ctx.h)
+        try:
+            _lib.check(ctx.lib.vab_ode_action_grad(
+                ctx.h, nb, ct.c_void_p(self._XP.data_ptr() + off), self._ld, float(rf_scale),
+                at(self._A, 8), at(self._me, 8), at(self._fe, 8),
+                ct.c_void_p(self._G.data_ptr() + off), self._ld), ctx.h)
+        finally:
+            if sub:
+                _lib.check(ctx.lib.vab_ode_set_fixed_params(ctx.h, ptr(self._pfix_dev), self.NP), ctx.h)
 
     def _est_slice(self, full):
         """(B, nX+NP) rows X ++ full P  ->  (B, nX+NPest) rows X ++ P[Pidx] (va_ode.py:715-732)."""
