@@ -48,8 +48,10 @@ def test_ladder_matches_reference_scipy_ladder(disc):
     assert np.all(rel[strict] <= 1e-6), rel
     assert np.all(rel[beta < 15] <= 5e-2), rel
     assert np.all(an.exitflags == 0)
-    # estimated forcing parameter on the well-conditioned rungs
-    assert np.all(np.abs(an.minpaths[strict, -1] - z[disc + "/params"][strict]) <= 1e-3)
+    # estimated forcing parameter: the action is flat in k at small RF (A agrees to 1e-7 while k
+    # differs in the 3rd digit), so k is compared where RF pins it down
+    pin = (beta >= 27) & (beta <= 54)
+    assert np.all(np.abs(an.minpaths[pin, -1] - z[disc + "/params"][pin]) <= 1e-4)
     # result layout = the reference's (va_ode.py:666-699)
     assert an.minpaths.shape == (20, 161 * 20 + 1) and an.A_array.shape == (20,)
     t5 = an.action_errors_table()
