@@ -32,6 +32,7 @@
 
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -454,10 +455,10 @@ __global__ void __launch_bounds__(NT, 1) lb_update_kernel(
     const double* __restrict__ GT, const double* __restrict__ Dv, double* __restrict__ S,
     double* __restrict__ Y, long long ld, long long n, long long hstride, const double* __restrict__ lo,
     const double* __restrict__ hi, const LbPath* __restrict__ st, int m, int nchunk,
-    double* __restrict__ part) {
+    double* __restrict__ part, int b0) {
   __shared__ double scratch[8 * NT];
   __shared__ double res[NACC_U];
-  const int b = blockIdx.y;
+  const int b = b0 + blockIdx.y;
   const LbPath& s = st[b];
   if (!s.accepted) return;
   const bool upd = s.do_update != 0;
@@ -513,8 +514,8 @@ __global__ void __launch_bounds__(NT, 1) lb_update_kernel(
 }
 
 // history bookkeeping + the two-loop recursion in coefficient space; one thread per path
-__global__ void lb_gram_kernel(LbPath* st, const double* part, int nchunk, int m) {
-  const int b = blockIdx.x;
+__global__ void lb_gram_kernel(LbPath* st, const double* part, int nchunk, int m, int b0) {
+  const int b = b0 + blockIdx.x;
   LbPath& s = st[b];
   if (!(s.accepted || s.redo_dir) || s.done) return;
   __shared__ double sum[NACC_U];
@@ -525,50 +526,63 @@ __global__ void lb_gram_kernel(LbPath* st, const double* part, int nchunk, int m
       sum[k] = a;
     }
   }
+  // the Gram blocks are walked by one thread: stage them in shared memory (global latency would
+  // dominate the ~m^2 dependent loads of the two-loop recursion)
+  __shared__ double SYs[MMAX * MMAX], YYs[MMAX * MMAX];
+  for (int k = threadIdx.x; k < MMAX * MMAX; k += blockDim.x) { SYs[k] = s.SY[k]; YYs[k] = s.YY[k]; }
   __syncthreads();
   if (threadIdx.x != 0) return;
+  double gS[MMAX], gY[MMAX];
+  for (int j = 0; j < MMAX; ++j) { gS[j] = s.gS[j]; gY[j] = s.gY[j]; }
+  int col = s.col, head = s.head;
+  double theta = s.theta;
   if (s.accepted) {
     if (s.do_update) {
       const int p = s.pslot;
       for (int j = 0; j < m; ++j) {
         if (j == p) continue;
-        s.SY[p * MMAX + j] = sum[2 * MMAX + j];      // s_p . y_j
-        s.SY[j * MMAX + p] = sum[3 * MMAX + j];      // s_j . y_p
-        s.YY[p * MMAX + j] = sum[4 * MMAX + j];
-        s.YY[j * MMAX + p] = sum[4 * MMAX + j];
+        SYs[p * MMAX + j] = sum[2 * MMAX + j];      // s_p . y_j
+        SYs[j * MMAX + p] = sum[3 * MMAX + j];      // s_j . y_p
+        YYs[p * MMAX + j] = sum[4 * MMAX + j];
+        YYs[j * MMAX + p] = sum[4 * MMAX + j];
       }
-      s.SY[p * MMAX + p] = s.dr;                     // s'y from the line search, as L-BFGS-B does
-      s.YY[p * MMAX + p] = sum[5 * MMAX];
-      s.theta = sum[5 * MMAX] / s.dr;
-      if (s.col < m) s.col += 1;
-      else s.head = (s.head + 1) % m;
-      for (int j = 0; j < m; ++j) { s.gS[j] = sum[j]; s.gY[j] = sum[MMAX + j]; }
-      s.gS[p] = sum[5 * MMAX + 1];
-      s.gY[p] = sum[5 * MMAX + 2];
+      SYs[p * MMAX + p] = s.dr;                     // s'y from the line search, as L-BFGS-B does
+      YYs[p * MMAX + p] = sum[5 * MMAX];
+      theta = sum[5 * MMAX] / s.dr;
+      if (col < m) col += 1;
+      else head = (head + 1) % m;
+      for (int j = 0; j < m; ++j) { gS[j] = sum[j]; gY[j] = sum[MMAX + j]; }
+      gS[p] = sum[5 * MMAX + 1];
+      gY[p] = sum[5 * MMAX + 2];
+      for (int j = 0; j < m; ++j) {                 // write back the row / column that changed
+        s.SY[p * MMAX + j] = SYs[p * MMAX + j]; s.SY[j * MMAX + p] = SYs[j * MMAX + p];
+        s.YY[p * MMAX + j] = YYs[p * MMAX + j]; s.YY[j * MMAX + p] = YYs[j * MMAX + p];
+      }
+      s.theta = theta; s.col = col; s.head = head;
     } else {
-      for (int j = 0; j < m; ++j) { s.gS[j] = sum[j]; s.gY[j] = sum[MMAX + j]; }
+      for (int j = 0; j < m; ++j) { gS[j] = sum[j]; gY[j] = sum[MMAX + j]; }
     }
+    for (int j = 0; j < m; ++j) { s.gS[j] = gS[j]; s.gY[j] = gY[j]; }
     s.gg = sum[5 * MMAX + 3];
   }
   // r = H ghat  as  cg * ghat + sum_j cs_j s_j + cy_j y_j   (d = -r)
   double cg = 1.0, cs[MMAX], cy[MMAX], alpha[MMAX];
   for (int j = 0; j < MMAX; ++j) { cs[j] = 0.0; cy[j] = 0.0; alpha[j] = 0.0; }
-  const int col = s.col, head = s.head;
   for (int k = col - 1; k >= 0; --k) {               // newest -> oldest
     const int i = (head + k) % m;
-    double sq = s.gS[i] * cg;
-    for (int j = 0; j < m; ++j) sq += cy[j] * s.SY[i * MMAX + j];
-    alpha[i] = sq / s.SY[i * MMAX + i];
+    double sq = gS[i] * cg;
+    for (int j = 0; j < m; ++j) sq += cy[j] * SYs[i * MMAX + j];
+    alpha[i] = sq / SYs[i * MMAX + i];
     cy[i] -= alpha[i];
   }
-  const double gamma = (col > 0) ? 1.0 / s.theta : 1.0;
+  const double gamma = (col > 0) ? 1.0 / theta : 1.0;
   cg *= gamma;
   for (int j = 0; j < m; ++j) cy[j] *= gamma;
   for (int k = 0; k < col; ++k) {                    // oldest -> newest
     const int i = (head + k) % m;
-    double yr = s.gY[i] * cg;
-    for (int j = 0; j < m; ++j) yr += cy[j] * s.YY[i * MMAX + j] + cs[j] * s.SY[j * MMAX + i];
-    const double beta = yr / s.SY[i * MMAX + i];
+    double yr = gY[i] * cg;
+    for (int j = 0; j < m; ++j) yr += cy[j] * YYs[i * MMAX + j] + cs[j] * SYs[j * MMAX + i];
+    const double beta = yr / SYs[i * MMAX + i];
     cs[i] += alpha[i] - beta;
   }
   s.cg = cg;
@@ -581,10 +595,10 @@ __global__ void __launch_bounds__(NT) lb_direction_kernel(
     const double* __restrict__ X, const double* __restrict__ G, double* __restrict__ Dv,
     const double* __restrict__ S, const double* __restrict__ Y, long long ld, long long n,
     long long hstride, const double* __restrict__ lo, const double* __restrict__ hi,
-    const LbPath* __restrict__ st, int m, int nchunk, double* __restrict__ part) {
+    const LbPath* __restrict__ st, int m, int nchunk, double* __restrict__ part, int b0) {
   __shared__ double scratch[8 * NT];
   __shared__ double res[3];
-  const int b = blockIdx.y;
+  const int b = b0 + blockIdx.y;
   const LbPath& s = st[b];
   if (!(s.accepted || s.redo_dir) || s.done) return;
   const Range r = chunk_range(n, nchunk, blockIdx.x);
@@ -636,9 +650,8 @@ __global__ void __launch_bounds__(NT) lb_direction_kernel(
 
 // start of a line search (lnsrlb, task = START)
 __global__ void lb_start_kernel(LbPath* st, int* act_eval, const double* part, int nchunk, LbOpts o,
-                                int bounded) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= (int)gridDim.x * (int)blockDim.x) return;
+                                int bounded, int b0) {
+  const int b = b0 + blockIdx.x;
   LbPath& s = st[b];
   if (!(s.accepted || s.redo_dir) || s.done) { if (s.done) { s.accepted = 0; s.redo_dir = 0; } return; }
   double dd = 0.0, gd = 0.0, stpmx = BIG;
@@ -706,8 +719,14 @@ __global__ void lb_export_kernel(const LbPath* st, int B, double* A, double* me,
   if (nfev2) nfev2[(long long)b * Nbeta + ib] = s.nfev;
 }
 
-int lb_nchunk(long long n) {
+// chunks (CTAs) per path of the vector kernels: 8192 elements each for large batches, smaller
+// chunks when the whole batch would not fill the machine (launch-latency-bound small problems)
+int lb_nchunk(long long n, int B = 1 << 20) {
   long long c = (n + 8191) / 8192;
+  const long long want = (592 + B - 1) / B;            // ~4 CTAs per SM over the batch
+  if (c < want) c = want;
+  const long long cmax = (n + 511) / 512;              // at least 512 elements per chunk
+  if (c > cmax) c = cmax;
   if (c < 1) c = 1;
   if (c > 4096) c = 4096;
   return (int)c;
@@ -736,7 +755,8 @@ int lb_reserve(vab_ctx* ctx, int B, long long ld, int m) {
     LB_CUDA(cudaMalloc((void**)&w->fet, sizeof(double) * B));
     w->st_cap = B;
   }
-  const int nchunk = lb_nchunk(ctx->n_unknowns());
+  int nchunk = lb_nchunk(ctx->n_unknowns(), B);
+  if (nchunk < ctx->num_sms) nchunk = ctx->num_sms;      // the path-sequential tail uses num_sms chunks
   rc = vab_reserve(ctx, &w->part, &w->part_cap, (size_t)B * nchunk * NACC_U);
   if (rc != VAB_OK) return rc;
   if (!w->n_running_dev) LB_CUDA(cudaMalloc((void**)&w->n_running_dev, sizeof(int)));
@@ -774,9 +794,18 @@ int lb_minimize_core(vab_ctx* ctx, int B, double* XP, long long ld, double rf_sc
   double* S = w->vec + 4 * vs;
   double* Y = w->vec + (4 + (size_t)o.m) * vs;
   const long long hstride = (long long)vs;
-  const int nchunk = lb_nchunk(n);
+  const int nchunk = lb_nchunk(n, B);
   const bool bounded = lo != nullptr;
   const dim3 vgrid(nchunk, B);
+  // Path-sequential tail: when one path's history (2m+4 vectors) fits in L2 but the batch's does
+  // not, run update -> gram -> direction -> start path by path so that the direction pass re-reads
+  // the S / Y vectors the update pass has just streamed from L2 instead of HBM.
+  const double path_ws = (double)(2 * o.m + 4) * (double)n * sizeof(double);
+  bool seq = false;   // measured on B200 (C2, B = 64): 2x slower than the lockstep passes (launch-bound)
+  (void)path_ws;
+  if (const char* e = getenv("VAB_LBFGS_SEQ")) seq = atoi(e) != 0;
+  const int nchunk_seq = seq ? (int)(n / 512 < (long long)ctx->num_sms ? (n / 512 > 0 ? n / 512 : 1) : ctx->num_sms) : nchunk;
+  const dim3 sgrid(nchunk_seq, 1);
 
   lb_init_kernel<<<(B + 127) / 128, 128, 0, st>>>(w->st, w->act_eval, B);
   if (bounded) lb_clip_kernel<<<dim3((unsigned)((n + 255) / 256), B), 256, 0, st>>>(XP, ld, n, lo, hi);
@@ -791,22 +820,70 @@ int lb_minimize_core(vab_ctx* ctx, int B, double* XP, long long ld, double rf_sc
   }
   long long cycles = 0;
   const long long max_cycles = o.maxfun + o.maxiter + 64;
+  auto enqueue_cycle = [&]() -> int {
+    lb_trial_kernel<<<vgrid, NT, 0, st>>>(XT, XP, Dv, ld, n, w->st, nchunk);
+    int r = vab_eval(ctx, B, XT, ld, rf_scale, w->act_eval, w->ft, w->met, w->fet, GT, ld);
+    if (r != VAB_OK) return r;
+    if (bounded) lb_gd_kernel<true><<<vgrid, NT, 0, st>>>(XT, GT, Dv, ld, n, lo, hi, w->st, nchunk, w->part);
+    else lb_gd_kernel<false><<<vgrid, NT, 0, st>>>(XT, GT, Dv, ld, n, lo, hi, w->st, nchunk, w->part);
+    lb_linesearch_kernel<<<B, 32, 0, st>>>(w->st, w->act_eval, w->ft, w->met, w->fet, w->part, nchunk, o, bounded ? 1 : 0);
+    ctx->launches += 3;
+    const int npass = seq ? B : 1;
+    for (int pb = 0; pb < npass; ++pb) {
+      const dim3 ug = seq ? sgrid : vgrid;
+      const int nc = seq ? nchunk_seq : nchunk;
+      if (bounded) lb_update_kernel<true><<<ug, NT, 0, st>>>(XP, G, XT, GT, Dv, S, Y, ld, n, hstride, lo, hi, w->st, o.m, nc, w->part, pb);
+      else lb_update_kernel<false><<<ug, NT, 0, st>>>(XP, G, XT, GT, Dv, S, Y, ld, n, hstride, lo, hi, w->st, o.m, nc, w->part, pb);
+      lb_gram_kernel<<<seq ? 1 : B, 64, 0, st>>>(w->st, w->part, nc, o.m, pb);
+      if (bounded) lb_direction_kernel<true><<<ug, NT, 0, st>>>(XP, G, Dv, S, Y, ld, n, hstride, lo, hi, w->st, o.m, nc, w->part, pb);
+      else lb_direction_kernel<false><<<ug, NT, 0, st>>>(XP, G, Dv, S, Y, ld, n, hstride, lo, hi, w->st, o.m, nc, w->part, pb);
+      lb_start_kernel<<<seq ? 1 : B, 1, 0, st>>>(w->st, w->act_eval, w->part, nc, o, bounded ? 1 : 0, pb);
+      ctx->launches += 4;
+    }
+    return VAB_OK;
+  };
+  // The first cycle runs eagerly (it may allocate workspaces); the steady-state cycle is then
+  // captured once into a CUDA graph and replayed: launch-bound small problems (a cycle of ten
+  // tiny kernels) no longer pay the per-launch host cost.
+  rc = enqueue_cycle();
+  if (rc != VAB_OK) return rc;
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t gexec = nullptr;
+  bool use_graph = true;
+  if (const char* e = getenv("VAB_LBFGS_GRAPH")) use_graph = atoi(e) != 0;
+  long long launches_per_cycle = 0;
+  if (use_graph) {
+    const long long l0 = ctx->launches;
+    cudaError_t ce = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+    if (ce == cudaSuccess) {
+      rc = enqueue_cycle();
+      cudaError_t ce2 = cudaStreamEndCapture(st, &graph);
+      launches_per_cycle = ctx->launches - l0;
+      ctx->launches = l0;
+      if (rc != VAB_OK || ce2 != cudaSuccess || graph == nullptr ||
+          cudaGraphInstantiate(&gexec, graph, 0) != cudaSuccess) {
+        if (graph) cudaGraphDestroy(graph);
+        graph = nullptr; gexec = nullptr;
+        cudaGetLastError();
+        if (rc != VAB_OK) return rc;
+      }
+    } else {
+      cudaGetLastError();
+    }
+  }
+  int rc_loop = VAB_OK;
   while (true) {
     for (int c = 0; c < poll; ++c) {
-      lb_trial_kernel<<<vgrid, NT, 0, st>>>(XT, XP, Dv, ld, n, w->st, nchunk);
-      rc = vab_eval(ctx, B, XT, ld, rf_scale, w->act_eval, w->ft, w->met, w->fet, GT, ld);
-      if (rc != VAB_OK) return rc;
-      if (bounded) lb_gd_kernel<true><<<vgrid, NT, 0, st>>>(XT, GT, Dv, ld, n, lo, hi, w->st, nchunk, w->part);
-      else lb_gd_kernel<false><<<vgrid, NT, 0, st>>>(XT, GT, Dv, ld, n, lo, hi, w->st, nchunk, w->part);
-      lb_linesearch_kernel<<<B, 32, 0, st>>>(w->st, w->act_eval, w->ft, w->met, w->fet, w->part, nchunk, o, bounded ? 1 : 0);
-      if (bounded) lb_update_kernel<true><<<vgrid, NT, 0, st>>>(XP, G, XT, GT, Dv, S, Y, ld, n, hstride, lo, hi, w->st, o.m, nchunk, w->part);
-      else lb_update_kernel<false><<<vgrid, NT, 0, st>>>(XP, G, XT, GT, Dv, S, Y, ld, n, hstride, lo, hi, w->st, o.m, nchunk, w->part);
-      lb_gram_kernel<<<B, 64, 0, st>>>(w->st, w->part, nchunk, o.m);
-      if (bounded) lb_direction_kernel<true><<<vgrid, NT, 0, st>>>(XP, G, Dv, S, Y, ld, n, hstride, lo, hi, w->st, o.m, nchunk, w->part);
-      else lb_direction_kernel<false><<<vgrid, NT, 0, st>>>(XP, G, Dv, S, Y, ld, n, hstride, lo, hi, w->st, o.m, nchunk, w->part);
-      lb_start_kernel<<<B, 1, 0, st>>>(w->st, w->act_eval, w->part, nchunk, o, bounded ? 1 : 0);
-      ctx->launches += 7;
+      if (gexec) {
+        cudaError_t ge = cudaGraphLaunch(gexec, st);
+        if (ge != cudaSuccess) { rc_loop = vab_cuda_fail(ctx, ge, "cudaGraphLaunch"); break; }
+        ctx->launches += launches_per_cycle;
+      } else {
+        rc_loop = enqueue_cycle();
+        if (rc_loop != VAB_OK) break;
+      }
     }
+    if (rc_loop != VAB_OK) break;
     cycles += poll;
     lb_count_kernel<<<1, 256, 0, st>>>(w->st, B, w->n_running_dev);
     ctx->launches += 1;
@@ -815,9 +892,11 @@ int lb_minimize_core(vab_ctx* ctx, int B, double* XP, long long ld, double rf_sc
     LB_CUDA(cudaEventSynchronize(w->ev));
     LB_CUDA(cudaGetLastError());
     if (*w->n_running_host == 0) break;
-    if (cycles > max_cycles) return vab_fail(ctx, VAB_ERR_STATE, "minimize: cycle limit exceeded (internal error)");
+    if (cycles > max_cycles) { rc_loop = vab_fail(ctx, VAB_ERR_STATE, "minimize: cycle limit exceeded (internal error)"); break; }
   }
-  return VAB_OK;
+  if (gexec) cudaGraphExecDestroy(gexec);
+  if (graph) cudaGraphDestroy(graph);
+  return rc_loop;
 }
 
 }  // namespace
