@@ -128,6 +128,148 @@ __global__ void __launch_bounds__(NT) nn_fused_kernel(const __grid_constant__ Nn
       }
       for (int j = tid; j < jb; j += NT) bs[j] = param(P.boff[n] + j0 + j);
       __syncthreads();
+      if (jb >= 16 && dn >= 16 && TM >= 16) {
+      // The three contractions use 4x4 register blocks; the 4 rows / columns a thread owns are
+      // strided (not adjacent) so that the lanes of a warp walk consecutive shared-memory words.
+      const int MT = (TM + 3) >> 2, JT = (jb + 3) >> 2, KT = (dn + 3) >> 2;
+      // (1) forward, residual, Delta:  z[m][j] = b[j] + sum_k X[m][k] W[j][k]
+      for (int item = tid; item < MT * JT; item += NT) {
+        const int mt = item / JT, jt = item - mt * JT;
+        double acc[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) acc[a][c] = 0.0;
+        const double* xr[4];
+        const double* wr[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) xr[a] = Xs + min(mt + a * MT, TM - 1) * dp;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) wr[c] = Ws + min(jt + c * JT, jb - 1) * dnp;
+        for (int k = 0; k < dn; ++k) {
+          double xv[4], wv[4];
+#pragma unroll
+          for (int a = 0; a < 4; ++a) xv[a] = xr[a][k];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) wv[c] = wr[c][k];
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[a][c] = fma(xv[a], wv[c], acc[a][c]);
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          const int m = mt + a * MT;
+          if (m >= TM) continue;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int j = jt + c * JT;
+            if (j >= jb) continue;
+            const double z = acc[a][c] + bs[j];
+            double lam = 0.0, dl = 0.0;
+            if (m < rows) {
+              const double sv = act_f(P.act, z);
+              const double e = Xn[m * dp + j0 + j] - sv;
+              lam = P.cf2 * e;
+              fe_acc = fma(lam, e, fe_acc);
+              dl = -lam * act_d(P.act, sv);
+            }
+            double gx = lam;
+            if (lastl && m < rows) {
+              const int so = P.slot_out[j0 + j];
+              if (so >= 0) {
+                const double diff = Xn[m * dp + j0 + j] - P.data_out[(long long)(m0 + m) * P.n_Lout + so];
+                me_acc = fma(P.wm_out * diff, diff, me_acc);
+                gx += P.wm_out * diff;
+              }
+            }
+            GXn[m * dp + j0 + j] = gx;
+            Ds[m * dp + j] = dl;
+          }
+        }
+      }
+      __syncthreads();
+      // (2) GX_n[m][k] += sum_j Delta[m][j] W[j][k]
+      for (int item = tid; item < MT * KT; item += NT) {
+        const int mt = item / KT, kt = item - mt * KT;
+        double acc[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) acc[a][c] = 0.0;
+        const double* dr[4];
+        int kk[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) dr[a] = Ds + min(mt + a * MT, TM - 1) * dp;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) kk[c] = min(kt + c * KT, dn - 1);
+        for (int j = 0; j < jb; ++j) {
+          double dv[4], wv[4];
+          const double* wj = Ws + j * dnp;
+#pragma unroll
+          for (int a = 0; a < 4; ++a) dv[a] = dr[a][j];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) wv[c] = wj[kk[c]];
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[a][c] = fma(dv[a], wv[c], acc[a][c]);
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          const int m = mt + a * MT;
+          if (m >= TM) continue;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int k = kt + c * KT;
+            if (k < dn) GXc[m * dp + k] += acc[a][c];
+          }
+        }
+      }
+      // (3) per-tile weight gradient partial  GW[j][k] = sum_m Delta[m][j] X[m][k]
+      for (int item = tid; item < JT * KT; item += NT) {
+        const int jt = item / KT, kt = item - jt * KT;
+        double acc[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) acc[a][c] = 0.0;
+        int jj[4], kk[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) jj[a] = min(jt + a * JT, jb - 1);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) kk[c] = min(kt + c * KT, dn - 1);
+        for (int m = 0; m < TM; ++m) {
+          double dv[4], xv[4];
+          const double* dm = Ds + m * dp;
+          const double* xm = Xs + m * dp;
+#pragma unroll
+          for (int a = 0; a < 4; ++a) dv[a] = dm[jj[a]];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) xv[c] = xm[kk[c]];
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[a][c] = fma(dv[a], xv[c], acc[a][c]);
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          const int j = jt + a * JT;
+          if (j >= jb) continue;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int k = kt + c * KT;
+            if (k < dn) gw[P.woff[n] + (j0 + j) * dn + k] = acc[a][c];
+          }
+        }
+      }
+      for (int j = tid; j < jb; j += NT) {
+        double acc = 0.0;
+        for (int m = 0; m < TM; ++m) acc += Ds[m * dp + j];
+        gw[P.boff[n] + j0 + j] = acc;
+      }
+          } else {
+      // small layers: one output per thread (register blocks would idle most of the CTA)
       // (1) forward, residual, Delta
       for (int idx = tid; idx < TM * jb; idx += NT) {
         const int m = idx / jb, j = idx - m * jb;
@@ -176,6 +318,7 @@ __global__ void __launch_bounds__(NT) nn_fused_kernel(const __grid_constant__ Nn
         for (int m = 0; m < TM; ++m) acc += Ds[m * dp + j];
         gw[P.boff[n] + j0 + j] = acc;
       }
+          }
     }
     __syncthreads();
     // gradient rows of layer n are complete
