@@ -145,3 +145,31 @@ def test_large_linearity_property_full_size():
     fd = (Ap - Am) / (2 * h)
     gd = np.sum(G1 * d, axis=1)
     assert np.all(np.abs(fd - gd) <= 1e-6 * np.abs(gd))
+
+
+@pytest.mark.parametrize("disc", DISCS)
+def test_edge_shapes_minimal_and_unobserved(disc):
+    """Smallest legal problems: N_model = 3 (one Simpson pair), a single observed component, and
+    batch sizes that leave most lanes of the last warp idle."""
+    _check("lorenz96", 8, 3, 1, disc, [5], [8.17], [0], 1.0, 0.5, B=1, seed=4)
+    _check("lorenz96", 4, 5, 1, disc, [0, 1, 2, 3], [8.17], [], 1.0, 0.5, B=7, seed=5)
+    _check("lorenz96", 12, 7, 2, disc, [11], [8.17], [0], 3.0, 0.1, B=2, seed=6)
+
+
+@pytest.mark.parametrize("disc", ["trapezoid", "SimpsonHermite", "rk4"])
+def test_l96_window_mode_wide_rows_long_paths(disc):
+    """D = 1000 rows are cut into column windows with redundant halo lanes; long paths exercise
+    64-bit indexing (n = 4e6 unknowns per path)."""
+    rng = np.random.RandomState(9)
+    D, N, B = 1000, 4001, 2
+    Lidx = list(range(0, D, 3))
+    Y = rng.randn(N, len(Lidx))
+    X0 = rng.randn(B, N, D)
+    P0 = np.full((B, 1), 8.17)
+    an = _annealer("lorenz96", D, Y, 0.01 * np.arange(N), None, X0, P0, 2.0, 1e-2, Lidx, [0], disc, beta=2)
+    XP = np.concatenate([X0.reshape(B, -1), P0], axis=1)
+    A, G = an.A_gradA(XP)
+    prob = OdeProblem("lorenz96", D, Y, Lidx, 0.01, disc, [8.17], [0], 2.0)
+    Ar, gr = prob.action_grad(XP[1], 1e-2 * 1.5 ** 2)
+    assert abs(A[1] - Ar) <= TOL * abs(Ar)
+    assert np.max(np.abs(G[1] - gr)) <= TOL * np.max(np.abs(gr))

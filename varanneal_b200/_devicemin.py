@@ -81,6 +81,16 @@ class DeviceMin(object):
     def _action_grad_native(self, rf_scale):
         raise NotImplementedError
 
+    def _download_paths(self):
+        """Device paths -> NumPy view (B, n) of a pinned staging buffer (valid until the next call):
+        one contiguous DMA instead of a strided pageable copy."""
+        torch = _torch()
+        if getattr(self, "_XP_full_pin", None) is None or self._XP_full_pin.shape != self._XP.shape:
+            self._XP_full_pin = torch.empty(self._XP.shape, dtype=torch.float64, pin_memory=True)
+        self._XP_full_pin.copy_(self._XP, non_blocking=True)
+        torch.cuda.current_stream(self._device).synchronize()
+        return self._XP_full_pin.numpy()[:, :self._n]
+
     # ------------------------------------------------------------------ eval seam
     def _rf_scale(self):
         return float(self.alpha) ** float(self.beta)

@@ -316,7 +316,7 @@ class Annealer(DeviceMin):
             self._upload_paths(self._est_slice(src))
         t0 = time.time()
         self._minimize_device(self._rf_scale())
-        XPmin = self._XP[:, :self._n].cpu().numpy()
+        XPmin = self._download_paths()
         A = self._A.cpu().numpy()
         me = self._me.cpu().numpy()
         fe = self._fe.cpu().numpy()
@@ -330,15 +330,16 @@ class Annealer(DeviceMin):
         P = self.P.reshape(B, self.NP)
         if self.NPest > 0:
             P[:, self.Pidx] = XPmin[:, self._nX:]
-        full = np.concatenate([XPmin[:, :self._nX], P], axis=1)
         if self.batched:
             self.A_array[:, b], self.me_array[:, b], self.fe_array[:, b] = A, me, fe
             self.exitflags[:, b], self.nit_array[:, b], self.nfev_array[:, b] = st, nit, nfev
-            self.minpaths[:, b] = full
+            self.minpaths[:, b, :self._nX] = XPmin[:, :self._nX]
+            self.minpaths[:, b, self._nX:] = P
         else:
             self.A_array[b], self.me_array[b], self.fe_array[b] = A[0], me[0], fe[0]
             self.exitflags[b], self.nit_array[b], self.nfev_array[b] = st[0], nit[0], nfev[0]
-            self.minpaths[b] = full[0]
+            self.minpaths[b, :self._nX] = XPmin[0, :self._nX]
+            self.minpaths[b, self._nX:] = P[0]
         if b < self.Nbeta - 1:
             self.betaidx += 1
             self.beta = self.beta_array[self.betaidx]
