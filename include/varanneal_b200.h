@@ -156,7 +156,8 @@ typedef struct {
   double ftol;        /* stop when (f_k - f_{k+1})/max(|f_k|,|f_{k+1}|,1) <= ftol */
   double pgtol;       /* stop when max|proj g| <= pgtol */
   int32_t poll_every; /* evaluations enqueued between host polls of the done flag (>=1) */
-  int32_t reserved;
+  int32_t method;     /* 0 = L-BFGS-B (min_lbfgs_scipy), 1 = nonlinear CG, Polak-Ribiere+ (min_cg_scipy,
+                         _autodiffmin.py:97-119); ftol / m are ignored by CG */
 } vab_lbfgs_opts;
 
 /* Replaces ADmin.min_lbfgs_scipy (_autodiffmin.py:72-95) for whichever problem (ODE or NN) was

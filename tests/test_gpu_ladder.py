@@ -157,3 +157,38 @@ def test_bounds_are_respected_nakl():
     assert np.all(X >= b[:4, 0] - 1e-12) and np.all(X <= b[:4, 1] + 1e-12)
     assert np.all(P >= b[4:, 0] - 1e-12) and np.all(P <= b[4:, 1] + 1e-12)
     assert np.all(np.isfinite(an.A_array)) and np.all(an.exitflags <= 1)
+
+
+def test_ncg_method_reaches_scipy_cg_minimum():
+    """method='NCG' (min_cg_scipy, _autodiffmin.py:97-119): the device Polak-Ribiere+ CG and
+    SciPy's CG on the oracle action converge to the same minimum (1e-6 relative on A) on a fully
+    observed, well-conditioned problem; status 0."""
+    import scipy.optimize as opt
+    from varanneal_b200 import va_ode
+    rng = np.random.RandomState(12)
+    D, N = 8, 31
+    Lidx = list(range(D))
+    t = 0.01 * np.arange(N)
+    Y = 2.0 * rng.randn(N, D)
+    X0 = Y + 0.3 * rng.randn(N, D)
+    an = va_ode.Annealer()
+    an.set_model("lorenz96", D)
+    an.set_data(Y, t=t)
+    X0c = X0.copy()
+    an.anneal(X0c, np.array([8.0]), 2.0, [8, 10], 1.0, 1e-2, Lidx, [0], disc="trapezoid", method="NCG",
+              init_to_data=False, opt_args={"gtol": 1e-7, "maxiter": 100000})
+    prob = OdeProblem("lorenz96", D, Y, Lidx, 0.01, "trapezoid", [8.0], [0], 1.0)
+    xp = np.append(X0.ravel(), 8.0)
+    for i, beta in enumerate([8, 10]):
+        rf = 1e-2 * 2.0 ** beta
+        res = opt.minimize(lambda z: prob.action_grad(z, rf), xp, method="CG", jac=True,
+                           options={"gtol": 1e-7, "maxiter": 100000})
+        xp = res.x
+        assert abs(an.A_array[i] - res.fun) <= 1e-6 * abs(res.fun), (an.A_array[i], res.fun)
+        A, g = prob.action_grad(an.minpaths[i], rf)
+        assert np.max(np.abs(g)) <= 1e-7
+    assert np.all(an.exitflags == 0)
+    with pytest.raises(NotImplementedError):
+        va_ode.Annealer().anneal_init  # attribute exists
+        an2 = va_ode.Annealer(); an2.set_model("lorenz96", D); an2.set_data(Y, t=t)
+        an2.anneal_init(X0.copy(), np.array([8.0]), 2.0, [1], 1.0, 1e-2, Lidx, [0], method="TNC")

@@ -177,7 +177,7 @@ class DeviceMin(object):
         self.taped = True
 
     # ------------------------------------------------------------------ minimise seam
-    def _lbfgs_opts(self):
+    def _lbfgs_opts(self, method=0):
         o = dict(self.opt_args or {})
         known = {"gtol", "ftol", "maxfun", "maxiter", "maxcor", "maxls", "poll_every",
                  "disp", "iprint", "eps", "maxiter_per_beta"}
@@ -192,14 +192,18 @@ class DeviceMin(object):
         opts.ftol = float(o.get("ftol", 2.220446049250313e-09))
         opts.pgtol = float(o.get("gtol", 1e-5))
         opts.poll_every = int(o.get("poll_every", 0))
-        opts.reserved = 0
+        opts.method = int(method)
+        if method == 1 and "maxiter" not in o:
+            opts.maxiter = 200 * self._n                     # SciPy CG default
         return opts
 
-    def _minimize_device(self, rf_scale):
-        """Runs the device L-BFGS-B on the paths currently in self._XP (in place)."""
-        opts = self._lbfgs_opts()
-        lo = ptr(getattr(self, "_lo_dev", None))
-        hi = ptr(getattr(self, "_hi_dev", None))
+    def _minimize_device(self, rf_scale, method=None):
+        """Runs the device minimiser on the paths currently in self._XP (in place)."""
+        if method is None:
+            method = 1 if getattr(self, "method", "L-BFGS-B") == "NCG" else 0
+        opts = self._lbfgs_opts(method)
+        lo = ptr(getattr(self, "_lo_dev", None)) if method == 0 else None     # SciPy's CG ignores bounds
+        hi = ptr(getattr(self, "_hi_dev", None)) if method == 0 else None
         _lib.check(self._ctx.lib.vab_minimize(
             self._ctx.h, self._B, ptr(self._XP), self._ld, float(rf_scale), ct.byref(opts),
             lo, hi, ptr(self._A), ptr(self._me), ptr(self._fe), ptr(self._status),
@@ -225,10 +229,30 @@ class DeviceMin(object):
     min_lbfgs = min_lbfgs_scipy
 
     def min_cg_scipy(self, XP0, xtrace=None):
-        raise NotImplementedError("method='NCG' (SURVEY.md 8(f2)) is not built yet on the device")
+        """Same contract as ADmin.min_cg_scipy (_autodiffmin.py:97-119), on the device: nonlinear
+        conjugate gradients (Polak-Ribiere+, More'-Thuente search with SciPy's c1 = 1e-4,
+        c2 = 0.4, stop on max|g| <= gtol or maxiter).  Bounds are ignored, as by SciPy's CG."""
+        XP0 = np.asarray(XP0, dtype=np.float64)
+        single = XP0.ndim == 1
+        self._upload_paths(XP0)
+        lo, hi = getattr(self, "_lo_dev", None), getattr(self, "_hi_dev", None)
+        self._lo_dev = self._hi_dev = None
+        try:
+            self._minimize_device(self._rf_scale(), method=1)
+        finally:
+            self._lo_dev, self._hi_dev = lo, hi
+        XPmin = self._XP[:, :self._n].cpu().numpy()
+        A = self._A.cpu().numpy()
+        st = self._status.cpu().numpy()
+        self.last_nit = self._nit.cpu().numpy()
+        self.last_nfev = self._nfev.cpu().numpy()
+        if single:
+            return XPmin[0], float(A[0]), int(st[0])
+        return XPmin, A, st
 
     def min_tnc_scipy(self, XP0, xtrace=None):
-        raise NotImplementedError("method='TNC' (SURVEY.md 8(f2)) is not built yet on the device")
+        raise NotImplementedError("method='TNC' (truncated Newton, SURVEY.md 8(f2)) is not built on the "
+                                  "device; use 'L-BFGS-B' (bounds supported) or 'NCG'")
 
     @property
     def gpu_launches(self):

@@ -23,7 +23,7 @@ class OdeDesc(ct.Structure):
 class LbfgsOpts(ct.Structure):
     _fields_ = [("m", ct.c_int32), ("maxls", ct.c_int32), ("maxfun", ct.c_int64),
                 ("maxiter", ct.c_int64), ("ftol", ct.c_double), ("pgtol", ct.c_double),
-                ("poll_every", ct.c_int32), ("reserved", ct.c_int32)]
+                ("poll_every", ct.c_int32), ("method", ct.c_int32)]
 
 
 DISC_IDS = {"euler": 0, "trapezoid": 1, "SimpsonHermite": 2, "forwardmap": 3, "rk4": 4}

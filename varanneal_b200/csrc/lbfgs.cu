@@ -52,6 +52,7 @@ struct LbPath {
   int iter, nfev, col, head, pslot, ifun, iback, nskip, status;
   double f, fold, me, fe;
   double stp, gd, gdold, dnorm, stpmx, theta, sbgnrm, dr;
+  double ls_ftol, ls_gtol, ls_xtol, cd, fprev;   // line-search constants; CG: coefficient of the old direction, f two iterates back
   // dcsrch
   int brackt, stage;
   double ginit, gtest, gx, gy, finit, fx, fy, stx, sty, stmin, stmax, width, width1;
@@ -66,6 +67,8 @@ struct LbOpts {
   int m, maxls;
   long long maxfun, maxiter;
   double ftol, pgtol;
+  int method;            // 0 = L-BFGS-B, 1 = nonlinear CG (Polak-Ribiere+)
+  double ls_ftol, ls_gtol, ls_xtol;   // sufficient-decrease / curvature / bracket constants of the line search
 };
 
 }  // namespace
@@ -178,7 +181,7 @@ __device__ void dcsrch_start(LbPath& s, double f, double g, double stpmax) {
   s.stage = 1;
   s.finit = f;
   s.ginit = g;
-  s.gtest = 1e-3 * g;
+  s.gtest = s.ls_ftol * g;
   s.width = stpmax - 0.0;
   s.width1 = s.width / 0.5;
   s.stx = 0.0; s.fx = f; s.gx = g;
@@ -189,7 +192,7 @@ __device__ void dcsrch_start(LbPath& s, double f, double g, double stpmax) {
 
 // dcsrch with task = 'FG': returns 0 = evaluate again at the new s.stp, 1 = convergence / warning
 __device__ int dcsrch_step(LbPath& s, double f, double g, double stpmin, double stpmax) {
-  const double ftol = 1e-3, gtol = 0.9, xtol = 0.1;
+  const double ftol = s.ls_ftol, gtol = s.ls_gtol, xtol = s.ls_xtol;
   const double ftest = s.finit + s.stp * s.gtest;
   if (s.stage == 1 && f <= ftest && g >= 0.0) s.stage = 2;
   int stop = 0;
@@ -288,7 +291,7 @@ __device__ void block_reduce(const double* v, const int* op, double* out, double
 }
 
 // ---------------------------------------------------------------------------------------------
-__global__ void lb_init_kernel(LbPath* st, int* act_eval, int B) {
+__global__ void lb_init_kernel(LbPath* st, int* act_eval, int B, double ls_ftol, double ls_gtol, double ls_xtol) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   LbPath& s = st[b];
@@ -298,7 +301,7 @@ __global__ void lb_init_kernel(LbPath* st, int* act_eval, int B) {
   s.f = 0.0; s.fold = 0.0; s.me = 0.0; s.fe = 0.0;
   s.stp = 0.0; s.gd = 0.0; s.gdold = 0.0; s.dnorm = 0.0; s.stpmx = BIG; s.theta = 1.0;
   s.sbgnrm = 0.0; s.dr = 0.0;
-  s.cg = 1.0;
+  s.cg = 1.0; s.cd = 0.0; s.ls_ftol = ls_ftol; s.ls_gtol = ls_gtol; s.ls_xtol = ls_xtol; s.fprev = 0.0; s.gg = 0.0;
   for (int j = 0; j < MMAX; ++j) { s.cs[j] = 0.0; s.cy[j] = 0.0; s.gS[j] = 0.0; s.gY[j] = 0.0; }
   act_eval[b] = 1;
 }
@@ -408,11 +411,16 @@ __global__ void lb_linesearch_kernel(LbPath* st, int* act_eval, const double* ft
     if (s.iter >= o.maxiter) { s.done = 1; s.status = 1; }
     else if (s.nfev > o.maxfun) { s.done = 1; s.status = 1; }
     else if (sbg <= o.pgtol) { s.done = 1; s.status = 0; }
-    else {
+    else if (o.method == 0) {
       const double ddum = fmax(fabs(s.fold), fmax(fabs(f), 1.0));
       if ((s.fold - f) <= o.ftol * ddum) { s.done = 1; s.status = 0; }
     }
-    if (!s.done) {
+    s.fprev = s.fold;
+    if (!s.done && o.method == 1) {
+      s.do_update = 1;             // CG keeps no history; the update pass supplies g.y and g.g
+      s.pslot = 0;
+      s.dr = 1.0;
+    } else if (!s.done) {
       double dr, dd;
       if (s.stp == 1.0) { dr = gd - s.gdold; dd = -s.gdold; }
       else { dr = (gd - s.gdold) * s.stp; dd = -s.gdold * s.stp; }
@@ -514,7 +522,7 @@ __global__ void __launch_bounds__(NT, 1) lb_update_kernel(
 }
 
 // history bookkeeping + the two-loop recursion in coefficient space; one thread per path
-__global__ void lb_gram_kernel(LbPath* st, const double* part, int nchunk, int m, int b0) {
+__global__ void lb_gram_kernel(LbPath* st, const double* part, int nchunk, int m, int b0, int method) {
   const int b = b0 + blockIdx.x;
   LbPath& s = st[b];
   if (!(s.accepted || s.redo_dir) || s.done) return;
@@ -532,6 +540,16 @@ __global__ void lb_gram_kernel(LbPath* st, const double* part, int nchunk, int m
   for (int k = threadIdx.x; k < MMAX * MMAX; k += blockDim.x) { SYs[k] = s.SY[k]; YYs[k] = s.YY[k]; }
   __syncthreads();
   if (threadIdx.x != 0) return;
+  if (method == 1) {
+    // Polak-Ribiere+:  d = -g + max(0, g_new.(g_new - g_old) / g_old.g_old) d_old
+    double beta = 0.0;
+    if (s.accepted && s.do_update && s.gg > 0.0) beta = fmax(0.0, sum[5 * MMAX + 2] / s.gg);
+    if (s.accepted) s.gg = sum[5 * MMAX + 3];
+    s.cd = beta;
+    s.cg = 1.0;
+    for (int j = 0; j < MMAX; ++j) { s.cs[j] = 0.0; s.cy[j] = 0.0; }
+    return;
+  }
   double gS[MMAX], gY[MMAX];
   for (int j = 0; j < MMAX; ++j) { gS[j] = s.gS[j]; gY[j] = s.gY[j]; }
   int col = s.col, head = s.head;
@@ -607,7 +625,7 @@ __global__ void __launch_bounds__(NT) lb_direction_kernel(
   double cs[MMAX], cy[MMAX];
 #pragma unroll
   for (int j = 0; j < MMAX; ++j) { cs[j] = s.cs[j]; cy[j] = s.cy[j]; }
-  const double cg = s.cg;
+  const double cg = s.cg, cd = s.cd;
   double v[3] = {0.0, 0.0, BIG};
   for (long long i = r.i0 + threadIdx.x; i < r.i1; i += NT) {
     const double g = G[off + i];
@@ -626,6 +644,7 @@ __global__ void __launch_bounds__(NT) lb_direction_kernel(
       }
     }
     double d = fr ? 0.0 : -rr;
+    if (cd != 0.0 && !fr) d = fma(cd, Dv[off + i], d);
     if (BOUNDED) {
       // keep x + stp d feasible: largest step before a bound is hit (lnsrlb)
       if (d < 0.0 && l > -DBL_MAX) {
@@ -674,7 +693,12 @@ __global__ void lb_start_kernel(LbPath* st, int* act_eval, const double* part, i
   if (bounded && s.iter == 0) stpmx = fmin(stpmx, 1.0);
   if (!(stpmx > 0.0)) { s.done = 1; s.status = 2; act_eval[b] = 0; return; }
   s.stpmx = stpmx;
-  if (s.iter == 0 && !bounded) s.stp = fmin(1.0 / s.dnorm, stpmx);
+  if (o.method == 1) {
+    // SciPy's CG: alpha_1 = min(1, 1.01 * 2 (f_k - f_{k-1}) / g.d), with f_{-1} = f_0 + |g|/2
+    double a1 = (s.iter == 0) ? 1.01 / s.dnorm : 1.01 * 2.0 * (s.f - s.fprev) / gd;
+    if (!(a1 > 0.0)) a1 = 1.0;
+    s.stp = fmin(fmin(1.0, a1), stpmx);
+  } else if (s.iter == 0 && !bounded) s.stp = fmin(1.0 / s.dnorm, stpmx);
   else s.stp = fmin(1.0, stpmx);
   s.fold = s.f;
   s.ifun = 1;
@@ -781,6 +805,14 @@ int lb_minimize_core(vab_ctx* ctx, int B, double* XP, long long ld, double rf_sc
   o.maxiter = uo && uo->maxiter > 0 ? uo->maxiter : 15000;
   o.ftol = uo ? uo->ftol : 2.220446049250313e-09;
   o.pgtol = uo ? uo->pgtol : 1e-5;
+  o.method = uo ? uo->method : 0;
+  if (o.method != 0 && o.method != 1) return vab_fail(ctx, VAB_ERR_INVALID, "minimize: method must be 0 (L-BFGS-B) or 1 (CG)");
+  o.ls_ftol = 1e-3; o.ls_gtol = 0.9; o.ls_xtol = 0.1;         // L-BFGS-B's lnsrlb
+  if (o.method == 1) {
+    o.m = 1;
+    o.ls_ftol = 1e-4; o.ls_gtol = 0.4; o.ls_xtol = 1e-14;      // scipy.optimize fmin_cg (c1, c2)
+    if (!(uo && uo->maxls > 0)) o.maxls = 100;
+  }
   int poll = uo && uo->poll_every > 0 ? uo->poll_every : 0;
   int rc = lb_reserve(ctx, B, ld, o.m);
   if (rc != VAB_OK) return rc;
@@ -807,7 +839,7 @@ int lb_minimize_core(vab_ctx* ctx, int B, double* XP, long long ld, double rf_sc
   const int nchunk_seq = seq ? (int)(n / 512 < (long long)ctx->num_sms ? (n / 512 > 0 ? n / 512 : 1) : ctx->num_sms) : nchunk;
   const dim3 sgrid(nchunk_seq, 1);
 
-  lb_init_kernel<<<(B + 127) / 128, 128, 0, st>>>(w->st, w->act_eval, B);
+  lb_init_kernel<<<(B + 127) / 128, 128, 0, st>>>(w->st, w->act_eval, B, o.ls_ftol, o.ls_gtol, o.ls_xtol);
   if (bounded) lb_clip_kernel<<<dim3((unsigned)((n + 255) / 256), B), 256, 0, st>>>(XP, ld, n, lo, hi);
   LB_CUDA(cudaMemcpyAsync(XT, XP, vs * sizeof(double), cudaMemcpyDeviceToDevice, st));
   LB_CUDA(cudaMemsetAsync(Dv, 0, vs * sizeof(double), st));
@@ -834,7 +866,7 @@ int lb_minimize_core(vab_ctx* ctx, int B, double* XP, long long ld, double rf_sc
       const int nc = seq ? nchunk_seq : nchunk;
       if (bounded) lb_update_kernel<true><<<ug, NT, 0, st>>>(XP, G, XT, GT, Dv, S, Y, ld, n, hstride, lo, hi, w->st, o.m, nc, w->part, pb);
       else lb_update_kernel<false><<<ug, NT, 0, st>>>(XP, G, XT, GT, Dv, S, Y, ld, n, hstride, lo, hi, w->st, o.m, nc, w->part, pb);
-      lb_gram_kernel<<<seq ? 1 : B, 64, 0, st>>>(w->st, w->part, nc, o.m, pb);
+      lb_gram_kernel<<<seq ? 1 : B, 64, 0, st>>>(w->st, w->part, nc, o.m, pb, o.method);
       if (bounded) lb_direction_kernel<true><<<ug, NT, 0, st>>>(XP, G, Dv, S, Y, ld, n, hstride, lo, hi, w->st, o.m, nc, w->part, pb);
       else lb_direction_kernel<false><<<ug, NT, 0, st>>>(XP, G, Dv, S, Y, ld, n, hstride, lo, hi, w->st, o.m, nc, w->part, pb);
       lb_start_kernel<<<seq ? 1 : B, 1, 0, st>>>(w->st, w->act_eval, w->part, nc, o, bounded ? 1 : 0, pb);

@@ -111,8 +111,9 @@ class Annealer(DeviceMin):
             raise ValueError("method='LM' is dead code in the reference (SURVEY.md App. B10)")
         if method not in ('L-BFGS-B', 'NCG', 'TNC'):
             raise ValueError("Optimization routine not recognized: %r" % (method,))
-        if method != 'L-BFGS-B':
-            raise NotImplementedError("method=%r is not built on the device yet (SURVEY.md 8(f2))" % (method,))
+        if method not in ('L-BFGS-B', 'NCG'):
+            raise NotImplementedError("method=%r is not built on the device (SURVEY.md 8(f2)); "
+                                      "use 'L-BFGS-B' or 'NCG'" % (method,))
         if action != 'A_gaussian' or disc != 'forwardmap':
             raise ValueError("va_nnet supports action='A_gaussian', disc='forwardmap' (va_nnet.py:260-264)")
         if self.structure is None or self.M == 0:

@@ -110,9 +110,9 @@ class Annealer(DeviceMin):
             raise ValueError("method='LM' is dead code in the reference (SURVEY.md App. B10)")
         if method not in ('L-BFGS-B', 'NCG', 'TNC'):
             raise ValueError("Optimization routine not recognized: %r" % (method,))
-        if method != 'L-BFGS-B':
-            raise NotImplementedError("method=%r: only 'L-BFGS-B' runs on the device so far "
-                                      "(SURVEY.md 8(f2))" % (method,))
+        if method not in ('L-BFGS-B', 'NCG'):
+            raise NotImplementedError("method=%r is not built on the device (SURVEY.md 8(f2)); "
+                                      "use 'L-BFGS-B' or 'NCG'" % (method,))
         self.method = method
         if action != 'A_gaussian':
             raise ValueError("only action='A_gaussian' exists (va_ode.py:130-136)")
