@@ -192,3 +192,52 @@ def test_ncg_method_reaches_scipy_cg_minimum():
         va_ode.Annealer().anneal_init  # attribute exists
         an2 = va_ode.Annealer(); an2.set_model("lorenz96", D); an2.set_data(Y, t=t)
         an2.anneal_init(X0.copy(), np.array([8.0]), 2.0, [1], 1.0, 1e-2, Lidx, [0], method="TNC")
+
+
+def test_vab_anneal_device_resident_ladder_equals_stepwise():
+    """C ABI vab_anneal (the whole beta loop on the device, one host sync at the end) gives
+    bit-identical tables / paths to the stepwise host loop over vab_minimize."""
+    import ctypes as ct
+    import torch
+    from varanneal_b200 import _lib, va_ode
+    from varanneal_b200._devicemin import ptr
+    rng = np.random.RandomState(21)
+    D, N, B = 20, 41, 3
+    Lidx = [0, 3, 6, 9, 12, 15, 18]
+    Y = rng.randn(N, len(Lidx))
+    t = 0.025 * np.arange(N)
+    X0 = rng.randn(B, N, D)
+    P0 = 8.0 + 0.1 * rng.randn(B, 1)
+    betas = np.array([10.0, 14.0, 18.0])
+    opts = {"gtol": 1e-9, "ftol": 1e-13, "maxiter": 400}
+
+    def fresh():
+        an = va_ode.Annealer()
+        an.set_model("lorenz96", D)
+        an.set_data(Y, t=t)
+        an.anneal_init(X0.copy(), P0.copy(), 1.5, betas, 4.0, 4e-6, Lidx, [0], disc="SimpsonHermite",
+                       init_to_data=False, opt_args=opts)
+        return an
+
+    ref = fresh()
+    for _ in betas:
+        ref.anneal_step()
+    an = fresh()
+    an._upload_paths(an._est_slice(an.minpaths[:, 0]))
+    o = an._lbfgs_opts(0)
+    nb = len(betas)
+    table = torch.zeros(B, nb, 5, dtype=torch.float64, device="cuda")
+    paths = torch.zeros(B, nb, an._ld, dtype=torch.float64, device="cuda")
+    stat = torch.zeros(B, nb, dtype=torch.int32, device="cuda")
+    nit = torch.zeros_like(stat)
+    nfev = torch.zeros_like(stat)
+    beta_c = (ct.c_double * nb)(*betas)
+    _lib.check(an._ctx.lib.vab_anneal(an._ctx.h, B, ptr(an._XP), an._ld, 1.5, beta_c, nb, ct.byref(o), None, None,
+                                      ptr(table), ptr(paths), ptr(stat), ptr(nit), ptr(nfev)), an._ctx.h)
+    tab = table.cpu().numpy()
+    assert np.array_equal(tab[:, :, 1], ref.A_array)
+    assert np.array_equal(tab[:, :, 2], ref.me_array) and np.array_equal(tab[:, :, 3], ref.fe_array)
+    assert np.array_equal(tab[:, :, 0], np.tile(betas, (B, 1)))
+    assert np.allclose(tab[:, :, 4], tab[:, :, 3] / 1.5 ** betas)
+    assert np.array_equal(paths.cpu().numpy()[:, :, :an._n], ref._est_slice(ref.minpaths.reshape(B * nb, -1)).reshape(B, nb, -1))
+    assert np.array_equal(nit.cpu().numpy(), ref.nit_array) and np.array_equal(stat.cpu().numpy(), ref.exitflags)
