@@ -26,12 +26,11 @@
 namespace {
 
 constexpr int NT = 256;
-constexpr int WCAP = 8192;         // doubles of W staged per chunk of output neurons
 
 struct NnParams {
   const double* XP; long long ldxp;
   double* G; long long ldg;
-  int B, M, NL, NDnet, NP, NPest, act, TM, ntiles, dpitch;
+  int B, M, NL, NDnet, NP, NPest, act, TM, ntiles, dpitch, wcap;
   long long NDens;
   const int* structure;   // (NL)
   const int* xoff;        // (NL+1) offsets of the layers inside an example
@@ -39,6 +38,7 @@ struct NnParams {
   const int* boff;        // (NL-1)
   const int* pmap;        // (NP) -> estimated index or -1
   const double* pfix; long long pfix_stride;
+  double* pfull;          // (B, NP) dense parameter vectors gathered before the fused kernel
   const int* slot_in;     // (d_0) column of data_in or -1
   const int* slot_out;    // (d_last)
   int n_Lin, n_Lout;
@@ -62,39 +62,65 @@ __device__ __forceinline__ double act_d(int act, double s) {   // derivative thr
   return 1.0;
 }
 
+// dense parameter vector of every path: estimated entries from XP, the others from pfix
+// (va_nnet.py:180-190); one coalesced pass so that the fused kernel stages weights with plain
+// independent loads instead of two dependent ones per element
+__global__ void nn_gather_params_kernel(const __grid_constant__ NnParams P) {
+  const int b = blockIdx.y;
+  if (P.active != nullptr && P.active[b] == 0) return;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= P.NP) return;
+  const int e = P.pmap[k];
+  P.pfull[(long long)b * P.NP + k] =
+      e >= 0 ? P.XP[(long long)b * P.ldxp + P.NDens + e] : P.pfix[(long long)b * P.pfix_stride + k];
+}
+
+// D(8x8) += A(8x4, row) * B(4x8, col) in fp64 on the tensor pipe (DMMA).  Fragment layout
+// (lane l): a = A[l/4][l%4], b = B[l%4][l/4], c0/c1 = C[l/4][2(l%4)], C[l/4][2(l%4)+1].
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double bb) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(bb));
+}
+
+constexpr int NTILE = 7;    // 8x8 output tiles a warp accumulates at once (A fragment reused)
+
+// One CTA = one tile of TM examples (multiple of 8) of one path, all layers.  Shared-memory
+// tiles have pitches = 4 (mod 8) doubles so that the 8x4 / 4x8 fragment loads are bank-conflict
+// free, and are zero-padded to multiples of 8 so that the MMAs need no edge handling.
 __global__ void __launch_bounds__(NT) nn_fused_kernel(const __grid_constant__ NnParams P) {
   extern __shared__ double sm[];
   const int b = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
   if (P.active != nullptr && P.active[b] == 0) return;
-  const int TM = P.TM, dp = P.dpitch;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int lr = lane >> 2, lc = lane & 3;            // fragment coordinates
+  const int TM = P.TM, dp = P.dpitch, wcap = P.wcap;
   double* Xs = sm;                       // [TM][dp] states of layer n
   double* Xn = Xs + TM * dp;             // layer n+1
   double* GXc = Xn + TM * dp;            // gradient rows of layer n
   double* GXn = GXc + TM * dp;           // gradient rows of layer n+1
   double* Ds = GXn + TM * dp;            // Delta chunk [TM][dp]
-  double* Ws = Ds + TM * dp;             // [JB][dnp]
-  double* bs = Ws + WCAP + 64;           // [JB]
+  double* Ws = Ds + TM * dp;             // [JBP][dnp]
+  double* bs = Ws + wcap;                // [JBP]
   __shared__ double red[2][NT / 32];
 
   const int m0 = tile * TM;
   const int rows = min(TM, P.M - m0);
   const double* xp = P.XP + (long long)b * P.ldxp;
   double* gp = P.G ? P.G + (long long)b * P.ldg : nullptr;
-  const double* pfix = P.pfix + (long long)b * P.pfix_stride;
+  const double* pfull = P.pfull + (long long)b * P.NP;
   double* gw = P.gwpart + ((long long)b * P.ntiles + tile) * P.NP;
-  auto param = [&](int k) -> double {
-    const int e = P.pmap[k];
-    return e >= 0 ? xp[P.NDens + e] : pfix[k];
-  };
+  auto param = [&](int k) -> double { return __ldg(pfull + k); };
   double me_acc = 0.0, fe_acc = 0.0;
+  const int MTL = TM >> 3;                            // 8-row tiles of examples
 
-  // layer 0 states + measurement term of the input layer
+  // layer 0 states (zero-padded) + measurement term of the input layer
   {
-    const int d0 = P.structure[0];
-    for (int idx = tid; idx < TM * d0; idx += NT) {
-      const int m = idx / d0, i = idx - m * d0;
+    const int d0 = P.structure[0], d0P = (d0 + 7) & ~7;
+    for (int idx = tid; idx < TM * d0P; idx += NT) {
+      const int m = idx / d0P, i = idx - m * d0P;
       double x = 0.0, gx = 0.0;
-      if (m < rows) {
+      if (m < rows && i < d0) {
         x = xp[(long long)(m0 + m) * P.NDnet + i];
         const int s = P.slot_in[i];
         if (s >= 0) {
@@ -109,216 +135,140 @@ __global__ void __launch_bounds__(NT) nn_fused_kernel(const __grid_constant__ Nn
   }
   for (int n = 0; n < P.NL - 1; ++n) {
     const int dn = P.structure[n], dn1 = P.structure[n + 1];
-    const int dnp = dn | 1;                               // odd pitch: conflict-free column walks
+    const int dnP = (dn + 7) & ~7, dn1P = (dn1 + 7) & ~7;
+    const int dnp = dnP + 4;                              // pitch of the staged weight rows
     const int xo1 = P.xoff[n + 1];
     const bool lastl = (n + 1 == P.NL - 1);
     __syncthreads();
-    for (int idx = tid; idx < TM * dn1; idx += NT) {
-      const int m = idx / dn1, j = idx - m * dn1;
-      Xn[m * dp + j] = (m < rows) ? xp[(long long)(m0 + m) * P.NDnet + xo1 + j] : 0.0;
+    for (int idx = tid; idx < TM * dn1P; idx += NT) {
+      const int m = idx / dn1P, j = idx - m * dn1P;
+      Xn[m * dp + j] = (m < rows && j < dn1) ? xp[(long long)(m0 + m) * P.NDnet + xo1 + j] : 0.0;
     }
-    int JB = WCAP / dnp;
-    if (JB > dn1) JB = dn1;
+    int JB = (wcap / dnp) & ~7;
+    if (JB > dn1P) JB = dn1P;
     for (int j0 = 0; j0 < dn1; j0 += JB) {
-      const int jb = min(JB, dn1 - j0);
+      const int jb = min(JB, dn1 - j0);                   // real rows of W in this chunk
+      const int jbP = (jb + 7) & ~7;
       __syncthreads();
-      for (int idx = tid; idx < jb * dn; idx += NT) {
-        const int j = idx / dn, k = idx - j * dn;
-        Ws[j * dnp + k] = param(P.woff[n] + (j0 + j) * dn + k);
+      for (int idx = tid; idx < jbP * dnP; idx += NT) {
+        const int j = idx / dnP, k = idx - j * dnP;
+        Ws[j * dnp + k] = (j < jb && k < dn) ? param(P.woff[n] + (j0 + j) * dn + k) : 0.0;
       }
-      for (int j = tid; j < jb; j += NT) bs[j] = param(P.boff[n] + j0 + j);
+      for (int j = tid; j < jbP; j += NT) bs[j] = (j < jb) ? param(P.boff[n] + j0 + j) : 0.0;
       __syncthreads();
-      if (jb >= 16 && dn >= 16 && TM >= 16) {
-      // The three contractions use 4x4 register blocks; the 4 rows / columns a thread owns are
-      // strided (not adjacent) so that the lanes of a warp walk consecutive shared-memory words.
-      const int MT = (TM + 3) >> 2, JT = (jb + 3) >> 2, KT = (dn + 3) >> 2;
-      // (1) forward, residual, Delta:  z[m][j] = b[j] + sum_k X[m][k] W[j][k]
-      for (int item = tid; item < MT * JT; item += NT) {
-        const int mt = item / JT, jt = item - mt * JT;
-        double acc[4][4];
+      // ---- (1) Z = X W^T: warp tasks = (8-row tile of examples) x (group of NTILE column tiles)
+      {
+        const int NTL = jbP >> 3, NG = (NTL + NTILE - 1) / NTILE;
+        for (int task = warp; task < MTL * NG; task += NT / 32) {
+          const int mt = task / NG, g = task - mt * NG;
+          const int nt0 = g * NTILE, ntn = min(NTILE, NTL - nt0);
+          double c0[NTILE], c1[NTILE];
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
+          for (int t = 0; t < NTILE; ++t) { c0[t] = 0.0; c1[t] = 0.0; }
+          const double* arow = Xs + (mt * 8 + lr) * dp + lc;
+          const double* brow = Ws + (nt0 * 8 + lr) * dnp + lc;
+          for (int k = 0; k < dnP; k += 4) {
+            const double a = arow[k];
 #pragma unroll
-          for (int c = 0; c < 4; ++c) acc[a][c] = 0.0;
-        const double* xr[4];
-        const double* wr[4];
+            for (int t = 0; t < NTILE; ++t)
+              if (t < ntn) dmma(c0[t], c1[t], a, brow[t * 8 * dnp + k]);
+          }
+          // epilogue on the accumulator fragments: residual, lambda, Delta
+          const int m = mt * 8 + lr;
 #pragma unroll
-        for (int a = 0; a < 4; ++a) xr[a] = Xs + min(mt + a * MT, TM - 1) * dp;
+          for (int t = 0; t < NTILE; ++t) {
+            if (t >= ntn) continue;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) wr[c] = Ws + min(jt + c * JT, jb - 1) * dnp;
-        for (int k = 0; k < dn; ++k) {
-          double xv[4], wv[4];
-#pragma unroll
-          for (int a = 0; a < 4; ++a) xv[a] = xr[a][k];
-#pragma unroll
-          for (int c = 0; c < 4; ++c) wv[c] = wr[c][k];
-#pragma unroll
-          for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int c = 0; c < 4; ++c) acc[a][c] = fma(xv[a], wv[c], acc[a][c]);
-        }
-#pragma unroll
-        for (int a = 0; a < 4; ++a) {
-          const int m = mt + a * MT;
-          if (m >= TM) continue;
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const int j = jt + c * JT;
-            if (j >= jb) continue;
-            const double z = acc[a][c] + bs[j];
-            double lam = 0.0, dl = 0.0;
-            if (m < rows) {
-              const double sv = act_f(P.act, z);
-              const double e = Xn[m * dp + j0 + j] - sv;
-              lam = P.cf2 * e;
-              fe_acc = fma(lam, e, fe_acc);
-              dl = -lam * act_d(P.act, sv);
-            }
-            double gx = lam;
-            if (lastl && m < rows) {
-              const int so = P.slot_out[j0 + j];
-              if (so >= 0) {
-                const double diff = Xn[m * dp + j0 + j] - P.data_out[(long long)(m0 + m) * P.n_Lout + so];
-                me_acc = fma(P.wm_out * diff, diff, me_acc);
-                gx += P.wm_out * diff;
+            for (int h = 0; h < 2; ++h) {
+              const int j = (nt0 + t) * 8 + 2 * lc + h;
+              const double z = (h ? c1[t] : c0[t]) + bs[j];
+              double lam = 0.0, dl = 0.0, gx = 0.0;
+              if (m < rows && j < jb) {
+                const double sv = act_f(P.act, z);
+                const double xn1 = Xn[m * dp + j0 + j];
+                const double e = xn1 - sv;
+                lam = P.cf2 * e;
+                fe_acc = fma(lam, e, fe_acc);
+                dl = -lam * act_d(P.act, sv);
+                gx = lam;
+                if (lastl) {
+                  const int so = P.slot_out[j0 + j];
+                  if (so >= 0) {
+                    const double diff = xn1 - P.data_out[(long long)(m0 + m) * P.n_Lout + so];
+                    me_acc = fma(P.wm_out * diff, diff, me_acc);
+                    gx += P.wm_out * diff;
+                  }
+                }
               }
+              if (j < jb) GXn[m * dp + j0 + j] = gx;
+              Ds[m * dp + j] = dl;                         // zero in the padding
             }
-            GXn[m * dp + j0 + j] = gx;
-            Ds[m * dp + j] = dl;
           }
         }
       }
       __syncthreads();
-      // (2) GX_n[m][k] += sum_j Delta[m][j] W[j][k]
-      for (int item = tid; item < MT * KT; item += NT) {
-        const int mt = item / KT, kt = item - mt * KT;
-        double acc[4][4];
+      // ---- (2) GX_n += Delta W: (8-row tile of examples) x (column tiles over d_n)
+      {
+        const int NTL = dnP >> 3, NG = (NTL + NTILE - 1) / NTILE;
+        for (int task = warp; task < MTL * NG; task += NT / 32) {
+          const int mt = task / NG, g = task - mt * NG;
+          const int nt0 = g * NTILE, ntn = min(NTILE, NTL - nt0);
+          double c0[NTILE], c1[NTILE];
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
+          for (int t = 0; t < NTILE; ++t) { c0[t] = 0.0; c1[t] = 0.0; }
+          const double* arow = Ds + (mt * 8 + lr) * dp + lc;          // A[m][j]
+          const double* brow = Ws + lc * dnp + nt0 * 8 + lr;          // B[j][k] = W[j][k]
+          for (int j = 0; j < jbP; j += 4) {
+            const double a = arow[j];
 #pragma unroll
-          for (int c = 0; c < 4; ++c) acc[a][c] = 0.0;
-        const double* dr[4];
-        int kk[4];
+            for (int t = 0; t < NTILE; ++t)
+              if (t < ntn) dmma(c0[t], c1[t], a, brow[j * dnp + t * 8]);
+          }
+          const int m = mt * 8 + lr;
 #pragma unroll
-        for (int a = 0; a < 4; ++a) dr[a] = Ds + min(mt + a * MT, TM - 1) * dp;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) kk[c] = min(kt + c * KT, dn - 1);
-        for (int j = 0; j < jb; ++j) {
-          double dv[4], wv[4];
-          const double* wj = Ws + j * dnp;
-#pragma unroll
-          for (int a = 0; a < 4; ++a) dv[a] = dr[a][j];
-#pragma unroll
-          for (int c = 0; c < 4; ++c) wv[c] = wj[kk[c]];
-#pragma unroll
-          for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int c = 0; c < 4; ++c) acc[a][c] = fma(dv[a], wv[c], acc[a][c]);
-        }
-#pragma unroll
-        for (int a = 0; a < 4; ++a) {
-          const int m = mt + a * MT;
-          if (m >= TM) continue;
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const int k = kt + c * KT;
-            if (k < dn) GXc[m * dp + k] += acc[a][c];
+          for (int t = 0; t < NTILE; ++t) {
+            if (t >= ntn) continue;
+            const int k = (nt0 + t) * 8 + 2 * lc;
+            GXc[m * dp + k] += c0[t];
+            GXc[m * dp + k + 1] += c1[t];
           }
         }
       }
-      // (3) per-tile weight gradient partial  GW[j][k] = sum_m Delta[m][j] X[m][k]
-      for (int item = tid; item < JT * KT; item += NT) {
-        const int jt = item / KT, kt = item - jt * KT;
-        double acc[4][4];
+      // ---- (3) per-tile partial of GW = Delta^T X: (8-row tile over j) x (column tiles over d_n)
+      {
+        const int JTL = jbP >> 3, NTL = dnP >> 3, NG = (NTL + NTILE - 1) / NTILE;
+        for (int task = warp; task < JTL * NG; task += NT / 32) {
+          const int jt = task / NG, g = task - jt * NG;
+          const int nt0 = g * NTILE, ntn = min(NTILE, NTL - nt0);
+          double c0[NTILE], c1[NTILE];
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
+          for (int t = 0; t < NTILE; ++t) { c0[t] = 0.0; c1[t] = 0.0; }
+          const double* arow = Ds + lc * dp + jt * 8 + lr;            // A[j][m] = Delta[m][j]
+          const double* brow = Xs + lc * dp + nt0 * 8 + lr;           // B[m][k] = X[m][k]
+          for (int m = 0; m < TM; m += 4) {
+            const double a = arow[m * dp];
 #pragma unroll
-          for (int c = 0; c < 4; ++c) acc[a][c] = 0.0;
-        int jj[4], kk[4];
+            for (int t = 0; t < NTILE; ++t)
+              if (t < ntn) dmma(c0[t], c1[t], a, brow[m * dp + t * 8]);
+          }
+          const int j = jt * 8 + lr;
+          if (j < jb) {
+            double* grow = gw + P.woff[n] + (long long)(j0 + j) * dn;
 #pragma unroll
-        for (int a = 0; a < 4; ++a) jj[a] = min(jt + a * JT, jb - 1);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) kk[c] = min(kt + c * KT, dn - 1);
-        for (int m = 0; m < TM; ++m) {
-          double dv[4], xv[4];
-          const double* dm = Ds + m * dp;
-          const double* xm = Xs + m * dp;
-#pragma unroll
-          for (int a = 0; a < 4; ++a) dv[a] = dm[jj[a]];
-#pragma unroll
-          for (int c = 0; c < 4; ++c) xv[c] = xm[kk[c]];
-#pragma unroll
-          for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int c = 0; c < 4; ++c) acc[a][c] = fma(dv[a], xv[c], acc[a][c]);
-        }
-#pragma unroll
-        for (int a = 0; a < 4; ++a) {
-          const int j = jt + a * JT;
-          if (j >= jb) continue;
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const int k = kt + c * KT;
-            if (k < dn) gw[P.woff[n] + (j0 + j) * dn + k] = acc[a][c];
+            for (int t = 0; t < NTILE; ++t) {
+              if (t >= ntn) continue;
+              const int k = (nt0 + t) * 8 + 2 * lc;
+              if (k < dn) grow[k] = c0[t];
+              if (k + 1 < dn) grow[k + 1] = c1[t];
+            }
           }
         }
-      }
-      for (int j = tid; j < jb; j += NT) {
-        double acc = 0.0;
-        for (int m = 0; m < TM; ++m) acc += Ds[m * dp + j];
-        gw[P.boff[n] + j0 + j] = acc;
-      }
-          } else {
-      // small layers: one output per thread (register blocks would idle most of the CTA)
-      // (1) forward, residual, Delta
-      for (int idx = tid; idx < TM * jb; idx += NT) {
-        const int m = idx / jb, j = idx - m * jb;
-        double z = bs[j];
-        const double* xr = Xs + m * dp;
-        const double* wr = Ws + j * dnp;
-        for (int k = 0; k < dn; ++k) z = fma(xr[k], wr[k], z);
-        double lam = 0.0, dl = 0.0;
-        if (m < rows) {
-          const double s = act_f(P.act, z);
-          const double e = Xn[m * dp + j0 + j] - s;
-          lam = P.cf2 * e;
-          fe_acc = fma(lam, e, fe_acc);
-          dl = -lam * act_d(P.act, s);
+        for (int j = tid; j < jb; j += NT) {
+          double acc = 0.0;
+          for (int m = 0; m < TM; ++m) acc += Ds[m * dp + j];
+          gw[P.boff[n] + j0 + j] = acc;
         }
-        double gx = lam;
-        if (lastl && m < rows) {
-          const int so = P.slot_out[j0 + j];
-          if (so >= 0) {
-            const double diff = Xn[m * dp + j0 + j] - P.data_out[(long long)(m0 + m) * P.n_Lout + so];
-            me_acc = fma(P.wm_out * diff, diff, me_acc);
-            gx += P.wm_out * diff;
-          }
-        }
-        GXn[m * dp + j0 + j] = gx;
-        Ds[m * dp + j] = dl;
       }
-      __syncthreads();
-      // (2) GX_n += Delta W
-      for (int idx = tid; idx < TM * dn; idx += NT) {
-        const int m = idx / dn, k = idx - m * dn;
-        double acc = 0.0;
-        const double* dr = Ds + m * dp;
-        for (int j = 0; j < jb; ++j) acc = fma(dr[j], Ws[j * dnp + k], acc);
-        GXc[m * dp + k] += acc;
-      }
-      // (3) per-tile weight / bias gradient partials
-      for (int idx = tid; idx < jb * dn; idx += NT) {
-        const int j = idx / dn, k = idx - j * dn;
-        double acc = 0.0;
-        for (int m = 0; m < TM; ++m) acc = fma(Ds[m * dp + j], Xs[m * dp + k], acc);
-        gw[P.woff[n] + (j0 + j) * dn + k] = acc;
-      }
-      for (int j = tid; j < jb; j += NT) {
-        double acc = 0.0;
-        for (int m = 0; m < TM; ++m) acc += Ds[m * dp + j];
-        gw[P.boff[n] + j0 + j] = acc;
-      }
-          }
     }
     __syncthreads();
     // gradient rows of layer n are complete
@@ -332,6 +282,7 @@ __global__ void __launch_bounds__(NT) nn_fused_kernel(const __grid_constant__ Nn
     __syncthreads();
     double* t = Xs; Xs = Xn; Xn = t;
     t = GXc; GXc = GXn; GXn = t;
+    // the new GXn will be accumulated into (as GXc) two layers on: clear its padding columns
   }
   if (gp) {
     const int dl = P.structure[P.NL - 1], xo = P.xoff[P.NL - 1];
@@ -398,6 +349,8 @@ struct NnProblem {
   double* pfix_zero = nullptr;
   double* gwpart = nullptr;
   size_t gwpart_cap = 0;
+  double* pfull = nullptr;
+  size_t pfull_cap = 0;
 };
 
 void nn_destroy(vab_ctx* ctx) {
@@ -406,6 +359,7 @@ void nn_destroy(vab_ctx* ctx) {
   cudaFree(p->ints);
   cudaFree(p->pfix_zero);
   cudaFree(p->gwpart);
+  cudaFree(p->pfull);
   delete p;
   ctx->nn = nullptr;
 }
@@ -433,25 +387,46 @@ int nn_eval(vab_ctx* ctx, int B, const double* XP, long long ldxp, double rf_sca
   P.wm_out = 2.0 * cm * p->rm_out;
   P.cf2 = 2.0 * p->rf0 * rf_scale / ((double)(p->NDnet - p->d0) * p->M);
   P.active = active_dev;
-  // tile height from the shared-memory budget: 5 [TM][dpitch] tiles + the staged weights
-  const int dpitch = p->dmax | 1;
-  const size_t budget = 200 * 1024;
-  const size_t wbytes = ((size_t)WCAP + 64 + (size_t)dpitch + 8) * sizeof(double);   // Ws + bs
-  int TM = (int)((budget - wbytes) / ((size_t)5 * dpitch * sizeof(double)));
-  if (TM > 32) TM = 32;
-  if (TM > p->M) TM = p->M;
-  if (TM < 1) return vab_fail(ctx, VAB_ERR_INVALID, "nn_action_grad: layer too wide for the shared-memory tiles");
-  if (dpitch > WCAP) return vab_fail(ctx, VAB_ERR_INVALID, "nn_action_grad: layer wider than 8191 neurons is not supported");
+  // Shared-memory plan: 5 [TM][dpitch] tiles + a chunk of weight rows.  Pitches are = 4 (mod 8)
+  // doubles; TM is a multiple of 8.  Prefer a footprint that lets two CTAs share an SM.
+  const int dP = (p->dmax + 7) & ~7;
+  const int dpitch = dP + 4;
+  if (dpitch * 8 > 8192) return vab_fail(ctx, VAB_ERR_INVALID, "nn_action_grad: layers wider than 1016 neurons are not supported");
+  const int Mp = (p->M + 7) & ~7;
+  const size_t budget2 = 110 * 1024, budget1 = 220 * 1024;
+  const size_t extra = (size_t)(dP + 8) * sizeof(double);          // bias chunk
+  int TM = 0, wcap = 0;
+  size_t smem = 0;
+  // first choice: two CTAs per SM with at least min(dP, 32) weight rows per chunk
+  for (int pass = 0; pass < 2 && TM == 0; ++pass) {
+    const size_t budget = pass == 0 ? budget2 : budget1;
+    const int jmin = pass == 0 ? (dP < 32 ? dP : 32) : 8;
+    for (int tm = (Mp < 32 ? Mp : 32); tm >= 8; tm -= 8) {
+      const size_t tiles = (size_t)5 * tm * dpitch * sizeof(double);
+      if (tiles + extra + (size_t)jmin * dpitch * sizeof(double) > budget) continue;
+      size_t w = (budget - tiles - extra) / sizeof(double);
+      if (w > (size_t)dP * dpitch) w = (size_t)dP * dpitch;         // the whole widest layer fits
+      TM = tm;
+      wcap = (int)w;
+      smem = tiles + extra + (size_t)wcap * sizeof(double);
+      break;
+    }
+  }
+  if (TM == 0) return vab_fail(ctx, VAB_ERR_INVALID, "nn_action_grad: layer too wide for the shared-memory tiles");
   P.TM = TM;
   P.dpitch = dpitch;
+  P.wcap = wcap;
   P.ntiles = (p->M + TM - 1) / TM;
-  const size_t smem = (size_t)5 * TM * dpitch * sizeof(double) + wbytes;
   int rc = vab_reserve(ctx, &ctx->partials, &ctx->partials_cap, (size_t)B * P.ntiles * 2);
   if (rc != VAB_OK) return rc;
   rc = vab_reserve(ctx, &p->gwpart, &p->gwpart_cap, (size_t)B * P.ntiles * p->NP);
   if (rc != VAB_OK) return rc;
+  rc = vab_reserve(ctx, &p->pfull, &p->pfull_cap, (size_t)B * (p->NP > 0 ? p->NP : 1));
+  if (rc != VAB_OK) return rc;
   P.partials = ctx->partials;
   P.gwpart = p->gwpart;
+  P.pfull = p->pfull;
+  if (p->NP > 0) nn_gather_params_kernel<<<dim3((p->NP + 255) / 256, B), 256, 0, ctx->stream>>>(P);
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(nn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
@@ -465,7 +440,7 @@ int nn_eval(vab_ctx* ctx, int B, const double* XP, long long ldxp, double rf_sca
   nn_reduce_kernel<<<dim3((nk + 255) / 256, B), 256, 0, ctx->stream>>>(P, A, me, fe);
   e = cudaGetLastError();
   if (e != cudaSuccess) return vab_cuda_fail(ctx, e, "nn_reduce_kernel launch");
-  ctx->launches += 2;
+  ctx->launches += 3;
   return VAB_OK;
 }
 
