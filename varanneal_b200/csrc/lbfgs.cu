@@ -492,7 +492,7 @@ __global__ void __launch_bounds__(NT, 1) lb_update_kernel(
     }
 #pragma unroll
     for (int j = 0; j < MMAX; ++j) {
-      if (j < m && (j < col || col == m)) {
+      if (j < m && (j < col || col == m) && !(upd && j == p)) {   // slot p is about to be replaced
         const double sj = S[(long long)j * hstride + off + i];
         const double yj = Y[(long long)j * hstride + off + i];
         acc[j] = fma(gh, sj, acc[j]);
