@@ -176,12 +176,22 @@ VAB_API int vab_minimize(vab_ctx* ctx, int32_t B, double* XP_dev, int64_t ldxp, 
  * va_nnet.py:281-286, 459-523): for i in range(Nbeta): minimise at RF0*alpha**beta[i] warm-started
  * from the previous minimiser.  table_dev: (B, Nbeta, 5) rows [beta, A, me, fe, fe/(alpha**beta)]
  * -- the caller divides column 4 by RF0 (va_ode.py:847-873).  minpaths_dev: (B, Nbeta, ldxp) or
- * NULL; status/nit/nfev: (B, Nbeta) or NULL. */
+ * NULL; status/nit/nfev: (B, Nbeta) or NULL.
+ * The ladder is asynchronous across paths: a path that has converged on rung i starts rung i+1
+ * at once instead of waiting for the slowest path of the batch (the paths are independent, so the
+ * results are those of the rung-by-rung loop, bit for bit). */
 VAB_API int vab_anneal(vab_ctx* ctx, int32_t B, double* XP_dev, int64_t ldxp, double alpha,
                const double* beta_host, int32_t Nbeta, const vab_lbfgs_opts* opts,
                const double* lo_dev, const double* hi_dev,
                double* table_dev, double* minpaths_dev,
                int32_t* status_dev, int32_t* nit_dev, int32_t* nfev_dev);
+
+/* Strided device -> host copy of `rows` rows of `width` doubles (pitches in doubles), on the
+ * context's stream, synchronous for the caller.  Used by the host mirror to lay the device
+ * result buffers of vab_anneal out as the reference's minpaths array (va_ode.py:666-667, 776:
+ * rows X ++ full P, so the host pitch differs from ldxp).  host_dst may be pageable. */
+VAB_API int vab_copy_rows_to_host(vab_ctx* ctx, double* host_dst, int64_t host_pitch,
+                          const double* src_dev, int64_t dev_pitch, int64_t width, int64_t rows);
 
 #ifdef __cplusplus
 }

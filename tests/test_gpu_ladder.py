@@ -241,3 +241,69 @@ def test_vab_anneal_device_resident_ladder_equals_stepwise():
     assert np.allclose(tab[:, :, 4], tab[:, :, 3] / 1.5 ** betas)
     assert np.array_equal(paths.cpu().numpy()[:, :, :an._n], ref._est_slice(ref.minpaths.reshape(B * nb, -1)).reshape(B, nb, -1))
     assert np.array_equal(nit.cpu().numpy(), ref.nit_array) and np.array_equal(stat.cpu().numpy(), ref.exitflags)
+
+
+def _nakl_annealer(B):
+    from varanneal_b200 import va_ode
+    c = [c for c in golden_util.ode_cases() if c["name"] == "nakl_trapezoid_18p"][0]
+    an = va_ode.Annealer()
+    an.set_model("nakl", 4)
+    an.set_data(c["Y"], stim=c["stim"], t=c["t"])
+    rng = np.random.RandomState(5)
+    X0 = np.tile(c["X0"], (B, 1, 1)) + 0.01 * rng.randn(B, *c["X0"].shape)
+    P0 = np.tile(c["P0"], (B, 1)) * (1.0 + 0.01 * rng.randn(B, len(c["P0"])))
+    return an, X0, P0
+
+
+def test_anneal_fast_path_equals_stepwise_loop():
+    """Annealer.anneal() without track_* runs the whole ladder in one native call (asynchronous
+    across paths); the public result arrays -- minpaths with the full parameter vector, P, A / me /
+    fe, exitflags -- are bit-identical to driving anneal_init + anneal_step from the host, here
+    with a partial Pidx so that estimated and fixed parameters interleave."""
+    B, betas, Pidx = 4, [30, 40, 50, 60, 70], [0, 3, 7, 17]
+    args = dict(disc="trapezoid", opt_args={"maxiter": 60, "gtol": 1e-9, "ftol": 1e-13})
+    a1, X0, P0 = _nakl_annealer(B)
+    a1.anneal(X0.copy(), P0.copy(), 1.1, betas, 1.0, [1e-8, 1e-4, 1e-4, 1e-4], [0], Pidx, **args)
+    a2, _, _ = _nakl_annealer(B)
+    a2.anneal_init(X0.copy(), P0.copy(), 1.1, betas, 1.0, [1e-8, 1e-4, 1e-4, 1e-4], [0], Pidx, **args)
+    for _ in betas:
+        a2.anneal_step()
+    # paths stop after different numbers of iterations, i.e. they really did run out of step
+    assert len(set(a1.nfev_array[:, 0].tolist())) > 1 or len(set(a1.nit_array.sum(1).tolist())) > 1
+    for name in ("A_array", "me_array", "fe_array", "exitflags", "nit_array", "nfev_array", "minpaths", "P"):
+        assert np.array_equal(getattr(a1, name), getattr(a2, name)), name
+    assert a1.betaidx == a2.betaidx and a1.beta == a2.beta and np.array_equal(a1.RF, a2.RF)
+    fixed = [k for k in range(18) if k not in Pidx]
+    assert np.array_equal(a1.minpaths[:, :, 404:][:, :, fixed], np.broadcast_to(P0[:, None, fixed], (B, 5, 14)))
+
+
+def test_tma_history_kernels_match_plain_kernels(monkeypatch):
+    """The bulk-copy-fed update / direction passes (lb_*_tma_kernel, both ring depths) and the
+    plain-load ones compute the same sums in a different order: same minima to rounding and the
+    same iteration counts within a few on a well-conditioned, fully observed problem, large enough
+    (n = 60 001) for chunks of several tiles with a ragged, odd-length tail."""
+    from varanneal_b200 import va_ode
+    rng = np.random.RandomState(3)
+    D, N, B = 20, 3000, 3
+    Lidx = list(range(D))
+    t = 0.01 * np.arange(N)
+    Y = 2.0 * rng.randn(N, D)
+    X0 = Y[None] + 0.3 * rng.randn(B, N, D)
+    out = {}
+    for key, tma, ns in (("tma4", "1", "4"), ("tma2", "1", "2"), ("plain", "0", "4")):
+        monkeypatch.setenv("VAB_LBFGS_TMA", tma)
+        monkeypatch.setenv("VAB_LBFGS_NS", ns)
+        an = va_ode.Annealer()
+        an.set_model("lorenz96", D)
+        an.set_data(Y, t=t)
+        an.anneal(X0.copy(), np.array([8.0]), 2.0, [6, 8], 1.0, 1e-2, Lidx, [0], disc="trapezoid",
+                  init_to_data=False, opt_args={"gtol": 1e-8, "ftol": 1e-15, "maxiter": 20000})
+        out[key] = an
+    b = out["plain"]
+    assert np.all(b.exitflags == 0), b.exitflags
+    for key in ("tma4", "tma2"):
+        a = out[key]
+        assert np.all(a.exitflags == 0), a.exitflags
+        assert np.max(np.abs(a.A_array - b.A_array) / np.abs(b.A_array)) <= 1e-9
+        assert np.max(np.abs(a.minpaths - b.minpaths)) <= 1e-5
+        assert np.all(np.abs(a.nit_array - b.nit_array) <= np.maximum(5, 0.2 * b.nit_array)), (a.nit_array, b.nit_array)

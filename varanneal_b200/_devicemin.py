@@ -209,6 +209,66 @@ class DeviceMin(object):
             lo, hi, ptr(self._A), ptr(self._me), ptr(self._fe), ptr(self._status),
             ptr(self._nit), ptr(self._nfev)), self._ctx.h)
 
+    # ------------------------------------------------------------------ device-resident ladder
+    def _ladder_fits_device(self):
+        """True when the (B, Nbeta, ld) buffer of minimising paths fits next to the minimiser's
+        workspace; otherwise anneal() walks the rungs from the host (anneal_step)."""
+        torch = _torch()
+        free, _ = torch.cuda.mem_get_info(self._device)
+        m = int((self.opt_args or {}).get("maxcor", 10))
+        work = (2 * m + 4) * self._B * self._ld * 8
+        return self._B * self.Nbeta * self._ld * 8 + work < 0.8 * free
+
+    def _anneal_device(self):
+        """The whole beta loop (reference: anneal + anneal_step, va_ode.py:473-490, 707-789;
+        va_nnet.py:281-286, 459-523) in one native call: ``vab_anneal`` runs every path down the
+        ladder on the device (paths advance rung by rung independently of each other), then the
+        result table and the minimising paths are laid out exactly as the stepwise loop does."""
+        torch = _torch()
+        B, nb, n, nX = self._B, self.Nbeta, self._n, self._nX
+        src = self.minpaths[:, 0] if self.batched else self.minpaths[0][None, :]
+        self._upload_paths(self._est_slice(src))
+        method = 1 if getattr(self, "method", "L-BFGS-B") == "NCG" else 0
+        opts = self._lbfgs_opts(method)
+        lo = ptr(getattr(self, "_lo_dev", None)) if method == 0 else None
+        hi = ptr(getattr(self, "_hi_dev", None)) if method == 0 else None
+        dev = self._device
+        table = torch.zeros(B, nb, 5, dtype=torch.float64, device=dev)
+        paths = torch.empty(B, nb, self._ld, dtype=torch.float64, device=dev)
+        stat = torch.zeros(B, nb, dtype=torch.int32, device=dev)
+        nit = torch.zeros_like(stat)
+        nfev = torch.zeros_like(stat)
+        betas = np.asarray(self.beta_array, dtype=np.float64)
+        beta_c = (ct.c_double * nb)(*betas)
+        lib, h = self._ctx.lib, self._ctx.h
+        _lib.check(lib.vab_anneal(h, B, ptr(self._XP), self._ld, float(self.alpha), beta_c, nb,
+                                  ct.byref(opts), lo, hi, ptr(table), ptr(paths), ptr(stat), ptr(nit),
+                                  ptr(nfev)), h)
+        tab = table.cpu().numpy()
+        shape = self.A_array.shape
+        self.A_array[...] = tab[:, :, 1].reshape(shape)
+        self.me_array[...] = tab[:, :, 2].reshape(shape)
+        self.fe_array[...] = tab[:, :, 3].reshape(shape)
+        self.exitflags[...] = stat.cpu().numpy().reshape(shape)
+        self.nit_array[...] = nit.cpu().numpy().reshape(shape)
+        self.nfev_array[...] = nfev.cpu().numpy().reshape(shape)
+        # states: one strided DMA from the device rows (pitch ld) into the host rows (pitch nX + NP)
+        mp = self.minpaths.reshape(B * nb, nX + self.NP)
+        _lib.check(lib.vab_copy_rows_to_host(h, ct.c_void_p(mp.ctypes.data), nX + self.NP, ptr(paths),
+                                             self._ld, nX, B * nb), h)
+        # parameters: the fixed values with the estimates of every rung written in
+        P = np.broadcast_to(self.P.reshape(B, 1, self.NP), (B, nb, self.NP)).copy()
+        if self.NPest > 0:
+            P[:, :, self.Pidx] = paths[:, :, nX:n].cpu().numpy()
+        mp[:, nX:] = P.reshape(B * nb, self.NP)
+        self.P.reshape(B, self.NP)[...] = P[:, -1]
+        del paths
+        self._dev_paths_current = True
+        self.betaidx = nb - 1
+        self.beta = self.beta_array[-1]
+        self.RF = self.RF0 * self.alpha ** float(self.beta)
+        self.taped = False
+
     def min_lbfgs_scipy(self, XP0, xtrace=None):
         """Same contract as ADmin.min_lbfgs_scipy (_autodiffmin.py:72-95): returns
         (XPmin, Amin, status) -- but the whole minimisation runs on the device.  With a batch,

@@ -28,15 +28,29 @@
 // The host only enqueues fixed "cycles" of these kernels and polls a counter of running paths
 // every few cycles; finished paths are masked out inside the kernels.  All reductions are
 // fixed-order (bit-reproducible runs).
+//
+// The two history passes are HBM-bound streams over 2m+4 vectors: for the unbounded L-BFGS case
+// they are fed by the bulk-copy engine (cp.async.bulk into a 4-stage shared-memory ring per CTA,
+// completion on mbarriers), so the bytes in flight do not depend on registers or occupancy.
+//
+// Asynchronous ladder (vab_anneal): every path carries its own rung index.  A path that has
+// converged on rung i has its row of the result table and its minimiser saved by the cycle's last
+// two kernels and starts rung i+1 (RF0 alpha**beta[i+1], handed to the action kernels through a
+// per-path scale array) in the very next cycle -- paths never wait for the slowest one of a rung.
+// Per-path arithmetic does not depend on what the other paths do, so the results are identical
+// to running the rungs one after the other.
 #include <cuda_runtime.h>
 
 #include <cfloat>
+#include <chrono>
+#include <cstdint>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <string>
 
 #include "vab_ctx.h"
+#include "vab_tma.cuh"
 
 namespace {
 
@@ -50,6 +64,7 @@ struct LbPath {
   // control flags (written by the single-CTA kernels, read by everything)
   int done, need_eval, accepted, do_update, redo_dir, first;
   int iter, nfev, col, head, pslot, ifun, iback, nskip, status;
+  int ib, finished;         // rung of the ladder this path is on; ladder complete
   double f, fold, me, fe;
   double stp, gd, gdold, dnorm, stpmx, theta, sbgnrm, dr;
   double ls_ftol, ls_gtol, ls_xtol, cd, fprev;   // line-search constants; CG: coefficient of the old direction, f two iterates back
@@ -87,9 +102,11 @@ struct LbfgsWork {
   double* fet = nullptr;
   double* part = nullptr;       // partial sums of the vector kernels
   size_t part_cap = 0;
-  int* n_running_dev = nullptr;
-  int* n_running_host = nullptr;   // pinned
-  cudaEvent_t ev = nullptr;
+  int* n_running_dev = nullptr;     // [2]
+  int* n_running_host = nullptr;    // pinned [2]
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  double* lad = nullptr;            // scales[Nbeta] | betas[Nbeta] | rf_path[B]
+  size_t lad_cap = 0;
 };
 
 namespace {
@@ -291,10 +308,8 @@ __device__ void block_reduce(const double* v, const int* op, double* out, double
 }
 
 // ---------------------------------------------------------------------------------------------
-__global__ void lb_init_kernel(LbPath* st, int* act_eval, int B, double ls_ftol, double ls_gtol, double ls_xtol) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
-  LbPath& s = st[b];
+// state of a path at the start of a minimisation (one rung)
+__device__ void lb_reset(LbPath& s, double ls_ftol, double ls_gtol, double ls_xtol) {
   s.done = 0; s.need_eval = 1; s.accepted = 0; s.do_update = 0; s.redo_dir = 0; s.first = 1;
   s.iter = 0; s.nfev = 0; s.col = 0; s.head = 0; s.pslot = 0; s.ifun = 0; s.iback = 0; s.nskip = 0;
   s.status = 2;
@@ -303,6 +318,16 @@ __global__ void lb_init_kernel(LbPath* st, int* act_eval, int B, double ls_ftol,
   s.sbgnrm = 0.0; s.dr = 0.0;
   s.cg = 1.0; s.cd = 0.0; s.ls_ftol = ls_ftol; s.ls_gtol = ls_gtol; s.ls_xtol = ls_xtol; s.fprev = 0.0; s.gg = 0.0;
   for (int j = 0; j < MMAX; ++j) { s.cs[j] = 0.0; s.cy[j] = 0.0; s.gS[j] = 0.0; s.gY[j] = 0.0; }
+}
+
+__global__ void lb_init_kernel(LbPath* st, int* act_eval, int B, double ls_ftol, double ls_gtol, double ls_xtol,
+                               const double* scales, double* rf_path) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  LbPath& s = st[b];
+  lb_reset(s, ls_ftol, ls_gtol, ls_xtol);
+  s.ib = 0; s.finished = 0;
+  rf_path[b] = scales[0];
   act_eval[b] = 1;
 }
 
@@ -320,12 +345,19 @@ __global__ void __launch_bounds__(NT) lb_trial_kernel(double* __restrict__ XT, c
                                                       const LbPath* __restrict__ st, int nchunk) {
   const int b = blockIdx.y;
   const LbPath& s = st[b];
-  if (s.done || !s.need_eval || s.first) return;
+  if (s.done || !s.need_eval) return;
   const double stp = s.stp;
   const Range r = chunk_range(n, nchunk, blockIdx.x);
   const double* x = X + (long long)b * ld;
   const double* d = Dv + (long long)b * ld;
   double* xt = XT + (long long)b * ld;
+  if (s.first) {                      // first evaluation of a minimisation: at x itself
+    for (long long i = r.i0 + 2LL * threadIdx.x; i < r.i1; i += 2LL * NT) {
+      if (i + 1 < r.i1) *reinterpret_cast<double2*>(xt + i) = *reinterpret_cast<const double2*>(x + i);
+      else xt[i] = x[i];
+    }
+    return;
+  }
   for (long long i = r.i0 + 2LL * threadIdx.x; i < r.i1; i += 2LL * NT) {
     if (i + 1 < r.i1) {
       const double2 xv = *reinterpret_cast<const double2*>(x + i);
@@ -667,6 +699,265 @@ __global__ void __launch_bounds__(NT) lb_direction_kernel(
   if (threadIdx.x < 3) part[((long long)b * nchunk + blockIdx.x) * 3 + threadIdx.x] = res[threadIdx.x];
 }
 
+// ---------------------------------------------------------------------------------------------
+// TMA-fed variants of the two history passes (unbounded L-BFGS; same arithmetic per element and
+// the same per-chunk partial layout as lb_update_kernel / lb_direction_kernel above).
+//
+// A CTA owns one chunk of one path and walks it in tiles of HTILE elements.  A stage of its
+// shared-memory ring holds the tile of every input vector (up to 2m+4 of them, 2 KB each).
+// Warp specialisation: a producer warp -- lane k owns vector k -- enqueues one cp.async.bulk per
+// vector, all completing on the stage's "full" mbarrier, up to HNS tiles ahead; HW consumer warps
+// do the arithmetic from shared memory and hand the stage back through its "empty" mbarrier.
+// No __syncthreads in the loop; the bytes in flight (up to HNS x 48 KB per SM) do not depend on
+// the register count of the 5m+4 running dot products.
+constexpr int HW = 4;                   // consumer warps
+constexpr int HT = HW * 32;             // consumer threads
+constexpr int HTILE = 2 * HT;           // elements per tile (two per consumer thread)
+constexpr int U_NSTR = 4 + 2 * MMAX;    // GT, G, D, XT, S_0.., Y_0..
+constexpr int D_NSTR = 1 + 2 * MMAX;    // G, S_0.., Y_0..
+static_assert(U_NSTR <= 32 && D_NSTR <= 32, "one producer lane per vector");
+// ring stages HNS (template parameter): 4 with one CTA per SM, or 2 with two CTAs per SM
+constexpr size_t hist_smem(int nstr, int hns) { return (size_t)hns * nstr * HTILE * sizeof(double) + 2 * hns * 8; }
+
+// producer warp: stream the chunk [0, len) of every vector with a non-null source (this lane's:
+// src) through the ring.  The last tile may be short; a bulk copy moves whole 16-byte units, the
+// odd element read past the end lies inside the row padding and is masked by the consumers.
+template <int NSTR, int HNS>
+__device__ __forceinline__ void hist_produce(uint32_t ring, uint32_t full, uint32_t empty,
+                                             const double* src, int nact, int ntile, long long len) {
+  const int lane = threadIdx.x & 31;
+  for (int t = 0; t < ntile; ++t) {
+    const int stage = t % HNS;
+    if (t >= HNS) vabs::mbar_wait(empty + 8u * (uint32_t)stage, (uint32_t)(((t / HNS) - 1) & 1));
+    const long long e0 = (long long)t * HTILE;
+    long long cnt = len - e0;
+    if (cnt > HTILE) cnt = HTILE;
+    cnt = (cnt + 1) & ~1LL;
+    const uint32_t bytes = (uint32_t)cnt * 8u;
+    const uint32_t bar = full + 8u * (uint32_t)stage;
+    if (lane == 0) vabs::mbar_expect_tx(bar, bytes * (uint32_t)nact);
+    __syncwarp();
+    if (src != nullptr)
+      vabs::tma_load(ring + (uint32_t)((stage * NSTR + lane) * (HTILE * 8)), src + e0, bytes, bar);
+  }
+}
+
+template <int HNS>
+__device__ __forceinline__ void hist_ring_init(uint32_t full, uint32_t empty) {
+#pragma unroll
+  for (int q = 0; q < HNS; ++q) {
+    vabs::mbar_init(full + 8u * q, 1);
+    vabs::mbar_init(empty + 8u * q, HW);
+  }
+  vabs::mbar_fence_init();
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void hist_consumer_sync() {          // the HT consumer threads only
+  asm volatile("bar.sync 1, %0;" ::"n"(HT) : "memory");
+}
+
+// fixed-order reduction of NV per-thread sums over the consumer threads: lanes by shuffle, then
+// the warps in order
+template <int NV>
+__device__ __forceinline__ void hist_reduce_store(const double* acc, double (*wred)[NV], double* out) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    double v = acc[k];
+#pragma unroll
+    for (int sft = 16; sft > 0; sft >>= 1) v += __shfl_down_sync(0xffffffffu, v, sft);
+    if (lane == 0) wred[warp][k] = v;
+  }
+  hist_consumer_sync();
+  for (int k = threadIdx.x; k < NV; k += HT) {
+    double a = wred[0][k];
+#pragma unroll
+    for (int w = 1; w < HW; ++w) a += wred[w][k];
+    out[k] = a;
+  }
+}
+
+template <int HNS>
+__global__ void __launch_bounds__(HT + 32, 1) lb_update_tma_kernel(
+    double* __restrict__ X, double* __restrict__ G, const double* __restrict__ XT,
+    const double* __restrict__ GT, const double* __restrict__ Dv, double* __restrict__ S,
+    double* __restrict__ Y, long long ld, long long n, long long hstride,
+    const LbPath* __restrict__ st, int m, int nchunk, double* __restrict__ part) {
+  extern __shared__ __align__(128) unsigned char hist_sm[];
+  __shared__ double wred[HW][NACC_U];
+  const int b = blockIdx.y, tid = threadIdx.x;
+  const LbPath& s = st[b];
+  if (!s.accepted) return;
+  const bool upd = s.do_update != 0;
+  const int p = s.pslot;
+  const double stp = s.stp;
+  const int col = s.col;
+  const Range r = chunk_range(n, nchunk, blockIdx.x);
+  const long long len = r.i1 - r.i0;
+  double* pout = part + ((long long)b * nchunk + blockIdx.x) * NACC_U;
+  if (len <= 0) {
+    for (int k = tid; k < NACC_U; k += HT + 32) pout[k] = 0.0;
+    return;
+  }
+  unsigned hmask = 0;                       // history slots whose old contents are read
+  for (int j = 0; j < MMAX; ++j)
+    if (j < m && (j < col || col == m) && !(upd && j == p)) hmask |= 1u << j;
+  const long long base = (long long)b * ld + r.i0;
+  double* tiles = reinterpret_cast<double*>(hist_sm);
+  const uint32_t ring = vabs::s32(tiles);
+  const uint32_t full = ring + (uint32_t)(HNS * U_NSTR * HTILE * 8);
+  const uint32_t empty = full + HNS * 8u;
+  const int ntile = (int)((len + HTILE - 1) / HTILE);
+  if (tid == 0) hist_ring_init<HNS>(full, empty);
+  __syncthreads();
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  if (warp == HW) {                         // ---- producer warp
+    const int k = tid & 31;
+    const double* src = nullptr;
+    if (k == 0) src = GT + base;
+    else if (k == 1) src = G + base;
+    else if (k == 2) src = upd ? Dv + base : nullptr;
+    else if (k == 3) src = XT + base;
+    else if (k < 4 + MMAX) src = ((hmask >> (k - 4)) & 1u) ? S + (long long)(k - 4) * hstride + base : nullptr;
+    else if (k < U_NSTR) src = ((hmask >> (k - 4 - MMAX)) & 1u) ? Y + (long long)(k - 4 - MMAX) * hstride + base : nullptr;
+    const int nact = 3 + (upd ? 1 : 0) + 2 * __popc(hmask);
+    hist_produce<U_NSTR, HNS>(ring, full, empty, src, nact, ntile, len);
+    return;
+  }
+  // ---- consumer warps
+  double acc[NACC_U];
+#pragma unroll
+  for (int k = 0; k < NACC_U; ++k) acc[k] = 0.0;
+  double* xo = X + base;
+  double* go = G + base;
+  double* so = S + (long long)p * hstride + base;
+  double* yo = Y + (long long)p * hstride + base;
+  for (int t = 0; t < ntile; ++t) {
+    const int stage = t % HNS;
+    vabs::mbar_wait(full + 8u * (uint32_t)stage, (uint32_t)((t / HNS) & 1));
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const double* tl = tiles + (size_t)stage * (U_NSTR * HTILE) + h * HT + tid;
+      const long long e = (long long)t * HTILE + h * HT + tid;
+      const bool valid = e < len;
+      const double gt = valid ? tl[0] : 0.0;
+      const double gold = valid ? tl[HTILE] : 0.0;
+      const double xt = valid ? tl[3 * HTILE] : 0.0;
+      double sv = 0.0, yv = 0.0;
+      if (upd) {
+        const double dv = valid ? tl[2 * HTILE] : 0.0;
+        sv = stp * dv;
+        yv = gt - gold;
+      }
+      const double gh = gt;
+#pragma unroll
+      for (int j = 0; j < MMAX; ++j) {
+        if ((hmask >> j) & 1u) {
+          const double sj = valid ? tl[(4 + j) * HTILE] : 0.0;
+          const double yj = valid ? tl[(4 + MMAX + j) * HTILE] : 0.0;
+          acc[j] = fma(gh, sj, acc[j]);
+          acc[MMAX + j] = fma(gh, yj, acc[MMAX + j]);
+          acc[2 * MMAX + j] = fma(sv, yj, acc[2 * MMAX + j]);
+          acc[3 * MMAX + j] = fma(yv, sj, acc[3 * MMAX + j]);
+          acc[4 * MMAX + j] = fma(yv, yj, acc[4 * MMAX + j]);
+        }
+      }
+      acc[5 * MMAX] = fma(yv, yv, acc[5 * MMAX]);
+      acc[5 * MMAX + 1] = fma(gh, sv, acc[5 * MMAX + 1]);
+      acc[5 * MMAX + 2] = fma(gh, yv, acc[5 * MMAX + 2]);
+      acc[5 * MMAX + 3] = fma(gh, gh, acc[5 * MMAX + 3]);
+      if (valid) {
+        xo[e] = xt;
+        go[e] = gt;
+        if (upd) {
+          so[e] = sv;
+          yo[e] = yv;
+        }
+      }
+    }
+    __syncwarp();
+    if ((tid & 31) == 0) vabs::mbar_arrive(empty + 8u * (uint32_t)stage);   // stage may be refilled
+  }
+  hist_reduce_store<NACC_U>(acc, wred, pout);
+}
+
+template <int HNS>
+__global__ void __launch_bounds__(HT + 32, 1) lb_direction_tma_kernel(
+    const double* __restrict__ G, double* __restrict__ Dv, const double* __restrict__ S,
+    const double* __restrict__ Y, long long ld, long long n, long long hstride,
+    const LbPath* __restrict__ st, int m, int nchunk, double* __restrict__ part) {
+  extern __shared__ __align__(128) unsigned char hist_sm[];
+  __shared__ double wred[HW][2];
+  const int b = blockIdx.y, tid = threadIdx.x;
+  const LbPath& s = st[b];
+  if (!(s.accepted || s.redo_dir) || s.done) return;
+  const Range r = chunk_range(n, nchunk, blockIdx.x);
+  const long long len = r.i1 - r.i0;
+  double* pout = part + ((long long)b * nchunk + blockIdx.x) * 3;
+  if (len <= 0) {
+    if (tid == 0) { pout[0] = 0.0; pout[1] = 0.0; pout[2] = BIG; }
+    return;
+  }
+  const int col = s.col;
+  unsigned hmask = 0;
+  for (int j = 0; j < MMAX; ++j)
+    if (j < m && (j < col || col == m)) hmask |= 1u << j;
+  const long long base = (long long)b * ld + r.i0;
+  double* tiles = reinterpret_cast<double*>(hist_sm);
+  const uint32_t ring = vabs::s32(tiles);
+  const uint32_t full = ring + (uint32_t)(HNS * D_NSTR * HTILE * 8);
+  const uint32_t empty = full + HNS * 8u;
+  const int ntile = (int)((len + HTILE - 1) / HTILE);
+  if (tid == 0) hist_ring_init<HNS>(full, empty);
+  __syncthreads();
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  if (warp == HW) {                         // ---- producer warp
+    const int k = tid & 31;
+    const double* src = nullptr;
+    if (k == 0) src = G + base;
+    else if (k < 1 + MMAX) src = ((hmask >> (k - 1)) & 1u) ? S + (long long)(k - 1) * hstride + base : nullptr;
+    else if (k < D_NSTR) src = ((hmask >> (k - 1 - MMAX)) & 1u) ? Y + (long long)(k - 1 - MMAX) * hstride + base : nullptr;
+    const int nact = 1 + 2 * __popc(hmask);
+    hist_produce<D_NSTR, HNS>(ring, full, empty, src, nact, ntile, len);
+    return;
+  }
+  double cs[MMAX], cy[MMAX];
+#pragma unroll
+  for (int j = 0; j < MMAX; ++j) { cs[j] = s.cs[j]; cy[j] = s.cy[j]; }
+  const double cg = s.cg;
+  double v[2] = {0.0, 0.0};
+  double* dout = Dv + base;
+  for (int t = 0; t < ntile; ++t) {
+    const int stage = t % HNS;
+    vabs::mbar_wait(full + 8u * (uint32_t)stage, (uint32_t)((t / HNS) & 1));
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const double* tl = tiles + (size_t)stage * (D_NSTR * HTILE) + h * HT + tid;
+      const long long e = (long long)t * HTILE + h * HT + tid;
+      const bool valid = e < len;
+      const double g = valid ? tl[0] : 0.0;
+      double rr = cg * g;
+#pragma unroll
+      for (int j = 0; j < MMAX; ++j) {
+        if ((hmask >> j) & 1u) {
+          const double sj = valid ? tl[(1 + j) * HTILE] : 0.0;
+          const double yj = valid ? tl[(1 + MMAX + j) * HTILE] : 0.0;
+          rr = fma(cs[j], sj, rr);
+          rr = fma(cy[j], yj, rr);
+        }
+      }
+      const double d = -rr;
+      if (valid) dout[e] = d;
+      v[0] = fma(d, d, v[0]);
+      v[1] = fma(g, d, v[1]);
+    }
+    __syncwarp();
+    if ((tid & 31) == 0) vabs::mbar_arrive(empty + 8u * (uint32_t)stage);
+  }
+  hist_reduce_store<2>(v, wred, pout);
+  if (tid == 0) pout[2] = BIG;
+}
+
 // start of a line search (lnsrlb, task = START)
 __global__ void lb_start_kernel(LbPath* st, int* act_eval, const double* part, int nchunk, LbOpts o,
                                 int bounded, int b0) {
@@ -708,9 +999,62 @@ __global__ void lb_start_kernel(LbPath* st, int* act_eval, const double* part, i
   act_eval[b] = 1;
 }
 
+// ---------------------------------------------------------------------------------------------
+// end of a rung.  A path whose minimisation has just stopped (done, ladder not finished) has its
+// minimiser copied to minpaths[b][ib] by lb_save_kernel; lb_advance_kernel then records the row
+// of the result table and either restarts the path on the next rung or retires it.
+struct LbLadder {
+  int Nbeta;
+  const double* scales;      // (Nbeta) alpha**beta
+  const double* betas;       // (Nbeta)
+  double* rf_path;           // (B) scale of the rung each path is on (read by the action kernels)
+  double* table;             // (B, Nbeta, 5) or nullptr
+  double* minpaths;          // (B, Nbeta, ld) or nullptr
+  int *status2, *nit2, *nfev2;   // (B, Nbeta) or nullptr
+};
+
+__global__ void __launch_bounds__(NT) lb_save_kernel(const double* __restrict__ X, long long ld, long long n,
+                                                     const LbPath* __restrict__ st, int nchunk, LbLadder L) {
+  const int b = blockIdx.y;
+  const LbPath& s = st[b];
+  if (!s.done || s.finished) return;
+  const Range r = chunk_range(n, nchunk, blockIdx.x);
+  const double* x = X + (long long)b * ld;
+  double* o = L.minpaths + ((long long)b * L.Nbeta + s.ib) * ld;
+  for (long long i = r.i0 + 2LL * threadIdx.x; i < r.i1; i += 2LL * NT) {
+    if (i + 1 < r.i1) *reinterpret_cast<double2*>(o + i) = *reinterpret_cast<const double2*>(x + i);
+    else o[i] = x[i];
+  }
+}
+
+__global__ void lb_advance_kernel(LbPath* st, int* act_eval, int B, LbLadder L, LbOpts o) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  LbPath& s = st[b];
+  if (!s.done || s.finished) return;
+  const int ib = s.ib;
+  if (L.table) {
+    double* row = L.table + ((long long)b * L.Nbeta + ib) * 5;
+    row[0] = L.betas[ib]; row[1] = s.f; row[2] = s.me; row[3] = s.fe; row[4] = s.fe / L.scales[ib];
+  }
+  if (L.status2) L.status2[(long long)b * L.Nbeta + ib] = s.status;
+  if (L.nit2) L.nit2[(long long)b * L.Nbeta + ib] = s.iter;
+  if (L.nfev2) L.nfev2[(long long)b * L.Nbeta + ib] = s.nfev;
+  if (ib + 1 < L.Nbeta) {
+    lb_reset(s, o.ls_ftol, o.ls_gtol, o.ls_xtol);      // warm start: x stays where it is
+    s.ib = ib + 1;
+    L.rf_path[b] = L.scales[ib + 1];
+    act_eval[b] = 1;
+  } else {
+    s.finished = 1;
+    s.accepted = 0; s.redo_dir = 0;
+    act_eval[b] = 0;
+  }
+}
+
 __global__ void lb_count_kernel(const LbPath* st, int B, int* n_running) {
   int c = 0;
-  for (int b = threadIdx.x; b < B; b += blockDim.x) c += st[b].done ? 0 : 1;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) c += st[b].finished ? 0 : 1;
   for (int sft = 16; sft > 0; sft >>= 1) c += __shfl_down_sync(0xffffffffu, c, sft);
   __shared__ int w[8];
   if ((threadIdx.x & 31) == 0) w[threadIdx.x >> 5] = c;
@@ -722,9 +1066,9 @@ __global__ void lb_count_kernel(const LbPath* st, int B, int* n_running) {
   }
 }
 
+// results of the rung a path finished last (vab_minimize: the only one)
 __global__ void lb_export_kernel(const LbPath* st, int B, double* A, double* me, double* fe,
-                                 int* status, int* nit, int* nfev, double* table, int Nbeta, int ib,
-                                 double beta, double rf_scale, int* st2, int* nit2, int* nfev2) {
+                                 int* status, int* nit, int* nfev) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   const LbPath& s = st[b];
@@ -734,19 +1078,17 @@ __global__ void lb_export_kernel(const LbPath* st, int B, double* A, double* me,
   if (status) status[b] = s.status;
   if (nit) nit[b] = s.iter;
   if (nfev) nfev[b] = s.nfev;
-  if (table) {
-    double* row = table + ((long long)b * Nbeta + ib) * 5;
-    row[0] = beta; row[1] = s.f; row[2] = s.me; row[3] = s.fe; row[4] = s.fe / rf_scale;
-  }
-  if (st2) st2[(long long)b * Nbeta + ib] = s.status;
-  if (nit2) nit2[(long long)b * Nbeta + ib] = s.iter;
-  if (nfev2) nfev2[(long long)b * Nbeta + ib] = s.nfev;
 }
 
 // chunks (CTAs) per path of the vector kernels: 8192 elements each for large batches, smaller
 // chunks when the whole batch would not fill the machine (launch-latency-bound small problems)
 int lb_nchunk(long long n, int B = 1 << 20) {
-  long long c = (n + 8191) / 8192;
+  static long long chunk = 0;
+  if (chunk == 0) {
+    const char* e = getenv("VAB_LBFGS_CHUNK");           // tuning knob
+    chunk = (e && atoll(e) >= 512) ? atoll(e) : 8192;
+  }
+  long long c = (n + chunk - 1) / chunk;
   const long long want = (592 + B - 1) / B;            // ~4 CTAs per SM over the batch
   if (c < want) c = want;
   const long long cmax = (n + 511) / 512;              // at least 512 elements per chunk
@@ -762,7 +1104,7 @@ int lb_nchunk(long long n, int B = 1 << 20) {
     if (e_ != cudaSuccess) return vab_cuda_fail(ctx, e_, #call);              \
   } while (0)
 
-int lb_reserve(vab_ctx* ctx, int B, long long ld, int m) {
+int lb_reserve(vab_ctx* ctx, int B, long long ld, int m, int Nbeta) {
   if (!ctx->lb) ctx->lb = new LbfgsWork();
   LbfgsWork* w = ctx->lb;
   const size_t nvec = (size_t)(2 * m + 4);
@@ -779,23 +1121,29 @@ int lb_reserve(vab_ctx* ctx, int B, long long ld, int m) {
     LB_CUDA(cudaMalloc((void**)&w->fet, sizeof(double) * B));
     w->st_cap = B;
   }
-  int nchunk = lb_nchunk(ctx->n_unknowns(), B);
-  if (nchunk < ctx->num_sms) nchunk = ctx->num_sms;      // the path-sequential tail uses num_sms chunks
+  const int nchunk = lb_nchunk(ctx->n_unknowns(), B);
   rc = vab_reserve(ctx, &w->part, &w->part_cap, (size_t)B * nchunk * NACC_U);
   if (rc != VAB_OK) return rc;
-  if (!w->n_running_dev) LB_CUDA(cudaMalloc((void**)&w->n_running_dev, sizeof(int)));
-  if (!w->n_running_host) LB_CUDA(cudaMallocHost((void**)&w->n_running_host, sizeof(int)));
-  if (!w->ev) LB_CUDA(cudaEventCreateWithFlags(&w->ev, cudaEventDisableTiming));
+  rc = vab_reserve(ctx, &w->lad, &w->lad_cap, (size_t)2 * Nbeta + B);
+  if (rc != VAB_OK) return rc;
+  if (!w->n_running_dev) LB_CUDA(cudaMalloc((void**)&w->n_running_dev, 2 * sizeof(int)));
+  if (!w->n_running_host) LB_CUDA(cudaMallocHost((void**)&w->n_running_host, 2 * sizeof(int)));
+  for (int k = 0; k < 2; ++k)
+    if (!w->ev[k]) LB_CUDA(cudaEventCreateWithFlags(&w->ev[k], cudaEventDisableTiming));
   w->B = B; w->ld = ld; w->m = m;
   return VAB_OK;
 }
 
-// minimise from XP (in place) at the given rf_scale; leaves the per-path results in w->st
-int lb_minimize_core(vab_ctx* ctx, int B, double* XP, long long ld, double rf_scale,
-                     const vab_lbfgs_opts* uo, const double* lo, const double* hi) {
+// Runs every path down the ladder scales_host[0..Nbeta) (Nbeta = 1: a plain minimisation) from XP,
+// in place; leaves the per-path state of the last rung in w->st.
+int lb_run(vab_ctx* ctx, int B, double* XP, long long ld, const double* scales_host,
+           const double* betas_host, int Nbeta, const vab_lbfgs_opts* uo, const double* lo,
+           const double* hi, double* table, double* minpaths, int* status2, int* nit2, int* nfev2) {
   const long long n = ctx->n_unknowns();
   if (n <= 0) return vab_fail(ctx, VAB_ERR_STATE, "minimize: no problem set on this context");
   if (B < 1 || !XP || ld < n || (ld & 1)) return vab_fail(ctx, VAB_ERR_INVALID, "minimize: bad batch / XP / ldxp");
+  if (((uintptr_t)XP & 15) || ((uintptr_t)minpaths & 15))
+    return vab_fail(ctx, VAB_ERR_INVALID, "minimize: XP / minpaths must be 16-byte aligned");
   if ((lo == nullptr) != (hi == nullptr)) return vab_fail(ctx, VAB_ERR_INVALID, "minimize: give both bounds or none");
   LbOpts o;
   o.m = uo && uo->m > 0 ? uo->m : 10;
@@ -814,7 +1162,7 @@ int lb_minimize_core(vab_ctx* ctx, int B, double* XP, long long ld, double rf_sc
     if (!(uo && uo->maxls > 0)) o.maxls = 100;
   }
   int poll = uo && uo->poll_every > 0 ? uo->poll_every : 0;
-  int rc = lb_reserve(ctx, B, ld, o.m);
+  int rc = lb_reserve(ctx, B, ld, o.m, Nbeta);
   if (rc != VAB_OK) return rc;
   LbfgsWork* w = ctx->lb;
   cudaStream_t st = ctx->stream;
@@ -829,19 +1177,38 @@ int lb_minimize_core(vab_ctx* ctx, int B, double* XP, long long ld, double rf_sc
   const int nchunk = lb_nchunk(n, B);
   const bool bounded = lo != nullptr;
   const dim3 vgrid(nchunk, B);
-  // Path-sequential tail: when one path's history (2m+4 vectors) fits in L2 but the batch's does
-  // not, run update -> gram -> direction -> start path by path so that the direction pass re-reads
-  // the S / Y vectors the update pass has just streamed from L2 instead of HBM.
-  const double path_ws = (double)(2 * o.m + 4) * (double)n * sizeof(double);
-  bool seq = false;   // measured on B200 (C2, B = 64): 2x slower than the lockstep passes (launch-bound)
-  (void)path_ws;
-  if (const char* e = getenv("VAB_LBFGS_SEQ")) seq = atoi(e) != 0;
-  const int nchunk_seq = seq ? (int)(n / 512 < (long long)ctx->num_sms ? (n / 512 > 0 ? n / 512 : 1) : ctx->num_sms) : nchunk;
-  const dim3 sgrid(nchunk_seq, 1);
+  // the TMA-fed history passes serve the unbounded L-BFGS case (VAB_LBFGS_TMA=0: plain kernels)
+  bool use_tma = !bounded && o.method == 0;
+  if (const char* e = getenv("VAB_LBFGS_TMA")) use_tma = use_tma && atoi(e) != 0;
+  // ring depth: 2 stages x 2 CTAs per SM (measured best on B200: C2 update 0.93 ms = 6.7 TB/s,
+  // direction 0.75 ms) or 4 stages x 1 CTA per SM (VAB_LBFGS_NS=4: 0.99 / 0.78 ms)
+  int hns = 2;
+  if (const char* e = getenv("VAB_LBFGS_NS")) hns = atoi(e) == 4 ? 4 : 2;
+  if (use_tma) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      LB_CUDA(cudaFuncSetAttribute(lb_update_tma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem(U_NSTR, 4)));
+      LB_CUDA(cudaFuncSetAttribute(lb_direction_tma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem(D_NSTR, 4)));
+      LB_CUDA(cudaFuncSetAttribute(lb_update_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem(U_NSTR, 2)));
+      LB_CUDA(cudaFuncSetAttribute(lb_direction_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem(D_NSTR, 2)));
+      attr_set = true;
+    }
+  }
 
-  lb_init_kernel<<<(B + 127) / 128, 128, 0, st>>>(w->st, w->act_eval, B, o.ls_ftol, o.ls_gtol, o.ls_xtol);
+  LbLadder L;
+  L.Nbeta = Nbeta;
+  L.scales = w->lad; L.betas = w->lad + Nbeta; L.rf_path = w->lad + 2 * (size_t)Nbeta;
+  L.table = table; L.minpaths = minpaths; L.status2 = status2; L.nit2 = nit2; L.nfev2 = nfev2;
+  {
+    std::string tmp((size_t)2 * Nbeta * sizeof(double), '\0');
+    double* t = reinterpret_cast<double*>(&tmp[0]);
+    for (int i = 0; i < Nbeta; ++i) { t[i] = scales_host[i]; t[Nbeta + i] = betas_host ? betas_host[i] : 0.0; }
+    LB_CUDA(cudaMemcpyAsync(w->lad, t, tmp.size(), cudaMemcpyHostToDevice, st));
+    LB_CUDA(cudaStreamSynchronize(st));           // tmp dies with this scope
+  }
+  lb_init_kernel<<<(B + 127) / 128, 128, 0, st>>>(w->st, w->act_eval, B, o.ls_ftol, o.ls_gtol, o.ls_xtol,
+                                                   L.scales, L.rf_path);
   if (bounded) lb_clip_kernel<<<dim3((unsigned)((n + 255) / 256), B), 256, 0, st>>>(XP, ld, n, lo, hi);
-  LB_CUDA(cudaMemcpyAsync(XT, XP, vs * sizeof(double), cudaMemcpyDeviceToDevice, st));
   LB_CUDA(cudaMemsetAsync(Dv, 0, vs * sizeof(double), st));
   LB_CUDA(cudaMemsetAsync(G, 0, vs * sizeof(double), st));
   ctx->launches += 2;
@@ -850,35 +1217,33 @@ int lb_minimize_core(vab_ctx* ctx, int B, double* XP, long long ld, double rf_sc
     // small problems are launch-bound (a cycle is ~30 us): poll rarely; large ones take ms per cycle
     poll = (n * (long long)B < (1LL << 22)) ? 64 : 8;
   }
-  long long cycles = 0;
-  const long long max_cycles = o.maxfun + o.maxiter + 64;
   auto enqueue_cycle = [&]() -> int {
     lb_trial_kernel<<<vgrid, NT, 0, st>>>(XT, XP, Dv, ld, n, w->st, nchunk);
-    int r = vab_eval(ctx, B, XT, ld, rf_scale, w->act_eval, w->ft, w->met, w->fet, GT, ld);
+    int r = vab_eval(ctx, B, XT, ld, 1.0, L.rf_path, w->act_eval, w->ft, w->met, w->fet, GT, ld);
     if (r != VAB_OK) return r;
     if (bounded) lb_gd_kernel<true><<<vgrid, NT, 0, st>>>(XT, GT, Dv, ld, n, lo, hi, w->st, nchunk, w->part);
     else lb_gd_kernel<false><<<vgrid, NT, 0, st>>>(XT, GT, Dv, ld, n, lo, hi, w->st, nchunk, w->part);
     lb_linesearch_kernel<<<B, 32, 0, st>>>(w->st, w->act_eval, w->ft, w->met, w->fet, w->part, nchunk, o, bounded ? 1 : 0);
-    ctx->launches += 3;
-    const int npass = seq ? B : 1;
-    for (int pb = 0; pb < npass; ++pb) {
-      const dim3 ug = seq ? sgrid : vgrid;
-      const int nc = seq ? nchunk_seq : nchunk;
-      if (bounded) lb_update_kernel<true><<<ug, NT, 0, st>>>(XP, G, XT, GT, Dv, S, Y, ld, n, hstride, lo, hi, w->st, o.m, nc, w->part, pb);
-      else lb_update_kernel<false><<<ug, NT, 0, st>>>(XP, G, XT, GT, Dv, S, Y, ld, n, hstride, lo, hi, w->st, o.m, nc, w->part, pb);
-      lb_gram_kernel<<<seq ? 1 : B, 64, 0, st>>>(w->st, w->part, nc, o.m, pb, o.method);
-      if (bounded) lb_direction_kernel<true><<<ug, NT, 0, st>>>(XP, G, Dv, S, Y, ld, n, hstride, lo, hi, w->st, o.m, nc, w->part, pb);
-      else lb_direction_kernel<false><<<ug, NT, 0, st>>>(XP, G, Dv, S, Y, ld, n, hstride, lo, hi, w->st, o.m, nc, w->part, pb);
-      lb_start_kernel<<<seq ? 1 : B, 1, 0, st>>>(w->st, w->act_eval, w->part, nc, o, bounded ? 1 : 0, pb);
-      ctx->launches += 4;
-    }
+    if (use_tma && hns == 4) lb_update_tma_kernel<4><<<vgrid, HT + 32, hist_smem(U_NSTR, 4), st>>>(XP, G, XT, GT, Dv, S, Y, ld, n, hstride, w->st, o.m, nchunk, w->part);
+    else if (use_tma) lb_update_tma_kernel<2><<<vgrid, HT + 32, hist_smem(U_NSTR, 2), st>>>(XP, G, XT, GT, Dv, S, Y, ld, n, hstride, w->st, o.m, nchunk, w->part);
+    else if (bounded) lb_update_kernel<true><<<vgrid, NT, 0, st>>>(XP, G, XT, GT, Dv, S, Y, ld, n, hstride, lo, hi, w->st, o.m, nchunk, w->part, 0);
+    else lb_update_kernel<false><<<vgrid, NT, 0, st>>>(XP, G, XT, GT, Dv, S, Y, ld, n, hstride, lo, hi, w->st, o.m, nchunk, w->part, 0);
+    lb_gram_kernel<<<B, 64, 0, st>>>(w->st, w->part, nchunk, o.m, 0, o.method);
+    if (use_tma && hns == 4) lb_direction_tma_kernel<4><<<vgrid, HT + 32, hist_smem(D_NSTR, 4), st>>>(G, Dv, S, Y, ld, n, hstride, w->st, o.m, nchunk, w->part);
+    else if (use_tma) lb_direction_tma_kernel<2><<<vgrid, HT + 32, hist_smem(D_NSTR, 2), st>>>(G, Dv, S, Y, ld, n, hstride, w->st, o.m, nchunk, w->part);
+    else if (bounded) lb_direction_kernel<true><<<vgrid, NT, 0, st>>>(XP, G, Dv, S, Y, ld, n, hstride, lo, hi, w->st, o.m, nchunk, w->part, 0);
+    else lb_direction_kernel<false><<<vgrid, NT, 0, st>>>(XP, G, Dv, S, Y, ld, n, hstride, lo, hi, w->st, o.m, nchunk, w->part, 0);
+    lb_start_kernel<<<B, 1, 0, st>>>(w->st, w->act_eval, w->part, nchunk, o, bounded ? 1 : 0, 0);
+    if (minpaths) { lb_save_kernel<<<vgrid, NT, 0, st>>>(XP, ld, n, w->st, nchunk, L); ctx->launches += 1; }
+    lb_advance_kernel<<<(B + 127) / 128, 128, 0, st>>>(w->st, w->act_eval, B, L, o);
+    ctx->launches += 8;
     return VAB_OK;
   };
   // The first cycle runs eagerly (it may allocate workspaces); the steady-state cycle is then
-  // captured once into a CUDA graph and replayed: launch-bound small problems (a cycle of ten
-  // tiny kernels) no longer pay the per-launch host cost.
+  // captured once into a CUDA graph and replayed.
   rc = enqueue_cycle();
   if (rc != VAB_OK) return rc;
+  LB_CUDA(cudaGetLastError());
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t gexec = nullptr;
   bool use_graph = true;
@@ -903,9 +1268,19 @@ int lb_minimize_core(vab_ctx* ctx, int B, double* XP, long long ld, double rf_sc
       cudaGetLastError();
     }
   }
+  // Polling is double-buffered: the next group of cycles is enqueued before the host waits for
+  // the counter of the previous group, so the device never idles on the host (the price is at
+  // most one group of empty cycles at the end).
   int rc_loop = VAB_OK;
+  long long groups = 0, cycles = 0;
+  double mc = (double)Nbeta * ((double)o.maxfun + (double)o.maxiter + 64.0) + 4.0 * poll;
+  const long long max_cycles = mc < 9.0e18 ? (long long)mc : (long long)9.0e18;
+  const double t_limit = getenv("VAB_LBFGS_MAX_SECONDS") ? atof(getenv("VAB_LBFGS_MAX_SECONDS")) : 0.0;
+  const auto t0 = std::chrono::steady_clock::now();
+  int gsize = poll < 4 ? poll : 4;              // groups grow 4, 8, ... poll: short runs waste little
   while (true) {
-    for (int c = 0; c < poll; ++c) {
+    const int k = (int)(groups & 1);
+    for (int c = 0; c < gsize; ++c) {
       if (gexec) {
         cudaError_t ge = cudaGraphLaunch(gexec, st);
         if (ge != cudaSuccess) { rc_loop = vab_cuda_fail(ctx, ge, "cudaGraphLaunch"); break; }
@@ -916,16 +1291,25 @@ int lb_minimize_core(vab_ctx* ctx, int B, double* XP, long long ld, double rf_sc
       }
     }
     if (rc_loop != VAB_OK) break;
-    cycles += poll;
-    lb_count_kernel<<<1, 256, 0, st>>>(w->st, B, w->n_running_dev);
+    cycles += gsize;
+    if (gsize < poll) gsize = (2 * gsize < poll) ? 2 * gsize : poll;
+    lb_count_kernel<<<1, 256, 0, st>>>(w->st, B, w->n_running_dev + k);
     ctx->launches += 1;
-    LB_CUDA(cudaMemcpyAsync(w->n_running_host, w->n_running_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
-    LB_CUDA(cudaEventRecord(w->ev, st));
-    LB_CUDA(cudaEventSynchronize(w->ev));
-    LB_CUDA(cudaGetLastError());
-    if (*w->n_running_host == 0) break;
+    LB_CUDA(cudaMemcpyAsync(w->n_running_host + k, w->n_running_dev + k, sizeof(int), cudaMemcpyDeviceToHost, st));
+    LB_CUDA(cudaEventRecord(w->ev[k], st));
+    groups += 1;
+    if (groups >= 2) {
+      LB_CUDA(cudaEventSynchronize(w->ev[1 - k]));
+      LB_CUDA(cudaGetLastError());
+      if (w->n_running_host[1 - k] == 0) break;
+    }
     if (cycles > max_cycles) { rc_loop = vab_fail(ctx, VAB_ERR_STATE, "minimize: cycle limit exceeded (internal error)"); break; }
+    if (t_limit > 0.0 &&
+        std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > t_limit) {
+      rc_loop = vab_fail(ctx, VAB_ERR_STATE, "minimize: VAB_LBFGS_MAX_SECONDS exceeded"); break;
+    }
   }
+  cudaStreamSynchronize(st);
   if (gexec) cudaGraphExecDestroy(gexec);
   if (graph) cudaGraphDestroy(graph);
   return rc_loop;
@@ -937,9 +1321,10 @@ void lbfgs_destroy(vab_ctx* ctx) {
   LbfgsWork* w = ctx->lb;
   if (!w) return;
   cudaFree(w->vec); cudaFree(w->st); cudaFree(w->act_eval); cudaFree(w->ft); cudaFree(w->met);
-  cudaFree(w->fet); cudaFree(w->part); cudaFree(w->n_running_dev);
+  cudaFree(w->fet); cudaFree(w->part); cudaFree(w->n_running_dev); cudaFree(w->lad);
   if (w->n_running_host) cudaFreeHost(w->n_running_host);
-  if (w->ev) cudaEventDestroy(w->ev);
+  for (int k = 0; k < 2; ++k)
+    if (w->ev[k]) cudaEventDestroy(w->ev[k]);
   delete w;
   ctx->lb = nullptr;
 }
@@ -952,11 +1337,11 @@ int vab_minimize(vab_ctx* ctx, int32_t B, double* XP_dev, int64_t ldxp, double r
                  int32_t* nit_dev, int32_t* nfev_dev) {
   if (!ctx) return VAB_ERR_INVALID;
   cudaSetDevice(ctx->device);
-  int rc = lb_minimize_core(ctx, B, XP_dev, ldxp, rf_scale, opts, lo_dev, hi_dev);
+  int rc = lb_run(ctx, B, XP_dev, ldxp, &rf_scale, nullptr, 1, opts, lo_dev, hi_dev, nullptr, nullptr,
+                  nullptr, nullptr, nullptr);
   if (rc != VAB_OK) return rc;
-  lb_export_kernel<<<(B + 127) / 128, 128, 0, ctx->stream>>>(
-      ctx->lb->st, B, A_dev, me_dev, fe_dev, status_dev, nit_dev, nfev_dev, nullptr, 0, 0, 0.0, 1.0,
-      nullptr, nullptr, nullptr);
+  lb_export_kernel<<<(B + 127) / 128, 128, 0, ctx->stream>>>(ctx->lb->st, B, A_dev, me_dev, fe_dev,
+                                                              status_dev, nit_dev, nfev_dev);
   ctx->launches += 1;
   cudaError_t e = cudaStreamSynchronize(ctx->stream);
   if (e != cudaSuccess) return vab_cuda_fail(ctx, e, "vab_minimize");
@@ -970,21 +1355,12 @@ int vab_anneal(vab_ctx* ctx, int32_t B, double* XP_dev, int64_t ldxp, double alp
   if (!ctx) return VAB_ERR_INVALID;
   if (!beta_host || Nbeta < 1) return vab_fail(ctx, VAB_ERR_INVALID, "anneal: empty beta ladder");
   cudaSetDevice(ctx->device);
-  for (int ib = 0; ib < Nbeta; ++ib) {
-    const double scale = pow(alpha, beta_host[ib]);
-    int rc = lb_minimize_core(ctx, B, XP_dev, ldxp, scale, opts, lo_dev, hi_dev);
-    if (rc != VAB_OK) return rc;
-    lb_export_kernel<<<(B + 127) / 128, 128, 0, ctx->stream>>>(
-        ctx->lb->st, B, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, table_dev, Nbeta, ib,
-        beta_host[ib], scale, status_dev, nit_dev, nfev_dev);
-    ctx->launches += 1;
-    if (minpaths_dev) {
-      cudaError_t e = cudaMemcpy2DAsync(minpaths_dev + (size_t)ib * ldxp, (size_t)Nbeta * ldxp * sizeof(double),
-                                        XP_dev, (size_t)ldxp * sizeof(double), (size_t)ldxp * sizeof(double),
-                                        B, cudaMemcpyDeviceToDevice, ctx->stream);
-      if (e != cudaSuccess) return vab_cuda_fail(ctx, e, "anneal: minpaths copy");
-    }
-  }
+  std::string buf((size_t)Nbeta * sizeof(double), '\0');
+  double* scales = reinterpret_cast<double*>(&buf[0]);
+  for (int ib = 0; ib < Nbeta; ++ib) scales[ib] = pow(alpha, beta_host[ib]);
+  int rc = lb_run(ctx, B, XP_dev, ldxp, scales, beta_host, Nbeta, opts, lo_dev, hi_dev, table_dev,
+                  minpaths_dev, status_dev, nit_dev, nfev_dev);
+  if (rc != VAB_OK) return rc;
   cudaError_t e = cudaStreamSynchronize(ctx->stream);
   if (e != cudaSuccess) return vab_cuda_fail(ctx, e, "vab_anneal");
   return VAB_OK;

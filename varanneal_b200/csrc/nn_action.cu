@@ -46,6 +46,8 @@ struct NnParams {
   const double* data_out; // (M, n_Lout)
   double wm_in, wm_out;   // 2 cm RM_in, 2 cm RM_out
   double cf2;             // 2 RF / ((NDnet - d_0) M)
+  double cf2_num, cf2_den; // 2 RF0 and (NDnet - d_0) M: cf2 of a path on its own rung = cf2_num * rf_path[b] / cf2_den
+  const double* rf_path;  // (B) or nullptr
   const int* active;
   double* partials;       // (B, ntiles, 2): me, fe
   double* gwpart;         // (B, ntiles, NP)
@@ -112,6 +114,7 @@ __global__ void __launch_bounds__(NT) nn_fused_kernel(const __grid_constant__ Nn
   double* gw = P.gwpart + ((long long)b * P.ntiles + tile) * P.NP;
   auto param = [&](int k) -> double { return __ldg(pfull + k); };
   double me_acc = 0.0, fe_acc = 0.0;
+  const double cf2 = (P.rf_path != nullptr) ? P.cf2_num * __ldg(P.rf_path + b) / P.cf2_den : P.cf2;
   const int MTL = TM >> 3;                            // 8-row tiles of examples
 
   // layer 0 states (zero-padded) + measurement term of the input layer
@@ -187,7 +190,7 @@ __global__ void __launch_bounds__(NT) nn_fused_kernel(const __grid_constant__ Nn
                 const double sv = act_f(P.act, z);
                 const double xn1 = Xn[m * dp + j0 + j];
                 const double e = xn1 - sv;
-                lam = P.cf2 * e;
+                lam = cf2 * e;
                 fe_acc = fma(lam, e, fe_acc);
                 dl = -lam * act_d(P.act, sv);
                 gx = lam;
@@ -367,7 +370,8 @@ void nn_destroy(vab_ctx* ctx) {
 long long nn_unknowns(const vab_ctx* ctx) { return ctx->nn ? ctx->nn->NDens + ctx->nn->NPest : 0; }
 
 int nn_eval(vab_ctx* ctx, int B, const double* XP, long long ldxp, double rf_scale,
-            const int* active_dev, double* A, double* me, double* fe, double* G, long long ldg) {
+            const double* rf_path_dev, const int* active_dev, double* A, double* me, double* fe,
+            double* G, long long ldg) {
   NnProblem* p = ctx->nn;
   if (!p) return vab_fail(ctx, VAB_ERR_STATE, "nn_action_grad: no NN problem set");
   const long long n = p->NDens + p->NPest;
@@ -386,6 +390,9 @@ int nn_eval(vab_ctx* ctx, int B, const double* XP, long long ldxp, double rf_sca
   P.wm_in = 2.0 * cm * p->rm_in;
   P.wm_out = 2.0 * cm * p->rm_out;
   P.cf2 = 2.0 * p->rf0 * rf_scale / ((double)(p->NDnet - p->d0) * p->M);
+  P.cf2_num = 2.0 * p->rf0;
+  P.cf2_den = (double)(p->NDnet - p->d0) * p->M;
+  P.rf_path = rf_path_dev;
   P.active = active_dev;
   // Shared-memory plan: 5 [TM][dpitch] tiles + a chunk of weight rows.  Pitches are = 4 (mod 8)
   // doubles; TM is a multiple of 8.  Prefer a footprint that lets two CTAs share an SM.
@@ -532,7 +539,7 @@ int vab_nn_action_grad(vab_ctx* ctx, int32_t B, const double* XP_dev, int64_t ld
   if (!ctx) return VAB_ERR_INVALID;
   if (ctx->problem != VAB_PROBLEM_NN) return vab_fail(ctx, VAB_ERR_STATE, "nn_action_grad: no NN problem set");
   cudaSetDevice(ctx->device);
-  return nn_eval(ctx, B, XP_dev, ldxp, rf_scale, nullptr, A_dev, me_dev, fe_dev, G_dev, ldg);
+  return nn_eval(ctx, B, XP_dev, ldxp, rf_scale, nullptr, nullptr, A_dev, me_dev, fe_dev, G_dev, ldg);
 }
 
 }  // extern "C"

@@ -98,15 +98,23 @@ SweepKernel sweep_kernel(int model, int C, int disc) {
 #define VAB_ST_MINB 4
 #endif
 
-template <class M, bool FAST>
+// MODE: 0 = run-time weights, 1 = scalar RM / RF (launch constants), 2 = the same with one RF per
+// path (ode_stream.cuh)
+template <class M, int MODE>
 SweepKernel stream_kernel_for(int disc) {
   switch (disc) {
-    case DISC_EULER: return stream_twopoint_kernel<M, DISC_EULER, VAB_ST_NS, VAB_ST_MINB, FAST>;
-    case DISC_TRAPEZOID: return stream_twopoint_kernel<M, DISC_TRAPEZOID, VAB_ST_NS, VAB_ST_MINB, FAST>;
-    case DISC_FORWARDMAP: return stream_twopoint_kernel<M, DISC_FORWARDMAP, VAB_ST_NS, VAB_ST_MINB, FAST>;
-    case DISC_SIMPSON: return stream_simpson_kernel<M, VAB_ST_NS, VAB_ST_MINB, FAST>;
+    case DISC_EULER: return stream_twopoint_kernel<M, DISC_EULER, VAB_ST_NS, VAB_ST_MINB, MODE>;
+    case DISC_TRAPEZOID: return stream_twopoint_kernel<M, DISC_TRAPEZOID, VAB_ST_NS, VAB_ST_MINB, MODE>;
+    case DISC_FORWARDMAP: return stream_twopoint_kernel<M, DISC_FORWARDMAP, VAB_ST_NS, VAB_ST_MINB, MODE>;
+    case DISC_SIMPSON: return stream_simpson_kernel<M, VAB_ST_NS, VAB_ST_MINB, MODE>;
   }
   return nullptr;
+}
+template <class M>
+SweepKernel stream_kernel_mode(int disc, int mode) {
+  if (mode == 1) return stream_kernel_for<M, 1>(disc);
+  if (mode == 2) return stream_kernel_for<M, 2>(disc);
+  return stream_kernel_for<M, 0>(disc);
 }
 int stream_variant() {
   static int variant = -1;
@@ -126,17 +134,18 @@ int stream_ns(int C, int disc, bool fast) {
   }
   return VAB_ST_NS;
 }
-SweepKernel stream_kernel(int C, int disc, bool fast) {
-  if (fast && C == 4 && disc == DISC_SIMPSON) {       // tuning variants of the flagship kernel
+SweepKernel stream_kernel(int C, int disc, bool fast, bool perpath) {
+  const int mode = fast ? (perpath ? 2 : 1) : 0;
+  if (mode == 1 && C == 4 && disc == DISC_SIMPSON) {       // tuning variants of the flagship kernel
     switch (stream_variant()) {
-      case 1: return stream_simpson_kernel<ModelL96<4>, 4, 5, true>;
-      case 2: return stream_simpson_kernel<ModelL96<4>, 3, 5, true>;
-      case 3: return stream_simpson_kernel<ModelL96<4>, 3, 4, true>;
-      default: return stream_simpson_kernel<ModelL96<4>, 4, 4, true>;
+      case 1: return stream_simpson_kernel<ModelL96<4>, 4, 5, 1>;
+      case 2: return stream_simpson_kernel<ModelL96<4>, 3, 5, 1>;
+      case 3: return stream_simpson_kernel<ModelL96<4>, 3, 4, 1>;
+      default: return stream_simpson_kernel<ModelL96<4>, 4, 4, 1>;
     }
   }
-  if (C == 4) return fast ? stream_kernel_for<ModelL96<4>, true>(disc) : stream_kernel_for<ModelL96<4>, false>(disc);
-  if (C == 2) return fast ? stream_kernel_for<ModelL96<2>, true>(disc) : stream_kernel_for<ModelL96<2>, false>(disc);
+  if (C == 4) return stream_kernel_mode<ModelL96<4>>(disc, mode);
+  if (C == 2) return stream_kernel_mode<ModelL96<2>>(disc, mode);
   return nullptr;
 }
 
@@ -181,7 +190,7 @@ int ode_sweep_prepare(int model, int disc, int D, int N, int B, int num_sms, int
     const int ns = stream_ns(g.C, disc, fast);
     const size_t smem = (size_t)4 * ns * stage_b + ((size_t)4 * ns + (size_t)128 * K) * sizeof(double);
     if (smem <= 200 * 1024) {
-      k = stream_kernel(g.C, disc, fast);
+      k = stream_kernel(g.C, disc, fast, P->rf_path != nullptr);
       nb = k ? blocks_per_sm(k, smem, cerr) : 0;
       if (nb < 0) return -2;
       if (nb > 0) { sl->stream = true; sl->smem = smem; }
@@ -226,7 +235,7 @@ int ode_sweep_prepare(int model, int disc, int D, int N, int B, int num_sms, int
 int ode_sweep_launch(const OdeParams& P, const SweepLaunch& sl, int model, int disc,
                      cudaStream_t st, double* A, double* me, double* fe, cudaError_t* cerr) {
   const bool fast = (P.nskip == 1 && P.rmd == nullptr && P.rf_arr == nullptr && P.L > 0);
-  SweepKernel k = sl.stream ? stream_kernel(sl.C, disc, fast) : sweep_kernel(model, sl.C, disc);
+  SweepKernel k = sl.stream ? stream_kernel(sl.C, disc, fast, P.rf_path != nullptr) : sweep_kernel(model, sl.C, disc);
   if (!k) return -1;
   k<<<sl.grid, 128, sl.smem, st>>>(P);
   cudaError_t e = cudaGetLastError();

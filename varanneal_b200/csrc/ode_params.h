@@ -17,6 +17,9 @@ struct OdeParams {
   double rf_scalar;       // RF0 * scale when rf_arr == nullptr
   const double* rf_arr;   // RF0 (N-1, D) or nullptr
   double rf_scale;
+  double rf0;             // RF0 when it is a scalar (rf_scalar = rf0 * rf_scale)
+  const double* rf_path;  // (B) or nullptr: per-path scale replacing rf_scale (asynchronous ladder:
+                          // every path sits on its own rung, lbfgs.cu)
   const double* stim;     // (N, S) or nullptr
   int S;
   int NP, NPest;

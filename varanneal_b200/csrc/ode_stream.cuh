@@ -27,6 +27,7 @@
 #include "ode_models.cuh"
 #include "ode_params.h"
 #include "vab_hd.h"
+#include "vab_tma.cuh"
 
 #ifndef VAB_FULL
 #define VAB_FULL 0xffffffffu
@@ -34,45 +35,16 @@
 
 namespace vabs {
 
-__device__ __forceinline__ uint32_t s32(const void* p) {
-  return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_fence_init() {
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-  } while (!ok);
-}
-// 1-D bulk copy global -> shared (TMA); bytes % 16 == 0, both addresses 16-byte aligned
-__device__ __forceinline__ void tma_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-      ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
-      : "memory");
-}
 __device__ __forceinline__ void lds2(uint32_t addr, double& a, double& b) {
   asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "r"(addr));
 }
 
-// FAST: nskip == 1, scalar RM, scalar RF (the common case); otherwise every weight / row test is
-// looked up at run time.
-template <class M, int NS, bool FAST>
+// MODE 1 (FAST): nskip == 1, scalar RM, scalar RF (the common case), the RF weight a launch
+// constant; MODE 2: the same with one RF per path (P.rf_path, asynchronous ladder: the weight
+// becomes a per-lane register); MODE 0: every weight / row test is looked up at run time.
+template <class M, int NS, int MODE>
 struct Stream {
+  static constexpr bool FAST = (MODE != 0), PERPATH = (MODE == 2);
   static constexpr int C = M::C, H = M::H, W = M::C + 2 * M::H, NPM = M::NPM;
   static_assert(H == 2 && (C == 4 || C == 2), "stream kernels: Lorenz96-type stencil, strips of 4 or 2");
   const OdeParams& P;
@@ -96,6 +68,7 @@ struct Stream {
   double p[NPM];
   double wob[C];               // 2 cm RM of the own components (0 = unobserved)
   double wfs;                  // 2 cf RF (scalar RF)
+  double rsc;                  // scale of an RF0 array (per path under the asynchronous ladder)
   double me_acc, fe_acc, pacc[NPM];
 
   __device__ __forceinline__ Stream(const OdeParams& P_) : P(P_) {}
@@ -179,7 +152,13 @@ struct Stream {
     }
 #pragma unroll
     for (int c = 0; c < C; ++c) wob[c] = out ? __ldg(P.wobs + i0 + c) : 0.0;
-    wfs = 2.0 * P.cf * P.rf_scalar;
+    if constexpr (MODE == 1) {
+      rsc = P.rf_scale;
+      wfs = 2.0 * P.cf * P.rf_scalar;
+    } else {
+      rsc = (P.rf_path != nullptr) ? __ldg(P.rf_path + b) : P.rf_scale;
+      wfs = 2.0 * P.cf * ((P.rf_path != nullptr) ? P.rf0 * rsc : P.rf_scalar);
+    }
     me_acc = 0.0;
     fe_acc = 0.0;
     // zero this warp's ring: rows that are never copied (path ends, rows without observations)
@@ -282,7 +261,7 @@ struct Stream {
   }
   __device__ __forceinline__ double wgt(int row, int c) const {   // 2 cf RF for residual (row, c)
     if (FAST) return wfs;
-    return P.rf_arr ? 2.0 * P.cf * P.rf_scale * __ldg(P.rf_arr + (long long)row * D + i0 + c) : wfs;
+    return P.rf_arr ? 2.0 * P.cf * rsc * __ldg(P.rf_arr + (long long)row * D + i0 + c) : wfs;
   }
   // measurement term of row r (va_ode.py:138-158), y staged at byte offset yoff:
   // d += 2 cm RM (x - y);  me_acc += 2 cm RM (x - y)^2.  Branch-free: unobserved components have
@@ -341,9 +320,9 @@ struct Stream {
 // One step per pair = one ring stage (rows b, c).  Rows a and b get their gradient in the step of
 // their pair; row c's partial seed is carried into the next pair, where it is row a.  Row a itself
 // is re-read from the previous stage (kept resident one step longer) instead of being carried.
-template <class M, int NS, int MINB, bool FAST>
+template <class M, int NS, int MINB, int MODE>
 __global__ void __launch_bounds__(128, MINB) stream_simpson_kernel(const __grid_constant__ OdeParams P) {
-  using ST = vabs::Stream<M, NS, FAST>;
+  using ST = vabs::Stream<M, NS, MODE>;
   constexpr int C = ST::C, H = ST::H, W = ST::W;
   extern __shared__ __align__(16) double smem[];
   ST S(P);
@@ -473,9 +452,9 @@ __global__ void __launch_bounds__(128, MINB) stream_simpson_kernel(const __grid_
 //   e_m = x_{m+1} - AL x_m - (CA f_m + CB f_{m+1}),  lam = 2 cf RF e
 //   g_r = [lam_{r-1} - AL lam_r] + meas_r - J^T(x_r) (CB lam_{r-1} + CA lam_r)
 // One step = one ring stage = two arriving rows.
-template <class M, int DISC, int NS, int MINB, bool FAST>
+template <class M, int DISC, int NS, int MINB, int MODE>
 __global__ void __launch_bounds__(128, MINB) stream_twopoint_kernel(const __grid_constant__ OdeParams P) {
-  using ST = vabs::Stream<M, NS, FAST>;
+  using ST = vabs::Stream<M, NS, MODE>;
   constexpr int C = ST::C, H = ST::H, W = ST::W;
   extern __shared__ __align__(16) double smem[];
   ST S(P);

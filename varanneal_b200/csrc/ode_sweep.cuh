@@ -36,6 +36,7 @@ struct SLane {
   double* gpath;
   double p[NPM];
   double wob[C];                       // 2 cm RM of the own components (0 = unobserved)
+  double rfs, rsc;                     // RF (scalar form) and the scale of an RF0 array, of this path
   double me_acc, fe_acc, pacc[NPM];
 
   __device__ __forceinline__ void init(const OdeParams& P) {
@@ -97,6 +98,8 @@ struct SLane {
     }
 #pragma unroll
     for (int c = 0; c < C; ++c) wob[c] = act ? __ldg(P.wobs + i0 + c) : 0.0;
+    rsc = (P.rf_path != nullptr) ? __ldg(P.rf_path + b) : P.rf_scale;
+    rfs = (P.rf_path != nullptr) ? P.rf0 * rsc : P.rf_scalar;
     me_acc = 0.0;
     fe_acc = 0.0;
   }
@@ -134,7 +137,7 @@ struct SLane {
     return (M::NSTIM > 0 && P.stim != nullptr) ? P.stim + (long long)row * P.S : nullptr;
   }
   __device__ __forceinline__ double wgt(const OdeParams& P, int row, int c) const {
-    return P.rf_arr ? __ldg(P.rf_arr + (long long)row * D + i0 + c) * P.rf_scale : P.rf_scalar;
+    return P.rf_arr ? __ldg(P.rf_arr + (long long)row * D + i0 + c) * rsc : rfs;
   }
   // measurement term of row r (va_ode.py:138-158): adds to the direct gradient and to me_acc
   // (me_acc collects sum 2 cm RM diff^2 = 2 me)

@@ -14,7 +14,8 @@
 void nn_destroy(vab_ctx* ctx);       // nn_action.cu
 void lbfgs_destroy(vab_ctx* ctx);    // lbfgs.cu
 int nn_eval(vab_ctx* ctx, int B, const double* XP, long long ldxp, double rf_scale,
-            const int* active_dev, double* A, double* me, double* fe, double* G, long long ldg);
+            const double* rf_path_dev, const int* active_dev, double* A, double* me, double* fe,
+            double* G, long long ldg);
 long long nn_unknowns(const vab_ctx* ctx);
 
 static thread_local std::string g_create_error;
@@ -145,6 +146,21 @@ int vab_sync(vab_ctx* ctx) {
   return VAB_OK;
 }
 
+int vab_copy_rows_to_host(vab_ctx* ctx, double* host_dst, int64_t host_pitch, const double* src_dev,
+                          int64_t dev_pitch, int64_t width, int64_t rows) {
+  if (!ctx) return VAB_ERR_INVALID;
+  if (!host_dst || !src_dev || width < 0 || rows < 0 || host_pitch < width || dev_pitch < width)
+    return vab_fail(ctx, VAB_ERR_INVALID, "copy_rows_to_host: bad arguments");
+  if (width == 0 || rows == 0) return VAB_OK;
+  cudaSetDevice(ctx->device);
+  cudaError_t e = cudaMemcpy2DAsync(host_dst, (size_t)host_pitch * sizeof(double), src_dev,
+                                    (size_t)dev_pitch * sizeof(double), (size_t)width * sizeof(double),
+                                    (size_t)rows, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) return vab_cuda_fail(ctx, e, "copy_rows_to_host");
+  return VAB_OK;
+}
+
 int vab_ode_problem_set(vab_ctx* ctx, const vab_ode_desc* d, const int32_t* Lidx_host,
                         const int32_t* Pidx_host, const double* Y_dev, const double* stim_dev) {
   if (!ctx || !d) return VAB_ERR_INVALID;
@@ -264,8 +280,8 @@ int vab_ode_set_fixed_params(vab_ctx* ctx, const double* pfix_dev, int64_t pfix_
 }  // extern "C"
 
 static int ode_eval(vab_ctx* ctx, int B, const double* XP, long long ldxp, double rf_scale,
-                    const int* active_dev, double* A, double* me, double* fe, double* G,
-                    long long ldg) {
+                    const double* rf_path_dev, const int* active_dev, double* A, double* me,
+                    double* fe, double* G, long long ldg) {
   const vab_ode_desc& d = ctx->od;
   const long long n = (long long)d.N_model * d.D + d.NPest;
   if (B < 1 || !XP) return vab_fail(ctx, VAB_ERR_INVALID, "ode_action_grad: bad batch / XP");
@@ -280,6 +296,7 @@ static int ode_eval(vab_ctx* ctx, int B, const double* XP, long long ldxp, doubl
   P.dt = d.dt_model;
   P.Y = ctx->Y_dense; P.wobs = ctx->wobs_dev; P.rmd = ctx->rm_dev;
   P.rf_scalar = ctx->rf0_scalar * rf_scale; P.rf_arr = ctx->rf0_dev; P.rf_scale = rf_scale;
+  P.rf0 = ctx->rf0_scalar; P.rf_path = rf_path_dev;
   P.stim = ctx->stim_dev; P.S = d.n_stim;
   P.NP = d.NP; P.NPest = d.NPest; P.pmap = ctx->pmap_dev;
   P.pfix = ctx->pfix_dev; P.pfix_stride = ctx->pfix_stride;
@@ -307,11 +324,12 @@ static int ode_eval(vab_ctx* ctx, int B, const double* XP, long long ldxp, doubl
 }
 
 int vab_eval(vab_ctx* ctx, int B, const double* XP, long long ldxp, double rf_scale,
-             const int* active_dev, double* A, double* me, double* fe, double* G, long long ldg) {
+             const double* rf_path_dev, const int* active_dev, double* A, double* me, double* fe,
+             double* G, long long ldg) {
   if (ctx->problem == VAB_PROBLEM_ODE)
-    return ode_eval(ctx, B, XP, ldxp, rf_scale, active_dev, A, me, fe, G, ldg);
+    return ode_eval(ctx, B, XP, ldxp, rf_scale, rf_path_dev, active_dev, A, me, fe, G, ldg);
   if (ctx->problem == VAB_PROBLEM_NN)
-    return nn_eval(ctx, B, XP, ldxp, rf_scale, active_dev, A, me, fe, G, ldg);
+    return nn_eval(ctx, B, XP, ldxp, rf_scale, rf_path_dev, active_dev, A, me, fe, G, ldg);
   return vab_fail(ctx, VAB_ERR_STATE, "no problem set on this context");
 }
 
@@ -321,5 +339,5 @@ extern "C" int vab_ode_action_grad(vab_ctx* ctx, int32_t B, const double* XP_dev
   if (!ctx) return VAB_ERR_INVALID;
   if (ctx->problem != VAB_PROBLEM_ODE) return vab_fail(ctx, VAB_ERR_STATE, "ode_action_grad: no ODE problem set");
   cudaSetDevice(ctx->device);
-  return ode_eval(ctx, B, XP_dev, ldxp, rf_scale, nullptr, A_dev, me_dev, fe_dev, G_dev, ldg);
+  return ode_eval(ctx, B, XP_dev, ldxp, rf_scale, nullptr, nullptr, A_dev, me_dev, fe_dev, G_dev, ldg);
 }

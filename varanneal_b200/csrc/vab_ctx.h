@@ -59,6 +59,8 @@ int vab_cuda_fail(vab_ctx* ctx, cudaError_t e, const char* where);
 int vab_reserve(vab_ctx* ctx, double** buf, size_t* cap, size_t need);
 
 // objective evaluation for the problem currently set (ODE or NN); used by the minimiser.
-// active_dev: (B) int mask or nullptr.
+// active_dev: (B) int mask or nullptr.  rf_path_dev: (B) per-path scale of RF0 (replaces rf_scale)
+// or nullptr.
 int vab_eval(vab_ctx* ctx, int B, const double* XP, long long ldxp, double rf_scale,
-             const int* active_dev, double* A, double* me, double* fe, double* G, long long ldg);
+             const double* rf_path_dev, const int* active_dev, double* A, double* me, double* fe,
+             double* G, long long ldg);

@@ -96,6 +96,9 @@ class Annealer(DeviceMin):
         if not self.annealing_initialized:
             self.anneal_init(X0, P0, alpha, beta_array, RM, RF0, Pidx, Lidx, init_to_data, action,
                              disc, method, bounds, opt_args, adolcID)
+        if not self.verbose and self.betaidx == 0 and self._ladder_fits_device():
+            self._anneal_device()           # the whole ladder in one native call
+            return
         for _ in range(self.Nbeta):
             if self.verbose:
                 print('------------------------------')

@@ -83,6 +83,10 @@ class Annealer(DeviceMin):
         if not self.annealing_initialized:
             self.anneal_init(X0, P0, alpha, beta_array, RM, RF0, Lidx, Pidx, dt_model,
                              init_to_data, action, disc, method, bounds, opt_args, adolcID)
+        tracked = not (track_paths is None and track_params is None and track_action_errors is None)
+        if not tracked and not self.verbose and self.betaidx == 0 and self._ladder_fits_device():
+            self._anneal_device()           # the whole ladder in one native call
+            return
         for _ in range(self.Nbeta):
             if self.verbose:
                 print('------------------------------')
