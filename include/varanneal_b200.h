@@ -186,6 +186,14 @@ VAB_API int vab_anneal(vab_ctx* ctx, int32_t B, double* XP_dev, int64_t ldxp, do
                double* table_dev, double* minpaths_dev,
                int32_t* status_dev, int32_t* nit_dev, int32_t* nfev_dev);
 
+/* Host sink for the minimising paths of the next vab_anneal call (which must be given a
+ * minpaths_dev buffer): as soon as a path has finished rung i, its minimiser (the first `width`
+ * doubles of the row) is copied to host_dst + (b * Nbeta + i) * host_pitch on a second stream while
+ * the other paths keep annealing, so the host array the reference fills rung by rung
+ * (minpaths, va_ode.py:776) is complete when vab_anneal returns and the transfer costs no wall
+ * time.  host_dst may be pageable.  The sink is cleared by the call that used it; NULL clears it. */
+VAB_API int vab_set_path_sink(vab_ctx* ctx, double* host_dst, int64_t host_pitch, int64_t width);
+
 /* Strided device -> host copy of `rows` rows of `width` doubles (pitches in doubles), on the
  * context's stream, synchronous for the caller.  Used by the host mirror to lay the device
  * result buffers of vab_anneal out as the reference's minpaths array (va_ode.py:666-667, 776:

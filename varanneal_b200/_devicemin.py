@@ -241,6 +241,10 @@ class DeviceMin(object):
         betas = np.asarray(self.beta_array, dtype=np.float64)
         beta_c = (ct.c_double * nb)(*betas)
         lib, h = self._ctx.lib, self._ctx.h
+        # states go home while the ladder runs: finished rungs are copied from the device rows
+        # (pitch ld) straight into the host rows (pitch nX + NP) of self.minpaths
+        mp = self.minpaths.reshape(B * nb, nX + self.NP)
+        _lib.check(lib.vab_set_path_sink(h, ct.c_void_p(mp.ctypes.data), nX + self.NP, nX), h)
         _lib.check(lib.vab_anneal(h, B, ptr(self._XP), self._ld, float(self.alpha), beta_c, nb,
                                   ct.byref(opts), lo, hi, ptr(table), ptr(paths), ptr(stat), ptr(nit),
                                   ptr(nfev)), h)
@@ -252,10 +256,6 @@ class DeviceMin(object):
         self.exitflags[...] = stat.cpu().numpy().reshape(shape)
         self.nit_array[...] = nit.cpu().numpy().reshape(shape)
         self.nfev_array[...] = nfev.cpu().numpy().reshape(shape)
-        # states: one strided DMA from the device rows (pitch ld) into the host rows (pitch nX + NP)
-        mp = self.minpaths.reshape(B * nb, nX + self.NP)
-        _lib.check(lib.vab_copy_rows_to_host(h, ct.c_void_p(mp.ctypes.data), nX + self.NP, ptr(paths),
-                                             self._ld, nX, B * nb), h)
         # parameters: the fixed values with the estimates of every rung written in
         P = np.broadcast_to(self.P.reshape(B, 1, self.NP), (B, nb, self.NP)).copy()
         if self.NPest > 0:

@@ -48,6 +48,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "vab_ctx.h"
 #include "vab_tma.cuh"
@@ -107,6 +108,10 @@ struct LbfgsWork {
   cudaEvent_t ev[2] = {nullptr, nullptr};
   double* lad = nullptr;            // scales[Nbeta] | betas[Nbeta] | rf_path[B]
   size_t lad_cap = 0;
+  int* prog_dev = nullptr;          // [2][B] rungs completed by each path, per poll buffer
+  int* prog_host = nullptr;         // pinned [2][B]
+  int prog_cap = 0;
+  cudaStream_t copy_stream = nullptr;   // device -> host sink of finished rungs
 };
 
 namespace {
@@ -1052,9 +1057,13 @@ __global__ void lb_advance_kernel(LbPath* st, int* act_eval, int B, LbLadder L, 
   }
 }
 
-__global__ void lb_count_kernel(const LbPath* st, int B, int* n_running) {
+__global__ void lb_count_kernel(const LbPath* st, int B, int* n_running, int* prog, int Nbeta) {
   int c = 0;
-  for (int b = threadIdx.x; b < B; b += blockDim.x) c += st[b].finished ? 0 : 1;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    const int fin = st[b].finished;
+    c += fin ? 0 : 1;
+    if (prog) prog[b] = fin ? Nbeta : st[b].ib;        // rungs this path has completed
+  }
   for (int sft = 16; sft > 0; sft >>= 1) c += __shfl_down_sync(0xffffffffu, c, sft);
   __shared__ int w[8];
   if ((threadIdx.x & 31) == 0) w[threadIdx.x >> 5] = c;
@@ -1126,6 +1135,15 @@ int lb_reserve(vab_ctx* ctx, int B, long long ld, int m, int Nbeta) {
   if (rc != VAB_OK) return rc;
   rc = vab_reserve(ctx, &w->lad, &w->lad_cap, (size_t)2 * Nbeta + B);
   if (rc != VAB_OK) return rc;
+  if (B > w->prog_cap) {
+    cudaFree(w->prog_dev);
+    if (w->prog_host) cudaFreeHost(w->prog_host);
+    w->prog_dev = nullptr; w->prog_host = nullptr;
+    LB_CUDA(cudaMalloc((void**)&w->prog_dev, 2 * sizeof(int) * B));
+    LB_CUDA(cudaMallocHost((void**)&w->prog_host, 2 * sizeof(int) * B));
+    w->prog_cap = B;
+  }
+  if (!w->copy_stream) LB_CUDA(cudaStreamCreateWithFlags(&w->copy_stream, cudaStreamNonBlocking));
   if (!w->n_running_dev) LB_CUDA(cudaMalloc((void**)&w->n_running_dev, 2 * sizeof(int)));
   if (!w->n_running_host) LB_CUDA(cudaMallocHost((void**)&w->n_running_host, 2 * sizeof(int)));
   for (int k = 0; k < 2; ++k)
@@ -1271,6 +1289,24 @@ int lb_run(vab_ctx* ctx, int B, double* XP, long long ld, const double* scales_h
   // Polling is double-buffered: the next group of cycles is enqueued before the host waits for
   // the counter of the previous group, so the device never idles on the host (the price is at
   // most one group of empty cycles at the end).
+  // host sink (vab_set_path_sink): rows of minpaths are sent home as the paths finish their rungs
+  double* sink = (minpaths != nullptr) ? ctx->sink_host : nullptr;
+  const long long sink_pitch = ctx->sink_pitch, sink_width = ctx->sink_width;
+  ctx->sink_host = nullptr; ctx->sink_pitch = 0; ctx->sink_width = 0;
+  if (sink != nullptr && sink_width > ld) return vab_fail(ctx, VAB_ERR_INVALID, "anneal: sink width > ldxp");
+  std::vector<int> sent(sink ? B : 0, 0);
+  auto send_rows = [&](const int* prog) -> cudaError_t {
+    for (int b = 0; b < B; ++b) {
+      const int upto = prog ? prog[b] : Nbeta;
+      for (; sent[b] < upto; ++sent[b]) {
+        const size_t row = (size_t)b * Nbeta + sent[b];
+        cudaError_t ce = cudaMemcpyAsync(sink + row * (size_t)sink_pitch, minpaths + row * (size_t)ld,
+                                         (size_t)sink_width * sizeof(double), cudaMemcpyDeviceToHost, w->copy_stream);
+        if (ce != cudaSuccess) return ce;
+      }
+    }
+    return cudaSuccess;
+  };
   int rc_loop = VAB_OK;
   long long groups = 0, cycles = 0;
   double mc = (double)Nbeta * ((double)o.maxfun + (double)o.maxiter + 64.0) + 4.0 * poll;
@@ -1293,14 +1329,16 @@ int lb_run(vab_ctx* ctx, int B, double* XP, long long ld, const double* scales_h
     if (rc_loop != VAB_OK) break;
     cycles += gsize;
     if (gsize < poll) gsize = (2 * gsize < poll) ? 2 * gsize : poll;
-    lb_count_kernel<<<1, 256, 0, st>>>(w->st, B, w->n_running_dev + k);
+    lb_count_kernel<<<1, 256, 0, st>>>(w->st, B, w->n_running_dev + k, sink ? w->prog_dev + (size_t)k * B : nullptr, Nbeta);
     ctx->launches += 1;
     LB_CUDA(cudaMemcpyAsync(w->n_running_host + k, w->n_running_dev + k, sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (sink) LB_CUDA(cudaMemcpyAsync(w->prog_host + (size_t)k * B, w->prog_dev + (size_t)k * B, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
     LB_CUDA(cudaEventRecord(w->ev[k], st));
     groups += 1;
     if (groups >= 2) {
       LB_CUDA(cudaEventSynchronize(w->ev[1 - k]));
       LB_CUDA(cudaGetLastError());
+      if (sink) LB_CUDA(send_rows(w->prog_host + (size_t)(1 - k) * B));
       if (w->n_running_host[1 - k] == 0) break;
     }
     if (cycles > max_cycles) { rc_loop = vab_fail(ctx, VAB_ERR_STATE, "minimize: cycle limit exceeded (internal error)"); break; }
@@ -1310,6 +1348,11 @@ int lb_run(vab_ctx* ctx, int B, double* XP, long long ld, const double* scales_h
     }
   }
   cudaStreamSynchronize(st);
+  if (sink && rc_loop == VAB_OK) {
+    cudaError_t ce = send_rows(nullptr);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(w->copy_stream);
+    if (ce != cudaSuccess) rc_loop = vab_cuda_fail(ctx, ce, "anneal: host sink");
+  }
   if (gexec) cudaGraphExecDestroy(gexec);
   if (graph) cudaGraphDestroy(graph);
   return rc_loop;
@@ -1321,7 +1364,9 @@ void lbfgs_destroy(vab_ctx* ctx) {
   LbfgsWork* w = ctx->lb;
   if (!w) return;
   cudaFree(w->vec); cudaFree(w->st); cudaFree(w->act_eval); cudaFree(w->ft); cudaFree(w->met);
-  cudaFree(w->fet); cudaFree(w->part); cudaFree(w->n_running_dev); cudaFree(w->lad);
+  cudaFree(w->fet); cudaFree(w->part); cudaFree(w->n_running_dev); cudaFree(w->lad); cudaFree(w->prog_dev);
+  if (w->prog_host) cudaFreeHost(w->prog_host);
+  if (w->copy_stream) cudaStreamDestroy(w->copy_stream);
   if (w->n_running_host) cudaFreeHost(w->n_running_host);
   for (int k = 0; k < 2; ++k)
     if (w->ev[k]) cudaEventDestroy(w->ev[k]);

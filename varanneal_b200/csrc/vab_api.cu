@@ -146,6 +146,16 @@ int vab_sync(vab_ctx* ctx) {
   return VAB_OK;
 }
 
+int vab_set_path_sink(vab_ctx* ctx, double* host_dst, int64_t host_pitch, int64_t width) {
+  if (!ctx) return VAB_ERR_INVALID;
+  if (host_dst != nullptr && (width < 1 || host_pitch < width))
+    return vab_fail(ctx, VAB_ERR_INVALID, "set_path_sink: bad pitch / width");
+  ctx->sink_host = host_dst;
+  ctx->sink_pitch = host_dst ? host_pitch : 0;
+  ctx->sink_width = host_dst ? width : 0;
+  return VAB_OK;
+}
+
 int vab_copy_rows_to_host(vab_ctx* ctx, double* host_dst, int64_t host_pitch, const double* src_dev,
                           int64_t dev_pitch, int64_t width, int64_t rows) {
   if (!ctx) return VAB_ERR_INVALID;

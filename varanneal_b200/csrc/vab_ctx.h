@@ -45,6 +45,10 @@ struct vab_ctx {
   // ---- NN problem
   NnProblem* nn = nullptr;
 
+  // ---- host sink of vab_anneal's minimising paths (vab_set_path_sink); consumed by the next call
+  double* sink_host = nullptr;
+  long long sink_pitch = 0, sink_width = 0;
+
   // ---- workspaces
   double* partials = nullptr;
   size_t partials_cap = 0;          // doubles
