@@ -108,3 +108,32 @@ def test_nn_ladder_vs_scipy():
         assert res2.nit <= 2 and abs(res2.fun - an.A_array[i]) <= 1e-9 * abs(res2.fun)
     assert an.minpaths.shape == (len(betas), M * NDnet + NP)
     assert np.all(an.exitflags == 0)
+
+
+@pytest.mark.parametrize("structure,M,B", [([25, 30, 4], 333, 2), ([100, 100, 100], 129, 2), ([12, 40], 70, 3)])
+def test_nn_split_kernels_agree_with_fused_kernel(structure, M, B, monkeypatch):
+    """The split design (nn_fb_kernel / nn_fix_kernel / nn_gw_kernel) and the fused example-tile
+    kernel are two decompositions of the same sums: value and gradient agree to rounding (and both
+    meet the oracle, see the tests above).  M is not a multiple of any tile size; the last case
+    has no middle layer (nn_fix_kernel is skipped)."""
+    rng = np.random.RandomState(11)
+    st = np.array(structure)
+    NDnet = int(st.sum())
+    NP = int(sum(st[n] * st[n + 1] + st[n + 1] for n in range(len(st) - 1)))
+    Lidx = [np.arange(st[0])[1::2], np.arange(st[-1])[::2]]
+    data_in, data_out = rng.rand(M, len(Lidx[0])), rng.rand(M, len(Lidx[1]))
+    X0 = rng.rand(B, M * NDnet)
+    P0 = 0.3 * rng.randn(B, NP)
+    Pidx = np.arange(1, NP, 2)
+    XP = np.concatenate([X0, P0[:, Pidx]], axis=1)
+    res = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("VAB_NN_SPLIT", flag)
+        an = _annealer(st, data_in, data_out, X0.copy(), P0.copy(), 1.1, [25.0], [2.0, 0.7], 1e-2, Pidx, Lidx=Lidx)
+        l0 = an.gpu_launches
+        A, G = an.A_gradA(XP)
+        res[flag] = (A.copy(), G.copy(), an.gpu_launches - l0, an.me_gaussian(XP), an.fe_gaussian(XP))
+    assert res["1"][2] != res["0"][2]                    # really two different launch sequences
+    assert np.max(np.abs(res["1"][0] - res["0"][0]) / np.abs(res["0"][0])) <= 1e-13
+    assert np.max(np.abs(res["1"][1] - res["0"][1])) <= 1e-12 * np.max(np.abs(res["0"][1]))
+    assert np.allclose(res["1"][3], res["0"][3], rtol=1e-13) and np.allclose(res["1"][4], res["0"][4], rtol=1e-13)

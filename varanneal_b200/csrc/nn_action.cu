@@ -17,6 +17,7 @@
 #include <cuda_runtime.h>
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -49,8 +50,19 @@ struct NnParams {
   double cf2_num, cf2_den; // 2 RF0 and (NDnet - d_0) M: cf2 of a path on its own rung = cf2_num * rf_path[b] / cf2_den
   const double* rf_path;  // (B) or nullptr
   const int* active;
-  double* partials;       // (B, ntiles, 2): me, fe
-  double* gwpart;         // (B, ntiles, NP)
+  double* partials;       // (B, nparts, 2): me, fe
+  double* gwpart;         // (B, ngw, NP)
+  int nparts, ngw;        // partials per path summed by nn_reduce_kernel (fused: ntiles, ntiles)
+  // split design (nn_fb_kernel / nn_gw_kernel)
+  int TMF, nmt;           // examples per forward/backward tile, tiles per layer
+  int gw_klen, gw_nsplit; // examples per split of the weight-gradient GEMM, number of splits
+  int gw_njs;             // CTAs sharing the row tiles of one W block
+  int gw_kp;              // examples per panel of the weight-gradient GEMM (multiple of 8)
+  const double* one;      // device constant 1.0 (source of the ones column)
+  double* me_parts;       // (B, n_me) per-block measurement-error sums of nn_fix_kernel, or nullptr
+  int n_me;
+  double* dbuf;           // (B, M, NDnet - d_0) Delta of every layer
+  double* lam;            // (B, M, NDnet - d_0) lambda = direct term of the next layer's gradient rows
 };
 
 __device__ __forceinline__ double act_f(int act, double z) {
@@ -309,6 +321,331 @@ __global__ void __launch_bounds__(NT) nn_fused_kernel(const __grid_constant__ Nn
   }
 }
 
+// =============================================================================================
+// Split design for layers whose weight matrix fits in shared memory (the twin and bar-image
+// networks of the examples): three kernels instead of one example-tile kernel walking all layers.
+//   nn_fb_kernel   one CTA = (layer n, tile of TMF examples): Z = X_n W_n^T, residual / lambda /
+//                  Delta in the accumulator epilogue, then Delta W_n with the same staged W_n.
+//                  Every (layer, tile) is independent (the states of all layers are unknowns), so
+//                  the grid is (tiles, layers, paths).  Delta goes to a global buffer for the
+//                  weight gradient; lambda (the direct term of layer n+1's gradient rows) to a
+//                  second one.
+//   nn_fix_kernel  G rows of the middle layers += lambda (two addends per entry: order-free).
+//   nn_gw_kernel   GW_n = Delta_n^T X_n as a split-K GEMM over the example axis: one CTA =
+//                  (split, layer, path) keeps the whole d_{n+1} x d_n block in accumulator
+//                  fragments while panels of 32 examples stream through shared memory; the few
+//                  per-split partials are summed in split order by nn_reduce_kernel.
+// This removes the per-tile weight-gradient partials (C4: 1.3 GB of traffic per batch) and the
+// chain of barrier-separated phases per layer of the fused kernel.
+// 8-byte asynchronous copy global -> shared (LDGSTS); nbytes = 0 writes zeros (padding)
+__device__ __forceinline__ void cp_async8(double* dst_smem, const double* src, int nbytes) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(src), "r"(nbytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// tile[r][c] (pitch) <- src[(row0 + r) * ld + c] for r < nr, c < ncP; entries with row0 + r >= row_end
+// or c >= nc are zero-filled.  One warp per row, lanes across the columns; all loads in flight.
+__device__ __forceinline__ void stage_tile_async(double* tile, int pitch, const double* src, long long ld,
+                                                 int row0, int row_end, int nr, int nc, int ncP,
+                                                 const double* one = nullptr) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int r = warp; r < nr; r += nwarps) {
+    const bool rv = row0 + r < row_end;
+    const double* srow = src + (long long)(rv ? row0 + r : row0) * ld;
+    double* drow = tile + r * pitch;
+    for (int c = lane; c < ncP; c += 32) {
+      const bool v = rv && c < nc;
+      if (one != nullptr && rv && c == nc) cp_async8(drow + c, one, 8);     // column of ones (bias gradient)
+      else cp_async8(drow + c, srow + (v ? c : 0), v ? 8 : 0);
+    }
+  }
+}
+
+constexpr int GW_MAXTASK = 2;      // (row tile, column group) tasks a warp may own; wider blocks are
+                                   // split over the rows of W among several CTAs (P.gw_njs)
+
+constexpr int NTF = 512;           // largest CTA of nn_fb_kernel (launched with 256 or 512 threads)
+__global__ void __launch_bounds__(NTF, 1) nn_fb_kernel(const __grid_constant__ NnParams P) {
+  extern __shared__ double sm[];
+  const int mtb = blockIdx.x, n = blockIdx.y, b = blockIdx.z, tid = threadIdx.x;
+  if (P.active != nullptr && P.active[b] == 0) return;
+  const int lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5, nthr = blockDim.x;
+  const int lr = lane >> 2, lc = lane & 3;
+  const int TM = P.TMF;
+  const int dn = P.structure[n], dn1 = P.structure[n + 1];
+  const int dnP = (dn + 7) & ~7, dn1P = (dn1 + 7) & ~7;
+  const int px = dnP + 4, pd = dn1P + 4;
+  double* Xs = sm;                       // [TM][px]    states of layer n
+  double* Ds = Xs + TM * px;             // [TM][pd]    Delta
+  double* Ws = Ds + TM * pd;             // [dn1P][px]  W_n
+  double* bs = Ws + dn1P * px;           // [dn1P]
+  __shared__ double red[2][NTF / 32];
+  const int m0 = mtb * TM;
+  const int rows = min(TM, P.M - m0);
+  const int xo = P.xoff[n], xo1 = P.xoff[n + 1], d0 = P.structure[0];
+  const int ND1 = P.NDnet - d0;
+  const bool lastl = (n + 1 == P.NL - 1);
+  const double* xp = P.XP + (long long)b * P.ldxp;
+  double* gp = P.G + (long long)b * P.ldg;
+  double* dbuf = P.dbuf + (long long)b * P.M * ND1;
+  double* lam = P.lam + (long long)b * P.M * ND1;
+  const double* pfull = P.pfull + (long long)b * P.NP;
+  const double cf2 = (P.rf_path != nullptr) ? P.cf2_num * __ldg(P.rf_path + b) / P.cf2_den : P.cf2;
+  double me_acc = 0.0, fe_acc = 0.0;
+  // stage X_n, X_{n+1} (into the Delta tile: the epilogue of (1) reads x_{n+1}[m][j] and overwrites
+  // the same entry with Delta[m][j]), W_n and b_n with asynchronous copies: everything in flight at once
+  stage_tile_async(Xs, px, xp + xo, P.NDnet, m0, P.M, TM, dn, dnP);
+  stage_tile_async(Ds, pd, xp + xo1, P.NDnet, m0, P.M, TM, dn1, dn1P);
+  stage_tile_async(Ws, px, pfull + P.woff[n], dn, 0, dn1, dn1P, dn, dnP);
+  for (int j = tid; j < dn1P; j += nthr) cp_async8(bs + j, pfull + P.boff[n] + (j < dn1 ? j : 0), j < dn1 ? 8 : 0);
+  cp_async_commit();
+  cp_async_wait<0>();
+  __syncthreads();
+  const int MTL = TM >> 3;
+  // ---- (1) Z = X W^T, epilogue: residual, lambda, Delta
+  {
+    const int NTL = dn1P >> 3, NG = (NTL + NTILE - 1) / NTILE;
+    for (int task = warp; task < MTL * NG; task += nwarps) {
+      const int mt = task / NG, g = task - mt * NG;
+      const int nt0 = g * NTILE, ntn = min(NTILE, NTL - nt0);
+      double c0[NTILE], c1[NTILE];
+#pragma unroll
+      for (int t = 0; t < NTILE; ++t) { c0[t] = 0.0; c1[t] = 0.0; }
+      const double* arow = Xs + (mt * 8 + lr) * px + lc;
+      const double* brow = Ws + (nt0 * 8 + lr) * px + lc;
+      for (int k = 0; k < dnP; k += 4) {
+        const double a = arow[k];
+#pragma unroll
+        for (int t = 0; t < NTILE; ++t)
+          if (t < ntn) dmma(c0[t], c1[t], a, brow[t * 8 * px + k]);
+      }
+      const int m = mt * 8 + lr;
+      const long long grow = (long long)(m0 + m);
+#pragma unroll
+      for (int t = 0; t < NTILE; ++t) {
+        if (t >= ntn) continue;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int j = (nt0 + t) * 8 + 2 * lc + h;
+          const double z = (h ? c1[t] : c0[t]) + bs[j];
+          double dl = 0.0;
+          if (m < rows && j < dn1) {
+            const double sv = act_f(P.act, z);
+            const double xn1 = Ds[m * pd + j];
+            const double e = xn1 - sv;
+            const double lm = cf2 * e;
+            fe_acc = fma(lm, e, fe_acc);
+            dl = -lm * act_d(P.act, sv);
+            // direct term of layer n+1's gradient rows: the last layer has no back term and is
+            // written here; the others are added to the back term by nn_fix_kernel
+            if (lastl) gp[grow * P.NDnet + xo1 + j] = lm;
+            else lam[grow * ND1 + (xo1 - d0) + j] = lm;
+            dbuf[grow * ND1 + (xo1 - d0) + j] = dl;
+          }
+          Ds[m * pd + j] = dl;                              // zero in the padding
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // ---- (2) back term of layer n's gradient rows: Delta W
+  {
+    const int NTL = dnP >> 3, NG = (NTL + NTILE - 1) / NTILE;
+    for (int task = warp; task < MTL * NG; task += nwarps) {
+      const int mt = task / NG, g = task - mt * NG;
+      const int nt0 = g * NTILE, ntn = min(NTILE, NTL - nt0);
+      double c0[NTILE], c1[NTILE];
+#pragma unroll
+      for (int t = 0; t < NTILE; ++t) { c0[t] = 0.0; c1[t] = 0.0; }
+      const double* arow = Ds + (mt * 8 + lr) * pd + lc;          // A[m][j]
+      const double* brow = Ws + lc * px + nt0 * 8 + lr;           // B[j][k] = W[j][k]
+      for (int j = 0; j < dn1P; j += 4) {
+        const double a = arow[j];
+#pragma unroll
+        for (int t = 0; t < NTILE; ++t)
+          if (t < ntn) dmma(c0[t], c1[t], a, brow[j * px + t * 8]);
+      }
+      const int m = mt * 8 + lr;
+      const long long grow = (long long)(m0 + m);
+      if (m < rows) {
+#pragma unroll
+        for (int t = 0; t < NTILE; ++t) {
+          if (t >= ntn) continue;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int k = (nt0 + t) * 8 + 2 * lc + h;
+            if (k >= dn) continue;
+            gp[grow * P.NDnet + xo + k] = h ? c1[t] : c0[t];
+          }
+        }
+      }
+    }
+  }
+  for (int sft = 16; sft > 0; sft >>= 1) {
+    me_acc += __shfl_down_sync(0xffffffffu, me_acc, sft);
+    fe_acc += __shfl_down_sync(0xffffffffu, fe_acc, sft);
+  }
+  if (lane == 0) { red[0][warp] = me_acc; red[1][warp] = fe_acc; }
+  __syncthreads();
+  if (tid == 0) {
+    double a = 0.0, c = 0.0;
+    for (int w = 0; w < nwarps; ++w) { a += red[0][w]; c += red[1][w]; }
+    const long long item = ((long long)b * (P.NL - 1) + n) * P.nmt + mtb;
+    P.partials[item * 2 + 0] = 0.5 * a;
+    P.partials[item * 2 + 1] = 0.5 * c;
+  }
+}
+
+// Elementwise pass over the gradient rows after nn_fb_kernel: columns of the middle layers
+// += lambda of the layer below; observed components of the input / output layer += the
+// measurement term (va_nnet.py:117-173), whose per-block sums are the me partials.
+constexpr int FIX_NT = 256;
+__global__ void __launch_bounds__(FIX_NT) nn_fix_kernel(const __grid_constant__ NnParams P) {
+  const int b = blockIdx.y;
+  if (P.active != nullptr && P.active[b] == 0) return;
+  const int d0 = P.structure[0], dl = P.structure[P.NL - 1];
+  const int ND = P.NDnet, ND1 = ND - d0, clast = ND - dl;
+  const long long total = (long long)P.M * ND;
+  double* gp = P.G + (long long)b * P.ldg;
+  const double* xp = P.XP + (long long)b * P.ldxp;
+  const double* lam = P.lam + (long long)b * P.M * ND1;
+  double me_acc = 0.0;
+  // (m, c) advance by a constant stride: no division in the loop
+  const long long stride = (long long)gridDim.x * FIX_NT;
+  const long long dm = stride / ND;
+  const int dc = (int)(stride - dm * ND);
+  long long i = (long long)blockIdx.x * FIX_NT + threadIdx.x;
+  long long m = i / ND;
+  int c = (int)(i - m * ND);
+  for (; i < total; i += stride) {
+    if (c < d0) {
+      const int s = P.slot_in[c];
+      if (s >= 0) {
+        const double diff = xp[i] - P.data_in[m * P.n_Lin + s];
+        me_acc = fma(P.wm_in * diff, diff, me_acc);
+        gp[i] += P.wm_in * diff;
+      }
+    } else if (c >= clast) {
+      const int s = P.slot_out[c - clast];
+      if (s >= 0) {
+        const double diff = xp[i] - P.data_out[m * P.n_Lout + s];
+        me_acc = fma(P.wm_out * diff, diff, me_acc);
+        gp[i] += P.wm_out * diff;
+      }
+    } else {
+      gp[i] += lam[m * ND1 + (c - d0)];
+    }
+    m += dm;
+    c += dc;
+    if (c >= ND) { c -= ND; m += 1; }
+  }
+  __shared__ double red[FIX_NT / 32];
+  for (int sft = 16; sft > 0; sft >>= 1) me_acc += __shfl_down_sync(0xffffffffu, me_acc, sft);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = me_acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0;
+    for (int w = 0; w < FIX_NT / 32; ++w) a += red[w];
+    P.me_parts[(long long)b * gridDim.x + blockIdx.x] = 0.5 * a;
+  }
+}
+
+__global__ void __launch_bounds__(NT, 2) nn_gw_kernel(const __grid_constant__ NnParams P) {
+  extern __shared__ double sm[];
+  const int sp = blockIdx.x / P.gw_njs, js = blockIdx.x - sp * P.gw_njs;
+  const int n = blockIdx.y, b = blockIdx.z, tid = threadIdx.x;
+  if (P.active != nullptr && P.active[b] == 0) return;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int lr = lane >> 2, lc = lane & 3;
+  const int dn = P.structure[n], dn1 = P.structure[n + 1];
+  // X is augmented by a column of ones: column dn of the product is the bias gradient sum_m Delta[m][j]
+  const int dnP = (dn + 1 + 7) & ~7, dn1P = (dn1 + 7) & ~7;
+  const int px = dnP + 4, pd = dn1P + 4;
+  const int KP = P.gw_kp;
+  const int pstride = KP * (px + pd);       // doubles per panel buffer: X panel then Delta panel
+  const int xo = P.xoff[n], d0 = P.structure[0];
+  const int ND1 = P.NDnet - d0, co = P.xoff[n + 1] - d0;
+  const double* xp = P.XP + (long long)b * P.ldxp;
+  const double* dbuf = P.dbuf + (long long)b * P.M * ND1;
+  const int mlo = sp * P.gw_klen, mhi = min(P.M, mlo + P.gw_klen);
+  const int JTL = dn1P >> 3, NTL = dnP >> 3;
+  const int jtper = (JTL + P.gw_njs - 1) / P.gw_njs;          // row tiles of W owned by this CTA
+  const int jt_lo = js * jtper, jt_n = max(0, min(JTL, jt_lo + jtper) - jt_lo);
+  // column tiles per task: NTILE, or fewer when that would leave warps without a task (tiny layers)
+  int gsz = NTILE;
+  if (jt_n * ((NTL + NTILE - 1) / NTILE) < NT / 32) gsz = max(1, (jt_n * NTL) / (NT / 32));
+  while (gsz < NTILE && jt_n * ((NTL + gsz - 1) / gsz) > GW_MAXTASK * (NT / 32)) ++gsz;
+  const int NG = (NTL + gsz - 1) / gsz;
+  const int ntask = jt_n * NG;
+  double c0[GW_MAXTASK][NTILE], c1[GW_MAXTASK][NTILE];
+#pragma unroll
+  for (int q = 0; q < GW_MAXTASK; ++q)
+#pragma unroll
+    for (int t = 0; t < NTILE; ++t) { c0[q][t] = 0.0; c1[q][t] = 0.0; }
+  auto load_panel = [&](int buf, int mp) {
+    double* Xp = sm + buf * pstride;
+    stage_tile_async(Xp, px, xp + xo, P.NDnet, mp, mhi, KP, dn, dnP, P.one);
+    stage_tile_async(Xp + KP * px, pd, dbuf + co, ND1, mp, mhi, KP, dn1, dn1P);
+    cp_async_commit();
+  };
+  const int npanel = (mhi - mlo + KP - 1) / KP;
+  load_panel(0, mlo);
+  for (int pi = 0; pi < npanel; ++pi) {
+    if (pi + 1 < npanel) {
+      load_panel((pi + 1) & 1, mlo + (pi + 1) * KP);          // next panel streams in during the MMAs
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const double* Xp = sm + (pi & 1) * pstride;
+    const double* Dp = Xp + KP * px;
+#pragma unroll
+    for (int q = 0; q < GW_MAXTASK; ++q) {
+      const int task = warp + q * (NT / 32);
+      if (task < ntask) {
+        const int jt = jt_lo + task / NG, g = task % NG;
+        const int nt0 = g * gsz, ntn = min(gsz, NTL - nt0);
+        const double* arow = Dp + lc * pd + jt * 8 + lr;            // A[j][m] = Delta[m][j]
+        const double* brow = Xp + lc * px + nt0 * 8 + lr;           // B[m][k] = X[m][k]
+#pragma unroll 2
+        for (int mm = 0; mm < KP; mm += 4) {
+          const double a = arow[mm * pd];
+#pragma unroll
+          for (int t = 0; t < NTILE; ++t)
+            if (t < ntn) dmma(c0[q][t], c1[q][t], a, brow[mm * px + t * 8]);
+        }
+      }
+    }
+    __syncthreads();                                              // buffer (pi & 1) is refilled next
+  }
+  double* gw = P.gwpart + ((long long)b * P.gw_nsplit + sp) * P.NP;
+#pragma unroll
+  for (int q = 0; q < GW_MAXTASK; ++q) {
+    const int task = warp + q * (NT / 32);
+    if (task < ntask) {
+      const int jt = jt_lo + task / NG, g = task % NG;
+      const int nt0 = g * gsz, ntn = min(gsz, NTL - nt0);
+      const int j = jt * 8 + lr;
+      if (j < dn1) {
+        double* grow = gw + P.woff[n] + (long long)j * dn;
+#pragma unroll
+        for (int t = 0; t < NTILE; ++t) {
+          if (t >= ntn) continue;
+          const int k = (nt0 + t) * 8 + 2 * lc;
+          if (k < dn) grow[k] = c0[q][t];
+          else if (k == dn) gw[P.boff[n] + j] = c0[q][t];
+          if (k + 1 < dn) grow[k + 1] = c1[q][t];
+          else if (k + 1 == dn) gw[P.boff[n] + j] = c1[q][t];
+        }
+      }
+    }
+  }
+}
+
 // sums the per-tile partials in tile order: A / me / fe and the gradient of the estimated params
 __global__ void nn_reduce_kernel(const __grid_constant__ NnParams P, double* A, double* me, double* fe) {
   const int b = blockIdx.y;
@@ -318,17 +655,19 @@ __global__ void nn_reduce_kernel(const __grid_constant__ NnParams P, double* A, 
     const int e = P.pmap[k];
     if (e >= 0) {
       double acc = 0.0;
-      const double* src = P.gwpart + (long long)b * P.ntiles * P.NP + k;
-      for (int t = 0; t < P.ntiles; ++t) acc += src[(long long)t * P.NP];
+      const double* src = P.gwpart + (long long)b * P.ngw * P.NP + k;
+      for (int t = 0; t < P.ngw; ++t) acc += src[(long long)t * P.NP];
       P.G[(long long)b * P.ldg + P.NDens + e] = acc;
     }
   }
   if (k == 0) {
     double m = 0.0, f = 0.0;
-    for (int t = 0; t < P.ntiles; ++t) {
-      m += P.partials[((long long)b * P.ntiles + t) * 2 + 0];
-      f += P.partials[((long long)b * P.ntiles + t) * 2 + 1];
+    for (int t = 0; t < P.nparts; ++t) {
+      m += P.partials[((long long)b * P.nparts + t) * 2 + 0];
+      f += P.partials[((long long)b * P.nparts + t) * 2 + 1];
     }
+    if (P.me_parts != nullptr)
+      for (int t = 0; t < P.n_me; ++t) m += P.me_parts[(long long)b * P.n_me + t];
     if (me) me[b] = m;
     if (fe) fe[b] = f;
     if (A) A[b] = m + f;
@@ -354,6 +693,12 @@ struct NnProblem {
   size_t gwpart_cap = 0;
   double* pfull = nullptr;
   size_t pfull_cap = 0;
+  double* dbuf = nullptr;          // split design: Delta and lambda buffers (B, M, NDnet - d_0)
+  size_t dbuf_cap = 0;
+  double* lam = nullptr;
+  size_t lam_cap = 0;
+  double* one_dev = nullptr;       // device constant 1.0
+  std::vector<int> st_host;        // layer widths (host copy, for launch planning)
 };
 
 void nn_destroy(vab_ctx* ctx) {
@@ -363,6 +708,9 @@ void nn_destroy(vab_ctx* ctx) {
   cudaFree(p->pfix_zero);
   cudaFree(p->gwpart);
   cudaFree(p->pfull);
+  cudaFree(p->dbuf);
+  cudaFree(p->lam);
+  cudaFree(p->one_dev);
   delete p;
   ctx->nn = nullptr;
 }
@@ -394,6 +742,115 @@ int nn_eval(vab_ctx* ctx, int B, const double* XP, long long ldxp, double rf_sca
   P.cf2_den = (double)(p->NDnet - p->d0) * p->M;
   P.rf_path = rf_path_dev;
   P.active = active_dev;
+  // ---- split design when every layer's W fits next to the tiles (and a gradient is wanted)
+  {
+    const char* env_split = getenv("VAB_NN_SPLIT");            // 0: always the fused kernel
+    const bool use_split = env_split ? (atoi(env_split) != 0) : true;
+    const size_t budget = 200 * 1024;
+    int TMF = 0;
+    size_t smem_fb = 0, smem_gw = 0;
+    bool fits = use_split && G != nullptr && p->NL >= 2;
+    if (fits) {
+      for (int tm = 256; tm >= 16 && TMF == 0; tm >>= 1) {
+        if (tm > 64 && tm * 4 > p->M) continue;                 // keep at least a few tiles per layer
+        size_t worst = 0;
+        for (int n = 0; n + 1 < p->NL; ++n) {
+          const int dnP = (p->st_host[n] + 7) & ~7, dn1P = (p->st_host[n + 1] + 7) & ~7;
+          const size_t s = ((size_t)tm * (dnP + 4) + (size_t)tm * (dn1P + 4) + (size_t)dn1P * (dnP + 4) + dn1P) * sizeof(double);
+          if (s > worst) worst = s;
+        }
+        // big tiles only while two CTAs still share an SM
+        if (worst <= (tm > 64 ? (size_t)100 * 1024 : budget)) { TMF = tm; smem_fb = worst; }
+      }
+      if (TMF == 0) fits = false;
+    }
+    int njs = 1, kp = 128;
+    if (fits) {
+      for (int n = 0; n + 1 < p->NL; ++n) {
+        const int dnP = (p->st_host[n] + 1 + 7) & ~7, dn1P = (p->st_host[n + 1] + 7) & ~7;   // X carries a ones column
+        while (kp > 32 && (size_t)2 * kp * ((dnP + 4) + (dn1P + 4)) * sizeof(double) > (size_t)100 * 1024) kp >>= 1;
+      }
+      for (int n = 0; n + 1 < p->NL; ++n) {
+        const int dnP = (p->st_host[n] + 1 + 7) & ~7, dn1P = (p->st_host[n + 1] + 7) & ~7;
+        const int NG = ((dnP >> 3) + NTILE - 1) / NTILE;
+        if (NG > GW_MAXTASK * (NT / 32)) fits = false;
+        // row tiles per CTA so that a warp owns at most GW_MAXTASK (row tile, column group) tasks
+        const int jtper = (GW_MAXTASK * (NT / 32)) / NG;
+        if (jtper >= 1) {
+          const int need = ((dn1P >> 3) + jtper - 1) / jtper;
+          if (need > njs) njs = need;
+        }
+        const size_t s = (size_t)2 * kp * ((dnP + 4) + (dn1P + 4)) * sizeof(double);   // two panel buffers
+        if (s > smem_gw) smem_gw = s;
+      }
+    }
+    if (fits) {
+      P.TMF = TMF;
+      P.nmt = (p->M + TMF - 1) / TMF;
+      P.gw_njs = njs;
+      P.gw_kp = kp;
+      P.one = p->one_dev;
+      const int per = (p->NL - 1) * B * njs;
+      int want = (8 * ctx->num_sms + per - 1) / per;               // ~8 CTAs per SM over the batch
+      if (want < 1) want = 1;
+      int klen = (p->M + want - 1) / want;
+      klen = ((klen + kp - 1) / kp) * kp;
+      P.gw_klen = klen;
+      P.gw_nsplit = (p->M + klen - 1) / klen;
+      P.nparts = (p->NL - 1) * P.nmt;
+      P.ngw = P.gw_nsplit;
+      const size_t nd1 = (size_t)(p->NDnet - p->d0);
+      long long nfix = ((long long)p->M * p->NDnet + FIX_NT * 8 - 1) / (FIX_NT * 8);     // ~8 entries per thread
+      if (nfix > 1024) nfix = 1024;
+      if (nfix < 1) nfix = 1;
+      P.n_me = (int)nfix;
+      int rc = vab_reserve(ctx, &ctx->partials, &ctx->partials_cap, (size_t)B * P.nparts * 2 + (size_t)B * nfix);
+      if (rc != VAB_OK) return rc;
+      rc = vab_reserve(ctx, &p->gwpart, &p->gwpart_cap, (size_t)B * P.ngw * (p->NP > 0 ? p->NP : 1));
+      if (rc != VAB_OK) return rc;
+      rc = vab_reserve(ctx, &p->pfull, &p->pfull_cap, (size_t)B * (p->NP > 0 ? p->NP : 1));
+      if (rc != VAB_OK) return rc;
+      rc = vab_reserve(ctx, &p->dbuf, &p->dbuf_cap, (size_t)B * p->M * nd1);
+      if (rc != VAB_OK) return rc;
+      rc = vab_reserve(ctx, &p->lam, &p->lam_cap, (size_t)B * p->M * nd1);
+      if (rc != VAB_OK) return rc;
+      P.partials = ctx->partials; P.gwpart = p->gwpart; P.pfull = p->pfull; P.dbuf = p->dbuf; P.lam = p->lam;
+      P.me_parts = ctx->partials + (size_t)B * P.nparts * 2;
+      static bool attr_split = false;
+      if (!attr_split) {
+        cudaError_t e = cudaFuncSetAttribute(nn_fb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(nn_gw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return vab_cuda_fail(ctx, e, "nn_action_grad smem opt-in (split)");
+        attr_split = true;
+      }
+      if (smem_gw > 200 * 1024) return vab_fail(ctx, VAB_ERR_INVALID, "nn_action_grad: internal plan error (gw smem)");
+      if (p->NP > 0) nn_gather_params_kernel<<<dim3((p->NP + 255) / 256, B), 256, 0, ctx->stream>>>(P);
+      {
+        // 16 warps when every warp still gets a (row tile, column group) task of the smallest layer pair
+        int min_tasks = 1 << 30;
+        for (int n = 0; n + 1 < p->NL; ++n) {
+          const int a = (((p->st_host[n] + 7) >> 3) + NTILE - 1) / NTILE, c = (((p->st_host[n + 1] + 7) >> 3) + NTILE - 1) / NTILE;
+          const int t = (TMF >> 3) * (a < c ? a : c);
+          if (t < min_tasks) min_tasks = t;
+        }
+        const int nthr = (min_tasks >= 16) ? NTF : NT;
+        nn_fb_kernel<<<dim3(P.nmt, p->NL - 1, B), nthr, smem_fb, ctx->stream>>>(P);
+      }
+      cudaError_t e = cudaGetLastError();
+      if (e != cudaSuccess) return vab_cuda_fail(ctx, e, "nn_fb_kernel launch");
+      int nl = 3;
+      nn_fix_kernel<<<dim3((unsigned)nfix, B), FIX_NT, 0, ctx->stream>>>(P);
+      nn_gw_kernel<<<dim3(P.gw_nsplit * njs, p->NL - 1, B), NT, smem_gw, ctx->stream>>>(P);
+      e = cudaGetLastError();
+      if (e != cudaSuccess) return vab_cuda_fail(ctx, e, "nn_gw_kernel launch");
+      const int nk = p->NP > 1 ? p->NP : 1;
+      nn_reduce_kernel<<<dim3((nk + 255) / 256, B), 256, 0, ctx->stream>>>(P, A, me, fe);
+      e = cudaGetLastError();
+      if (e != cudaSuccess) return vab_cuda_fail(ctx, e, "nn_reduce_kernel launch");
+      ctx->launches += nl + 2;
+      return VAB_OK;
+    }
+  }
   // Shared-memory plan: 5 [TM][dpitch] tiles + a chunk of weight rows.  Pitches are = 4 (mod 8)
   // doubles; TM is a multiple of 8.  Prefer a footprint that lets two CTAs share an SM.
   const int dP = (p->dmax + 7) & ~7;
@@ -433,6 +890,8 @@ int nn_eval(vab_ctx* ctx, int B, const double* XP, long long ldxp, double rf_sca
   P.partials = ctx->partials;
   P.gwpart = p->gwpart;
   P.pfull = p->pfull;
+  P.nparts = P.ntiles;
+  P.ngw = P.ntiles;
   if (p->NP > 0) nn_gather_params_kernel<<<dim3((p->NP + 255) / 256, B), 256, 0, ctx->stream>>>(P);
   static bool attr_set = false;
   if (!attr_set) {
@@ -482,6 +941,7 @@ int vab_nn_problem_set(vab_ctx* ctx, int32_t n_layers, const int32_t* structure_
     woff[n] = np; np += st[n] * st[n + 1];
     boff[n] = np; np += st[n + 1];
   }
+  p->st_host = st;
   p->NDnet = xoff[n_layers]; p->NDens = (long long)p->NDnet * M; p->NP = np; p->d0 = st[0];
   if (NPest < 0 || NPest > np) return vab_fail(ctx, VAB_ERR_INVALID, "nn_problem_set: bad NPest");
   p->NPest = NPest;
@@ -509,6 +969,8 @@ int vab_nn_problem_set(vab_ctx* ctx, int32_t n_layers, const int32_t* structure_
   if (e == cudaSuccess) e = cudaMemcpy(p->ints, all.data(), all.size() * sizeof(int), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMalloc((void**)&p->pfix_zero, (size_t)(np > 0 ? np : 1) * sizeof(double));
   if (e == cudaSuccess) e = cudaMemset(p->pfix_zero, 0, (size_t)(np > 0 ? np : 1) * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&p->one_dev, sizeof(double));
+  if (e == cudaSuccess) { const double one = 1.0; e = cudaMemcpy(p->one_dev, &one, sizeof(double), cudaMemcpyHostToDevice); }
   if (e != cudaSuccess) return vab_cuda_fail(ctx, e, "nn_problem_set");
   p->structure = p->ints + o_st; p->xoff = p->ints + o_x; p->woff = p->ints + o_w; p->boff = p->ints + o_b;
   p->pmap = p->ints + o_p; p->slot_in = p->ints + o_si; p->slot_out = p->ints + o_so;
