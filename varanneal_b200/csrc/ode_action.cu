@@ -53,18 +53,32 @@ namespace {
 typedef void (*SweepKernel)(const OdeParams);
 
 template <class M, int MINB>
-SweepKernel sweep_kernel_for(int disc) {
+SweepKernel sweep_kernel_for(int disc, bool window) {
   switch (disc) {
     case DISC_EULER: return sweep_twopoint_kernel<M, DISC_EULER, VAB_SW_PD2, MINB>;
     case DISC_TRAPEZOID: return sweep_twopoint_kernel<M, DISC_TRAPEZOID, VAB_SW_PD2, MINB>;
     case DISC_FORWARDMAP: return sweep_twopoint_kernel<M, DISC_FORWARDMAP, VAB_SW_PD2, MINB>;
     case DISC_SIMPSON: return sweep_simpson_kernel<M, VAB_SW_PDS, MINB>;
-    case DISC_RK4: return sweep_rk4_kernel<M, VAB_SW_PDR, MINB>;
+    case DISC_RK4: {
+      // The RK4 body (4 stage states + adjoint seeds live at once) spills at 128 registers.
+      // Measured on B200: rows that fit one lane group (D = 100, B = 64) still prefer 4 resident
+      // CTAs per SM (0.357 ms vs 0.562 ms at 3); window mode (D = 1000, B = 8) prefers the
+      // spill-free 164-register build at 3 CTAs per SM (1.67 ms vs 2.65 ms).  VAB_RK4_MINB overrides.
+      static int forced = -1;
+      if (forced < 0) {
+        const char* e = getenv("VAB_RK4_MINB");
+        forced = e ? atoi(e) : 0;
+      }
+      const int minb = forced ? forced : (window ? 3 : 4);
+      if (minb == 2) return sweep_rk4_kernel<M, VAB_SW_PDR, 2>;
+      if (minb == 3) return sweep_rk4_kernel<M, VAB_SW_PDR, 3>;
+      return sweep_rk4_kernel<M, VAB_SW_PDR, 4>;
+    }
   }
   return nullptr;
 }
 
-SweepKernel sweep_kernel(int model, int C, int disc) {
+SweepKernel sweep_kernel(int model, int C, int disc, bool window) {
   if (model == 0) {
     if (C == 4) {
       if (disc == DISC_SIMPSON) {                 // tuning variants of the flagship kernel
@@ -80,14 +94,14 @@ SweepKernel sweep_kernel(int model, int C, int disc) {
           default: return sweep_simpson_kernel<ModelL96<4>, 1, 4>;
         }
       }
-      return sweep_kernel_for<ModelL96<4>, VAB_SW_MINB>(disc);
+      return sweep_kernel_for<ModelL96<4>, VAB_SW_MINB>(disc, window);
     }
-    if (C == 2) return sweep_kernel_for<ModelL96<2>, VAB_SW_MINB>(disc);
-    if (C == 1) return sweep_kernel_for<ModelL96<1>, VAB_SW_MINB>(disc);
+    if (C == 2) return sweep_kernel_for<ModelL96<2>, VAB_SW_MINB>(disc, window);
+    if (C == 1) return sweep_kernel_for<ModelL96<1>, VAB_SW_MINB>(disc, window);
     return nullptr;
   }
-  if (model == 1) return sweep_kernel_for<ModelL63, VAB_SW_MINB>(disc);
-  if (model == 2) return sweep_kernel_for<ModelNaKL, 2>(disc);
+  if (model == 1) return sweep_kernel_for<ModelL63, VAB_SW_MINB>(disc, window);
+  if (model == 2) return sweep_kernel_for<ModelNaKL, 2>(disc, window);
   return nullptr;
 }
 
@@ -197,7 +211,7 @@ int ode_sweep_prepare(int model, int disc, int D, int N, int B, int num_sms, int
     }
   }
   if (!sl->stream) {
-    k = sweep_kernel(model, g.C, disc);
+    k = sweep_kernel(model, g.C, disc, g.nwin > 1);
     if (!k) return -1;
     nb = blocks_per_sm(k, sl->smem, cerr);
     if (nb < 0) return -2;
@@ -235,7 +249,7 @@ int ode_sweep_prepare(int model, int disc, int D, int N, int B, int num_sms, int
 int ode_sweep_launch(const OdeParams& P, const SweepLaunch& sl, int model, int disc,
                      cudaStream_t st, double* A, double* me, double* fe, cudaError_t* cerr) {
   const bool fast = (P.nskip == 1 && P.rmd == nullptr && P.rf_arr == nullptr && P.L > 0);
-  SweepKernel k = sl.stream ? stream_kernel(sl.C, disc, fast, P.rf_path != nullptr) : sweep_kernel(model, sl.C, disc);
+  SweepKernel k = sl.stream ? stream_kernel(sl.C, disc, fast, P.rf_path != nullptr) : sweep_kernel(model, sl.C, disc, P.nwin > 1);
   if (!k) return -1;
   k<<<sl.grid, 128, sl.smem, st>>>(P);
   cudaError_t e = cudaGetLastError();
