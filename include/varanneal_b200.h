@@ -201,6 +201,16 @@ VAB_API int vab_set_path_sink(vab_ctx* ctx, double* host_dst, int64_t host_pitch
 VAB_API int vab_copy_rows_to_host(vab_ctx* ctx, double* host_dst, int64_t host_pitch,
                           const double* src_dev, int64_t dev_pitch, int64_t width, int64_t rows);
 
+/* Asynchronous strided copy of `rows` rows of `width` doubles between host and device (pitches in
+ * doubles) on `stream` (a cudaStream_t passed as void*; NULL = the context's stream).
+ * to_device != 0: host_ptr -> dev_ptr, else dev_ptr -> host_ptr.  One DMA with both pitches, no
+ * staging: the host mirror uses it to move (B, n) host batches to / from the (B, ldxp) device
+ * buffers of the eval seam (A_gradA_taped, _autodiffmin.py:57-58) while the kernels of the
+ * neighbouring groups of paths run.  host_ptr should be pinned for the copy to be asynchronous. */
+VAB_API int vab_copy_rows_async(vab_ctx* ctx, int32_t to_device, double* dev_ptr, int64_t dev_pitch,
+                        double* host_ptr, int64_t host_pitch, int64_t width, int64_t rows,
+                        void* stream);
+
 #ifdef __cplusplus
 }
 #endif

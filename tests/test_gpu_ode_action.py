@@ -173,3 +173,27 @@ def test_l96_window_mode_wide_rows_long_paths(disc):
     Ar, gr = prob.action_grad(XP[1], 1e-2 * 1.5 ** 2)
     assert abs(A[1] - Ar) <= TOL * abs(Ar)
     assert np.max(np.abs(G[1] - gr)) <= TOL * np.max(np.abs(gr))
+
+
+@pytest.mark.parametrize("B", [1, 5, 37])
+def test_pinned_pipelined_eval_matches_plain_eval(B):
+    """A_gradA(pinned host tensor) -- the end-to-end seam bench.py times: strided DMAs on two copy
+    streams pipelined against the kernels of groups of paths (ramped group sizes) -- returns
+    exactly what the plain NumPy-in / NumPy-out call returns, for batches that do and do not
+    divide into the groups, with per-path fixed parameters."""
+    import torch
+    rng = np.random.RandomState(17)
+    D, N = 20, 75
+    Lidx = [1, 4, 9, 16]
+    Y = rng.randn(N, len(Lidx))
+    X0 = rng.randn(B, N, D)
+    P0 = 8.0 + rng.rand(B, 1)
+    an = _annealer("lorenz96", D, Y, 0.02 * np.arange(N), None, X0, P0, 4.0, 4e-3, Lidx, [], "SimpsonHermite")
+    XP = X0.reshape(B, -1).copy()
+    A0, G0 = an.A_gradA(XP)
+    XP_pin = torch.from_numpy(XP).pin_memory()
+    A1, G1 = an.A_gradA(XP_pin)
+    assert np.array_equal(A1.numpy(), A0) and np.array_equal(G1.numpy(), G0)
+    prob = OdeProblem("lorenz96", D, Y, Lidx, 0.02, "SimpsonHermite", P0[B - 1], [], 4.0)
+    Ar, gr = prob.action_grad(XP[B - 1], 4e-3 * 1.5 ** 7)
+    assert abs(A0[B - 1] - Ar) <= TOL * abs(Ar) and np.max(np.abs(G0[B - 1] - gr)) <= TOL * np.max(np.abs(gr))

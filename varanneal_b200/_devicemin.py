@@ -129,37 +129,63 @@ class DeviceMin(object):
             return float(A[0]), G[0]
         return A, G
 
+    @staticmethod
+    def _pipeline_spans(B, chunks=8):
+        """Groups of paths for the pipelined eval: small groups at both ends (the first upload and
+        the last download overlap nothing, so they are kept short), groups of B/chunks between."""
+        big = max(1, -(-B // max(1, chunks)))
+        if B < 4 * big or big < 4:
+            sizes = [big] * (B // big) + ([B % big] if B % big else [])
+        else:
+            ramp = []
+            k = 1
+            while k < big:
+                ramp.append(k)
+                k *= 2
+            mid = B - 2 * sum(ramp)
+            sizes = ramp + [big] * (mid // big) + ([mid % big] if mid % big else []) + ramp[::-1]
+        spans, lo = [], 0
+        for sz in sizes:
+            spans.append((lo, lo + sz))
+            lo += sz
+        return spans
+
     def _pipelined_eval(self, XP_pin, G_pin, A_pin, chunks=8):
         """Host -> device -> host evaluation of a pinned batch, software-pipelined over groups of
         paths: the upload of group i+1 and the download of group i-1 overlap the kernel of group i
-        (both PCIe directions busy)."""
+        (both PCIe directions busy).  The copies are single strided DMAs (vab_copy_rows_async:
+        host pitch n, device pitch ld) on their own streams."""
         torch = _torch()
         main = torch.cuda.current_stream(self._device)
         if getattr(self, "_s_h2d", None) is None:
             self._s_h2d = torch.cuda.Stream(self._device)
             self._s_d2h = torch.cuda.Stream(self._device)
-        B, n = self._B, self._n
-        nch = max(1, min(chunks, B))
-        per = -(-B // nch)
-        spans = [(lo, min(lo + per, B)) for lo in range(0, B, per)]
+        B, n, ld = self._B, self._n, self._ld
+        lib, h = self._ctx.lib, self._ctx.h
+        spans = self._pipeline_spans(B, chunks)
         scale = self._rf_scale()
         self._s_h2d.wait_stream(main)
+        self._s_d2h.wait_stream(main)
+        s_in, s_out = ct.c_void_p(self._s_h2d.cuda_stream), ct.c_void_p(self._s_d2h.cuda_stream)
+        xp_h, g_h = XP_pin.data_ptr(), G_pin.data_ptr()
+        xp_d, g_d = self._XP.data_ptr(), self._G.data_ptr()
         ev_in = []
         for lo, hi in spans:
-            with torch.cuda.stream(self._s_h2d):
-                self._XP[lo:hi, :n].copy_(XP_pin[lo:hi], non_blocking=True)
-                e = torch.cuda.Event()
-                e.record(self._s_h2d)
-                ev_in.append(e)
+            _lib.check(lib.vab_copy_rows_async(h, 1, ct.c_void_p(xp_d + lo * ld * 8), ld,
+                                               ct.c_void_p(xp_h + lo * n * 8), n, n, hi - lo, s_in), h)
+            e = torch.cuda.Event()
+            e.record(self._s_h2d)
+            ev_in.append(e)
         for (lo, hi), e in zip(spans, ev_in):
             main.wait_event(e)
             self._action_grad_native(scale, lo, hi - lo)
             eo = torch.cuda.Event()
             eo.record(main)
-            with torch.cuda.stream(self._s_d2h):
-                self._s_d2h.wait_event(eo)
-                G_pin[lo:hi].copy_(self._G[lo:hi, :n], non_blocking=True)
-                A_pin[lo:hi].copy_(self._A[lo:hi], non_blocking=True)
+            self._s_d2h.wait_event(eo)
+            _lib.check(lib.vab_copy_rows_async(h, 0, ct.c_void_p(g_d + lo * ld * 8), ld,
+                                               ct.c_void_p(g_h + lo * n * 8), n, n, hi - lo, s_out), h)
+        with torch.cuda.stream(self._s_d2h):
+            A_pin.copy_(self._A, non_blocking=True)
         main.wait_stream(self._s_d2h)
         main.synchronize()
 

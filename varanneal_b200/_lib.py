@@ -54,6 +54,7 @@ _SIGS = {
     "vab_anneal": (ct.c_int, [_VP, ct.c_int32, _VP, ct.c_int64, ct.c_double, c_double_p,
                               ct.c_int32, ct.POINTER(LbfgsOpts), _VP, _VP, _VP, _VP, _VP, _VP,
                               _VP]),
+    "vab_copy_rows_async": (ct.c_int, [_VP, ct.c_int32, _VP, ct.c_int64, _VP, ct.c_int64, ct.c_int64, ct.c_int64, _VP]),
     "vab_set_path_sink": (ct.c_int, [_VP, _VP, ct.c_int64, ct.c_int64]),
     "vab_copy_rows_to_host": (ct.c_int, [_VP, _VP, ct.c_int64, _VP, ct.c_int64, ct.c_int64, ct.c_int64]),
 }

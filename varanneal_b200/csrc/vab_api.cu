@@ -146,6 +146,25 @@ int vab_sync(vab_ctx* ctx) {
   return VAB_OK;
 }
 
+int vab_copy_rows_async(vab_ctx* ctx, int32_t to_device, double* dev_ptr, int64_t dev_pitch,
+                        double* host_ptr, int64_t host_pitch, int64_t width, int64_t rows, void* stream) {
+  if (!ctx) return VAB_ERR_INVALID;
+  if (!dev_ptr || !host_ptr || width < 0 || rows < 0 || host_pitch < width || dev_pitch < width)
+    return vab_fail(ctx, VAB_ERR_INVALID, "copy_rows_async: bad arguments");
+  if (width == 0 || rows == 0) return VAB_OK;
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  cudaError_t e;
+  if (to_device)
+    e = cudaMemcpy2DAsync(dev_ptr, (size_t)dev_pitch * sizeof(double), host_ptr, (size_t)host_pitch * sizeof(double),
+                          (size_t)width * sizeof(double), (size_t)rows, cudaMemcpyHostToDevice, st);
+  else
+    e = cudaMemcpy2DAsync(host_ptr, (size_t)host_pitch * sizeof(double), dev_ptr, (size_t)dev_pitch * sizeof(double),
+                          (size_t)width * sizeof(double), (size_t)rows, cudaMemcpyDeviceToHost, st);
+  if (e != cudaSuccess) return vab_cuda_fail(ctx, e, "copy_rows_async");
+  return VAB_OK;
+}
+
 int vab_set_path_sink(vab_ctx* ctx, double* host_dst, int64_t host_pitch, int64_t width) {
   if (!ctx) return VAB_ERR_INVALID;
   if (host_dst != nullptr && (width < 1 || host_pitch < width))
