@@ -36,25 +36,11 @@ METRIC = "action+gradient evals/sec (Lorenz96 D=100 N=5001 SimpsonHermite, 64 pa
 UNIT = "evals/s"
 
 
-def l96(x, k):
-    return np.roll(x, 1, -1) * (np.roll(x, -1, -1) - np.roll(x, 2, -1)) - x + k
-
-
 def twin_data(seed=100):
     """SURVEY.md 8(d) C2 recipe: RK4-integrate L96, drop a transient, add N(0, 0.5^2) noise."""
-    rng = np.random.RandomState(seed)
-    x = K_FORCING + rng.randn(D)
-    rows = []
-    for n in range(1000 + N_MODEL):
-        k1 = l96(x, K_FORCING)
-        k2 = l96(x + 0.5 * DT * k1, K_FORCING)
-        k3 = l96(x + 0.5 * DT * k2, K_FORCING)
-        k4 = l96(x + DT * k3, K_FORCING)
-        x = x + DT / 6.0 * (k1 + 2 * k2 + 2 * k3 + k4)
-        if n >= 1000:
-            rows.append(x.copy())
-    truth = np.array(rows)
-    Y = truth[:, LIDX] + 0.5 * np.random.RandomState(seed + 1).randn(N_MODEL, len(LIDX))
+    from varanneal_b200 import datagen
+    _, truth, Y = datagen.lorenz96_twin(D=D, N=N_MODEL, dt=DT, k=K_FORCING, sigma=0.5, Lidx=LIDX,
+                                        seed=seed, transient=1000)
     return truth, Y
 
 
