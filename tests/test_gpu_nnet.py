@@ -127,13 +127,17 @@ def test_nn_split_kernels_agree_with_fused_kernel(structure, M, B, monkeypatch):
     Pidx = np.arange(1, NP, 2)
     XP = np.concatenate([X0, P0[:, Pidx]], axis=1)
     res = {}
-    for flag in ("1", "0"):
-        monkeypatch.setenv("VAB_NN_SPLIT", flag)
+    # "1": split design (small networks: the all-layers tile kernel), "L": split design with the
+    # per-layer kernels forced, "0": fused example-tile kernel
+    for flag, split, alll in (("1", "1", "1"), ("L", "1", "0"), ("0", "0", "1")):
+        monkeypatch.setenv("VAB_NN_SPLIT", split)
+        monkeypatch.setenv("VAB_NN_ALL_LAYERS", alll)
         an = _annealer(st, data_in, data_out, X0.copy(), P0.copy(), 1.1, [25.0], [2.0, 0.7], 1e-2, Pidx, Lidx=Lidx)
         l0 = an.gpu_launches
         A, G = an.A_gradA(XP)
         res[flag] = (A.copy(), G.copy(), an.gpu_launches - l0, an.me_gaussian(XP), an.fe_gaussian(XP))
     assert res["1"][2] != res["0"][2]                    # really two different launch sequences
-    assert np.max(np.abs(res["1"][0] - res["0"][0]) / np.abs(res["0"][0])) <= 1e-13
-    assert np.max(np.abs(res["1"][1] - res["0"][1])) <= 1e-12 * np.max(np.abs(res["0"][1]))
-    assert np.allclose(res["1"][3], res["0"][3], rtol=1e-13) and np.allclose(res["1"][4], res["0"][4], rtol=1e-13)
+    for k in ("1", "L"):
+        assert np.max(np.abs(res[k][0] - res["0"][0]) / np.abs(res["0"][0])) <= 1e-13
+        assert np.max(np.abs(res[k][1] - res["0"][1])) <= 1e-12 * np.max(np.abs(res["0"][1]))
+        assert np.allclose(res[k][3], res["0"][3], rtol=1e-13) and np.allclose(res[k][4], res["0"][4], rtol=1e-13)

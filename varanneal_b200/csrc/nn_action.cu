@@ -61,6 +61,7 @@ struct NnParams {
   const double* one;      // device constant 1.0 (source of the ones column)
   double* me_parts;       // (B, n_me) per-block measurement-error sums of nn_fix_kernel, or nullptr
   int n_me;
+  int fba_pxn, fba_pd;    // nn_fba_kernel: pitch of the all-layer state / gradient tiles, of the Delta tile
   double* dbuf;           // (B, M, NDnet - d_0) Delta of every layer
   double* lam;            // (B, M, NDnet - d_0) lambda = direct term of the next layer's gradient rows
 };
@@ -499,6 +500,186 @@ __global__ void __launch_bounds__(NTF, 1) nn_fb_kernel(const __grid_constant__ N
   }
 }
 
+// Small networks (all layers of an example tile and every W fit in shared memory together, e.g.
+// the bar-image classifier [25, 30, 4]): one CTA = one tile of TMF examples walks ALL layers with
+// the states, the gradient rows and the weights resident.  X is read once and G written once per
+// example (no lambda buffer, no elementwise pass); Delta still goes to the global buffer of the
+// split-K weight-gradient kernel.  grid (tiles, paths).
+//   Xs [TMF][pxn]  all layers of the tile's examples, pxn >= NDnet, = 4 (mod 8)
+//   Gs [TMF][pxn]  gradient rows: measurement terms, then per layer lambda (direct) and Delta W (back)
+//   Ds [TMF][pd]   Delta of the layer in flight
+//   Ws             W_n [dn1P][dnP + 4] of every layer, then the biases
+__global__ void __launch_bounds__(NT, 2) nn_fba_kernel(const __grid_constant__ NnParams P) {
+  extern __shared__ double sm[];
+  const int mtb = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+  if (P.active != nullptr && P.active[b] == 0) return;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int lr = lane >> 2, lc = lane & 3;
+  const int TM = P.TMF, pxn = P.fba_pxn, pd = P.fba_pd, ND = P.NDnet;
+  double* Xs = sm;
+  double* Gs = Xs + TM * pxn + 16;       // 16 doubles of zero slack behind the X tile (fragment
+  double* Ds = Gs + TM * pxn;            // loads of the last layer run past its width)
+  double* Ws = Ds + TM * pd;
+  __shared__ double red[2][NT / 32];
+  __shared__ int wofs[64], bofs[64];     // shared-memory offsets of W_n / b_n (NL - 1 <= 64)
+  const int m0 = mtb * TM;
+  const int rows = min(TM, P.M - m0);
+  const int d0 = P.structure[0];
+  const int ND1 = ND - d0;
+  const double* xp = P.XP + (long long)b * P.ldxp;
+  double* gp = P.G + (long long)b * P.ldg;
+  double* dbuf = P.dbuf + (long long)b * P.M * ND1;
+  const double* pfull = P.pfull + (long long)b * P.NP;
+  const double cf2 = (P.rf_path != nullptr) ? P.cf2_num * __ldg(P.rf_path + b) / P.cf2_den : P.cf2;
+  double me_acc = 0.0, fe_acc = 0.0;
+  if (tid == 0) {
+    int o = 0;
+    for (int n = 0; n + 1 < P.NL; ++n) {
+      const int dnP = (P.structure[n] + 7) & ~7, dn1P = (P.structure[n + 1] + 7) & ~7;
+      wofs[n] = o;
+      o += dn1P * (dnP + 4);
+    }
+    for (int n = 0; n + 1 < P.NL; ++n) {
+      bofs[n] = o;
+      o += (P.structure[n + 1] + 7) & ~7;
+    }
+  }
+  __syncthreads();
+  // stage the states of the tile (rows are contiguous in X), all weights and biases
+  stage_tile_async(Xs, pxn, xp, ND, m0, P.M, TM, ND, pxn);
+  for (int n = 0; n + 1 < P.NL; ++n) {
+    const int dn = P.structure[n], dn1 = P.structure[n + 1];
+    const int dnP = (dn + 7) & ~7, dn1P = (dn1 + 7) & ~7;
+    stage_tile_async(Ws + wofs[n], dnP + 4, pfull + P.woff[n], dn, 0, dn1, dn1P, dn, dnP);
+    for (int j = tid; j < dn1P; j += NT) cp_async8(Ws + bofs[n] + j, pfull + P.boff[n] + (j < dn1 ? j : 0), j < dn1 ? 8 : 0);
+  }
+  cp_async_commit();
+  for (int i = tid; i < TM * pxn; i += NT) Gs[i] = 0.0;
+  if (tid < 16) Xs[TM * pxn + tid] = 0.0;
+  cp_async_wait<0>();
+  __syncthreads();
+  // measurement terms of the input and output layer (va_nnet.py:117-173)
+  {
+    const int dl = P.structure[P.NL - 1], clast = ND - dl;
+    for (int idx = tid; idx < rows * d0; idx += NT) {
+      const int m = idx / d0, c = idx - m * d0;
+      const int s = P.slot_in[c];
+      if (s >= 0) {
+        const double diff = Xs[m * pxn + c] - P.data_in[(long long)(m0 + m) * P.n_Lin + s];
+        me_acc = fma(P.wm_in * diff, diff, me_acc);
+        Gs[m * pxn + c] += P.wm_in * diff;
+      }
+    }
+    __syncthreads();                      // a one-layer-pair network has input and output columns only
+    for (int idx = tid; idx < rows * dl; idx += NT) {
+      const int m = idx / dl, c = idx - m * dl;
+      const int s = P.slot_out[c];
+      if (s >= 0) {
+        const double diff = Xs[m * pxn + clast + c] - P.data_out[(long long)(m0 + m) * P.n_Lout + s];
+        me_acc = fma(P.wm_out * diff, diff, me_acc);
+        Gs[m * pxn + clast + c] += P.wm_out * diff;
+      }
+    }
+  }
+  const int MTL = TM >> 3;
+  for (int n = 0; n + 1 < P.NL; ++n) {
+    const int dn = P.structure[n], dn1 = P.structure[n + 1];
+    const int dnP = (dn + 7) & ~7, dn1P = (dn1 + 7) & ~7;
+    const int pw = dnP + 4;
+    const int xo = P.xoff[n], xo1 = P.xoff[n + 1];
+    const double* Wn = Ws + wofs[n];
+    const double* bn = Ws + bofs[n];
+    __syncthreads();
+    // ---- (1) Z = X_n W_n^T, epilogue: residual, lambda (into the gradient tile), Delta
+    {
+      const int NTL = dn1P >> 3, NG = (NTL + NTILE - 1) / NTILE;
+      for (int task = warp; task < MTL * NG; task += NT / 32) {
+        const int mt = task / NG, g = task - mt * NG;
+        const int nt0 = g * NTILE, ntn = min(NTILE, NTL - nt0);
+        double c0[NTILE], c1[NTILE];
+#pragma unroll
+        for (int t = 0; t < NTILE; ++t) { c0[t] = 0.0; c1[t] = 0.0; }
+        const double* arow = Xs + (mt * 8 + lr) * pxn + xo + lc;
+        const double* brow = Wn + (nt0 * 8 + lr) * pw + lc;
+        for (int k = 0; k < dnP; k += 4) {
+          const double a = arow[k];
+#pragma unroll
+          for (int t = 0; t < NTILE; ++t)
+            if (t < ntn) dmma(c0[t], c1[t], a, brow[t * 8 * pw + k]);
+        }
+        const int m = mt * 8 + lr;
+        const long long grow = (long long)(m0 + m);
+#pragma unroll
+        for (int t = 0; t < NTILE; ++t) {
+          if (t >= ntn) continue;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int j = (nt0 + t) * 8 + 2 * lc + h;
+            const double z = (h ? c1[t] : c0[t]) + bn[j];
+            double dl = 0.0;
+            if (m < rows && j < dn1) {
+              const double sv = act_f(P.act, z);
+              const double e = Xs[m * pxn + xo1 + j] - sv;
+              const double lm = cf2 * e;
+              fe_acc = fma(lm, e, fe_acc);
+              dl = -lm * act_d(P.act, sv);
+              Gs[m * pxn + xo1 + j] += lm;
+              dbuf[grow * ND1 + (xo1 - d0) + j] = dl;
+            }
+            Ds[m * pd + j] = dl;
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // ---- (2) gradient rows of layer n += Delta W_n
+    {
+      const int NTL = dnP >> 3, NG = (NTL + NTILE - 1) / NTILE;
+      for (int task = warp; task < MTL * NG; task += NT / 32) {
+        const int mt = task / NG, g = task - mt * NG;
+        const int nt0 = g * NTILE, ntn = min(NTILE, NTL - nt0);
+        double c0[NTILE], c1[NTILE];
+#pragma unroll
+        for (int t = 0; t < NTILE; ++t) { c0[t] = 0.0; c1[t] = 0.0; }
+        const double* arow = Ds + (mt * 8 + lr) * pd + lc;
+        const double* brow = Wn + lc * pw + nt0 * 8 + lr;
+        for (int j = 0; j < dn1P; j += 4) {
+          const double a = arow[j];
+#pragma unroll
+          for (int t = 0; t < NTILE; ++t)
+            if (t < ntn) dmma(c0[t], c1[t], a, brow[j * pw + t * 8]);
+        }
+        const int m = mt * 8 + lr;
+#pragma unroll
+        for (int t = 0; t < NTILE; ++t) {
+          if (t >= ntn) continue;
+          const int k = (nt0 + t) * 8 + 2 * lc;
+          if (k < dn) Gs[m * pxn + xo + k] += c0[t];
+          if (k + 1 < dn) Gs[m * pxn + xo + k + 1] += c1[t];
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (int idx = tid; idx < rows * ND; idx += NT) {
+    const int m = idx / ND, c = idx - m * ND;
+    gp[(long long)(m0 + m) * ND + c] = Gs[m * pxn + c];
+  }
+  for (int sft = 16; sft > 0; sft >>= 1) {
+    me_acc += __shfl_down_sync(0xffffffffu, me_acc, sft);
+    fe_acc += __shfl_down_sync(0xffffffffu, fe_acc, sft);
+  }
+  if (lane == 0) { red[0][warp] = me_acc; red[1][warp] = fe_acc; }
+  __syncthreads();
+  if (tid == 0) {
+    double a = 0.0, c = 0.0;
+    for (int w = 0; w < NT / 32; ++w) { a += red[0][w]; c += red[1][w]; }
+    const long long item = (long long)b * P.nmt + mtb;
+    P.partials[item * 2 + 0] = 0.5 * a;
+    P.partials[item * 2 + 1] = 0.5 * c;
+  }
+}
+
 // Elementwise pass over the gradient rows after nn_fb_kernel: columns of the middle layers
 // += lambda of the layer below; observed components of the input / output layer += the
 // measurement term (va_nnet.py:117-173), whose per-block sums are the me partials.
@@ -750,7 +931,29 @@ int nn_eval(vab_ctx* ctx, int B, const double* XP, long long ldxp, double rf_sca
     int TMF = 0;
     size_t smem_fb = 0, smem_gw = 0;
     bool fits = use_split && G != nullptr && p->NL >= 2;
-    if (fits) {
+    // small networks: all layers of an example tile + every W resident (nn_fba_kernel)
+    bool all_layers = false;
+    int fba_pxn = 0, fba_pd = 0;
+    size_t smem_fba = 0;
+    if (fits && p->NL - 1 <= 64) {
+      const char* env_fba = getenv("VAB_NN_ALL_LAYERS");      // 0: per-layer kernels even for small networks
+      if (!(env_fba && atoi(env_fba) == 0)) {
+        fba_pxn = ((p->NDnet + 7) & ~7) + 4;
+        size_t wsz = 0;
+        int d1max = 0;
+        for (int n = 0; n + 1 < p->NL; ++n) {
+          const int dnP = (p->st_host[n] + 7) & ~7, dn1P = (p->st_host[n + 1] + 7) & ~7;
+          wsz += (size_t)dn1P * (dnP + 4) + dn1P;
+          if (dn1P > d1max) d1max = dn1P;
+        }
+        fba_pd = d1max + 4;
+        for (int tm = 128; tm >= 32 && !all_layers; tm >>= 1) {
+          const size_t s = ((size_t)2 * tm * fba_pxn + 16 + (size_t)tm * fba_pd + wsz) * sizeof(double);
+          if (s <= (size_t)100 * 1024 && (tm <= 32 || tm * 4 <= p->M)) { all_layers = true; TMF = tm; smem_fba = s; }
+        }
+      }
+    }
+    if (fits && !all_layers) {
       for (int tm = 256; tm >= 16 && TMF == 0; tm >>= 1) {
         if (tm > 64 && tm * 4 > p->M) continue;                 // keep at least a few tiles per layer
         size_t worst = 0;
@@ -797,8 +1000,9 @@ int nn_eval(vab_ctx* ctx, int B, const double* XP, long long ldxp, double rf_sca
       klen = ((klen + kp - 1) / kp) * kp;
       P.gw_klen = klen;
       P.gw_nsplit = (p->M + klen - 1) / klen;
-      P.nparts = (p->NL - 1) * P.nmt;
+      P.nparts = all_layers ? P.nmt : (p->NL - 1) * P.nmt;
       P.ngw = P.gw_nsplit;
+      P.fba_pxn = fba_pxn; P.fba_pd = fba_pd;
       const size_t nd1 = (size_t)(p->NDnet - p->d0);
       long long nfix = ((long long)p->M * p->NDnet + FIX_NT * 8 - 1) / (FIX_NT * 8);     // ~8 entries per thread
       if (nfix > 1024) nfix = 1024;
@@ -815,17 +1019,25 @@ int nn_eval(vab_ctx* ctx, int B, const double* XP, long long ldxp, double rf_sca
       rc = vab_reserve(ctx, &p->lam, &p->lam_cap, (size_t)B * p->M * nd1);
       if (rc != VAB_OK) return rc;
       P.partials = ctx->partials; P.gwpart = p->gwpart; P.pfull = p->pfull; P.dbuf = p->dbuf; P.lam = p->lam;
-      P.me_parts = ctx->partials + (size_t)B * P.nparts * 2;
+      P.me_parts = all_layers ? nullptr : ctx->partials + (size_t)B * P.nparts * 2;
       static bool attr_split = false;
       if (!attr_split) {
         cudaError_t e = cudaFuncSetAttribute(nn_fb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(nn_gw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(nn_fba_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
         if (e != cudaSuccess) return vab_cuda_fail(ctx, e, "nn_action_grad smem opt-in (split)");
         attr_split = true;
       }
       if (smem_gw > 200 * 1024) return vab_fail(ctx, VAB_ERR_INVALID, "nn_action_grad: internal plan error (gw smem)");
       if (p->NP > 0) nn_gather_params_kernel<<<dim3((p->NP + 255) / 256, B), 256, 0, ctx->stream>>>(P);
-      {
+      int nl = 3;
+      cudaError_t e = cudaSuccess;
+      if (all_layers) {
+        nn_fba_kernel<<<dim3(P.nmt, B), NT, smem_fba, ctx->stream>>>(P);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return vab_cuda_fail(ctx, e, "nn_fba_kernel launch");
+        nl = 2;
+      } else {
         // 16 warps when every warp still gets a (row tile, column group) task of the smallest layer pair
         int min_tasks = 1 << 30;
         for (int n = 0; n + 1 < p->NL; ++n) {
@@ -835,11 +1047,10 @@ int nn_eval(vab_ctx* ctx, int B, const double* XP, long long ldxp, double rf_sca
         }
         const int nthr = (min_tasks >= 16) ? NTF : NT;
         nn_fb_kernel<<<dim3(P.nmt, p->NL - 1, B), nthr, smem_fb, ctx->stream>>>(P);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return vab_cuda_fail(ctx, e, "nn_fb_kernel launch");
+        nn_fix_kernel<<<dim3((unsigned)nfix, B), FIX_NT, 0, ctx->stream>>>(P);
       }
-      cudaError_t e = cudaGetLastError();
-      if (e != cudaSuccess) return vab_cuda_fail(ctx, e, "nn_fb_kernel launch");
-      int nl = 3;
-      nn_fix_kernel<<<dim3((unsigned)nfix, B), FIX_NT, 0, ctx->stream>>>(P);
       nn_gw_kernel<<<dim3(P.gw_nsplit * njs, p->NL - 1, B), NT, smem_gw, ctx->stream>>>(P);
       e = cudaGetLastError();
       if (e != cudaSuccess) return vab_cuda_fail(ctx, e, "nn_gw_kernel launch");
