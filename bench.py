@@ -187,6 +187,84 @@ def workload_config(n_gpus):
             "l2_policy": "inputs larger than L2 (XP + grad = 512 MB per step per GPU vs 126 MB L2)"}
 
 
+# ------------------------------------------------------------------------------------ other configs
+def other_configs(device):
+    """Evaluation rates of the other BASELINE.json configs at their per-path sizes (device
+    resident, a handful of paths): C3 = Lorenz96 D=1000, N=100000 (rk4 and SimpsonHermite), C4 =
+    nnet_twin 5x100 M=1000, C5 = bar images [25,30,4] M=10000.  Reported next to the headline line;
+    they are not the metric."""
+    import ctypes as ct
+    import torch
+    from varanneal_b200 import _lib, va_nnet
+    out = {}
+    dev = torch.device("cuda", device)
+
+    def timed(fn, reps):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    # ---- C3 shape straight through the C ABI (no host copies of 0.8 GB paths)
+    D3, B3 = 1000, 4
+    L3 = [i for i in range(D3) if i % 5 in (0, 2)]
+    for disc, N3 in (("rk4", 100000), ("SimpsonHermite", 100001)):
+        ctx = _lib.Context(device, torch.cuda.current_stream(dev).cuda_stream)
+        n = N3 * D3 + 1
+        ld = (n + 15) // 16 * 16
+        gen = torch.Generator(device=dev).manual_seed(2000)
+        Y = torch.randn(N3, len(L3), dtype=torch.float64, device=dev, generator=gen)
+        XP = torch.randn(B3, ld, dtype=torch.float64, device=dev, generator=gen) * 3.0
+        XP[:, N3 * D3:] = K_FORCING
+        G = torch.empty_like(XP)
+        A = torch.zeros(B3, dtype=torch.float64, device=dev)
+        pfix = torch.full((1,), K_FORCING, dtype=torch.float64, device=dev)
+        desc = _lib.OdeDesc(0, _lib.DISC_IDS[disc], D3, N3, N3, 1, len(L3), 1, 1, 0, DT)
+        p = lambda t: ct.c_void_p(t.data_ptr())  # noqa: E731
+        _lib.check(ctx.lib.vab_ode_problem_set(ctx.h, desc, _lib.int_array(L3), _lib.int_array([0]), p(Y), None), ctx.h)
+        _lib.check(ctx.lib.vab_ode_set_weights(ctx.h, RM, None, RF0, None), ctx.h)
+        _lib.check(ctx.lib.vab_ode_set_fixed_params(ctx.h, p(pfix), 0), ctx.h)
+        scale = ALPHA ** BETA_EVAL
+        ms = timed(lambda: _lib.check(ctx.lib.vab_ode_action_grad(ctx.h, B3, p(XP), ld, scale, p(A), None, None, p(G), ld), ctx.h), 5)
+        byt = B3 * 16.0 * N3 * D3 + 8.0 * N3 * len(L3)
+        out["C3_%s" % disc] = {"shape": "Lorenz96 D=1000 N=%d L=400, %d paths resident" % (N3, B3),
+                               "evals_per_s": B3 / ms * 1e3, "ms_per_launch": ms,
+                               "algorithmic_GBps": byt / ms / 1e6, "finite": bool(torch.isfinite(A).all().item())}
+        ctx.close()
+        del XP, G, Y
+    # ---- NN shapes through va_nnet.Annealer
+    for name, st, M in (("C4", [100] * 5, 1000), ("C5", [25, 30, 4], 10000)):
+        st = np.array(st)
+        B4 = 64
+        NDnet = int(st.sum())
+        NP = int(sum(st[k] * st[k + 1] + st[k + 1] for k in range(len(st) - 1)))
+        rng = np.random.RandomState(0)
+        an = va_nnet.Annealer(device=device)
+        an.set_structure(st)
+        an.set_activation("sigmoid")
+        an.set_input_data(rng.rand(M, st[0]))
+        an.set_output_data(rng.rand(M, st[-1]))
+        X0 = rng.rand(B4, M * NDnet)
+        P0 = 0.3 * rng.randn(B4, NP)
+        an.anneal_init(X0, P0, 1.1, [20.0], 1.0, 1e-2, np.arange(NP), init_to_data=False)
+        an._XP[:, :an._n].copy_(torch.from_numpy(np.concatenate([X0, P0], axis=1)))
+        ms = timed(lambda: an._action_grad_native(6.7), 10)
+        flops = 6.0 * M * sum(st[k] * st[k + 1] for k in range(len(st) - 1)) * B4
+        byt = (16.0 * M * NDnet + 16.0 * NP) * B4
+        out[name] = {"shape": "va_nnet %s M=%d, %d paths" % (list(map(int, st)), M, B4),
+                     "evals_per_s": B4 / ms * 1e3, "ms_per_launch": ms, "fp64_TFLOPs": flops / ms / 1e9,
+                     "algorithmic_GBps": byt / ms / 1e6}
+        del an
+    torch.cuda.empty_cache()
+    return out
+
+
 # ------------------------------------------------------------------------------------ GPU arm
 def run_ours(args):
     import torch
@@ -350,6 +428,11 @@ def run_ours(args):
                     "api": "va_ode.Annealer.A_gradA(pinned XP) -> (A, grad) pinned"},
             "gpu_launches": int(launches), "clocks": clocks, "ladder": ladder,
         }
+        if world == 1 and not args.no_extra:
+            try:
+                line["other_configs"] = other_configs(local)
+            except Exception as exc:                          # never lose the headline line
+                line["other_configs"] = {"error": repr(exc)}
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline_single_core(Y)
         print(json.dumps(line))
@@ -365,6 +448,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-ladder", action="store_true", help="skip the full-ladder leg")
+    ap.add_argument("--no-extra", action="store_true", help="skip the C3 / C4 / C5 evaluation-rate probes")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
