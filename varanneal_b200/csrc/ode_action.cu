@@ -115,20 +115,34 @@ SweepKernel sweep_kernel(int model, int C, int disc, bool window) {
 // MODE: 0 = run-time weights, 1 = scalar RM / RF (launch constants), 2 = the same with one RF per
 // path (ode_stream.cuh)
 template <class M, int MODE>
-SweepKernel stream_kernel_for(int disc) {
+SweepKernel stream_kernel_for(int disc, bool window) {
   switch (disc) {
     case DISC_EULER: return stream_twopoint_kernel<M, DISC_EULER, VAB_ST_NS, VAB_ST_MINB, MODE>;
     case DISC_TRAPEZOID: return stream_twopoint_kernel<M, DISC_TRAPEZOID, VAB_ST_NS, VAB_ST_MINB, MODE>;
     case DISC_FORWARDMAP: return stream_twopoint_kernel<M, DISC_FORWARDMAP, VAB_ST_NS, VAB_ST_MINB, MODE>;
     case DISC_SIMPSON: return stream_simpson_kernel<M, VAB_ST_NS, VAB_ST_MINB, MODE>;
+    case DISC_RK4: {
+      // resident CTAs per SM the register budget allows.  Measured on B200: one lane group per
+      // row (D = 100, B = 64) 0.280 ms at 4 (128 registers, spills) vs 0.304 ms at 3; window mode
+      // (D = 1000, B = 8) 1.34 ms at 3 (168 registers, no spills) vs 1.76 ms at 4.
+      static int forced = -1;
+      if (forced < 0) {
+        const char* e = getenv("VAB_RK4_STREAM_MINB");
+        forced = e ? atoi(e) : 0;
+      }
+      const int minb = forced ? forced : (window ? 3 : 4);
+      if (minb == 4) return stream_rk4_kernel<M, VAB_ST_NS, 4, MODE>;
+      if (minb == 2) return stream_rk4_kernel<M, VAB_ST_NS, 2, MODE>;
+      return stream_rk4_kernel<M, VAB_ST_NS, 3, MODE>;
+    }
   }
   return nullptr;
 }
 template <class M>
-SweepKernel stream_kernel_mode(int disc, int mode) {
-  if (mode == 1) return stream_kernel_for<M, 1>(disc);
-  if (mode == 2) return stream_kernel_for<M, 2>(disc);
-  return stream_kernel_for<M, 0>(disc);
+SweepKernel stream_kernel_mode(int disc, int mode, bool window) {
+  if (mode == 1) return stream_kernel_for<M, 1>(disc, window);
+  if (mode == 2) return stream_kernel_for<M, 2>(disc, window);
+  return stream_kernel_for<M, 0>(disc, window);
 }
 int stream_variant() {
   static int variant = -1;
@@ -148,7 +162,7 @@ int stream_ns(int C, int disc, bool fast) {
   }
   return VAB_ST_NS;
 }
-SweepKernel stream_kernel(int C, int disc, bool fast, bool perpath) {
+SweepKernel stream_kernel(int C, int disc, bool fast, bool perpath, bool window) {
   const int mode = fast ? (perpath ? 2 : 1) : 0;
   if (mode == 1 && C == 4 && disc == DISC_SIMPSON) {       // tuning variants of the flagship kernel
     switch (stream_variant()) {
@@ -158,8 +172,8 @@ SweepKernel stream_kernel(int C, int disc, bool fast, bool perpath) {
       default: return stream_simpson_kernel<ModelL96<4>, 4, 4, 1>;
     }
   }
-  if (C == 4) return stream_kernel_mode<ModelL96<4>>(disc, mode);
-  if (C == 2) return stream_kernel_mode<ModelL96<2>>(disc, mode);
+  if (C == 4) return stream_kernel_mode<ModelL96<4>>(disc, mode, window);
+  if (C == 2) return stream_kernel_mode<ModelL96<2>>(disc, mode, window);
   return nullptr;
 }
 
@@ -204,7 +218,7 @@ int ode_sweep_prepare(int model, int disc, int D, int N, int B, int num_sms, int
     const int ns = stream_ns(g.C, disc, fast);
     const size_t smem = (size_t)4 * ns * stage_b + ((size_t)4 * ns + (size_t)128 * K) * sizeof(double);
     if (smem <= 200 * 1024) {
-      k = stream_kernel(g.C, disc, fast, P->rf_path != nullptr);
+      k = stream_kernel(g.C, disc, fast, P->rf_path != nullptr, g.nwin > 1);
       nb = k ? blocks_per_sm(k, smem, cerr) : 0;
       if (nb < 0) return -2;
       if (nb > 0) { sl->stream = true; sl->smem = smem; }
@@ -249,7 +263,7 @@ int ode_sweep_prepare(int model, int disc, int D, int N, int B, int num_sms, int
 int ode_sweep_launch(const OdeParams& P, const SweepLaunch& sl, int model, int disc,
                      cudaStream_t st, double* A, double* me, double* fe, cudaError_t* cerr) {
   const bool fast = (P.nskip == 1 && P.rmd == nullptr && P.rf_arr == nullptr && P.L > 0);
-  SweepKernel k = sl.stream ? stream_kernel(sl.C, disc, fast, P.rf_path != nullptr) : sweep_kernel(model, sl.C, disc, P.nwin > 1);
+  SweepKernel k = sl.stream ? stream_kernel(sl.C, disc, fast, P.rf_path != nullptr, P.nwin > 1) : sweep_kernel(model, sl.C, disc, P.nwin > 1);
   if (!k) return -1;
   k<<<sl.grid, 128, sl.smem, st>>>(P);
   cudaError_t e = cudaGetLastError();

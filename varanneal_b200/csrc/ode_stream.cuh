@@ -552,3 +552,136 @@ __global__ void __launch_bounds__(128, MINB) stream_twopoint_kernel(const __grid
   }
   S.finish(red);
 }
+
+// --------------------------------------------------------------------------------------------
+// rk4 (extension; intent of the commented-out va_ode.py:383-402):
+//   e_m = x_{m+1} - x_m - dt/6 (k1 + 2 k2 + 2 k3 + k4),  k1 = f(x_m), k2 = f(x_m + dt/2 k1), ...
+// Same ring / row schedule as the two-point kernel: when row m arrives, residual m-1 is formed
+// from the carried row m-1 (its x halo comes from the staged row; only the three stage states and
+// the four adjoint seeds are exchanged by shuffles) and row m-1's gradient
+//   g_{m-1} = lam_{m-2} - lam_{m-1} + meas_{m-1} + [adjoint of -dt/6 K(x_{m-1}) lam_{m-1}]
+// is finalised by reverse accumulation through the stages (discrete adjoint of RK4).
+template <class M, int NS, int MINB, int MODE>
+__global__ void __launch_bounds__(128, MINB) stream_rk4_kernel(const __grid_constant__ OdeParams P) {
+  using ST = vabs::Stream<M, NS, MODE>;
+  constexpr int C = ST::C, H = ST::H, W = ST::W;
+  extern __shared__ __align__(16) double smem[];
+  ST S(P);
+  if (!S.init(smem)) return;
+  double* red = smem + ((size_t)4 * NS * S.stage_b) / 8 + 4 * NS;
+  const double dt = P.dt, hdt = 0.5 * dt, dt6 = dt / 6.0, dt3 = dt / 3.0;
+  const int r0 = S.r0, r1 = S.r1, N = S.N;
+  const uint32_t rb = S.row_b;
+  S.rowbase = r0 - 2;                       // stage q holds rows (r0 - 2 + 2q, r0 - 1 + 2q)
+  S.qmax = (min(r1, N - 1) - r0 + 2) / 2;
+#pragma unroll
+  for (int q = 0; q < NS; ++q) S.issue(q);
+
+  double X1[W], lamp[C];
+  bool valid1;
+  // row m arrives (staged at byte offset xoff); finalises row m-1 (its Y row at yoff) when fin
+  auto sub = [&](int m, uint32_t xoff, uint32_t yoff, bool vm, bool fin) {
+    double xm[C], lam[C];
+    if (vm) {
+      S.read_own(xoff, xm);
+    } else {
+#pragma unroll
+      for (int c = 0; c < C; ++c) xm[c] = 0.0;
+    }
+    const bool ve = vm && valid1;                 // residual m-1 exists
+    const bool own = (m - 1 >= r0) && (m - 1 < r1);
+    if (ve) {                                     // warp-uniform
+      double Y2[W], Y3[W], Y4[W], k[C], ks[C];
+      M::f(X1, S.p, nullptr, k);
+#pragma unroll
+      for (int c = 0; c < C; ++c) { ks[c] = k[c]; Y2[H + c] = fma(hdt, k[c], X1[H + c]); }
+      S.halo(Y2);
+      M::f(Y2, S.p, nullptr, k);
+#pragma unroll
+      for (int c = 0; c < C; ++c) { ks[c] = fma(2.0, k[c], ks[c]); Y3[H + c] = fma(hdt, k[c], X1[H + c]); }
+      S.halo(Y3);
+      M::f(Y3, S.p, nullptr, k);
+#pragma unroll
+      for (int c = 0; c < C; ++c) { ks[c] = fma(2.0, k[c], ks[c]); Y4[H + c] = fma(dt, k[c], X1[H + c]); }
+      S.halo(Y4);
+      M::f(Y4, S.p, nullptr, k);
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const double e = (xm[c] - X1[H + c]) - dt6 * (ks[c] + k[c]);
+        const double l = S.wgt(m - 1, c) * e;
+        if (own) S.fe_acc = fma(l, e, S.fe_acc);
+        lam[c] = l;
+      }
+      if (fin) {
+        // reverse sweep through the stages: xb collects d e_{m-1} / d x_{m-1} applied to lam
+        // (the seeds carry the minus sign of the residual, finish() negates pacc: collect locally)
+        double KB[W], jt[C], xb[C], gr[C], pl[ST::NPM];
+#pragma unroll
+        for (int q = 0; q < ST::NPM; ++q) pl[q] = 0.0;
+#pragma unroll
+        for (int c = 0; c < C; ++c) { xb[c] = -lam[c]; KB[H + c] = -dt6 * lam[c]; }
+        S.halo(KB);
+        M::adj(Y4, KB, S.p, jt, pl);
+#pragma unroll
+        for (int c = 0; c < C; ++c) { xb[c] += jt[c]; KB[H + c] = fma(dt, jt[c], -dt3 * lam[c]); }
+        S.halo(KB);
+        M::adj(Y3, KB, S.p, jt, pl);
+#pragma unroll
+        for (int c = 0; c < C; ++c) { xb[c] += jt[c]; KB[H + c] = fma(hdt, jt[c], -dt3 * lam[c]); }
+        S.halo(KB);
+        M::adj(Y2, KB, S.p, jt, pl);
+#pragma unroll
+        for (int c = 0; c < C; ++c) { xb[c] += jt[c]; KB[H + c] = fma(hdt, jt[c], -dt6 * lam[c]); }
+        S.halo(KB);
+        M::adj(X1, KB, S.p, jt, pl);
+#pragma unroll
+        for (int q = 0; q < ST::NPM; ++q) S.pacc[q] -= pl[q];
+#pragma unroll
+        for (int c = 0; c < C; ++c) gr[c] = lamp[c] + (xb[c] + jt[c]);
+        S.measure(m - 1, yoff, X1 + H, gr);
+        S.store(m - 1, gr);
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < C; ++c) lam[c] = 0.0;
+      if (fin) {                                  // last row of the path: no residual starts here
+        double gr[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) gr[c] = lamp[c];
+        S.measure(m - 1, yoff, X1 + H, gr);
+        S.store(m - 1, gr);
+      }
+    }
+    if (vm) {
+      S.read_halo(xoff, X1);
+#pragma unroll
+      for (int c = 0; c < C; ++c) X1[H + c] = xm[c];
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) lamp[c] = lam[c];
+    valid1 = vm;
+  };
+
+  // ---- prologue: row r0 - 1 (second row of stage 0)
+  S.wait(0);
+  valid1 = (r0 >= 1);
+  if (valid1) {
+    S.read_row(S.slot_off(0) + rb, X1);
+  } else {
+#pragma unroll
+    for (int c = 0; c < W; ++c) X1[c] = 0.0;
+  }
+#pragma unroll
+  for (int c = 0; c < C; ++c) lamp[c] = 0.0;
+  const int tmax = (r1 - r0) / 2;                               // last step (m1 = r0 + 2 tmax <= r1)
+  for (int t = 0; t <= tmax; ++t) {
+    const int q = t + 1, m1 = r0 + 2 * t;
+    S.wait(q);
+    const uint32_t sq = S.slot_off(q), sp = S.slot_off(q - 1);
+    sub(m1, sq, sp + 3u * rb, m1 < N, t >= 1);
+    if (m1 + 1 <= r1) sub(m1 + 1, sq + rb, sq + 2u * rb, m1 + 1 < N, true);
+    __syncwarp();
+    S.issue(q - 1 + NS);
+  }
+  S.finish(red);
+}
