@@ -261,6 +261,26 @@ def other_configs(device):
                      "evals_per_s": B4 / ms * 1e3, "ms_per_launch": ms, "fp64_TFLOPs": flops / ms / 1e9,
                      "algorithmic_GBps": byt / ms / 1e6}
         del an
+    # ---- C1: the shipped example's shape (D=20, N=161, 8 observed, 101 betas), full ladder
+    from varanneal_b200 import datagen, va_ode
+    L1 = [0, 2, 4, 6, 8, 10, 14, 16]
+    t1, _, Y1 = datagen.lorenz96_twin(D=20, N=161, dt=0.025, k=8.17, sigma=0.5, Lidx=L1, seed=100)
+    for B1 in (1, 64):
+        rng = np.random.RandomState(12345)
+        X0 = 20.0 * rng.rand(B1, 161, 20) - 10.0
+        P0 = 4.0 * rng.rand(B1, 1) + 6.0
+        an = va_ode.Annealer(device=device)
+        an.set_model("lorenz96", 20)
+        an.set_data(Y1, t=t1)
+        t0 = time.perf_counter()
+        an.anneal(X0, P0, 1.5, np.linspace(0, 100, 101), 4.0, 4e-6, L1, [0], dt_model=0.025, init_to_data=True,
+                  disc="trapezoid", opt_args={"gtol": 1e-8, "ftol": 1e-8, "maxfun": 1000000, "maxiter": 1000000})
+        dt1 = time.perf_counter() - t0
+        out["C1_B%d" % B1] = {"shape": "Lorenz96 D=20 N=161 L=8 trapezoid, 101 betas, %d path(s), Annealer.anneal()" % B1,
+                              "ladder_wall_s": dt1, "nfev_total": int(an.nfev_array.sum()),
+                              "converged_fraction": float(np.mean(an.exitflags == 0)),
+                              "A_last_rung_min": float(np.min(an.A_array[..., -1]))}
+        del an
     torch.cuda.empty_cache()
     return out
 
