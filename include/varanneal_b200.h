@@ -149,7 +149,7 @@ VAB_API int vab_nn_action_grad(vab_ctx* ctx, int32_t B, const double* XP_dev, in
  * (_autodiffmin.py:85-86): gtol -> pgtol, ftol -> ftol (factr = ftol/eps), maxfun, maxiter,
  * maxcor -> m, maxls. */
 typedef struct {
-  int32_t m;          /* history size, SciPy default 10 */
+  int32_t m;          /* history size, SciPy default 10; method 2: maxCGit (0 = max(1, min(50, n/2))) */
   int32_t maxls;      /* line-search steps per iteration, SciPy default 20 */
   int64_t maxfun;     /* SciPy default 15000 */
   int64_t maxiter;    /* SciPy default 15000 */
@@ -157,7 +157,10 @@ typedef struct {
   double pgtol;       /* stop when max|proj g| <= pgtol */
   int32_t poll_every; /* evaluations enqueued between host polls of the done flag (>=1) */
   int32_t method;     /* 0 = L-BFGS-B (min_lbfgs_scipy), 1 = nonlinear CG, Polak-Ribiere+ (min_cg_scipy,
-                         _autodiffmin.py:97-119); ftol / m are ignored by CG */
+                         _autodiffmin.py:97-119; ftol / m are ignored), 2 = truncated Newton
+                         (min_tnc_scipy, _autodiffmin.py:121-143; vab_minimize only, no bounds;
+                         status = SciPy's TNC return code: 0 local minimum, 1 f converged,
+                         2 x converged, 3 evaluation limit, 4 line search failed) */
 } vab_lbfgs_opts;
 
 /* Replaces ADmin.min_lbfgs_scipy (_autodiffmin.py:72-95) for whichever problem (ODE or NN) was

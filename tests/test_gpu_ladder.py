@@ -188,10 +188,54 @@ def test_ncg_method_reaches_scipy_cg_minimum():
         A, g = prob.action_grad(an.minpaths[i], rf)
         assert np.max(np.abs(g)) <= 1e-7
     assert np.all(an.exitflags == 0)
+
+
+def test_tnc_method_reaches_scipy_tnc_minimum():
+    """method='TNC' (min_tnc_scipy, _autodiffmin.py:121-143): the device truncated Newton and
+    SciPy's TNC on the oracle action converge to the same minimum (1e-6 relative on A; the
+    iterates differ -- plain CG + More'-Thuente instead of Nash's preconditioned CG + getptc, see
+    csrc/tnc.cu) on a fully observed, well-conditioned problem; a batch of paths; the seam keeps
+    the reference's return triple; bounds are refused."""
+    import scipy.optimize as opt
+    from varanneal_b200 import va_ode
+    rng = np.random.RandomState(12)
+    D, N, B = 8, 31, 3
+    Lidx = list(range(D))
+    t = 0.01 * np.arange(N)
+    Y = 2.0 * rng.randn(N, D)
+    X0 = Y[None] + 0.3 * rng.randn(B, N, D)
+    an = va_ode.Annealer()
+    an.set_model("lorenz96", D)
+    an.set_data(Y, t=t)
+    P0 = np.tile(np.array([8.0]), (B, 1))
+    an.anneal(X0.copy(), P0, 2.0, [8, 10], 1.0, 1e-2, Lidx, [0], disc="trapezoid", method="TNC",
+              init_to_data=False, opt_args={"gtol": 1e-7, "maxfun": 100000})
+    assert an.A_array.shape == (B, 2) and np.all(an.exitflags <= 2), an.exitflags
+    prob = OdeProblem("lorenz96", D, Y, Lidx, 0.01, "trapezoid", [8.0], [0], 1.0)
+    for b in (0, B - 1):
+        xp = np.append(X0[b].ravel(), 8.0)
+        for i, beta in enumerate([8, 10]):
+            rf = 1e-2 * 2.0 ** beta
+            res = opt.minimize(lambda z: prob.action_grad(z, rf), xp, method="TNC", jac=True,
+                               options={"gtol": 1e-9, "maxfun": 100000})
+            xp = res.x
+            assert abs(an.A_array[b, i] - res.fun) <= 1e-6 * abs(res.fun), (an.A_array[b, i], res.fun)
+            A, g = prob.action_grad(an.minpaths[b, i], rf)
+            assert abs(A - an.A_array[b, i]) <= 1e-10 * abs(A) and np.max(np.abs(g)) <= 1e-6
+    # far fewer evaluations than unknowns: the inner CG solves are truncated
+    assert np.all(an.nfev_array < 40 * 20) and np.all(an.nit_array >= 1)
+    # the seam
+    an1 = va_ode.Annealer(); an1.set_model("lorenz96", D); an1.set_data(Y, t=t)
+    an1.anneal_init(X0[0].copy(), np.array([8.0]), 2.0, [8], 1.0, 1e-2, Lidx, [0], disc="trapezoid",
+                    method="TNC", init_to_data=False, opt_args={"gtol": 1e-7, "maxfun": 100000})
+    XPmin, Amin, status = an1.min_tnc_scipy(np.append(X0[0].ravel(), 8.0))
+    assert XPmin.shape == (N * D + 1,) and isinstance(Amin, float) and status in (0, 1, 2)
+    assert abs(Amin - an.A_array[0, 0]) <= 1e-9 * abs(Amin)
+    an2 = va_ode.Annealer(); an2.set_model("lorenz96", D); an2.set_data(Y, t=t)
+    an2.anneal_init(X0[0].copy(), np.array([8.0]), 2.0, [8], 1.0, 1e-2, Lidx, [0], disc="trapezoid",
+                    method="TNC", bounds=[[-50.0, 50.0]] * (D + 1), init_to_data=False)
     with pytest.raises(NotImplementedError):
-        va_ode.Annealer().anneal_init  # attribute exists
-        an2 = va_ode.Annealer(); an2.set_model("lorenz96", D); an2.set_data(Y, t=t)
-        an2.anneal_init(X0.copy(), np.array([8.0]), 2.0, [1], 1.0, 1e-2, Lidx, [0], method="TNC")
+        an2.anneal_step()
 
 
 def test_vab_anneal_device_resident_ladder_equals_stepwise():

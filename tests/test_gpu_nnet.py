@@ -141,3 +141,40 @@ def test_nn_split_kernels_agree_with_fused_kernel(structure, M, B, monkeypatch):
         assert np.max(np.abs(res[k][0] - res["0"][0]) / np.abs(res["0"][0])) <= 1e-13
         assert np.max(np.abs(res[k][1] - res["0"][1])) <= 1e-12 * np.max(np.abs(res["0"][1]))
         assert np.allclose(res[k][3], res["0"][3], rtol=1e-13) and np.allclose(res[k][4], res["0"][4], rtol=1e-13)
+
+
+def test_nn_tnc_method_minimises_the_oracle_action():
+    """va_nnet with method='TNC' (min_tnc_scipy): the device truncated Newton reaches the minimum
+    SciPy's TNC reaches on the oracle action (1e-6 relative) on the well-conditioned twin problem
+    of the ladder test above (weights held at perturbed teacher values, RF large enough for the
+    model error to shape the minimum; with free weights the valley is flat and SciPy's own
+    L-BFGS-B runs 1e5 iterations without converging)."""
+    rng = np.random.RandomState(8)
+    st = np.array([4, 6, 3])
+    M = 12
+    NDnet, NP = int(st.sum()), int(4 * 6 + 6 + 6 * 3 + 3)
+    Wt = [rng.randn(6, 4), rng.randn(3, 6)]
+    xin = rng.rand(M, 4)
+    h = 1 / (1 + np.exp(-(xin @ Wt[0].T)))
+    yout = 1 / (1 + np.exp(-(h @ Wt[1].T))) + 0.05 * rng.randn(M, 3)
+    X0 = rng.rand(M * NDnet)
+    P0 = np.concatenate([Wt[0].ravel(), np.zeros(6), Wt[1].ravel(), np.zeros(3)]) * (1 + 0.05 * rng.randn(NP))
+    Pidx = np.arange(0)
+    alpha, betas, RM, RF0 = 2.0, [4.0, 8.0], 400.0, 1.0
+    from varanneal_b200 import va_nnet
+    an = va_nnet.Annealer()
+    an.set_structure(st); an.set_activation(va_nnet.sigmoid)
+    an.set_input_data(xin); an.set_output_data(yout)
+    X0d = X0.copy()
+    an.anneal(X0d, P0.copy(), alpha, betas, RM, RF0, Pidx, method="TNC", opt_args={"gtol": 1e-9, "maxfun": 200000})
+    assert np.all(an.exitflags <= 2), an.exitflags           # local minimum / f converged / x converged
+    prob = nnet_port.NnetProblem(st, xin, yout, None, P0, Pidx, RM)
+    xp = X0d.copy()
+    for i, beta in enumerate(betas):
+        rf = RF0 * alpha ** beta
+        res = opt.minimize(lambda z: prob.action_grad(z, rf), xp, method="TNC", jac=True,
+                           options={"gtol": 1e-10, "maxfun": 200000})
+        xp = res.x
+        assert abs(an.A_array[i] - res.fun) <= 1e-6 * abs(res.fun), (i, an.A_array[i], res.fun)
+        A, g = prob.action_grad(an.minpaths[i][:M * NDnet], rf)
+        assert abs(A - an.A_array[i]) <= 1e-10 * abs(A) and np.max(np.abs(g)) <= 1e-5 * max(1.0, abs(A))

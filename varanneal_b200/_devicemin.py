@@ -207,6 +207,8 @@ class DeviceMin(object):
         o = dict(self.opt_args or {})
         known = {"gtol", "ftol", "maxfun", "maxiter", "maxcor", "maxls", "poll_every",
                  "disp", "iprint", "eps", "maxiter_per_beta"}
+        if method == 2:     # scipy.optimize.minimize(method='TNC') options; the ones the device driver has no
+            known |= {"maxCGit", "eta", "stepmx", "accuracy", "minfev", "rescale", "xtol", "scale", "offset"}   # use for are accepted and ignored
         bad = set(o) - known
         if bad:
             raise ValueError("unsupported opt_args keys for the device L-BFGS-B: %s" % sorted(bad))
@@ -221,13 +223,25 @@ class DeviceMin(object):
         opts.method = int(method)
         if method == 1 and "maxiter" not in o:
             opts.maxiter = 200 * self._n                     # SciPy CG default
+        if method == 2:
+            # SciPy's TNC: maxfun (alias maxiter) bounds the evaluations, default max(100, 10 n);
+            # ftol < 0 -> 0 (off), gtol < 0 -> 1e-2 sqrt(accuracy) with accuracy = sqrt(eps)
+            opts.m = int(o.get("maxCGit", 0))
+            lim = o.get("maxfun", o.get("maxiter", max(100, 10 * self._n)))
+            opts.maxfun = int(min(float(lim), 2 ** 62))
+            opts.maxiter = opts.maxfun
+            opts.ftol = max(0.0, float(o.get("ftol", -1.0)))
+            g = float(o.get("gtol", -1.0))
+            opts.pgtol = g if g >= 0.0 else 1e-2 * (2.220446049250313e-16 ** 0.25)
         return opts
 
     def _minimize_device(self, rf_scale, method=None):
         """Runs the device minimiser on the paths currently in self._XP (in place)."""
         if method is None:
-            method = 1 if getattr(self, "method", "L-BFGS-B") == "NCG" else 0
+            method = {"NCG": 1, "TNC": 2}.get(getattr(self, "method", "L-BFGS-B"), 0)
         opts = self._lbfgs_opts(method)
+        if method == 2 and getattr(self, "_lo_dev", None) is not None:
+            raise NotImplementedError("method='TNC' on the device takes no bounds; use 'L-BFGS-B' for bounded problems")
         lo = ptr(getattr(self, "_lo_dev", None)) if method == 0 else None     # SciPy's CG ignores bounds
         hi = ptr(getattr(self, "_hi_dev", None)) if method == 0 else None
         _lib.check(self._ctx.lib.vab_minimize(
@@ -254,7 +268,7 @@ class DeviceMin(object):
         B, nb, n, nX = self._B, self.Nbeta, self._n, self._nX
         src = self.minpaths[:, 0] if self.batched else self.minpaths[0][None, :]
         self._upload_paths(self._est_slice(src))
-        method = 1 if getattr(self, "method", "L-BFGS-B") == "NCG" else 0
+        method = 1 if getattr(self, "method", "L-BFGS-B") == "NCG" else 0     # TNC never gets here (anneal())
         opts = self._lbfgs_opts(method)
         lo = ptr(getattr(self, "_lo_dev", None)) if method == 0 else None
         hi = ptr(getattr(self, "_hi_dev", None)) if method == 0 else None
@@ -337,8 +351,22 @@ class DeviceMin(object):
         return XPmin, A, st
 
     def min_tnc_scipy(self, XP0, xtrace=None):
-        raise NotImplementedError("method='TNC' (truncated Newton, SURVEY.md 8(f2)) is not built on the "
-                                  "device; use 'L-BFGS-B' (bounds supported) or 'NCG'")
+        """Same contract as ADmin.min_tnc_scipy (_autodiffmin.py:121-143), on the device: truncated
+        Newton (CG inner solve on gradient-difference Hessian-vector products, More'-Thuente
+        search); status = SciPy's TNC return code.  See csrc/tnc.cu for what differs from Nash's
+        TNC.  No bounds."""
+        XP0 = np.asarray(XP0, dtype=np.float64)
+        single = XP0.ndim == 1
+        self._upload_paths(XP0)
+        self._minimize_device(self._rf_scale(), method=2)
+        XPmin = self._XP[:, :self._n].cpu().numpy()
+        A = self._A.cpu().numpy()
+        st = self._status.cpu().numpy()
+        self.last_nit = self._nit.cpu().numpy()
+        self.last_nfev = self._nfev.cpu().numpy()
+        if single:
+            return XPmin[0], float(A[0]), int(st[0])
+        return XPmin, A, st
 
     @property
     def gpu_launches(self):

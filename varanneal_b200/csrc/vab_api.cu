@@ -13,6 +13,7 @@
 
 void nn_destroy(vab_ctx* ctx);       // nn_action.cu
 void lbfgs_destroy(vab_ctx* ctx);    // lbfgs.cu
+void tnc_destroy(vab_ctx* ctx);      // tnc.cu
 int nn_eval(vab_ctx* ctx, int B, const double* XP, long long ldxp, double rf_scale,
             const double* rf_path_dev, const int* active_dev, double* A, double* me, double* fe,
             double* G, long long ldg);
@@ -128,6 +129,7 @@ int vab_ctx_destroy(vab_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   nn_destroy(ctx);
   lbfgs_destroy(ctx);
+  tnc_destroy(ctx);
   cudaFree(ctx->pmap_dev);
   cudaFree(ctx->lcomp_dev);
   cudaFree(ctx->Y_dense);

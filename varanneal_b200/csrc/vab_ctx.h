@@ -10,7 +10,8 @@
 #include "ode_plan.h"
 
 struct NnProblem;   // nn_action.h
-struct LbfgsWork;   // lbfgs.h
+struct LbfgsWork;   // lbfgs.cu
+struct TncWork;     // tnc.cu
 
 enum { VAB_PROBLEM_NONE = 0, VAB_PROBLEM_ODE = 1, VAB_PROBLEM_NN = 2 };
 
@@ -53,6 +54,7 @@ struct vab_ctx {
   double* partials = nullptr;
   size_t partials_cap = 0;          // doubles
   LbfgsWork* lb = nullptr;
+  TncWork* tn = nullptr;
 
   long long n_unknowns() const;     // per path, for the problem currently set
 };

@@ -96,7 +96,7 @@ class Annealer(DeviceMin):
         if not self.annealing_initialized:
             self.anneal_init(X0, P0, alpha, beta_array, RM, RF0, Pidx, Lidx, init_to_data, action,
                              disc, method, bounds, opt_args, adolcID)
-        if not self.verbose and self.betaidx == 0 and self._ladder_fits_device():
+        if not self.verbose and self.betaidx == 0 and self.method != 'TNC' and self._ladder_fits_device():
             self._anneal_device()           # the whole ladder in one native call
             return
         for _ in range(self.Nbeta):
@@ -114,9 +114,6 @@ class Annealer(DeviceMin):
             raise ValueError("method='LM' is dead code in the reference (SURVEY.md App. B10)")
         if method not in ('L-BFGS-B', 'NCG', 'TNC'):
             raise ValueError("Optimization routine not recognized: %r" % (method,))
-        if method not in ('L-BFGS-B', 'NCG'):
-            raise NotImplementedError("method=%r is not built on the device (SURVEY.md 8(f2)); "
-                                      "use 'L-BFGS-B' or 'NCG'" % (method,))
         if action != 'A_gaussian' or disc != 'forwardmap':
             raise ValueError("va_nnet supports action='A_gaussian', disc='forwardmap' (va_nnet.py:260-264)")
         if self.structure is None or self.M == 0:

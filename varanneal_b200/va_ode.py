@@ -12,7 +12,8 @@ Differences from the reference, all deliberate:
   * errors raise ``ValueError`` instead of ``print`` + ``sys.exit(1)``.
   * ``exitflags`` is filled with the minimiser's status (the reference never writes it, B3).
   * ``set_data_fromfile`` works (the reference's is broken, B5).
-  * ``method``: 'L-BFGS-B' only for now; 'LM' is dead code in the reference (B10).
+  * ``method``: 'L-BFGS-B', 'NCG' and 'TNC' run on the device ('TNC' rung by rung, no bounds);
+    'LM' is dead code in the reference (B10).
   * batches: ``X0`` of shape (B, N, D) [+ ``P0`` (B, NP) or (NP,)] anneals B independent
     initialisations concurrently; every result array gains a leading B axis.  With the
     reference's shapes the results have exactly the reference's shapes.
@@ -84,7 +85,8 @@ class Annealer(DeviceMin):
             self.anneal_init(X0, P0, alpha, beta_array, RM, RF0, Lidx, Pidx, dt_model,
                              init_to_data, action, disc, method, bounds, opt_args, adolcID)
         tracked = not (track_paths is None and track_params is None and track_action_errors is None)
-        if not tracked and not self.verbose and self.betaidx == 0 and self._ladder_fits_device():
+        if (not tracked and not self.verbose and self.betaidx == 0 and self.method != 'TNC'
+                and self._ladder_fits_device()):
             self._anneal_device()           # the whole ladder in one native call
             return
         for _ in range(self.Nbeta):
@@ -114,9 +116,6 @@ class Annealer(DeviceMin):
             raise ValueError("method='LM' is dead code in the reference (SURVEY.md App. B10)")
         if method not in ('L-BFGS-B', 'NCG', 'TNC'):
             raise ValueError("Optimization routine not recognized: %r" % (method,))
-        if method not in ('L-BFGS-B', 'NCG'):
-            raise NotImplementedError("method=%r is not built on the device (SURVEY.md 8(f2)); "
-                                      "use 'L-BFGS-B' or 'NCG'" % (method,))
         self.method = method
         if action != 'A_gaussian':
             raise ValueError("only action='A_gaussian' exists (va_ode.py:130-136)")
