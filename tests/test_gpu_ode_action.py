@@ -197,3 +197,31 @@ def test_pinned_pipelined_eval_matches_plain_eval(B):
     prob = OdeProblem("lorenz96", D, Y, Lidx, 0.02, "SimpsonHermite", P0[B - 1], [], 4.0)
     Ar, gr = prob.action_grad(XP[B - 1], 4e-3 * 1.5 ** 7)
     assert abs(A0[B - 1] - Ar) <= TOL * abs(Ar) and np.max(np.abs(G0[B - 1] - gr)) <= TOL * np.max(np.abs(gr))
+
+
+def test_jacobian_and_hessian_seams():
+    """ADmin.jacA_taped / A_jacaA_taped / hessianA_taped (_autodiffmin.py:60-67): the (1, n)
+    Jacobian is the gradient; the dense Hessian (central differences of the device gradient)
+    matches the complex-step Hessian of the oracle's gradient... here: finite differences of the
+    oracle gradient at a tighter step, to 1e-6."""
+    rng = np.random.RandomState(4)
+    D, N = 4, 6
+    Y = rng.randn(N, 2)
+    X0 = rng.randn(N, D)
+    an = _annealer("lorenz96", D, Y, 0.05 * np.arange(N), None, X0, np.array([8.0]), 4.0, 0.5, [0, 2], [0],
+                   "trapezoid")
+    XP = np.append(X0.ravel(), 8.0)
+    A, g = an.A_gradA(XP)
+    J = an.jacA_taped(XP)
+    assert J.shape == (1, XP.size) and np.array_equal(J[0], g)
+    A2, J2 = an.A_jacaA_taped(XP)
+    assert A2 == A and np.array_equal(J2, J)
+    H = an.hessianA_taped(XP)
+    assert H.shape == (XP.size, XP.size) and np.array_equal(H, H.T)
+    prob = OdeProblem("lorenz96", D, Y, [0, 2], 0.05, "trapezoid", [8.0], [0], 4.0)
+    rf = 0.5 * 1.5 ** 7
+    Href = np.empty_like(H)
+    for j in range(XP.size):
+        e = np.zeros(XP.size); e[j] = 1e-6 * (1 + abs(XP[j]))
+        Href[:, j] = (prob.action_grad(XP + e, rf)[1] - prob.action_grad(XP - e, rf)[1]) / (2 * e[j])
+    assert np.max(np.abs(H - 0.5 * (Href + Href.T))) <= 1e-6 * np.max(np.abs(Href))

@@ -198,6 +198,40 @@ class DeviceMin(object):
     def gradA_taped(self, XP):
         return self.A_gradA(XP)[1]
 
+    def jacA_taped(self, XP):
+        """ADmin.jacA_taped (_autodiffmin.py:60-61): the Jacobian of the scalar action, i.e. the
+        gradient as a (1, n) array (per path: (B, 1, n))."""
+        g = np.asarray(self.A_gradA(XP)[1])
+        return g.reshape(g.shape[:-1] + (1, g.shape[-1]))
+
+    def A_jacaA_taped(self, XP):
+        """ADmin.A_jacaA_taped (sic, _autodiffmin.py:63-64)."""
+        A, g = self.A_gradA(XP)
+        g = np.asarray(g)
+        return A, g.reshape(g.shape[:-1] + (1, g.shape[-1]))
+
+    def hessianA_taped(self, XP, rel_step=1e-6):
+        """ADmin.hessianA_taped (_autodiffmin.py:66-67): dense (n, n) Hessian of the action at a
+        single path.  ADOL-C differentiates the tape twice; here the analytic device gradient is
+        differenced centrally, column by column (2 n evaluations, steps rel_step (1 + |x_j|)) and
+        symmetrised -- accurate to ~1e-9 relative, meant for the small problems a dense Hessian
+        makes sense for."""
+        XP = np.asarray(XP, dtype=np.float64)
+        if XP.ndim != 1 or self._B != 1:
+            raise ValueError("hessianA_taped takes one flat path on a single-path Annealer")
+        n = XP.shape[0]
+        H = np.empty((n, n))
+        x = XP.copy()
+        for j in range(n):
+            h = rel_step * (1.0 + abs(XP[j]))
+            x[j] = XP[j] + h
+            gp = self.A_gradA(x)[1]
+            x[j] = XP[j] - h
+            gm = self.A_gradA(x)[1]
+            x[j] = XP[j]
+            H[:, j] = (gp - gm) / (2.0 * h)
+        return 0.5 * (H + H.T)
+
     def tape_A(self, xtrace=None):
         """No-op: nothing is taped (kept for API compatibility, _autodiffmin.py:32-49)."""
         self.taped = True
