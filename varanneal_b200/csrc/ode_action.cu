@@ -216,7 +216,8 @@ int ode_sweep_prepare(int model, int disc, int D, int N, int B, int num_sms, int
     const size_t stage_b = (size_t)g.GPW * 4 * (size_t)g.GW * g.C * sizeof(double);
     const bool fast = (P->nskip == 1 && P->rmd == nullptr && P->rf_arr == nullptr && P->L > 0);
     const int ns = stream_ns(g.C, disc, fast);
-    const size_t smem = (size_t)4 * ns * stage_b + ((size_t)4 * ns + (size_t)128 * K) * sizeof(double);
+    // ring + barriers + reduction scratch (+ one double per thread: the per-path RF weight of MODE 2)
+    const size_t smem = (size_t)4 * ns * stage_b + ((size_t)4 * ns + (size_t)128 * K + 128) * sizeof(double);
     if (smem <= 200 * 1024) {
       k = stream_kernel(g.C, disc, fast, P->rf_path != nullptr, g.nwin > 1);
       nb = k ? blocks_per_sm(k, smem, cerr) : 0;

@@ -68,6 +68,8 @@ struct Stream {
   double p[NPM];
   double wob[C];               // 2 cm RM of the own components (0 = unobserved)
   double wfs;                  // 2 cf RF (scalar RF)
+  uint32_t a_wfs;              // MODE 2: shared address of this lane's copy of wfs (a live 64-bit
+                               // value would not fit the 128-register budget: it is re-read at use)
   double rsc;                  // scale of an RF0 array (per path under the asynchronous ladder)
   double me_acc, fe_acc, pacc[NPM];
 
@@ -158,6 +160,12 @@ struct Stream {
     } else {
       rsc = (P.rf_path != nullptr) ? __ldg(P.rf_path + b) : P.rf_scale;
       wfs = 2.0 * P.cf * ((P.rf_path != nullptr) ? P.rf0 * rsc : P.rf_scalar);
+    }
+    a_wfs = 0;
+    if constexpr (MODE == 2) {
+      // slot behind the ring, the barriers and the reduction scratch (128 K doubles)
+      a_wfs = s32(smem) + 4u * NS * stage_b + 4u * NS * 8u + (uint32_t)(128 * P.K) * 8u + (uint32_t)threadIdx.x * 8u;
+      asm volatile("st.shared.f64 [%0], %1;" ::"r"(a_wfs), "d"(wfs) : "memory");
     }
     me_acc = 0.0;
     fe_acc = 0.0;
@@ -260,6 +268,11 @@ struct Stream {
     V[H + C + 1] = __shfl_sync(VAB_FULL, V[H + 1], srcP1);
   }
   __device__ __forceinline__ double wgt(int row, int c) const {   // 2 cf RF for residual (row, c)
+    if constexpr (MODE == 2) {
+      double v;
+      asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a_wfs));
+      return v;
+    }
     if (FAST) return wfs;
     return P.rf_arr ? 2.0 * P.cf * rsc * __ldg(P.rf_arr + (long long)row * D + i0 + c) : wfs;
   }
@@ -350,14 +363,16 @@ __global__ void __launch_bounds__(128, MINB) stream_simpson_kernel(const __grid_
       S.read_row(sq + rb, Xc);
       M::f(Xb, S.p, nullptr, Fb);
       M::f(Xc, S.p, nullptr, Fc);
+      double wq = 0.0;                      // scalar-RF modes: one weight for the whole pair
+      if constexpr (ST::FAST) wq = S.wgt(a, 0);
 #pragma unroll
       for (int c = 0; c < C; ++c) {
         xc[c] = Xc[H + c];
         const double s = fma(4.0, Fb[c], Fa[c]) + Fc[c];
         const double e1 = fma(-dt3, s, xc[c] - xa[c]);
         const double e2 = fma(-dt4, Fa[c] - Fc[c], fma(-0.5, xa[c] + xc[c], Xb[H + c]));
-        l1[c] = S.wgt(a, c) * e1;
-        l2[c] = S.wgt(a + 1, c) * e2;
+        l1[c] = (ST::FAST ? wq : S.wgt(a, c)) * e1;
+        l2[c] = (ST::FAST ? wq : S.wgt(a + 1, c)) * e2;
         if (STORE) S.fe_acc = fma(l1[c], e1, fma(l2[c], e2, S.fe_acc));
       }
     }
@@ -487,12 +502,14 @@ __global__ void __launch_bounds__(128, MINB) stream_twopoint_kernel(const __grid
     }
     const bool ve = vm && valid1;
     const bool own = (m - 1 >= r0) && (m - 1 < r1);
+    double wq = 0.0;                        // scalar-RF modes: one weight for the whole row
+    if constexpr (ST::FAST) wq = S.wgt(m - 1, 0);
 #pragma unroll
     for (int c = 0; c < C; ++c) {
       double l = 0.0;
       if (ve) {
         const double e = Xm[H + c] - al * X1[H + c] - fma(ca, F1[c], cb * Fm[c]);
-        l = S.wgt(m - 1, c) * e;
+        l = (ST::FAST ? wq : S.wgt(m - 1, c)) * e;
         if (own) S.fe_acc = fma(l, e, S.fe_acc);
       }
       lam[c] = l;
@@ -605,10 +622,12 @@ __global__ void __launch_bounds__(128, MINB) stream_rk4_kernel(const __grid_cons
       for (int c = 0; c < C; ++c) { ks[c] = fma(2.0, k[c], ks[c]); Y4[H + c] = fma(dt, k[c], X1[H + c]); }
       S.halo(Y4);
       M::f(Y4, S.p, nullptr, k);
+      double wq = 0.0;                      // scalar-RF modes: one weight for the whole row
+      if constexpr (ST::FAST) wq = S.wgt(m - 1, 0);
 #pragma unroll
       for (int c = 0; c < C; ++c) {
         const double e = (xm[c] - X1[H + c]) - dt6 * (ks[c] + k[c]);
-        const double l = S.wgt(m - 1, c) * e;
+        const double l = (ST::FAST ? wq : S.wgt(m - 1, c)) * e;
         if (own) S.fe_acc = fma(l, e, S.fe_acc);
         lam[c] = l;
       }
