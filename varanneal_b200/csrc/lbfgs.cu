@@ -66,6 +66,7 @@ struct LbPath {
   int done, need_eval, accepted, do_update, redo_dir, first;
   int iter, nfev, col, head, pslot, ifun, iback, nskip, status;
   int ib, finished;         // rung of the ladder this path is on; ladder complete
+  int xt_ready;             // the direction pass has already written the first trial point xt = x + d
   double f, fold, me, fe;
   double stp, gd, gdold, dnorm, stpmx, theta, sbgnrm, dr;
   double ls_ftol, ls_gtol, ls_xtol, cd, fprev;   // line-search constants; CG: coefficient of the old direction, f two iterates back
@@ -133,6 +134,7 @@ __device__ __forceinline__ bool frozen(double x, double g, double lo, double hi)
 // state of a path at the start of a minimisation (one rung)
 __device__ void lb_reset(LbPath& s, double ls_ftol, double ls_gtol, double ls_xtol) {
   s.done = 0; s.need_eval = 1; s.accepted = 0; s.do_update = 0; s.redo_dir = 0; s.first = 1;
+  s.xt_ready = 0;
   s.iter = 0; s.nfev = 0; s.col = 0; s.head = 0; s.pslot = 0; s.ifun = 0; s.iback = 0; s.nskip = 0;
   s.status = 2;
   s.f = 0.0; s.fold = 0.0; s.me = 0.0; s.fe = 0.0;
@@ -167,7 +169,7 @@ __global__ void __launch_bounds__(NT) lb_trial_kernel(double* __restrict__ XT, c
                                                       const LbPath* __restrict__ st, int nchunk) {
   const int b = blockIdx.y;
   const LbPath& s = st[b];
-  if (s.done || !s.need_eval) return;
+  if (s.done || !s.need_eval || s.xt_ready) return;
   const double stp = s.stp;
   const Range r = chunk_range(n, nchunk, blockIdx.x);
   const double* x = X + (long long)b * ld;
@@ -238,6 +240,7 @@ __global__ void lb_linesearch_kernel(LbPath* st, int* act_eval, const double* ft
     return;
   }
   s.nfev += 1;
+  s.xt_ready = 0;                  // any further trial of this search goes through lb_trial_kernel
   const double f = ft[b];
   if (s.first) {
     s.first = 0;
@@ -536,7 +539,7 @@ constexpr int HW = 4;                   // consumer warps
 constexpr int HT = HW * 32;             // consumer threads
 constexpr int HTILE = 2 * HT;           // elements per tile (two per consumer thread)
 constexpr int U_NSTR = 4 + 2 * MMAX;    // GT, G, D, XT, S_0.., Y_0..
-constexpr int D_NSTR = 1 + 2 * MMAX;    // G, S_0.., Y_0..
+constexpr int D_NSTR = 2 + 2 * MMAX;    // G, X, S_0.., Y_0..
 static_assert(U_NSTR <= 32 && D_NSTR <= 32, "one producer lane per vector");
 // ring stages HNS (template parameter): 4 with one CTA per SM, or 2 with two CTAs per SM
 constexpr size_t hist_smem(int nstr, int hns) { return (size_t)hns * nstr * HTILE * sizeof(double) + 2 * hns * 8; }
@@ -706,8 +709,9 @@ __global__ void __launch_bounds__(HT + 32, 1) lb_update_tma_kernel(
 template <int HNS>
 __global__ void __launch_bounds__(HT + 32, 1) lb_direction_tma_kernel(
     const double* __restrict__ G, double* __restrict__ Dv, const double* __restrict__ S,
-    const double* __restrict__ Y, long long ld, long long n, long long hstride,
-    const LbPath* __restrict__ st, int m, int nchunk, double* __restrict__ part) {
+    const double* __restrict__ Y, const double* __restrict__ X, double* __restrict__ XT, long long ld,
+    long long n, long long hstride, const LbPath* __restrict__ st, int m, int nchunk,
+    double* __restrict__ part) {
   extern __shared__ __align__(128) unsigned char hist_sm[];
   __shared__ double wred[HW][2];
   const int b = blockIdx.y, tid = threadIdx.x;
@@ -724,6 +728,9 @@ __global__ void __launch_bounds__(HT + 32, 1) lb_direction_tma_kernel(
   unsigned hmask = 0;
   for (int j = 0; j < MMAX; ++j)
     if (j < m && (j < col || col == m)) hmask |= 1u << j;
+  // After the first iteration the search starts at stp = 1 (lb_start_kernel): the first trial point
+  // xt = x + d is written here, in the same pass, and lb_trial_kernel is skipped for it.
+  const bool wxt = s.iter > 0;
   const long long base = (long long)b * ld + r.i0;
   double* tiles = reinterpret_cast<double*>(hist_sm);
   const uint32_t ring = vabs::s32(tiles);
@@ -737,9 +744,10 @@ __global__ void __launch_bounds__(HT + 32, 1) lb_direction_tma_kernel(
     const int k = tid & 31;
     const double* src = nullptr;
     if (k == 0) src = G + base;
-    else if (k < 1 + MMAX) src = ((hmask >> (k - 1)) & 1u) ? S + (long long)(k - 1) * hstride + base : nullptr;
-    else if (k < D_NSTR) src = ((hmask >> (k - 1 - MMAX)) & 1u) ? Y + (long long)(k - 1 - MMAX) * hstride + base : nullptr;
-    const int nact = 1 + 2 * __popc(hmask);
+    else if (k == 1) src = wxt ? X + base : nullptr;
+    else if (k < 2 + MMAX) src = ((hmask >> (k - 2)) & 1u) ? S + (long long)(k - 2) * hstride + base : nullptr;
+    else if (k < D_NSTR) src = ((hmask >> (k - 2 - MMAX)) & 1u) ? Y + (long long)(k - 2 - MMAX) * hstride + base : nullptr;
+    const int nact = 1 + (wxt ? 1 : 0) + 2 * __popc(hmask);
     hist_produce<D_NSTR, HNS>(ring, full, empty, src, nact, ntile, len);
     return;
   }
@@ -749,6 +757,7 @@ __global__ void __launch_bounds__(HT + 32, 1) lb_direction_tma_kernel(
   const double cg = s.cg;
   double v[2] = {0.0, 0.0};
   double* dout = Dv + base;
+  double* xtout = XT + base;
   for (int t = 0; t < ntile; ++t) {
     const int stage = t % HNS;
     vabs::mbar_wait(full + 8u * (uint32_t)stage, (uint32_t)((t / HNS) & 1));
@@ -762,14 +771,17 @@ __global__ void __launch_bounds__(HT + 32, 1) lb_direction_tma_kernel(
 #pragma unroll
       for (int j = 0; j < MMAX; ++j) {
         if ((hmask >> j) & 1u) {
-          const double sj = valid ? tl[(1 + j) * HTILE] : 0.0;
-          const double yj = valid ? tl[(1 + MMAX + j) * HTILE] : 0.0;
+          const double sj = valid ? tl[(2 + j) * HTILE] : 0.0;
+          const double yj = valid ? tl[(2 + MMAX + j) * HTILE] : 0.0;
           rr = fma(cs[j], sj, rr);
           rr = fma(cy[j], yj, rr);
         }
       }
       const double d = -rr;
-      if (valid) dout[e] = d;
+      if (valid) {
+        dout[e] = d;
+        if (wxt) xtout[e] = fma(1.0, d, tl[HTILE]);        // = lb_trial_kernel's fma(stp, d, x) at stp = 1
+      }
       v[0] = fma(d, d, v[0]);
       v[1] = fma(g, d, v[1]);
     }
@@ -782,7 +794,7 @@ __global__ void __launch_bounds__(HT + 32, 1) lb_direction_tma_kernel(
 
 // start of a line search (lnsrlb, task = START)
 __global__ void lb_start_kernel(LbPath* st, int* act_eval, const double* part, int nchunk, LbOpts o,
-                                int bounded, int b0) {
+                                int bounded, int b0, int xt_fused) {
   const int b = b0 + blockIdx.x;
   LbPath& s = st[b];
   if (!(s.accepted || s.redo_dir) || s.done) { if (s.done) { s.accepted = 0; s.redo_dir = 0; } return; }
@@ -818,6 +830,7 @@ __global__ void lb_start_kernel(LbPath* st, int* act_eval, const double* part, i
   s.iback = 0;
   dcsrch_start(s, s.f, gd, stpmx);
   s.need_eval = 1;
+  s.xt_ready = (xt_fused && s.iter > 0 && s.stp == 1.0) ? 1 : 0;   // lb_direction_tma_kernel wrote xt = x + d
   act_eval[b] = 1;
 }
 
@@ -1046,11 +1059,11 @@ int lb_run(vab_ctx* ctx, int B, double* XP, long long ld, const double* scales_h
     else if (bounded) lb_update_kernel<true><<<vgrid, NT, 0, st>>>(XP, G, XT, GT, Dv, S, Y, ld, n, hstride, lo, hi, w->st, o.m, nchunk, w->part, 0);
     else lb_update_kernel<false><<<vgrid, NT, 0, st>>>(XP, G, XT, GT, Dv, S, Y, ld, n, hstride, lo, hi, w->st, o.m, nchunk, w->part, 0);
     lb_gram_kernel<<<B, 64, 0, st>>>(w->st, w->part, nchunk, o.m, 0, o.method);
-    if (use_tma && hns == 4) lb_direction_tma_kernel<4><<<vgrid, HT + 32, hist_smem(D_NSTR, 4), st>>>(G, Dv, S, Y, ld, n, hstride, w->st, o.m, nchunk, w->part);
-    else if (use_tma) lb_direction_tma_kernel<2><<<vgrid, HT + 32, hist_smem(D_NSTR, 2), st>>>(G, Dv, S, Y, ld, n, hstride, w->st, o.m, nchunk, w->part);
+    if (use_tma && hns == 4) lb_direction_tma_kernel<4><<<vgrid, HT + 32, hist_smem(D_NSTR, 4), st>>>(G, Dv, S, Y, XP, XT, ld, n, hstride, w->st, o.m, nchunk, w->part);
+    else if (use_tma) lb_direction_tma_kernel<2><<<vgrid, HT + 32, hist_smem(D_NSTR, 2), st>>>(G, Dv, S, Y, XP, XT, ld, n, hstride, w->st, o.m, nchunk, w->part);
     else if (bounded) lb_direction_kernel<true><<<vgrid, NT, 0, st>>>(XP, G, Dv, S, Y, ld, n, hstride, lo, hi, w->st, o.m, nchunk, w->part, 0);
     else lb_direction_kernel<false><<<vgrid, NT, 0, st>>>(XP, G, Dv, S, Y, ld, n, hstride, lo, hi, w->st, o.m, nchunk, w->part, 0);
-    lb_start_kernel<<<B, 1, 0, st>>>(w->st, w->act_eval, w->part, nchunk, o, bounded ? 1 : 0, 0);
+    lb_start_kernel<<<B, 1, 0, st>>>(w->st, w->act_eval, w->part, nchunk, o, bounded ? 1 : 0, 0, use_tma ? 1 : 0);
     if (minpaths) { lb_save_kernel<<<vgrid, NT, 0, st>>>(XP, ld, n, w->st, nchunk, L); ctx->launches += 1; }
     lb_advance_kernel<<<(B + 127) / 128, 128, 0, st>>>(w->st, w->act_eval, B, L, o);
     ctx->launches += 8;
