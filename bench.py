@@ -299,6 +299,8 @@ def run_ours(args):
             raise SystemExit("launch with torchrun --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
     torch.cuda.set_device(local)
     if world > 1:
+        # NCCL's own log lines (e.g. "NCCL version ...") go to stderr: stdout carries the JSON line only
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     B = PATHS_PER_GPU
