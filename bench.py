@@ -187,6 +187,27 @@ def workload_config(n_gpus):
             "l2_policy": "inputs larger than L2 (XP + grad = 512 MB per step per GPU vs 126 MB L2)"}
 
 
+def bind_to_gpu_numa_node(local):
+    """Pins this process to the CPUs NVML reports as local to its GPU, before any pinned host
+    buffer is allocated: on a multi-socket box the staging buffers of the end-to-end leg are then
+    first-touched on the GPU's own NUMA node instead of crossing the socket interconnect.
+    VAB_BENCH_BIND=0 disables it.  Returns a short description for the JSON line."""
+    if os.environ.get("VAB_BENCH_BIND", "1") == "0":
+        return "off"
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        pr = torch.cuda.get_device_properties(local)
+        bus = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode() if hasattr(bus, "encode") else bus)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        cpus = sorted(os.sched_getaffinity(0))
+        return "cpus %d-%d (%d)" % (cpus[0], cpus[-1], len(cpus))
+    except Exception as exc:
+        return "unavailable (%s)" % type(exc).__name__
+
+
 # ------------------------------------------------------------------------------------ other configs
 def other_configs(device):
     """Evaluation rates of the other BASELINE.json configs at their per-path sizes (device
@@ -298,6 +319,7 @@ def run_ours(args):
         if world == 1 and args.gpus > 1:
             raise SystemExit("launch with torchrun --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
     torch.cuda.set_device(local)
+    bound = bind_to_gpu_numa_node(local)
     if world > 1:
         # NCCL's own log lines (e.g. "NCCL version ...") go to stderr: stdout carries the JSON line only
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
@@ -448,7 +470,7 @@ def run_ours(args):
                     "h2d_bytes_per_step": int(XP_host.numel() * 8),
                     "d2h_bytes_per_step": int(G_h.numel() * 8 + A_h.numel() * 8),
                     "api": "va_ode.Annealer.A_gradA(pinned XP) -> (A, grad) pinned"},
-            "gpu_launches": int(launches), "clocks": clocks, "ladder": ladder,
+            "gpu_launches": int(launches), "clocks": clocks, "ladder": ladder, "cpu_binding": bound,
         }
         if world == 1 and not args.no_extra:
             try:

@@ -14,6 +14,9 @@ namespace {
 __global__ void ode_finalize_kernel(const __grid_constant__ OdeParams P, double* A, double* me,
                                     double* fe) {
   const int b = blockIdx.x, k = threadIdx.x;
+  vab_pdl_wait();              // the walk kernel has completed: its partials are visible
+  vab_pdl_trigger();           // the next evaluation's walk kernel may start its prologue (it waits
+                               // again before it overwrites the partials read here)
   if (P.active != nullptr && P.active[b] == 0) return;
   double v = 0.0;
   if (k < P.K)
@@ -262,15 +265,35 @@ int ode_sweep_prepare(int model, int disc, int D, int N, int B, int num_sms, int
 }
 
 int ode_sweep_launch(const OdeParams& P, const SweepLaunch& sl, int model, int disc,
-                     cudaStream_t st, double* A, double* me, double* fe, cudaError_t* cerr) {
+                     cudaStream_t st, double* A, double* me, double* fe, cudaError_t* cerr, bool pdl) {
   const bool fast = (P.nskip == 1 && P.rmd == nullptr && P.rf_arr == nullptr && P.L > 0);
   SweepKernel k = sl.stream ? stream_kernel(sl.C, disc, fast, P.rf_path != nullptr, P.nwin > 1) : sweep_kernel(model, sl.C, disc, P.nwin > 1);
   if (!k) return -1;
-  k<<<sl.grid, 128, sl.smem, st>>>(P);
-  cudaError_t e = cudaGetLastError();
-  if (e == cudaSuccess) {
-    ode_finalize_kernel<<<P.B, 32, 0, st>>>(P, A, me, fe);
+  cudaError_t e;
+  if (pdl) {
+    // back-to-back evaluations (vab_ode_action_grad): programmatic dependent launch hides the
+    // launch latency of the finalize kernel behind the walk kernel and lets the next walk kernel
+    // run its prologue while this finalize kernel sums the partials
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(sl.grid); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = sl.smem; cfg.stream = st;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, k, P);
+    if (e == cudaSuccess) {
+      cudaLaunchConfig_t cf2 = {};
+      cf2.gridDim = dim3(P.B); cf2.blockDim = dim3(32); cf2.dynamicSmemBytes = 0; cf2.stream = st;
+      cf2.attrs = at; cf2.numAttrs = 1;
+      e = cudaLaunchKernelEx(&cf2, ode_finalize_kernel, P, A, me, fe);
+    }
+  } else {
+    k<<<sl.grid, 128, sl.smem, st>>>(P);
     e = cudaGetLastError();
+    if (e == cudaSuccess) {
+      ode_finalize_kernel<<<P.B, 32, 0, st>>>(P, A, me, fe);
+      e = cudaGetLastError();
+    }
   }
   if (cerr) *cerr = e;
   return e == cudaSuccess ? 0 : -2;

@@ -15,5 +15,6 @@ struct SweepLaunch {
 };
 int ode_sweep_prepare(int model, int disc, int D, int N, int B, int num_sms, int tseg_override,
                       bool allow_stream, OdeParams* P, SweepLaunch* sl, cudaError_t* cerr);
+// pdl: launch both kernels with programmatic stream serialization (stand-alone evaluations only)
 int ode_sweep_launch(const OdeParams& P, const SweepLaunch& sl, int model, int disc,
-                     cudaStream_t st, double* A, double* me, double* fe, cudaError_t* cerr);
+                     cudaStream_t st, double* A, double* me, double* fe, cudaError_t* cerr, bool pdl);

@@ -339,6 +339,7 @@ __global__ void __launch_bounds__(128, MINB) stream_simpson_kernel(const __grid_
   constexpr int C = ST::C, H = ST::H, W = ST::W;
   extern __shared__ __align__(16) double smem[];
   ST S(P);
+  vab_pdl_trigger();          // the finalize kernel may be scheduled behind this one right away
   if (!S.init(smem)) return;
   double* red = smem + ((size_t)4 * NS * S.stage_b) / 8 + 4 * NS;
   const double dt = P.dt, dt3 = dt / 3.0, dt4 = dt / 4.0, dt43 = 4.0 * dt / 3.0;
@@ -459,6 +460,7 @@ __global__ void __launch_bounds__(128, MINB) stream_simpson_kernel(const __grid_
     for (int c = 0; c < C; ++c) gr[c] = (gr[c] + V[H + c]) - t[c];
     S.store(N - 1, gr);
   }
+  vab_pdl_wait();             // partials of the previous evaluation have been consumed by its finalize kernel
   S.finish(red);
 }
 
@@ -473,6 +475,7 @@ __global__ void __launch_bounds__(128, MINB) stream_twopoint_kernel(const __grid
   constexpr int C = ST::C, H = ST::H, W = ST::W;
   extern __shared__ __align__(16) double smem[];
   ST S(P);
+  vab_pdl_trigger();          // the finalize kernel may be scheduled behind this one right away
   if (!S.init(smem)) return;
   double* red = smem + ((size_t)4 * NS * S.stage_b) / 8 + 4 * NS;
   const double dt = P.dt;
@@ -567,6 +570,7 @@ __global__ void __launch_bounds__(128, MINB) stream_twopoint_kernel(const __grid
     __syncwarp();
     S.issue(q - 1 + NS);
   }
+  vab_pdl_wait();             // partials of the previous evaluation have been consumed by its finalize kernel
   S.finish(red);
 }
 
@@ -584,6 +588,7 @@ __global__ void __launch_bounds__(128, MINB) stream_rk4_kernel(const __grid_cons
   constexpr int C = ST::C, H = ST::H, W = ST::W;
   extern __shared__ __align__(16) double smem[];
   ST S(P);
+  vab_pdl_trigger();          // the finalize kernel may be scheduled behind this one right away
   if (!S.init(smem)) return;
   double* red = smem + ((size_t)4 * NS * S.stage_b) / 8 + 4 * NS;
   const double dt = P.dt, hdt = 0.5 * dt, dt6 = dt / 6.0, dt3 = dt / 3.0;
@@ -702,5 +707,6 @@ __global__ void __launch_bounds__(128, MINB) stream_rk4_kernel(const __grid_cons
     __syncwarp();
     S.issue(q - 1 + NS);
   }
+  vab_pdl_wait();             // partials of the previous evaluation have been consumed by its finalize kernel
   S.finish(red);
 }

@@ -193,6 +193,7 @@ __global__ void __launch_bounds__(128, MINB) sweep_twopoint_kernel(const __grid_
   constexpr int C = LN::C, H = LN::H, W = LN::W;
   extern __shared__ double smem[];
   LN L;
+  vab_pdl_trigger();
   L.init(P);
   const double dt = P.dt;
   const double ca = (DISC == DISC_EULER) ? dt : (DISC == DISC_TRAPEZOID ? 0.5 * dt : 1.0);
@@ -254,6 +255,7 @@ __global__ void __launch_bounds__(128, MINB) sweep_twopoint_kernel(const __grid_
       for (int c = 0; c < C; ++c) { F1[c] = Fm[c]; lamp[c] = lam[c]; }
     }
   }
+  vab_pdl_wait();
   L.finish(P, smem, -1.0);
 }
 
@@ -269,6 +271,7 @@ __global__ void __launch_bounds__(128, MINB) sweep_simpson_kernel(const __grid_c
   constexpr int C = LN::C, H = LN::H, W = LN::W;
   extern __shared__ double smem[];
   LN L;
+  vab_pdl_trigger();
   L.init(P);
   const double dt = P.dt;
   const double cf2 = 2.0 * P.cf;
@@ -362,6 +365,7 @@ __global__ void __launch_bounds__(128, MINB) sweep_simpson_kernel(const __grid_c
       for (int c = 0; c < C; ++c) { Fa[c] = Fc[c]; vcp[c] = vcn[c]; dcp[c] = dcn[c]; }
     }
   }
+  vab_pdl_wait();
   L.finish(P, smem, -1.0);
 }
 
@@ -375,6 +379,7 @@ __global__ void __launch_bounds__(128, MINB) sweep_rk4_kernel(const __grid_const
   constexpr int C = LN::C, H = LN::H, W = LN::W, NPM = LN::NPM;
   extern __shared__ double smem[];
   LN L;
+  vab_pdl_trigger();
   L.init(P);
   const double dt = P.dt;
   const double cf2 = 2.0 * P.cf;
@@ -464,5 +469,6 @@ __global__ void __launch_bounds__(128, MINB) sweep_rk4_kernel(const __grid_const
       for (int c = 0; c < C; ++c) { lamp[c] = lam[c]; x0[c] = xn[c]; }
     }
   }
+  vab_pdl_wait();
   L.finish(P, smem, 1.0);
 }

@@ -346,7 +346,15 @@ static int ode_eval(vab_ctx* ctx, int B, const double* XP, long long ldxp, doubl
     rc = vab_reserve(ctx, &ctx->partials, &ctx->partials_cap, (size_t)P.nunits * P.K);
     if (rc != VAB_OK) return rc;
     P.partials = ctx->partials;
-    rc = ode_sweep_launch(P, sl, d.model, d.disc, ctx->stream, A, me, fe, &cerr);
+    // stand-alone evaluations (no mask, no per-path RF: vab_ode_action_grad) use dependent launch;
+    // inside the minimiser's captured cycles the kernels are launched the ordinary way
+    static int pdl_on = -1;
+    if (pdl_on < 0) {
+      const char* e = getenv("VAB_PDL");
+      pdl_on = e ? (atoi(e) != 0) : 1;
+    }
+    const bool pdl = pdl_on && active_dev == nullptr && rf_path_dev == nullptr;
+    rc = ode_sweep_launch(P, sl, d.model, d.disc, ctx->stream, A, me, fe, &cerr, pdl);
   }
   if (rc == -1) return vab_fail(ctx, VAB_ERR_INVALID, "ode_action_grad: no kernel for this model/disc");
   if (rc != 0) return vab_cuda_fail(ctx, cerr, "ode_action_grad launch");

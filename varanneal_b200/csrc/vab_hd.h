@@ -60,3 +60,13 @@ VAB_HD void vab_store_strip(double* dst, const double* src) {
 #pragma unroll
   for (int j = 0; j < C; ++j) dst[j] = src[j];
 }
+
+// Programmatic dependent launch (PDL).  Kernels launched back to back with the
+// programmatic-stream-serialization attribute may start before their predecessor has finished:
+// vab_pdl_trigger() lets the next kernel in the stream begin launching, vab_pdl_wait() blocks
+// until the previous kernel has completed and its writes are visible.  Both are no-ops for a
+// kernel launched the ordinary way.
+#if defined(__CUDACC__)
+__device__ __forceinline__ void vab_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void vab_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
