@@ -345,6 +345,29 @@ def test_tma_history_kernels_match_plain_kernels(monkeypatch):
         out[key] = an
     b = out["plain"]
     assert np.all(b.exitflags == 0), b.exitflags
+    # in-place trial points (TMA path) and searches that fail: with maxls = 1..3 a search that would
+    # need more evaluations fails -- the memory is dropped and the iteration restarted, or, with an
+    # empty memory, the path terminates (status 2), as in L-BFGS-B.  Either way x must have been put
+    # back to the start of the search (lb_restore_kernel): the action at the returned point is
+    # exactly the reported one.
+    monkeypatch.setenv("VAB_LBFGS_TMA", "1")
+    monkeypatch.setenv("VAB_LBFGS_NS", "2")
+    rng2 = np.random.RandomState(4)
+    X1 = Y[None] + 3.0 * rng2.randn(B, N, D)                 # far start: early steps overshoot
+    seen = set()
+    for maxls in (1, 2, 3, 20):
+        an = va_ode.Annealer()
+        an.set_model("lorenz96", D)
+        an.set_data(Y, t=t)
+        an.anneal(X1.copy(), np.array([8.0]), 2.0, [8], 1.0, 1e-2, Lidx, [0], disc="trapezoid",
+                  init_to_data=False, opt_args={"gtol": 1e-8, "ftol": 1e-15, "maxiter": 20000, "maxls": maxls})
+        assert set(np.unique(an.exitflags)) <= {0, 2}, an.exitflags
+        seen |= set(np.unique(an.exitflags).tolist())
+        A_at = an.A_gaussian(an.minpaths[:, 0, :])           # all parameters are estimated: minpaths rows are XP
+        assert np.max(np.abs(A_at - an.A_array[:, 0]) / np.abs(A_at)) <= 1e-13, (maxls, A_at, an.A_array[:, 0])
+        if maxls == 20:
+            assert np.all(an.exitflags == 0)
+    assert seen == {0, 2}                                    # both outcomes were exercised
     for key in ("tma4", "tma2"):
         a = out[key]
         assert np.all(a.exitflags == 0), a.exitflags

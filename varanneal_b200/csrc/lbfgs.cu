@@ -67,6 +67,8 @@ struct LbPath {
   int iter, nfev, col, head, pslot, ifun, iback, nskip, status;
   int ib, finished;         // rung of the ladder this path is on; ladder complete
   int xt_ready;             // the direction pass has already written the first trial point xt = x + d
+  double stp_at, restore;   // in-place trials (TMA path): x currently sits at x0 + stp_at d; a failed
+                            // search leaves restore = that step for lb_restore_kernel to undo
   double f, fold, me, fe;
   double stp, gd, gdold, dnorm, stpmx, theta, sbgnrm, dr;
   double ls_ftol, ls_gtol, ls_xtol, cd, fprev;   // line-search constants; CG: coefficient of the old direction, f two iterates back
@@ -134,7 +136,7 @@ __device__ __forceinline__ bool frozen(double x, double g, double lo, double hi)
 // state of a path at the start of a minimisation (one rung)
 __device__ void lb_reset(LbPath& s, double ls_ftol, double ls_gtol, double ls_xtol) {
   s.done = 0; s.need_eval = 1; s.accepted = 0; s.do_update = 0; s.redo_dir = 0; s.first = 1;
-  s.xt_ready = 0;
+  s.xt_ready = 0; s.stp_at = 0.0; s.restore = 0.0;
   s.iter = 0; s.nfev = 0; s.col = 0; s.head = 0; s.pslot = 0; s.ifun = 0; s.iback = 0; s.nskip = 0;
   s.status = 2;
   s.f = 0.0; s.fold = 0.0; s.me = 0.0; s.fe = 0.0;
@@ -163,17 +165,32 @@ __global__ void lb_clip_kernel(double* X, long long ld, long long n, const doubl
   x[i] = fmin(fmax(x[i], lo[i]), hi[i]);
 }
 
-// xt = x + stp d
-__global__ void __launch_bounds__(NT) lb_trial_kernel(double* __restrict__ XT, const double* __restrict__ X,
+// xt = x + stp d.  inplace (TMA path, unbounded): there is no separate trial buffer -- x itself moves
+// along d, from the step it sits at (stp_at) to the new one; the accepted point then needs no copy.
+__global__ void __launch_bounds__(NT) lb_trial_kernel(double* __restrict__ XT, double* __restrict__ X,
                                                       const double* __restrict__ Dv, long long ld, long long n,
-                                                      const LbPath* __restrict__ st, int nchunk) {
+                                                      const LbPath* __restrict__ st, int nchunk, int inplace) {
   const int b = blockIdx.y;
   const LbPath& s = st[b];
   if (s.done || !s.need_eval || s.xt_ready) return;
   const double stp = s.stp;
   const Range r = chunk_range(n, nchunk, blockIdx.x);
-  const double* x = X + (long long)b * ld;
+  double* x = X + (long long)b * ld;
   const double* d = Dv + (long long)b * ld;
+  if (inplace) {
+    if (s.first) return;              // first evaluation of a minimisation: at x itself
+    const double a = stp - s.stp_at;
+    for (long long i = r.i0 + 2LL * threadIdx.x; i < r.i1; i += 2LL * NT) {
+      if (i + 1 < r.i1) {
+        const double2 xv = *reinterpret_cast<const double2*>(x + i);
+        const double2 dv = *reinterpret_cast<const double2*>(d + i);
+        *reinterpret_cast<double2*>(x + i) = make_double2(fma(a, dv.x, xv.x), fma(a, dv.y, xv.y));
+      } else {
+        x[i] = fma(a, d[i], x[i]);
+      }
+    }
+    return;
+  }
   double* xt = XT + (long long)b * ld;
   if (s.first) {                      // first evaluation of a minimisation: at x itself
     for (long long i = r.i0 + 2LL * threadIdx.x; i < r.i1; i += 2LL * NT) {
@@ -191,6 +208,20 @@ __global__ void __launch_bounds__(NT) lb_trial_kernel(double* __restrict__ XT, c
       xt[i] = fma(stp, d[i], x[i]);
     }
   }
+}
+
+// in-place trials: a failed line search leaves x at x0 + restore d; put it back
+__global__ void __launch_bounds__(NT) lb_restore_kernel(double* __restrict__ X, const double* __restrict__ Dv,
+                                                        long long ld, long long n, const LbPath* __restrict__ st,
+                                                        int nchunk) {
+  const int b = blockIdx.y;
+  const LbPath& s = st[b];
+  const double a = s.restore;
+  if (a == 0.0) return;
+  const Range r = chunk_range(n, nchunk, blockIdx.x);
+  double* x = X + (long long)b * ld;
+  const double* d = Dv + (long long)b * ld;
+  for (long long i = r.i0 + threadIdx.x; i < r.i1; i += NT) x[i] = fma(-a, d[i], x[i]);
 }
 
 // partials [gd, max |proj g|] of the trial point
@@ -253,6 +284,7 @@ __global__ void lb_linesearch_kernel(LbPath* st, int* act_eval, const double* ft
   }
   // an evaluation that produced a NaN / Inf cannot be used by the search: treat as a failed step
   const bool finite = isfinite(f) && isfinite(gd);
+  const double stp_eval = s.stp;                       // the step this evaluation was taken at
   int conv = 0;
   if (finite) conv = dcsrch_step(s, f, gd, 0.0, s.stpmx);
   else s.iback = o.maxls;      // force the restart branch below
@@ -291,13 +323,16 @@ __global__ void lb_linesearch_kernel(LbPath* st, int* act_eval, const double* ft
     if (s.done) act_eval[b] = 0;
     return;
   }
+  s.stp_at = stp_eval;                                 // in-place trials: where x sits now
   if (finite) {
     s.ifun += 1;
     s.iback = s.ifun - 1;
   }
   if (s.iback >= o.maxls) {
-    // line search failed: x, g, f still hold the start of the search
+    // line search failed: x, g, f still hold the start of the search (in-place trials: x is put
+    // back by lb_restore_kernel)
     s.need_eval = 0;
+    s.restore = stp_eval;
     if (s.col == 0) {
       s.done = 1; s.status = 2; act_eval[b] = 0;      // ABNORMAL_TERMINATION_IN_LNSRCH
     } else {
@@ -538,7 +573,7 @@ __global__ void __launch_bounds__(NT) lb_direction_kernel(
 constexpr int HW = 4;                   // consumer warps
 constexpr int HT = HW * 32;             // consumer threads
 constexpr int HTILE = 2 * HT;           // elements per tile (two per consumer thread)
-constexpr int U_NSTR = 4 + 2 * MMAX;    // GT, G, D, XT, S_0.., Y_0..
+constexpr int U_NSTR = 3 + 2 * MMAX;    // GT, G, D, S_0.., Y_0..  (x moves in place: no trial buffer to copy)
 constexpr int D_NSTR = 2 + 2 * MMAX;    // G, X, S_0.., Y_0..
 static_assert(U_NSTR <= 32 && D_NSTR <= 32, "one producer lane per vector");
 // ring stages HNS (template parameter): 4 with one CTA per SM, or 2 with two CTAs per SM
@@ -604,7 +639,7 @@ __device__ __forceinline__ void hist_reduce_store(const double* acc, double (*wr
 
 template <int HNS>
 __global__ void __launch_bounds__(HT + 32, 1) lb_update_tma_kernel(
-    double* __restrict__ X, double* __restrict__ G, const double* __restrict__ XT,
+    double* __restrict__ G,
     const double* __restrict__ GT, const double* __restrict__ Dv, double* __restrict__ S,
     double* __restrict__ Y, long long ld, long long n, long long hstride,
     const LbPath* __restrict__ st, int m, int nchunk, double* __restrict__ part) {
@@ -642,10 +677,9 @@ __global__ void __launch_bounds__(HT + 32, 1) lb_update_tma_kernel(
     if (k == 0) src = GT + base;
     else if (k == 1) src = G + base;
     else if (k == 2) src = upd ? Dv + base : nullptr;
-    else if (k == 3) src = XT + base;
-    else if (k < 4 + MMAX) src = ((hmask >> (k - 4)) & 1u) ? S + (long long)(k - 4) * hstride + base : nullptr;
-    else if (k < U_NSTR) src = ((hmask >> (k - 4 - MMAX)) & 1u) ? Y + (long long)(k - 4 - MMAX) * hstride + base : nullptr;
-    const int nact = 3 + (upd ? 1 : 0) + 2 * __popc(hmask);
+    else if (k < 3 + MMAX) src = ((hmask >> (k - 3)) & 1u) ? S + (long long)(k - 3) * hstride + base : nullptr;
+    else if (k < U_NSTR) src = ((hmask >> (k - 3 - MMAX)) & 1u) ? Y + (long long)(k - 3 - MMAX) * hstride + base : nullptr;
+    const int nact = 2 + (upd ? 1 : 0) + 2 * __popc(hmask);
     hist_produce<U_NSTR, HNS>(ring, full, empty, src, nact, ntile, len);
     return;
   }
@@ -653,7 +687,6 @@ __global__ void __launch_bounds__(HT + 32, 1) lb_update_tma_kernel(
   double acc[NACC_U];
 #pragma unroll
   for (int k = 0; k < NACC_U; ++k) acc[k] = 0.0;
-  double* xo = X + base;
   double* go = G + base;
   double* so = S + (long long)p * hstride + base;
   double* yo = Y + (long long)p * hstride + base;
@@ -667,7 +700,6 @@ __global__ void __launch_bounds__(HT + 32, 1) lb_update_tma_kernel(
       const bool valid = e < len;
       const double gt = valid ? tl[0] : 0.0;
       const double gold = valid ? tl[HTILE] : 0.0;
-      const double xt = valid ? tl[3 * HTILE] : 0.0;
       double sv = 0.0, yv = 0.0;
       if (upd) {
         const double dv = valid ? tl[2 * HTILE] : 0.0;
@@ -678,8 +710,8 @@ __global__ void __launch_bounds__(HT + 32, 1) lb_update_tma_kernel(
 #pragma unroll
       for (int j = 0; j < MMAX; ++j) {
         if ((hmask >> j) & 1u) {
-          const double sj = valid ? tl[(4 + j) * HTILE] : 0.0;
-          const double yj = valid ? tl[(4 + MMAX + j) * HTILE] : 0.0;
+          const double sj = valid ? tl[(3 + j) * HTILE] : 0.0;
+          const double yj = valid ? tl[(3 + MMAX + j) * HTILE] : 0.0;
           acc[j] = fma(gh, sj, acc[j]);
           acc[MMAX + j] = fma(gh, yj, acc[MMAX + j]);
           acc[2 * MMAX + j] = fma(sv, yj, acc[2 * MMAX + j]);
@@ -692,7 +724,6 @@ __global__ void __launch_bounds__(HT + 32, 1) lb_update_tma_kernel(
       acc[5 * MMAX + 2] = fma(gh, yv, acc[5 * MMAX + 2]);
       acc[5 * MMAX + 3] = fma(gh, gh, acc[5 * MMAX + 3]);
       if (valid) {
-        xo[e] = xt;
         go[e] = gt;
         if (upd) {
           so[e] = sv;
@@ -709,7 +740,7 @@ __global__ void __launch_bounds__(HT + 32, 1) lb_update_tma_kernel(
 template <int HNS>
 __global__ void __launch_bounds__(HT + 32, 1) lb_direction_tma_kernel(
     const double* __restrict__ G, double* __restrict__ Dv, const double* __restrict__ S,
-    const double* __restrict__ Y, const double* __restrict__ X, double* __restrict__ XT, long long ld,
+    const double* __restrict__ Y, double* __restrict__ X, long long ld,
     long long n, long long hstride, const LbPath* __restrict__ st, int m, int nchunk,
     double* __restrict__ part) {
   extern __shared__ __align__(128) unsigned char hist_sm[];
@@ -728,8 +759,8 @@ __global__ void __launch_bounds__(HT + 32, 1) lb_direction_tma_kernel(
   unsigned hmask = 0;
   for (int j = 0; j < MMAX; ++j)
     if (j < m && (j < col || col == m)) hmask |= 1u << j;
-  // After the first iteration the search starts at stp = 1 (lb_start_kernel): the first trial point
-  // xt = x + d is written here, in the same pass, and lb_trial_kernel is skipped for it.
+  // After the first iteration the search starts at stp = 1 (lb_start_kernel): x is moved to the first
+  // trial point x + d here, in the same pass (trials are in place), and lb_trial_kernel is skipped.
   const bool wxt = s.iter > 0;
   const long long base = (long long)b * ld + r.i0;
   double* tiles = reinterpret_cast<double*>(hist_sm);
@@ -757,7 +788,7 @@ __global__ void __launch_bounds__(HT + 32, 1) lb_direction_tma_kernel(
   const double cg = s.cg;
   double v[2] = {0.0, 0.0};
   double* dout = Dv + base;
-  double* xtout = XT + base;
+  double* xtout = X + base;
   for (int t = 0; t < ntile; ++t) {
     const int stage = t % HNS;
     vabs::mbar_wait(full + 8u * (uint32_t)stage, (uint32_t)((t / HNS) & 1));
@@ -797,7 +828,8 @@ __global__ void lb_start_kernel(LbPath* st, int* act_eval, const double* part, i
                                 int bounded, int b0, int xt_fused) {
   const int b = b0 + blockIdx.x;
   LbPath& s = st[b];
-  if (!(s.accepted || s.redo_dir) || s.done) { if (s.done) { s.accepted = 0; s.redo_dir = 0; } return; }
+  if (!(s.accepted || s.redo_dir) || s.done) { if (s.done) { s.accepted = 0; s.redo_dir = 0; s.restore = 0.0; } return; }
+  s.restore = 0.0;
   double dd = 0.0, gd = 0.0, stpmx = BIG;
   for (int c = 0; c < nchunk; ++c) {
     dd += part[((long long)b * nchunk + c) * 3 + 0];
@@ -812,7 +844,12 @@ __global__ void lb_start_kernel(LbPath* st, int* act_eval, const double* part, i
   if (!(gd < 0.0) || !(dd > 0.0)) {
     // not a descent direction (info = -4): drop the memory and restart, or give up
     if (s.col == 0) { s.done = 1; s.status = (dd == 0.0) ? 0 : 2; act_eval[b] = 0; }
-    else { s.col = 0; s.head = 0; s.theta = 1.0; s.redo_dir = 1; }
+    else {
+      s.col = 0; s.head = 0; s.theta = 1.0; s.redo_dir = 1;
+      // in-place trials: the direction pass has already moved x by this (rejected) direction;
+      // lb_restore_kernel takes it back in the next cycle, before the new direction is formed
+      if (xt_fused && s.iter > 0) s.restore = 1.0;
+    }
     return;
   }
   if (bounded && s.iter == 0) stpmx = fmin(stpmx, 1.0);
@@ -831,6 +868,7 @@ __global__ void lb_start_kernel(LbPath* st, int* act_eval, const double* part, i
   dcsrch_start(s, s.f, gd, stpmx);
   s.need_eval = 1;
   s.xt_ready = (xt_fused && s.iter > 0 && s.stp == 1.0) ? 1 : 0;   // lb_direction_tma_kernel wrote xt = x + d
+  s.stp_at = s.xt_ready ? 1.0 : 0.0;
   act_eval[b] = 1;
 }
 
@@ -1048,19 +1086,21 @@ int lb_run(vab_ctx* ctx, int B, double* XP, long long ld, const double* scales_h
     poll = (n * (long long)B < (1LL << 22)) ? 64 : 8;
   }
   auto enqueue_cycle = [&]() -> int {
-    lb_trial_kernel<<<vgrid, NT, 0, st>>>(XT, XP, Dv, ld, n, w->st, nchunk);
-    int r = vab_eval(ctx, B, XT, ld, 1.0, L.rf_path, w->act_eval, w->ft, w->met, w->fet, GT, ld);
+    const int inplace = use_tma ? 1 : 0;       // unbounded L-BFGS: x moves in place, no trial buffer
+    lb_trial_kernel<<<vgrid, NT, 0, st>>>(XT, XP, Dv, ld, n, w->st, nchunk, inplace);
+    int r = vab_eval(ctx, B, inplace ? XP : XT, ld, 1.0, L.rf_path, w->act_eval, w->ft, w->met, w->fet, GT, ld);
     if (r != VAB_OK) return r;
     if (bounded) lb_gd_kernel<true><<<vgrid, NT, 0, st>>>(XT, GT, Dv, ld, n, lo, hi, w->st, nchunk, w->part);
     else lb_gd_kernel<false><<<vgrid, NT, 0, st>>>(XT, GT, Dv, ld, n, lo, hi, w->st, nchunk, w->part);
     lb_linesearch_kernel<<<B, 32, 0, st>>>(w->st, w->act_eval, w->ft, w->met, w->fet, w->part, nchunk, o, bounded ? 1 : 0);
-    if (use_tma && hns == 4) lb_update_tma_kernel<4><<<vgrid, HT + 32, hist_smem(U_NSTR, 4), st>>>(XP, G, XT, GT, Dv, S, Y, ld, n, hstride, w->st, o.m, nchunk, w->part);
-    else if (use_tma) lb_update_tma_kernel<2><<<vgrid, HT + 32, hist_smem(U_NSTR, 2), st>>>(XP, G, XT, GT, Dv, S, Y, ld, n, hstride, w->st, o.m, nchunk, w->part);
+    if (inplace) { lb_restore_kernel<<<vgrid, NT, 0, st>>>(XP, Dv, ld, n, w->st, nchunk); ctx->launches += 1; }
+    if (use_tma && hns == 4) lb_update_tma_kernel<4><<<vgrid, HT + 32, hist_smem(U_NSTR, 4), st>>>(G, GT, Dv, S, Y, ld, n, hstride, w->st, o.m, nchunk, w->part);
+    else if (use_tma) lb_update_tma_kernel<2><<<vgrid, HT + 32, hist_smem(U_NSTR, 2), st>>>(G, GT, Dv, S, Y, ld, n, hstride, w->st, o.m, nchunk, w->part);
     else if (bounded) lb_update_kernel<true><<<vgrid, NT, 0, st>>>(XP, G, XT, GT, Dv, S, Y, ld, n, hstride, lo, hi, w->st, o.m, nchunk, w->part, 0);
     else lb_update_kernel<false><<<vgrid, NT, 0, st>>>(XP, G, XT, GT, Dv, S, Y, ld, n, hstride, lo, hi, w->st, o.m, nchunk, w->part, 0);
     lb_gram_kernel<<<B, 64, 0, st>>>(w->st, w->part, nchunk, o.m, 0, o.method);
-    if (use_tma && hns == 4) lb_direction_tma_kernel<4><<<vgrid, HT + 32, hist_smem(D_NSTR, 4), st>>>(G, Dv, S, Y, XP, XT, ld, n, hstride, w->st, o.m, nchunk, w->part);
-    else if (use_tma) lb_direction_tma_kernel<2><<<vgrid, HT + 32, hist_smem(D_NSTR, 2), st>>>(G, Dv, S, Y, XP, XT, ld, n, hstride, w->st, o.m, nchunk, w->part);
+    if (use_tma && hns == 4) lb_direction_tma_kernel<4><<<vgrid, HT + 32, hist_smem(D_NSTR, 4), st>>>(G, Dv, S, Y, XP, ld, n, hstride, w->st, o.m, nchunk, w->part);
+    else if (use_tma) lb_direction_tma_kernel<2><<<vgrid, HT + 32, hist_smem(D_NSTR, 2), st>>>(G, Dv, S, Y, XP, ld, n, hstride, w->st, o.m, nchunk, w->part);
     else if (bounded) lb_direction_kernel<true><<<vgrid, NT, 0, st>>>(XP, G, Dv, S, Y, ld, n, hstride, lo, hi, w->st, o.m, nchunk, w->part, 0);
     else lb_direction_kernel<false><<<vgrid, NT, 0, st>>>(XP, G, Dv, S, Y, ld, n, hstride, lo, hi, w->st, o.m, nchunk, w->part, 0);
     lb_start_kernel<<<B, 1, 0, st>>>(w->st, w->act_eval, w->part, nchunk, o, bounded ? 1 : 0, 0, use_tma ? 1 : 0);
