@@ -62,6 +62,7 @@ struct NnParams {
   double* me_parts;       // (B, n_me) per-block measurement-error sums of nn_fix_kernel, or nullptr
   int n_me;
   int fba_pxn, fba_pd;    // nn_fba_kernel: pitch of the all-layer state / gradient tiles, of the Delta tile
+  int fb_T, fb_nbuf;      // nn_fb_kernel: example tiles per CTA (W_n resident), tile buffers (1 or 2)
   double* dbuf;           // (B, M, NDnet - d_0) Delta of every layer
   double* lam;            // (B, M, NDnet - d_0) lambda = direct term of the next layer's gradient rows
 };
@@ -369,9 +370,12 @@ constexpr int GW_MAXTASK = 2;      // (row tile, column group) tasks a warp may 
                                    // split over the rows of W among several CTAs (P.gw_njs)
 
 constexpr int NTF = 512;           // largest CTA of nn_fb_kernel (launched with 256 or 512 threads)
+// One CTA = (layer n, P.fb_T consecutive tiles of TMF examples): W_n and b_n are staged once and stay
+// resident; the state tiles are double-buffered (P.fb_nbuf = 2) so that the cp.async copies of tile
+// i+1 run under the MMAs of tile i.
 __global__ void __launch_bounds__(NTF, 1) nn_fb_kernel(const __grid_constant__ NnParams P) {
   extern __shared__ double sm[];
-  const int mtb = blockIdx.x, n = blockIdx.y, b = blockIdx.z, tid = threadIdx.x;
+  const int n = blockIdx.y, b = blockIdx.z, tid = threadIdx.x;
   if (P.active != nullptr && P.active[b] == 0) return;
   const int lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5, nthr = blockDim.x;
   const int lr = lane >> 2, lc = lane & 3;
@@ -379,13 +383,10 @@ __global__ void __launch_bounds__(NTF, 1) nn_fb_kernel(const __grid_constant__ N
   const int dn = P.structure[n], dn1 = P.structure[n + 1];
   const int dnP = (dn + 7) & ~7, dn1P = (dn1 + 7) & ~7;
   const int px = dnP + 4, pd = dn1P + 4;
-  double* Xs = sm;                       // [TM][px]    states of layer n
-  double* Ds = Xs + TM * px;             // [TM][pd]    Delta
-  double* Ws = Ds + TM * pd;             // [dn1P][px]  W_n
+  const int tile_sz = TM * (px + pd);    // one buffer: [TM][px] states of layer n, then [TM][pd] x_{n+1} / Delta
+  double* Ws = sm + P.fb_nbuf * tile_sz; // [dn1P][px]  W_n
   double* bs = Ws + dn1P * px;           // [dn1P]
   __shared__ double red[2][NTF / 32];
-  const int m0 = mtb * TM;
-  const int rows = min(TM, P.M - m0);
   const int xo = P.xoff[n], xo1 = P.xoff[n + 1], d0 = P.structure[0];
   const int ND1 = P.NDnet - d0;
   const bool lastl = (n + 1 == P.NL - 1);
@@ -395,108 +396,130 @@ __global__ void __launch_bounds__(NTF, 1) nn_fb_kernel(const __grid_constant__ N
   double* lam = P.lam + (long long)b * P.M * ND1;
   const double* pfull = P.pfull + (long long)b * P.NP;
   const double cf2 = (P.rf_path != nullptr) ? P.cf2_num * __ldg(P.rf_path + b) / P.cf2_den : P.cf2;
-  double me_acc = 0.0, fe_acc = 0.0;
+  const int t_lo = blockIdx.x * P.fb_T, t_hi = min(P.nmt, t_lo + P.fb_T);
   // stage X_n, X_{n+1} (into the Delta tile: the epilogue of (1) reads x_{n+1}[m][j] and overwrites
-  // the same entry with Delta[m][j]), W_n and b_n with asynchronous copies: everything in flight at once
-  stage_tile_async(Xs, px, xp + xo, P.NDnet, m0, P.M, TM, dn, dnP);
-  stage_tile_async(Ds, pd, xp + xo1, P.NDnet, m0, P.M, TM, dn1, dn1P);
+  // the same entry with Delta[m][j]) with asynchronous copies
+  auto stage = [&](int buf, int mtb) {
+    double* Xs = sm + buf * tile_sz;
+    stage_tile_async(Xs, px, xp + xo, P.NDnet, mtb * TM, P.M, TM, dn, dnP);
+    stage_tile_async(Xs + TM * px, pd, xp + xo1, P.NDnet, mtb * TM, P.M, TM, dn1, dn1P);
+  };
   stage_tile_async(Ws, px, pfull + P.woff[n], dn, 0, dn1, dn1P, dn, dnP);
   for (int j = tid; j < dn1P; j += nthr) cp_async8(bs + j, pfull + P.boff[n] + (j < dn1 ? j : 0), j < dn1 ? 8 : 0);
+  stage(0, t_lo);
   cp_async_commit();
-  cp_async_wait<0>();
-  __syncthreads();
   const int MTL = TM >> 3;
-  // ---- (1) Z = X W^T, epilogue: residual, lambda, Delta
-  {
-    const int NTL = dn1P >> 3, NG = (NTL + NTILE - 1) / NTILE;
-    for (int task = warp; task < MTL * NG; task += nwarps) {
-      const int mt = task / NG, g = task - mt * NG;
-      const int nt0 = g * NTILE, ntn = min(NTILE, NTL - nt0);
-      double c0[NTILE], c1[NTILE];
-#pragma unroll
-      for (int t = 0; t < NTILE; ++t) { c0[t] = 0.0; c1[t] = 0.0; }
-      const double* arow = Xs + (mt * 8 + lr) * px + lc;
-      const double* brow = Ws + (nt0 * 8 + lr) * px + lc;
-      for (int k = 0; k < dnP; k += 4) {
-        const double a = arow[k];
-#pragma unroll
-        for (int t = 0; t < NTILE; ++t)
-          if (t < ntn) dmma(c0[t], c1[t], a, brow[t * 8 * px + k]);
-      }
-      const int m = mt * 8 + lr;
-      const long long grow = (long long)(m0 + m);
-#pragma unroll
-      for (int t = 0; t < NTILE; ++t) {
-        if (t >= ntn) continue;
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int j = (nt0 + t) * 8 + 2 * lc + h;
-          const double z = (h ? c1[t] : c0[t]) + bs[j];
-          double dl = 0.0;
-          if (m < rows && j < dn1) {
-            const double sv = act_f(P.act, z);
-            const double xn1 = Ds[m * pd + j];
-            const double e = xn1 - sv;
-            const double lm = cf2 * e;
-            fe_acc = fma(lm, e, fe_acc);
-            dl = -lm * act_d(P.act, sv);
-            // direct term of layer n+1's gradient rows: the last layer has no back term and is
-            // written here; the others are added to the back term by nn_fix_kernel
-            if (lastl) gp[grow * P.NDnet + xo1 + j] = lm;
-            else lam[grow * ND1 + (xo1 - d0) + j] = lm;
-            dbuf[grow * ND1 + (xo1 - d0) + j] = dl;
-          }
-          Ds[m * pd + j] = dl;                              // zero in the padding
-        }
-      }
+  for (int mtb = t_lo; mtb < t_hi; ++mtb) {
+    const int buf = (P.fb_nbuf == 2) ? ((mtb - t_lo) & 1) : 0;
+    if (P.fb_nbuf == 2 && mtb + 1 < t_hi) {
+      stage(buf ^ 1, mtb + 1);                              // next tile streams in under this tile's MMAs
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
     }
-  }
-  __syncthreads();
-  // ---- (2) back term of layer n's gradient rows: Delta W
-  {
-    const int NTL = dnP >> 3, NG = (NTL + NTILE - 1) / NTILE;
-    for (int task = warp; task < MTL * NG; task += nwarps) {
-      const int mt = task / NG, g = task - mt * NG;
-      const int nt0 = g * NTILE, ntn = min(NTILE, NTL - nt0);
-      double c0[NTILE], c1[NTILE];
+    __syncthreads();
+    double* Xs = sm + buf * tile_sz;
+    double* Ds = Xs + TM * px;
+    const int m0 = mtb * TM;
+    const int rows = min(TM, P.M - m0);
+    double me_acc = 0.0, fe_acc = 0.0;
+    // ---- (1) Z = X W^T, epilogue: residual, lambda, Delta
+    {
+      const int NTL = dn1P >> 3, NG = (NTL + NTILE - 1) / NTILE;
+      for (int task = warp; task < MTL * NG; task += nwarps) {
+        const int mt = task / NG, g = task - mt * NG;
+        const int nt0 = g * NTILE, ntn = min(NTILE, NTL - nt0);
+        double c0[NTILE], c1[NTILE];
 #pragma unroll
-      for (int t = 0; t < NTILE; ++t) { c0[t] = 0.0; c1[t] = 0.0; }
-      const double* arow = Ds + (mt * 8 + lr) * pd + lc;          // A[m][j]
-      const double* brow = Ws + lc * px + nt0 * 8 + lr;           // B[j][k] = W[j][k]
-      for (int j = 0; j < dn1P; j += 4) {
-        const double a = arow[j];
+        for (int t = 0; t < NTILE; ++t) { c0[t] = 0.0; c1[t] = 0.0; }
+        const double* arow = Xs + (mt * 8 + lr) * px + lc;
+        const double* brow = Ws + (nt0 * 8 + lr) * px + lc;
+        for (int k = 0; k < dnP; k += 4) {
+          const double a = arow[k];
 #pragma unroll
-        for (int t = 0; t < NTILE; ++t)
-          if (t < ntn) dmma(c0[t], c1[t], a, brow[j * px + t * 8]);
-      }
-      const int m = mt * 8 + lr;
-      const long long grow = (long long)(m0 + m);
-      if (m < rows) {
+          for (int t = 0; t < NTILE; ++t)
+            if (t < ntn) dmma(c0[t], c1[t], a, brow[t * 8 * px + k]);
+        }
+        const int m = mt * 8 + lr;
+        const long long grow = (long long)(m0 + m);
 #pragma unroll
         for (int t = 0; t < NTILE; ++t) {
           if (t >= ntn) continue;
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
-            const int k = (nt0 + t) * 8 + 2 * lc + h;
-            if (k >= dn) continue;
-            gp[grow * P.NDnet + xo + k] = h ? c1[t] : c0[t];
+            const int j = (nt0 + t) * 8 + 2 * lc + h;
+            const double z = (h ? c1[t] : c0[t]) + bs[j];
+            double dl = 0.0;
+            if (m < rows && j < dn1) {
+              const double sv = act_f(P.act, z);
+              const double xn1 = Ds[m * pd + j];
+              const double e = xn1 - sv;
+              const double lm = cf2 * e;
+              fe_acc = fma(lm, e, fe_acc);
+              dl = -lm * act_d(P.act, sv);
+              // direct term of layer n+1's gradient rows: the last layer has no back term and is
+              // written here; the others are added to the back term by nn_fix_kernel
+              if (lastl) gp[grow * P.NDnet + xo1 + j] = lm;
+              else lam[grow * ND1 + (xo1 - d0) + j] = lm;
+              dbuf[grow * ND1 + (xo1 - d0) + j] = dl;
+            }
+            Ds[m * pd + j] = dl;                            // zero in the padding
           }
         }
       }
     }
-  }
-  for (int sft = 16; sft > 0; sft >>= 1) {
-    me_acc += __shfl_down_sync(0xffffffffu, me_acc, sft);
-    fe_acc += __shfl_down_sync(0xffffffffu, fe_acc, sft);
-  }
-  if (lane == 0) { red[0][warp] = me_acc; red[1][warp] = fe_acc; }
-  __syncthreads();
-  if (tid == 0) {
-    double a = 0.0, c = 0.0;
-    for (int w = 0; w < nwarps; ++w) { a += red[0][w]; c += red[1][w]; }
-    const long long item = ((long long)b * (P.NL - 1) + n) * P.nmt + mtb;
-    P.partials[item * 2 + 0] = 0.5 * a;
-    P.partials[item * 2 + 1] = 0.5 * c;
+    __syncthreads();
+    // ---- (2) back term of layer n's gradient rows: Delta W
+    {
+      const int NTL = dnP >> 3, NG = (NTL + NTILE - 1) / NTILE;
+      for (int task = warp; task < MTL * NG; task += nwarps) {
+        const int mt = task / NG, g = task - mt * NG;
+        const int nt0 = g * NTILE, ntn = min(NTILE, NTL - nt0);
+        double c0[NTILE], c1[NTILE];
+#pragma unroll
+        for (int t = 0; t < NTILE; ++t) { c0[t] = 0.0; c1[t] = 0.0; }
+        const double* arow = Ds + (mt * 8 + lr) * pd + lc;        // A[m][j]
+        const double* brow = Ws + lc * px + nt0 * 8 + lr;         // B[j][k] = W[j][k]
+        for (int j = 0; j < dn1P; j += 4) {
+          const double a = arow[j];
+#pragma unroll
+          for (int t = 0; t < NTILE; ++t)
+            if (t < ntn) dmma(c0[t], c1[t], a, brow[j * px + t * 8]);
+        }
+        const int m = mt * 8 + lr;
+        const long long grow = (long long)(m0 + m);
+        if (m < rows) {
+#pragma unroll
+          for (int t = 0; t < NTILE; ++t) {
+            if (t >= ntn) continue;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int k = (nt0 + t) * 8 + 2 * lc + h;
+              if (k >= dn) continue;
+              gp[grow * P.NDnet + xo + k] = h ? c1[t] : c0[t];
+            }
+          }
+        }
+      }
+    }
+    for (int sft = 16; sft > 0; sft >>= 1) {
+      me_acc += __shfl_down_sync(0xffffffffu, me_acc, sft);
+      fe_acc += __shfl_down_sync(0xffffffffu, fe_acc, sft);
+    }
+    if (lane == 0) { red[0][warp] = me_acc; red[1][warp] = fe_acc; }
+    __syncthreads();            // also: every warp is done with this buffer before it is refilled
+    if (tid == 0) {
+      double a = 0.0, c = 0.0;
+      for (int w = 0; w < nwarps; ++w) { a += red[0][w]; c += red[1][w]; }
+      const long long item = ((long long)b * (P.NL - 1) + n) * P.nmt + mtb;
+      P.partials[item * 2 + 0] = 0.5 * a;
+      P.partials[item * 2 + 1] = 0.5 * c;
+    }
+    if (P.fb_nbuf == 1 && mtb + 1 < t_hi) {                 // single buffer: the next tile can only be staged now
+      stage(0, mtb + 1);
+      cp_async_commit();
+    }
   }
 }
 
@@ -953,15 +976,34 @@ int nn_eval(vab_ctx* ctx, int B, const double* XP, long long ldxp, double rf_sca
         }
       }
     }
+    int fb_T = 1, fb_nbuf = 1;
     if (fits && !all_layers) {
-      for (int tm = 256; tm >= 16 && TMF == 0; tm >>= 1) {
-        if (tm > 64 && tm * 4 > p->M) continue;                 // keep at least a few tiles per layer
+      auto fb_smem = [&](int tm, int nbuf) {
         size_t worst = 0;
         for (int n = 0; n + 1 < p->NL; ++n) {
           const int dnP = (p->st_host[n] + 7) & ~7, dn1P = (p->st_host[n + 1] + 7) & ~7;
-          const size_t s = ((size_t)tm * (dnP + 4) + (size_t)tm * (dn1P + 4) + (size_t)dn1P * (dnP + 4) + dn1P) * sizeof(double);
+          const size_t s = ((size_t)nbuf * tm * ((dnP + 4) + (dn1P + 4)) + (size_t)dn1P * (dnP + 4) + dn1P) * sizeof(double);
           if (s > worst) worst = s;
         }
+        return worst;
+      };
+      // first choice: W resident over several tiles of 64 examples with double-buffered staging.
+      // (Measured on B200: with 32-example tiles -- all that fits next to a 100-wide W -- the 8-warp
+      // CTA is slower than one 64-example tile on 16 warps, C4 1.36 vs 1.29 ms; small layers gain,
+      // 20 x 10: 66k -> 73k evals/s.)
+      const char* env_db = getenv("VAB_NN_FB_DB");              // 0: one tile per CTA, single buffer
+      if (!(env_db && atoi(env_db) == 0)) {
+        for (int tm = 64; tm >= 64 && TMF == 0; tm >>= 1) {
+          const int nmt = (p->M + tm - 1) / tm;
+          if (nmt >= 8 && fb_smem(tm, 2) <= budget) {
+            TMF = tm; smem_fb = fb_smem(tm, 2); fb_nbuf = 2;
+            fb_T = nmt >= 32 ? 8 : 4;
+          }
+        }
+      }
+      for (int tm = 256; tm >= 16 && TMF == 0; tm >>= 1) {
+        if (tm > 64 && tm * 4 > p->M) continue;                 // keep at least a few tiles per layer
+        const size_t worst = fb_smem(tm, 1);
         // big tiles only while two CTAs still share an SM
         if (worst <= (tm > 64 ? (size_t)100 * 1024 : budget)) { TMF = tm; smem_fb = worst; }
       }
@@ -1003,6 +1045,7 @@ int nn_eval(vab_ctx* ctx, int B, const double* XP, long long ldxp, double rf_sca
       P.nparts = all_layers ? P.nmt : (p->NL - 1) * P.nmt;
       P.ngw = P.gw_nsplit;
       P.fba_pxn = fba_pxn; P.fba_pd = fba_pd;
+      P.fb_T = fb_T; P.fb_nbuf = fb_nbuf;
       const size_t nd1 = (size_t)(p->NDnet - p->d0);
       long long nfix = ((long long)p->M * p->NDnet + FIX_NT * 8 - 1) / (FIX_NT * 8);     // ~8 entries per thread
       if (nfix > 1024) nfix = 1024;
@@ -1046,7 +1089,7 @@ int nn_eval(vab_ctx* ctx, int B, const double* XP, long long ldxp, double rf_sca
           if (t < min_tasks) min_tasks = t;
         }
         const int nthr = (min_tasks >= 16) ? NTF : NT;
-        nn_fb_kernel<<<dim3(P.nmt, p->NL - 1, B), nthr, smem_fb, ctx->stream>>>(P);
+        nn_fb_kernel<<<dim3((P.nmt + fb_T - 1) / fb_T, p->NL - 1, B), nthr, smem_fb, ctx->stream>>>(P);
         e = cudaGetLastError();
         if (e != cudaSuccess) return vab_cuda_fail(ctx, e, "nn_fb_kernel launch");
         nn_fix_kernel<<<dim3((unsigned)nfix, B), FIX_NT, 0, ctx->stream>>>(P);
