@@ -426,10 +426,14 @@ __global__ void __launch_bounds__(NTF, 1) nn_fb_kernel(const __grid_constant__ N
     double me_acc = 0.0, fe_acc = 0.0;
     // ---- (1) Z = X W^T, epilogue: residual, lambda, Delta
     {
-      const int NTL = dn1P >> 3, NG = (NTL + NTILE - 1) / NTILE;
+      // column tiles per task: NTILE, or fewer when that would leave warps without a task
+      const int NTL = dn1P >> 3;
+      int gsz = NTILE;
+      if (MTL * ((NTL + NTILE - 1) / NTILE) < nwarps) gsz = max(1, (MTL * NTL) / nwarps);
+      const int NG = (NTL + gsz - 1) / gsz;
       for (int task = warp; task < MTL * NG; task += nwarps) {
         const int mt = task / NG, g = task - mt * NG;
-        const int nt0 = g * NTILE, ntn = min(NTILE, NTL - nt0);
+        const int nt0 = g * gsz, ntn = min(gsz, NTL - nt0);
         double c0[NTILE], c1[NTILE];
 #pragma unroll
         for (int t = 0; t < NTILE; ++t) { c0[t] = 0.0; c1[t] = 0.0; }
@@ -472,10 +476,13 @@ __global__ void __launch_bounds__(NTF, 1) nn_fb_kernel(const __grid_constant__ N
     __syncthreads();
     // ---- (2) back term of layer n's gradient rows: Delta W
     {
-      const int NTL = dnP >> 3, NG = (NTL + NTILE - 1) / NTILE;
+      const int NTL = dnP >> 3;
+      int gsz = NTILE;
+      if (MTL * ((NTL + NTILE - 1) / NTILE) < nwarps) gsz = max(1, (MTL * NTL) / nwarps);
+      const int NG = (NTL + gsz - 1) / gsz;
       for (int task = warp; task < MTL * NG; task += nwarps) {
         const int mt = task / NG, g = task - mt * NG;
-        const int nt0 = g * NTILE, ntn = min(NTILE, NTL - nt0);
+        const int nt0 = g * gsz, ntn = min(gsz, NTL - nt0);
         double c0[NTILE], c1[NTILE];
 #pragma unroll
         for (int t = 0; t < NTILE; ++t) { c0[t] = 0.0; c1[t] = 0.0; }
@@ -993,7 +1000,9 @@ int nn_eval(vab_ctx* ctx, int B, const double* XP, long long ldxp, double rf_sca
       // 20 x 10: 66k -> 73k evals/s.)
       const char* env_db = getenv("VAB_NN_FB_DB");              // 0: one tile per CTA, single buffer
       if (!(env_db && atoi(env_db) == 0)) {
-        for (int tm = 64; tm >= 64 && TMF == 0; tm >>= 1) {
+        const char* env_tm = getenv("VAB_NN_FB_TM32");          // 1: also try 32-example tiles (A/B knob)
+        const int tm_min = (env_tm && atoi(env_tm) != 0) ? 32 : 64;
+        for (int tm = 64; tm >= tm_min && TMF == 0; tm >>= 1) {
           const int nmt = (p->M + tm - 1) / tm;
           if (nmt >= 8 && fb_smem(tm, 2) <= budget) {
             TMF = tm; smem_fb = fb_smem(tm, 2); fb_nbuf = 2;
@@ -1088,7 +1097,10 @@ int nn_eval(vab_ctx* ctx, int B, const double* XP, long long ldxp, double rf_sca
           const int t = (TMF >> 3) * (a < c ? a : c);
           if (t < min_tasks) min_tasks = t;
         }
-        const int nthr = (min_tasks >= 16) ? NTF : NT;
+        // (with fewer coarse tasks the kernel splits the column groups, so 16 warps still pay off
+        // as long as there are enough 8x8 output tiles: VAB_NN_FB_THREADS forces 256 / 512)
+        int nthr = (min_tasks >= 16) ? NTF : NT;
+        if (const char* et = getenv("VAB_NN_FB_THREADS")) nthr = atoi(et) == 512 ? NTF : NT;
         nn_fb_kernel<<<dim3((P.nmt + fb_T - 1) / fb_T, p->NL - 1, B), nthr, smem_fb, ctx->stream>>>(P);
         e = cudaGetLastError();
         if (e != cudaSuccess) return vab_cuda_fail(ctx, e, "nn_fb_kernel launch");
