@@ -348,7 +348,7 @@ def test_tma_history_kernels_match_plain_kernels(monkeypatch):
     # in-place trial points (TMA path) and searches that fail: with maxls = 1..3 a search that would
     # need more evaluations fails -- the memory is dropped and the iteration restarted, or, with an
     # empty memory, the path terminates (status 2), as in L-BFGS-B.  Either way x must have been put
-    # back to the start of the search (lb_restore_kernel): the action at the returned point is
+    # back to the start of the search (top of lb_update_tma_kernel): the action at the returned point is
     # exactly the reported one.
     monkeypatch.setenv("VAB_LBFGS_TMA", "1")
     monkeypatch.setenv("VAB_LBFGS_NS", "2")

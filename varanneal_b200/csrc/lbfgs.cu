@@ -68,7 +68,7 @@ struct LbPath {
   int ib, finished;         // rung of the ladder this path is on; ladder complete
   int xt_ready;             // the direction pass has already written the first trial point xt = x + d
   double stp_at, restore;   // in-place trials (TMA path): x currently sits at x0 + stp_at d; a failed
-                            // search leaves restore = that step for lb_restore_kernel to undo
+                            // search leaves restore = that step for lb_update_tma_kernel to undo
   double f, fold, me, fe;
   double stp, gd, gdold, dnorm, stpmx, theta, sbgnrm, dr;
   double ls_ftol, ls_gtol, ls_xtol, cd, fprev;   // line-search constants; CG: coefficient of the old direction, f two iterates back
@@ -210,20 +210,6 @@ __global__ void __launch_bounds__(NT) lb_trial_kernel(double* __restrict__ XT, d
   }
 }
 
-// in-place trials: a failed line search leaves x at x0 + restore d; put it back
-__global__ void __launch_bounds__(NT) lb_restore_kernel(double* __restrict__ X, const double* __restrict__ Dv,
-                                                        long long ld, long long n, const LbPath* __restrict__ st,
-                                                        int nchunk) {
-  const int b = blockIdx.y;
-  const LbPath& s = st[b];
-  const double a = s.restore;
-  if (a == 0.0) return;
-  const Range r = chunk_range(n, nchunk, blockIdx.x);
-  double* x = X + (long long)b * ld;
-  const double* d = Dv + (long long)b * ld;
-  for (long long i = r.i0 + threadIdx.x; i < r.i1; i += NT) x[i] = fma(-a, d[i], x[i]);
-}
-
 // partials [gd, max |proj g|] of the trial point
 template <bool BOUNDED>
 __global__ void __launch_bounds__(NT) lb_gd_kernel(const double* __restrict__ XT, const double* __restrict__ GT,
@@ -330,7 +316,7 @@ __global__ void lb_linesearch_kernel(LbPath* st, int* act_eval, const double* ft
   }
   if (s.iback >= o.maxls) {
     // line search failed: x, g, f still hold the start of the search (in-place trials: x is put
-    // back by lb_restore_kernel)
+    // back at the top of lb_update_tma_kernel)
     s.need_eval = 0;
     s.restore = stp_eval;
     if (s.col == 0) {
@@ -639,7 +625,7 @@ __device__ __forceinline__ void hist_reduce_store(const double* acc, double (*wr
 
 template <int HNS>
 __global__ void __launch_bounds__(HT + 32, 1) lb_update_tma_kernel(
-    double* __restrict__ G,
+    double* __restrict__ X, double* __restrict__ G,
     const double* __restrict__ GT, const double* __restrict__ Dv, double* __restrict__ S,
     double* __restrict__ Y, long long ld, long long n, long long hstride,
     const LbPath* __restrict__ st, int m, int nchunk, double* __restrict__ part) {
@@ -647,12 +633,21 @@ __global__ void __launch_bounds__(HT + 32, 1) lb_update_tma_kernel(
   __shared__ double wred[HW][NACC_U];
   const int b = blockIdx.y, tid = threadIdx.x;
   const LbPath& s = st[b];
+  const Range r = chunk_range(n, nchunk, blockIdx.x);
+  if (s.restore != 0.0) {
+    // in-place trials: a failed line search (never an accepted step) leaves x at x0 + restore d;
+    // put it back before the direction pass forms the next trial point
+    const double a = s.restore;
+    double* x = X + (long long)b * ld;
+    const double* d = Dv + (long long)b * ld;
+    for (long long i = r.i0 + tid; i < r.i1; i += HT + 32) x[i] = fma(-a, d[i], x[i]);
+    return;
+  }
   if (!s.accepted) return;
   const bool upd = s.do_update != 0;
   const int p = s.pslot;
   const double stp = s.stp;
   const int col = s.col;
-  const Range r = chunk_range(n, nchunk, blockIdx.x);
   const long long len = r.i1 - r.i0;
   double* pout = part + ((long long)b * nchunk + blockIdx.x) * NACC_U;
   if (len <= 0) {
@@ -847,7 +842,7 @@ __global__ void lb_start_kernel(LbPath* st, int* act_eval, const double* part, i
     else {
       s.col = 0; s.head = 0; s.theta = 1.0; s.redo_dir = 1;
       // in-place trials: the direction pass has already moved x by this (rejected) direction;
-      // lb_restore_kernel takes it back in the next cycle, before the new direction is formed
+      // lb_update_tma_kernel takes it back in the next cycle, before the new direction is formed
       if (xt_fused && s.iter > 0) s.restore = 1.0;
     }
     return;
@@ -1093,9 +1088,8 @@ int lb_run(vab_ctx* ctx, int B, double* XP, long long ld, const double* scales_h
     if (bounded) lb_gd_kernel<true><<<vgrid, NT, 0, st>>>(XT, GT, Dv, ld, n, lo, hi, w->st, nchunk, w->part);
     else lb_gd_kernel<false><<<vgrid, NT, 0, st>>>(XT, GT, Dv, ld, n, lo, hi, w->st, nchunk, w->part);
     lb_linesearch_kernel<<<B, 32, 0, st>>>(w->st, w->act_eval, w->ft, w->met, w->fet, w->part, nchunk, o, bounded ? 1 : 0);
-    if (inplace) { lb_restore_kernel<<<vgrid, NT, 0, st>>>(XP, Dv, ld, n, w->st, nchunk); ctx->launches += 1; }
-    if (use_tma && hns == 4) lb_update_tma_kernel<4><<<vgrid, HT + 32, hist_smem(U_NSTR, 4), st>>>(G, GT, Dv, S, Y, ld, n, hstride, w->st, o.m, nchunk, w->part);
-    else if (use_tma) lb_update_tma_kernel<2><<<vgrid, HT + 32, hist_smem(U_NSTR, 2), st>>>(G, GT, Dv, S, Y, ld, n, hstride, w->st, o.m, nchunk, w->part);
+    if (use_tma && hns == 4) lb_update_tma_kernel<4><<<vgrid, HT + 32, hist_smem(U_NSTR, 4), st>>>(XP, G, GT, Dv, S, Y, ld, n, hstride, w->st, o.m, nchunk, w->part);
+    else if (use_tma) lb_update_tma_kernel<2><<<vgrid, HT + 32, hist_smem(U_NSTR, 2), st>>>(XP, G, GT, Dv, S, Y, ld, n, hstride, w->st, o.m, nchunk, w->part);
     else if (bounded) lb_update_kernel<true><<<vgrid, NT, 0, st>>>(XP, G, XT, GT, Dv, S, Y, ld, n, hstride, lo, hi, w->st, o.m, nchunk, w->part, 0);
     else lb_update_kernel<false><<<vgrid, NT, 0, st>>>(XP, G, XT, GT, Dv, S, Y, ld, n, hstride, lo, hi, w->st, o.m, nchunk, w->part, 0);
     lb_gram_kernel<<<B, 64, 0, st>>>(w->st, w->part, nchunk, o.m, 0, o.method);
