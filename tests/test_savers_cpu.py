@@ -98,3 +98,17 @@ def test_ode_savers_layouts_cpu(tmp_path):
     m1 = np.loadtxt(tmp_path / "D4_M2_PATH7.dat")
     assert m1.shape == (Nbeta, 3 + N * D + NP) and np.allclose(m1[:, 0], [0, 2, 5]) and np.allclose(m1[:, 1], [0, 1, 0])
     assert np.allclose(m1[:, 2], an.A_array) and np.allclose(m1[:, 3:], an.minpaths)
+
+
+def test_pipeline_spans_cover_the_batch_with_short_ends():
+    """Groups of paths of the pipelined host-to-host evaluation (DeviceMin._pipeline_spans): a
+    partition of [0, B) in order, with small groups at both ends (the first upload and the last
+    download overlap nothing) for batches large enough to ramp."""
+    from varanneal_b200._devicemin import DeviceMin
+    for B in (1, 2, 3, 7, 8, 16, 31, 64, 100, 257):
+        spans = DeviceMin._pipeline_spans(B)
+        assert spans[0][0] == 0 and spans[-1][1] == B
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        assert all(hi > lo for lo, hi in spans)
+    sizes = [hi - lo for lo, hi in DeviceMin._pipeline_spans(64)]
+    assert sizes[0] == 1 and sizes[-1] == 1 and max(sizes) == 8 and sizes[:3] == [1, 2, 4]
