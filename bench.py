@@ -1,18 +1,29 @@
 #!/usr/bin/env python
-"""bench.py -- action+gradient evals/s of the annealing hot path (BASELINE.json metric).
+"""bench.py -- action+gradient evals/s and full-ladder anneal wall time of the annealing hot path
+(BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config C2|C1|C3|C4|C5]
 
-Workload (BASELINE.json configs[1], SURVEY.md 8(d) "C2"): Lorenz96 D=100, N=5001 model points
-(Simpson-Hermite needs an odd N), L=40 observed components, a batch of 64
-independent paths per GPU, synthetic twin-experiment data.  One *step* = one fused
-action+gradient evaluation of the whole batch = 64 evals.  Under torchrun every rank owns its
-own batch of 64 paths (weak scaling, no collective on the data path); time = max over ranks.
+Default workload (BASELINE.json configs[1], SURVEY.md 8(d) "C2"): Lorenz96 D=100, N=5001 model
+points (Simpson-Hermite needs an odd N), L=40 observed components, a batch of 64
+independent paths per GPU, synthetic twin-experiment data.  One *step* = LAUNCHES_PER_STEP
+back-to-back fused action+gradient evaluations of the whole batch (so that the timed region is
+>= 100 ms and the clocks settle) = 64 x LAUNCHES_PER_STEP evals.  Under torchrun every rank owns
+its own batch of 64 paths (weak scaling, no collective on the data path); time = max over ranks.
 
 JSON keys: see the contract in the task statement.  ``value`` = device-resident evals/s,
 ``e2e`` = the same through ``va_ode.Annealer.A_gradA`` with pinned host buffers (H2D of XP and
 D2H of A and grad inside the timed region), ``roofline`` = algorithmic bytes / kernel time
-against MEASURED_PEAKS.json, ``cpu_baseline`` = the NumPy oracle port on one host core.
+against MEASURED_PEAKS.json, ``cpu_baseline`` = the NumPy oracle port on one host core,
+``parity_checked`` = path 0 of the *timed* launch compared with the oracle (A, ||grad||) before
+anything is printed, ``ladder`` = the 20-rung anneal of the 64 paths with its per-beta parity
+against the reference + SciPy golden of path 0 (``max_rel_dA_vs_cpu``).
+
+The other BASELINE configs are separate legs (``--config``), each printing the same contract line:
+  C1  the shipped example (D=20, N=161, 101 betas): ladder wall time, 1 path and 64 paths
+  C3  Lorenz96 D=1000, N=100000, rk4, 128 initial paths per GPU (1024 / 8) annealed in waves
+  C4  va_nnet twin network 5 x 100, M=1000: evals/s and a short ladder
+  C5  va_nnet bar images [25, 30, 4], M=10000, 32 initial networks per GPU (256 / 8): ladder
 """
 import argparse
 import json
@@ -32,8 +43,10 @@ D, N_MODEL, DT, K_FORCING = 100, 5001, 0.025, 8.17
 PATHS_PER_GPU = 64
 RM, RF0, ALPHA, BETA_EVAL, N_BETA = 4.0, 4e-6, 2.5, 10, 20
 LIDX = [i for i in range(D) if i % 5 in (0, 2)]
+LAUNCHES_PER_STEP = 50
 METRIC = "action+gradient evals/sec (Lorenz96 D=100 N=5001 SimpsonHermite, 64 paths/GPU)"
 UNIT = "evals/s"
+PARITY_TOL = 1e-10
 
 
 def twin_data(seed=100):
@@ -59,6 +72,25 @@ def algorithmic_bytes(B):
     (16 N D) plus the observations, which the B paths of a batch share, once
     (8 N_data L).  DESIGN.md section 4."""
     return B * 16 * N_MODEL * D + 8 * N_MODEL * len(LIDX)
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return json.load(fh), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+def load_traffic(key):
+    """DRAM bytes per launch of the kernel from this round's `ncu --set full` capture
+    (profiles/traffic.json names the capture it was read from)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            t = json.load(fh)
+        return t.get(key), t.get("source")
+    except Exception:
+        return None, None
 
 
 # ------------------------------------------------------------------------------------ clocks
@@ -116,21 +148,33 @@ def _oracle_problem(Y):
     return OdeProblem("lorenz96", D, Y, LIDX, DT, "SimpsonHermite", np.array([K_FORCING]), [0], RM)
 
 
-def _cpu_worker(args):
-    Y, seed, reps = args
+_W = {}
+
+
+def _cpu_init(Y, seed0):
+    """Pool initialiser: every worker builds its problem and its path once (not inside the timed
+    loop); the worker's index picks its path."""
+    import multiprocessing as mp
     os.environ["OMP_NUM_THREADS"] = "1"
-    prob = _oracle_problem(Y)
-    X0, P0 = initial_paths(1, seed)
-    XP = np.append(X0[0].ravel(), P0[0])
-    rf = RF0 * ALPHA ** BETA_EVAL
+    ident = mp.current_process()._identity
+    k = (ident[0] - 1) if ident else 0
+    X0, P0 = initial_paths(1, seed0 + k)
+    X0[0][:, LIDX] = Y                                   # init_to_data, as the GPU arm
+    _W["prob"] = _oracle_problem(Y)
+    _W["XP"] = np.append(X0[0].ravel(), P0[0])
+    _W["rf"] = RF0 * ALPHA ** BETA_EVAL
+
+
+def _cpu_worker(reps):
     for _ in range(reps):
-        prob.action_grad(XP, rf)
+        _W["prob"].action_grad(_W["XP"], _W["rf"])
     return reps
 
 
 def cpu_baseline_single_core(Y, budget_s=12.0):
     prob = _oracle_problem(Y)
     X0, P0 = initial_paths(1, 1000)
+    X0[0][:, LIDX] = Y
     XP = np.append(X0[0].ravel(), P0[0])
     rf = RF0 * ALPHA ** BETA_EVAL
     prob.action_grad(XP, rf)
@@ -145,9 +189,56 @@ def cpu_baseline_single_core(Y, budget_s=12.0):
                       "adjoint, stand-in for pyadolc which is not installable), %.1f s" % (reps, dt)}
 
 
+def cpu_ladder_c1(budget_s=240.0):
+    """The reference's own ladder on the host: BASELINE.json configs[0] as shipped (D=20, N=161,
+    8 observed, 101 betas, trapezoid, gtol = ftol = 1e-8, seed 12345) through the oracle action +
+    SciPy L-BFGS-B on one core, warm-starting rung to rung as anneal_step does (va_ode.py:707-789).
+    Stops early (and says so) if the budget runs out."""
+    import scipy.optimize as opt
+    from oracle.ode_port import OdeProblem
+    z = np.load(os.path.join(ROOT, "tests", "golden", "l96_ladder_golden.npz"))
+    data = z["data"]
+    L1 = [0, 2, 4, 6, 8, 10, 14, 16]
+    np.random.seed(12345)
+    X0 = (20.0 * np.random.rand(161 * 20) - 10.0).reshape((161, 20))
+    P0 = np.array([4.0 * np.random.rand() + 6.0])
+    X0[:, L1] = data[:, 1:][:, L1]
+    prob = OdeProblem("lorenz96", 20, data[:, 1:][:, L1], L1, 0.025, "trapezoid", P0, [0], 4.0)
+    xp = np.append(X0.ravel(), P0)
+    t0 = time.perf_counter()
+    nfev, done, A = 0, 0, None
+    for beta in range(101):
+        rf = 4e-6 * 1.5 ** beta
+        r = opt.minimize(lambda v: prob.action_grad(v, rf), xp, method="L-BFGS-B", jac=True,
+                         options={"gtol": 1e-8, "ftol": 1e-8, "maxfun": 1000000, "maxiter": 1000000})
+        xp, A = r.x, float(r.fun)
+        nfev += int(r.nfev)
+        done += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    wall = time.perf_counter() - t0
+    return {"config": "C1 as shipped: Lorenz96 D=20 N=161 L=8 trapezoid, 101 betas, 1 initial path, "
+                      "oracle action + SciPy L-BFGS-B, 1 core",
+            "wall_s": wall, "betas_done": done, "betas": 101, "nfev": nfev,
+            "evals_per_s_incl_optimizer": nfev / wall, "A_last": A}
+
+
+def c2_slice_recorded():
+    """CPU wall time of one C2 initialisation's 20-rung ladder (reference anneal() + SciPy on the
+    oracle action), recorded when the golden fixture was generated in the build container
+    (tests/golden/make_ladder_golden.py) -- ~20 minutes of one core, too long to repeat here."""
+    try:
+        z = np.load(os.path.join(ROOT, "tests", "golden", "c2_slice_ladder_golden.npz"))
+        return {"wall_s_one_path_one_core": float(z["meta"][5]), "nfev": int(z["counts"][:, 1].sum()),
+                "note": "recorded at fixture generation (8-core build container), not measured in this run"}
+    except Exception:
+        return None
+
+
 def run_reference(args):
     """--impl reference: the CPU path (oracle port; pyadolc/python2 are absent so the reference
-    itself cannot run) on all host cores, one path per process like the reference's SGE array."""
+    itself cannot run) on all host cores, one path per process like the reference's SGE array.
+    The problem and the path of every worker are built once, outside the timed steps."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -156,18 +247,18 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     reps = 2
     ctx = mp.get_context("fork")
-    with ctx.Pool(cores) as pool:
-        jobs = [(Y, 1000 + c, reps) for c in range(cores)]
-        for _ in range(args.warmup):
-            pool.map(_cpu_worker, jobs)
+    with ctx.Pool(cores, initializer=_cpu_init, initargs=(Y, 1000)) as pool:
+        jobs = [reps] * cores
+        for _ in range(max(args.warmup, 1)):
+            pool.map(_cpu_worker, jobs, chunksize=1)
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            pool.map(_cpu_worker, jobs)
+            pool.map(_cpu_worker, jobs, chunksize=1)
         dt = time.perf_counter() - t0
     evals = cores * reps * args.steps
     val = evals / dt
     sample = ("each step = %d processes x %d evals of one C2 path each (NumPy oracle port, "
-              "stand-in for pyadolc)" % (cores, reps))
+              "stand-in for pyadolc); problem set-up outside the timed region" % (cores, reps))
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -176,6 +267,9 @@ def run_reference(args):
                              "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+    if not args.no_ladder:
+        line["ladder"] = cpu_ladder_c1()
+        line["ladder"]["c2_slice"] = c2_slice_recorded()
     print(json.dumps(line))
 
 
@@ -183,8 +277,9 @@ def workload_config(n_gpus):
     return {"workload": "C2: Lorenz96 D=100, N_model=5001, L=40 observed, SimpsonHermite, "
                         "RF=RF0*alpha**beta at beta=%d, twin-experiment data" % BETA_EVAL,
             "paths_per_gpu": PATHS_PER_GPU, "global_paths": PATHS_PER_GPU * n_gpus,
+            "launches_per_step": LAUNCHES_PER_STEP,
             "unknowns_per_path": N_MODEL * D + 1, "parallelism": "paths sharded over GPUs, no collective",
-            "l2_policy": "inputs larger than L2 (XP + grad = 512 MB per step per GPU vs 126 MB L2)"}
+            "l2_policy": "inputs larger than L2 (XP + grad = 512 MB per launch per GPU vs 126 MB L2)"}
 
 
 def bind_to_gpu_numa_node(local):
@@ -208,123 +303,60 @@ def bind_to_gpu_numa_node(local):
         return "unavailable (%s)" % type(exc).__name__
 
 
-# ------------------------------------------------------------------------------------ other configs
-def other_configs(device):
-    """Evaluation rates of the other BASELINE.json configs at their per-path sizes (device
-    resident, a handful of paths): C3 = Lorenz96 D=1000, N=100000 (rk4 and SimpsonHermite), C4 =
-    nnet_twin 5x100 M=1000, C5 = bar images [25,30,4] M=10000.  Reported next to the headline line;
-    they are not the metric."""
-    import ctypes as ct
-    import torch
-    from varanneal_b200 import _lib, va_nnet
-    out = {}
-    dev = torch.device("cuda", device)
+# ------------------------------------------------------------------------------------ helpers
+class Dist(object):
+    """Rank bookkeeping + the barrier / max-over-ranks the contract asks for."""
 
-    def timed(fn, reps):
-        for _ in range(2):
-            fn()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(reps):
-            fn()
-        e1.record()
-        torch.cuda.synchronize()
-        return e0.elapsed_time(e1) / reps
-
-    # ---- C3 shape straight through the C ABI (no host copies of 0.8 GB paths)
-    D3, B3 = 1000, 4
-    L3 = [i for i in range(D3) if i % 5 in (0, 2)]
-    for disc, N3 in (("rk4", 100000), ("SimpsonHermite", 100001)):
-        ctx = _lib.Context(device, torch.cuda.current_stream(dev).cuda_stream)
-        n = N3 * D3 + 1
-        ld = (n + 15) // 16 * 16
-        gen = torch.Generator(device=dev).manual_seed(2000)
-        Y = torch.randn(N3, len(L3), dtype=torch.float64, device=dev, generator=gen)
-        XP = torch.randn(B3, ld, dtype=torch.float64, device=dev, generator=gen) * 3.0
-        XP[:, N3 * D3:] = K_FORCING
-        G = torch.empty_like(XP)
-        A = torch.zeros(B3, dtype=torch.float64, device=dev)
-        pfix = torch.full((1,), K_FORCING, dtype=torch.float64, device=dev)
-        desc = _lib.OdeDesc(0, _lib.DISC_IDS[disc], D3, N3, N3, 1, len(L3), 1, 1, 0, DT)
-        p = lambda t: ct.c_void_p(t.data_ptr())  # noqa: E731
-        _lib.check(ctx.lib.vab_ode_problem_set(ctx.h, desc, _lib.int_array(L3), _lib.int_array([0]), p(Y), None), ctx.h)
-        _lib.check(ctx.lib.vab_ode_set_weights(ctx.h, RM, None, RF0, None), ctx.h)
-        _lib.check(ctx.lib.vab_ode_set_fixed_params(ctx.h, p(pfix), 0), ctx.h)
-        scale = ALPHA ** BETA_EVAL
-        ms = timed(lambda: _lib.check(ctx.lib.vab_ode_action_grad(ctx.h, B3, p(XP), ld, scale, p(A), None, None, p(G), ld), ctx.h), 5)
-        byt = B3 * 16.0 * N3 * D3 + 8.0 * N3 * len(L3)
-        out["C3_%s" % disc] = {"shape": "Lorenz96 D=1000 N=%d L=400, %d paths resident" % (N3, B3),
-                               "evals_per_s": B3 / ms * 1e3, "ms_per_launch": ms,
-                               "algorithmic_GBps": byt / ms / 1e6, "finite": bool(torch.isfinite(A).all().item())}
-        ctx.close()
-        del XP, G, Y
-    # ---- NN shapes through va_nnet.Annealer
-    for name, st, M in (("C4", [100] * 5, 1000), ("C5", [25, 30, 4], 10000)):
-        st = np.array(st)
-        B4 = 64
-        NDnet = int(st.sum())
-        NP = int(sum(st[k] * st[k + 1] + st[k + 1] for k in range(len(st) - 1)))
-        rng = np.random.RandomState(0)
-        an = va_nnet.Annealer(device=device)
-        an.set_structure(st)
-        an.set_activation("sigmoid")
-        an.set_input_data(rng.rand(M, st[0]))
-        an.set_output_data(rng.rand(M, st[-1]))
-        X0 = rng.rand(B4, M * NDnet)
-        P0 = 0.3 * rng.randn(B4, NP)
-        an.anneal_init(X0, P0, 1.1, [20.0], 1.0, 1e-2, np.arange(NP), init_to_data=False)
-        an._XP[:, :an._n].copy_(torch.from_numpy(np.concatenate([X0, P0], axis=1)))
-        ms = timed(lambda: an._action_grad_native(6.7), 10)
-        flops = 6.0 * M * sum(st[k] * st[k + 1] for k in range(len(st) - 1)) * B4
-        byt = (16.0 * M * NDnet + 16.0 * NP) * B4
-        out[name] = {"shape": "va_nnet %s M=%d, %d paths" % (list(map(int, st)), M, B4),
-                     "evals_per_s": B4 / ms * 1e3, "ms_per_launch": ms, "fp64_TFLOPs": flops / ms / 1e9,
-                     "algorithmic_GBps": byt / ms / 1e6}
-        del an
-    # ---- C1: the shipped example's shape (D=20, N=161, 8 observed, 101 betas), full ladder
-    from varanneal_b200 import datagen, va_ode
-    L1 = [0, 2, 4, 6, 8, 10, 14, 16]
-    t1, _, Y1 = datagen.lorenz96_twin(D=20, N=161, dt=0.025, k=8.17, sigma=0.5, Lidx=L1, seed=100)
-    for B1 in (1, 64):
-        rng = np.random.RandomState(12345)
-        X0 = 20.0 * rng.rand(B1, 161, 20) - 10.0
-        P0 = 4.0 * rng.rand(B1, 1) + 6.0
-        an = va_ode.Annealer(device=device)
-        an.set_model("lorenz96", 20)
-        an.set_data(Y1, t=t1)
-        t0 = time.perf_counter()
-        an.anneal(X0, P0, 1.5, np.linspace(0, 100, 101), 4.0, 4e-6, L1, [0], dt_model=0.025, init_to_data=True,
-                  disc="trapezoid", opt_args={"gtol": 1e-8, "ftol": 1e-8, "maxfun": 1000000, "maxiter": 1000000})
-        dt1 = time.perf_counter() - t0
-        out["C1_B%d" % B1] = {"shape": "Lorenz96 D=20 N=161 L=8 trapezoid, 101 betas, %d path(s), Annealer.anneal()" % B1,
-                              "ladder_wall_s": dt1, "nfev_total": int(an.nfev_array.sum()),
-                              "converged_fraction": float(np.mean(an.exitflags == 0)),
-                              "A_last_rung_min": float(np.min(an.A_array[..., -1]))}
-        del an
-    torch.cuda.empty_cache()
-    return out
-
-
-# ------------------------------------------------------------------------------------ GPU arm
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
-    from varanneal_b200 import va_ode
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if self.world != args.gpus and self.world == 1 and args.gpus > 1:
             raise SystemExit("launch with torchrun --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
-    torch.cuda.set_device(local)
-    bound = bind_to_gpu_numa_node(local)
-    if world > 1:
-        # NCCL's own log lines (e.g. "NCCL version ...") go to stderr: stdout carries the JSON line only
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        torch.cuda.set_device(self.local)
+        self.bound = bind_to_gpu_numa_node(self.local)
+        if self.world > 1:
+            os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # stdout carries the JSON line only
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
 
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def reduce(self, value, op="max"):
+        t = self.torch.tensor([float(value)], dtype=self.torch.float64, device="cuda")
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX if op == "max" else self.dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def oracle_check(A_dev, G_dev, Ar, gr):
+    """Relative deviation of the device's (A, grad) of one path from the oracle's."""
+    ea = abs(float(A_dev) - Ar) / abs(Ar)
+    eg = float(np.max(np.abs(np.asarray(G_dev) - gr)) / np.max(np.abs(gr)))
+    return {"rel_err_A": ea, "rel_err_grad": eg, "grad_norm": float(np.linalg.norm(gr)), "tol": PARITY_TOL,
+            "ok": bool(ea <= PARITY_TOL and eg <= PARITY_TOL)}
+
+
+def base_line(metric, unit, value, dd, args, ms_per_step, config, dtype="f64", scaling="weak"):
+    return {"metric": metric, "value": value, "unit": unit, "n_gpus": dd.world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling,
+            "vs_baseline": None, "dtype": dtype, "data": "synthetic", "config": config}
+
+
+# ------------------------------------------------------------------------------------ C2 (default)
+def leg_c2(args, dd):
+    import torch
+    from varanneal_b200 import va_ode
+    rank, world, local = dd.rank, dd.world, dd.local
     B = PATHS_PER_GPU
     _, Y = twin_data()
     X0, P0 = initial_paths(B, 1000 + rank * B)
@@ -335,70 +367,74 @@ def run_ours(args):
                    init_to_data=True, opt_args={"gtol": 1e-8, "ftol": 1e-8})
     n = an._n
     XP_host = torch.empty(B, n, dtype=torch.float64, pin_memory=True)
-    XP_host[:, :N_MODEL * D] = torch.from_numpy(X0.reshape(B, -1))
+    XP_host[:, :N_MODEL * D] = torch.from_numpy(X0.reshape(B, -1))      # X0 carries the data (init_to_data)
     XP_host[:, N_MODEL * D:] = torch.from_numpy(P0)
     an._XP[:, :n].copy_(XP_host)
     scale = an._rf_scale()
     stream = torch.cuda.current_stream()
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    K = LAUNCHES_PER_STEP
 
     # ---- device-resident evals/s
     for _ in range(args.warmup):
-        an._action_grad_native(scale)
-    barrier()
+        for _ in range(K):
+            an._action_grad_native(scale)
+    dd.barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     l0 = an.gpu_launches
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    barrier()
+    dd.barrier()
     ev[0].record(stream)
     for i in range(args.steps):
-        an._action_grad_native(scale)
+        for _ in range(K):
+            an._action_grad_native(scale)
         ev[i + 1].record(stream)
-    barrier()
+    dd.barrier()
     launches = an.gpu_launches - l0
     total_ms = ev[0].elapsed_time(ev[-1])
     per_step = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
-    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms_max = float(t.item())
-    value = world * B * args.steps / (total_ms_max * 1e-3)
+    total_ms_max = dd.reduce(total_ms, "max")
+    value = world * B * K * args.steps / (total_ms_max * 1e-3)
+
+    # ---- the timed launch against the oracle (rank 0, path 0): its outputs are still on the device
+    parity = None
+    if rank == 0:
+        prob = _oracle_problem(Y)
+        xp0 = XP_host[0].numpy()
+        Ar, gr = prob.action_grad(xp0, RF0 * ALPHA ** BETA_EVAL)
+        parity = oracle_check(an._A[0].item(), an._G[0, :n].cpu().numpy(), Ar, gr)
+        parity["what"] = "path 0 of the last timed launch vs oracle.ode_port (A and max-norm gradient)"
+        if not parity["ok"]:
+            raise SystemExit("bench: the timed launch disagrees with the oracle: %r" % (parity,))
 
     # ---- end to end through the public eval seam, pinned host buffers
     for _ in range(2):
         an.A_gradA(XP_host)
-    barrier()
-    t0 = time.perf_counter()
+    dd.barrier()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
     e2e_steps = max(3, min(args.steps, 10))
+    t0 = time.perf_counter()
+    e0.record(stream)
     for _ in range(e2e_steps):
         A_h, G_h = an.A_gradA(XP_host)
     e1.record(stream)
-    barrier()
-    e2e_ms = max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t0) * 0.0)
-    t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_val = world * B * e2e_steps / (float(t.item()) * 1e-3)
+    dd.barrier()
+    wall_ms = 1e3 * (time.perf_counter() - t0)
+    e2e_ms = max(e0.elapsed_time(e1), wall_ms)      # A_gradA returns after its own synchronize: both clocks cover the region
+    e2e_val = world * B * e2e_steps / (dd.reduce(e2e_ms, "max") * 1e-3)
 
     # ---- full ladder: 20 rungs, every rank its own 64 initial paths, one gather at the end
     ladder = None
     if not args.no_ladder:
         from varanneal_b200 import parallel
+        from varanneal_b200 import _lib as _vlib
         X0l, P0l = initial_paths(B, 1000 + rank * B)
         anl = va_ode.Annealer(device=local)
         anl.set_model("lorenz96", D)
         anl.set_data(Y, t=DT * np.arange(N_MODEL))
-        barrier()
+        dd.barrier()
         native = {}
-        from varanneal_b200 import _lib as _vlib
         lib = _vlib.load()
         orig_anneal = lib.vab_anneal
 
@@ -415,84 +451,381 @@ def run_ours(args):
         finally:
             lib.vab_anneal = orig_anneal
         tables = np.stack([anl.action_errors_table(init=i) for i in range(B)])
+        local_tab0 = tables[0].copy()
         tables = parallel.gather_blocks(tables, B * world)          # the design's only collective
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
-        tt = torch.tensor([wall, float(anl.nfev_array.sum())], dtype=torch.float64, device="cuda")
-        if world > 1:
-            tw = tt.clone()
-            dist.all_reduce(tw[:1], op=dist.ReduceOp.MAX)
-            dist.all_reduce(tt[1:], op=dist.ReduceOp.SUM)
-            tt[0] = tw[0]
-        ladder = {"wall_s": float(tt[0].item()), "device_ladder_s": native.get("s"),
+        wall_max = dd.reduce(wall, "max")
+        nfev_tot = dd.reduce(float(anl.nfev_array.sum()), "sum")
+        ladder = {"wall_s": wall_max, "device_ladder_s": native.get("s"),
                   "note": "wall_s = Annealer.anneal() from host X0/P0 to host minpaths (B, Nbeta, N*D+NP) "
                           "+ gathered tables; device_ladder_s = the vab_anneal call inside it (rank 0)",
                   "paths": B * world, "betas": N_BETA,
                   "alpha": ALPHA, "opt_args": "gtol=ftol=1e-8 (examples/Lorenz96_D20)",
-                  "nfev_total": int(tt[1].item()), "evals_per_s_incl_optimizer": float(tt[1].item() / tt[0].item()),
+                  "nfev_total": int(nfev_tot), "evals_per_s_incl_optimizer": nfev_tot / wall_max,
                   "converged_fraction": float(np.mean(anl.exitflags == 0)),
                   "A_last_rung_mean": float(tables[:, -1, 1].mean()),
-                  "gathered_table_shape": list(tables.shape)}
+                  "gathered_table_shape": list(tables.shape),
+                  "graph_replayed_cycles": anl._ctx.graph_launches}
+        if rank == 0:
+            # per-beta parity of path 0 (seed 1000) against the reference anneal() + SciPy golden
+            try:
+                z = np.load(os.path.join(ROOT, "tests", "golden", "c2_slice_ladder_golden.npz"))
+                ref = z["table"][:, 1]
+                rel = np.abs(local_tab0[:, 1] - ref) / np.abs(ref)
+                ladder["max_rel_dA_vs_cpu"] = float(rel.max())
+                ladder["rel_dA_vs_cpu_per_beta"] = [float(v) for v in rel]
+                if "table_ulp1" in z.files:
+                    band = np.abs(z["table_ulp1"][:, 1] - ref) / np.abs(ref)
+                    ladder["reference_self_spread_max"] = float(band.max())
+                    ladder["reference_self_spread_note"] = (
+                        "the same reference + SciPy ladder started from X0 (1 + 2^-52): how far the CPU "
+                        "path drifts from itself (shipped tolerances gtol = ftol = 1e-8 stop in flat valleys)")
+                ladder["cpu_c2_slice"] = c2_slice_recorded()
+            except Exception as exc:
+                ladder["max_rel_dA_vs_cpu"] = None
+                ladder["parity_error"] = repr(exc)
         del anl
 
-    # the clock sampler has been running since the start of the timed region: device-resident
-    # loop, end-to-end loop and the full ladder (tens of seconds under load)
     clocks = sampler.stop() if rank == 0 else None
-    if rank == 0:
-        peaks = {}
-        pk_src = "fallback"
-        try:
-            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
-                peaks = json.load(fh)
-            pk_src = "measured"
-        except Exception:
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        kern_ms = float(np.mean(per_step))
-        achieved = algorithmic_bytes(B) / (kern_ms * 1e-3) / 1e9
-        traffic = None
-        try:
-            with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
-                traffic = json.load(fh).get("ode_walk_bytes_per_launch")
-        except Exception:
-            pass
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": workload_config(world),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "peak_source": pk_src,
-                         "kernel": "stream_simpson_kernel<ModelL96<4>> (TMA ring, + ~3 us finalize)",
-                         "algorithmic_bytes_per_launch": algorithmic_bytes(B),
-                         "kernel_ms": kern_ms},
-            "e2e": {"value": e2e_val, "unit": UNIT,
-                    "h2d_bytes_per_step": int(XP_host.numel() * 8),
-                    "d2h_bytes_per_step": int(G_h.numel() * 8 + A_h.numel() * 8),
-                    "api": "va_ode.Annealer.A_gradA(pinned XP) -> (A, grad) pinned"},
-            "gpu_launches": int(launches), "clocks": clocks, "ladder": ladder, "cpu_binding": bound,
-        }
-        if world == 1 and not args.no_extra:
-            try:
-                line["other_configs"] = other_configs(local)
-            except Exception as exc:                          # never lose the headline line
-                line["other_configs"] = {"error": repr(exc)}
-        if world == 1 and not args.no_cpu:
-            line["cpu_baseline"] = cpu_baseline_single_core(Y)
+    if rank != 0:
+        return None
+    peaks, pk_src = load_peaks()
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    kern_ms = float(np.mean(per_step)) / K
+    achieved = algorithmic_bytes(B) / (kern_ms * 1e-3) / 1e9
+    traffic, traffic_src = load_traffic("ode_walk_bytes_per_launch")
+    line = base_line(METRIC, UNIT, value, dd, args, total_ms_max / args.steps, workload_config(world))
+    line.update({
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                     "peak_source": pk_src, "frac_of_nominal_8TBs": achieved / 8000.0,
+                     "kernel": "stream_simpson_kernel<ModelL96<4>> (TMA ring, + ~3 us finalize)",
+                     "algorithmic_bytes_per_launch": algorithmic_bytes(B),
+                     "kernel_ms": kern_ms},
+        "e2e": {"value": e2e_val, "unit": UNIT,
+                "h2d_bytes_per_step": int(XP_host.numel() * 8),
+                "d2h_bytes_per_step": int(G_h.numel() * 8 + A_h.numel() * 8),
+                "api": "va_ode.Annealer.A_gradA(pinned XP) -> (A, grad) pinned, one call = one batch of 64 evals"},
+        "gpu_launches": int(launches), "clocks": clocks, "ladder": ladder, "cpu_binding": dd.bound,
+        "parity_checked": bool(parity and parity["ok"]), "parity": parity,
+        "fp64_tflops_builder_measured": an._ctx.fp64_peak_tflops(),
+    })
+    if world == 1 and not args.no_cpu:
+        line["cpu_baseline"] = cpu_baseline_single_core(Y)
+    return line
+
+
+# ------------------------------------------------------------------------------------ C1
+def leg_c1(args, dd):
+    """The shipped example (BASELINE.json configs[0]): shipped data file, 101 betas, trapezoid,
+    gtol = ftol = 1e-8, seed 12345.  value = evals/s including the optimiser for the 64-path batch;
+    the 1-path ladder is what the reference's user sees."""
+    import torch
+    from varanneal_b200 import va_ode
+    z = np.load(os.path.join(ROOT, "tests", "golden", "l96_ladder_golden.npz"))
+    g = np.load(os.path.join(ROOT, "tests", "golden", "c1_shipped_ladder_golden.npz"))
+    data = z["data"]
+    L1 = [0, 2, 4, 6, 8, 10, 14, 16]
+    out = {}
+    sampler = ClockSampler(dd.local)
+    if dd.rank == 0:
+        sampler.start()
+    for B1 in (1, 64):
+        rng = np.random.RandomState(12345 + dd.rank)
+        X0 = 20.0 * rng.rand(B1, 161, 20) - 10.0
+        P0 = 4.0 * rng.rand(B1, 1) + 6.0
+        if B1 == 1 and dd.rank == 0:
+            X0[0], P0[0] = g["trapezoid/X0"], g["trapezoid/P0"]
+        an = va_ode.Annealer(device=dd.local)
+        an.set_model("lorenz96", 20)
+        an.set_data(data[:, 1:][:, L1], t=data[:, 0])
+        dd.barrier()
+        t0 = time.perf_counter()
+        an.anneal(X0, P0, 1.5, np.linspace(0, 100, 101), 4.0, 4e-6, L1, [0], dt_model=0.025, init_to_data=True,
+                  disc="trapezoid", opt_args={"gtol": 1e-8, "ftol": 1e-8, "maxfun": 1000000, "maxiter": 1000000})
+        torch.cuda.synchronize()
+        wall = dd.reduce(time.perf_counter() - t0, "max")
+        nfev = dd.reduce(float(an.nfev_array.sum()), "sum")
+        out[B1] = {"ladder_wall_s": wall, "nfev_total": int(nfev), "paths": B1 * dd.world,
+                   "evals_per_s_incl_optimizer": nfev / wall,
+                   "converged_fraction": float(np.mean(an.exitflags == 0)),
+                   "launches": an.gpu_launches, "graph_replayed_cycles": an._ctx.graph_launches}
+        if B1 == 1 and dd.rank == 0:
+            ref = g["trapezoid/table"][:, 1]
+            rel = np.abs(an.A_array[0] - ref) / np.abs(ref)
+            band = np.abs(g["trapezoid/table_ulp1"][:, 1] - ref) / np.abs(ref) if "trapezoid/table_ulp1" in g.files else None
+            out[B1]["max_rel_dA_vs_cpu"] = float(rel.max())
+            out[B1]["median_rel_dA_vs_cpu"] = float(np.median(rel))
+            if band is not None:
+                out[B1]["reference_self_spread_max"] = float(band.max())
+            out[B1]["cpu_reference_wall_s"] = float(g["trapezoid/meta"][5])
+    clocks = sampler.stop() if dd.rank == 0 else None
+    if dd.rank != 0:
+        return None
+    v = out[64]
+    line = base_line("anneal evals/sec incl. optimiser (C1: shipped Lorenz96 D=20 example, 101 betas, 64 paths/GPU)",
+                     UNIT, v["evals_per_s_incl_optimizer"], dd, args, 1e3 * v["ladder_wall_s"],
+                     {"workload": "C1: examples/Lorenz96_D20 as shipped (D=20, N=161, L=8, trapezoid, 101 betas, "
+                                  "gtol=ftol=1e-8), full ladder = one step", "paths_per_gpu": 64,
+                      "l2_policy": "problem is 26 KB per path: L2/launch-latency bound by nature"})
+    line.update({"steps": 1, "warmup": 0, "roofline": None, "e2e": {"value": v["evals_per_s_incl_optimizer"], "unit": UNIT,
+                 "h2d_bytes_per_step": 64 * 3221 * 8, "d2h_bytes_per_step": 64 * 101 * 3221 * 8,
+                 "api": "va_ode.Annealer.anneal(): host X0/P0 in, host minpaths out"},
+                 "gpu_launches": v["launches"], "clocks": clocks, "one_path": out[1], "batch": out[64]})
+    return line
+
+
+# ------------------------------------------------------------------------------------ C3
+def leg_c3(args, dd):
+    """BASELINE.json configs[2]: Lorenz96 D=1000, N=100000, rk4, 1024 initial paths over 8 GPUs =
+    128 per GPU, annealed in memory-sized waves (a path's minimiser state is 26 vectors x 0.8 GB).
+    A 2-rung ladder with maxiter iterations per rung is the bounded sample that is timed; the
+    initial paths are drawn on the device (seeds 2000 + b) -- 128 x 0.8 GB do not belong in host
+    memory; keep_paths='none' (the per-rung parameter estimates and the action table are kept)."""
+    import torch
+    from varanneal_b200 import datagen, va_ode
+    D3, N3 = 1000, int(os.environ.get("VAB_C3_N", "100000"))
+    Bg = int(os.environ.get("VAB_C3_PATHS", "128"))
+    maxiter = int(os.environ.get("VAB_C3_MAXITER", "6"))
+    L3 = [i for i in range(D3) if i % 5 in (0, 2)]
+    dev = torch.device("cuda", dd.local)
+    t_gen = time.perf_counter()
+    _, _, Y = datagen.lorenz96_twin(D=D3, N=N3, dt=DT, k=K_FORCING, sigma=0.5, Lidx=L3, seed=100, transient=1000)
+    t_gen = time.perf_counter() - t_gen
+
+    def x0_block(b0, b1):
+        out = torch.empty(b1 - b0, N3, D3, dtype=torch.float64, device=dev)
+        for b in range(b0, b1):
+            gen = torch.Generator(device=dev).manual_seed(2000 + dd.rank * Bg + b)
+            out[b - b0] = 20.0 * torch.rand(N3, D3, dtype=torch.float64, device=dev, generator=gen) - 10.0
+        return out
+
+    P0 = np.array([[4.0 * np.random.RandomState(2000 + dd.rank * Bg + b).rand() + 6.0] for b in range(Bg)])
+    an = va_ode.Annealer(device=dd.local)
+    an.keep_paths = 'none'
+    an.set_model("lorenz96", D3)
+    an.set_data(Y, t=DT * np.arange(N3))
+    sampler = ClockSampler(dd.local)
+    if dd.rank == 0:
+        sampler.start()
+    dd.barrier()
+    t0 = time.perf_counter()
+    an.anneal(x0_block, P0, ALPHA, [0, 1], RM, RF0, L3, [0], disc="rk4", init_to_data=True,
+              opt_args={"gtol": 1e-8, "ftol": 1e-8, "maxiter": maxiter})
+    torch.cuda.synchronize()
+    wall = dd.reduce(time.perf_counter() - t0, "max")
+    nfev = dd.reduce(float(an.nfev_array.sum()), "sum")
+    # ---- evaluation rate of the resident wave + oracle check of one path of that launch
+    Bw = an._B
+    an._load_wave(0, Bw)
+    scale = ALPHA ** 1.0
+    for _ in range(2):
+        an._action_grad_native(scale)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 5
+    e0.record()
+    for _ in range(reps):
+        an._action_grad_native(scale)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    parity = None
+    if dd.rank == 0 and not args.no_cpu:
+        from oracle.ode_port import OdeProblem
+        prob = OdeProblem("lorenz96", D3, Y, L3, DT, "rk4", [K_FORCING], [0], RM)
+        xp0 = an._XP[0, :an._n].cpu().numpy()
+        tcpu = time.perf_counter()
+        Ar, gr = prob.action_grad(xp0, RF0 * scale)
+        tcpu = time.perf_counter() - tcpu
+        parity = oracle_check(an._A[0].item(), an._G[0, :an._n].cpu().numpy(), Ar, gr)
+        parity["what"] = "path 0 of the timed rk4 launch (n = %d) vs oracle.ode_port" % an._n
+        parity["oracle_eval_s_one_core"] = tcpu
+    clocks = sampler.stop() if dd.rank == 0 else None
+    if dd.rank != 0:
+        return None
+    peaks, pk_src = load_peaks()
+    byt = Bw * 16.0 * N3 * D3 + 8.0 * N3 * len(L3)
+    fp64_peak = an._ctx.fp64_peak_tflops()
+    flops = 100.0 * N3 * D3 * Bw                      # ~100 flop per element-row (SURVEY.md 8(d))
+    ach = byt / ms / 1e6
+    line = base_line("anneal evals/sec incl. optimiser (C3: Lorenz96 D=1000 N=%d rk4, %d paths/GPU in waves)" % (N3, Bg),
+                     UNIT, nfev / wall, dd, args, 1e3 * wall,
+                     {"workload": "C3: Lorenz96 D=1000, N_model=%d, L=400, rk4, 2-rung ladder (alpha 2.5, beta 0..1), "
+                                  "maxiter=%d per rung (bounded sample), one step = the whole job" % (N3, maxiter),
+                      "paths_per_gpu": Bg, "global_paths": Bg * dd.world, "resident_paths_per_wave": Bw,
+                      "waves_per_gpu": an.n_waves, "keep_paths": "none",
+                      "l2_policy": "0.8 GB per vector: nothing fits L2"})
+    line.update({"steps": 1, "warmup": 0,
+                 "roofline": {"bound": "hbm", "achieved": ach, "peak": float(peaks.get("hbm_gbs", 6650.0)), "unit": "GB/s",
+                              "frac": ach / float(peaks.get("hbm_gbs", 6650.0)), "traffic": None, "peak_source": pk_src,
+                              "kernel": "stream_rk4_kernel (window mode), %d resident paths" % Bw, "kernel_ms": ms,
+                              "algorithmic_bytes_per_launch": byt,
+                              "fp64": {"achieved_tflops": flops / ms / 1e9, "peak_tflops_builder_measured": fp64_peak,
+                                       "frac": flops / ms / 1e9 / fp64_peak if fp64_peak else None,
+                                       "flops_per_element": 100}},
+                 "e2e": {"value": nfev / wall, "unit": UNIT, "h2d_bytes_per_step": int(Y.nbytes + P0.nbytes),
+                         "d2h_bytes_per_step": int(an.A_array.nbytes * 3 + an.params_array.nbytes),
+                         "api": "va_ode.Annealer.anneal(X0=callable drawing the paths on the device, keep_paths='none')"},
+                 "gpu_launches": an.gpu_launches, "clocks": clocks, "ladder_wall_s": wall, "nfev_total": int(nfev),
+                 "eval_rate_resident_wave": Bw / ms * 1e3, "parity_checked": bool(parity and parity["ok"]),
+                 "parity": parity, "twin_data_generation_s": t_gen,
+                 "A_last_rung_mean": float(an.A_array[:, -1].mean()),
+                 "finite": bool(np.all(np.isfinite(an.A_array)))})
+    return line
+
+
+# ------------------------------------------------------------------------------------ C4 / C5
+def _nn_problem(name, rank):
+    from varanneal_b200 import datagen
+    if name == "C4":
+        st = np.array([100] * 5)
+        M = 1000
+        (W, b), = datagen.nnet_twin_params(st, seed=17439860)
+        din, dout, _ = datagen.nnet_twin_io(W, b, M, sigma=0.005, seed=43650832)
+        RMn = 1.0 / 0.005 ** 2
+    else:
+        st = np.array([25, 30, 4])
+        M = 10000
+        data, labels = datagen.bar_images(dim=5, Nsets=2500, imagetype="centered", seed=85964309)
+        din, dout = data[:M], labels[:M].astype(np.float64)
+        RMn = 1.0
+    NDnet = int(st.sum())
+    RF0n = 1e-8 * RMn * float(NDnet - st[0]) / float(st[0] + st[-1])     # nnet_twin_anneal.py:46-50
+    return st, M, din, dout, RMn, RF0n
+
+
+def leg_nn(args, dd, name):
+    """BASELINE.json configs[3] / [4]: va_nnet evaluation rate (value) with the timed launch checked
+    against the oracle, and a ladder over the examples' beta range (alpha 1.1; every 12th of the
+    436 betas for C4, all 436 for C5) with every weight estimated and biases fixed at 0
+    (nnet_twin_anneal.py:101-119)."""
+    import torch
+    from varanneal_b200 import va_nnet
+    st, M, din, dout, RMn, RF0n = _nn_problem(name, dd.rank)
+    B = 64 if name == "C4" else 32                     # C5: 256 initial networks / 8 GPUs
+    NDnet = int(st.sum())
+    NP = int(sum(st[k] * st[k + 1] + st[k + 1] for k in range(len(st) - 1)))
+    Pidx, off = [], 0
+    for k in range(len(st) - 1):
+        Pidx.extend(range(off, off + st[k] * st[k + 1]))
+        off += st[k] * st[k + 1] + st[k + 1]
+    Pidx = np.array(Pidx)
+    rng = np.random.RandomState(89072545 + dd.rank)
+    X0 = rng.rand(B, M * NDnet)
+    P0 = np.zeros((B, NP))
+    P0[:, Pidx] = (2.0 * rng.rand(B, len(Pidx)) - 1.0) / 10.0
+    betas = np.arange(0.0, 436.0, 12.0) if name == "C4" else np.arange(0.0, 436.0, 1.0)
+    an = va_nnet.Annealer(device=dd.local)
+    an.set_structure(st)
+    an.set_activation("sigmoid")
+    an.set_input_data(din)
+    an.set_output_data(dout)
+    an.anneal_init(X0, P0, 1.1, [100.0], RMn, RF0n, Pidx, init_to_data=True)
+    an._load_wave(0, B)
+    scale = 1.1 ** 100.0
+    sampler = ClockSampler(dd.local)
+    if dd.rank == 0:
+        sampler.start()
+    K = 20
+    for _ in range(max(args.warmup, 3)):
+        an._action_grad_native(scale)
+    dd.barrier()
+    l0 = an.gpu_launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps * K):
+        an._action_grad_native(scale)
+    e1.record()
+    dd.barrier()
+    launches = an.gpu_launches - l0
+    ms_tot = dd.reduce(e0.elapsed_time(e1), "max")
+    ms = ms_tot / (args.steps * K)
+    value = dd.world * B / ms * 1e3
+    parity = None
+    if dd.rank == 0:
+        from oracle.nnet_port import NnetProblem
+        prob = NnetProblem(st, din, dout, None, P0[0], Pidx, RMn)
+        xp0 = an._XP[0, :an._n].cpu().numpy()
+        Ar, gr = prob.action_grad(xp0, RF0n * scale)
+        parity = oracle_check(an._A[0].item(), an._G[0, :an._n].cpu().numpy(), Ar, gr)
+        parity["what"] = "path 0 of the timed launch vs oracle.nnet_port"
+        if not parity["ok"]:
+            raise SystemExit("bench: the timed %s launch disagrees with the oracle: %r" % (name, parity))
+    ladder = None
+    if not args.no_ladder:
+        anl = va_nnet.Annealer(device=dd.local)
+        anl.set_structure(st)
+        anl.set_activation("sigmoid")
+        anl.set_input_data(din)
+        anl.set_output_data(dout)
+        anl.keep_paths = 'last'          # all rungs of all paths would be 10 GB (C4) / 66 GB (C5) of host memory
+        dd.barrier()
+        t0 = time.perf_counter()
+        anl.anneal(X0.copy(), P0.copy(), 1.1, betas, RMn, RF0n, Pidx, init_to_data=True,
+                   opt_args={"gtol": 1e-12, "ftol": 1e-12, "maxfun": 1000000, "maxiter": 2000})
+        torch.cuda.synchronize()
+        wall = dd.reduce(time.perf_counter() - t0, "max")
+        nfev = dd.reduce(float(anl.nfev_array.sum()), "sum")
+        ladder = {"wall_s": wall, "paths": B * dd.world, "betas": len(betas), "nfev_total": int(nfev),
+                  "evals_per_s_incl_optimizer": nfev / wall, "converged_fraction": float(np.mean(anl.exitflags == 0)),
+                  "A_first_last_mean": [float(anl.A_array[:, 0].mean()), float(anl.A_array[:, -1].mean())],
+                  "keep_paths": anl.keep_paths, "opt_args": "gtol=ftol=1e-12 (examples/nnet_twin), maxiter 2000 per rung"}
+    clocks = sampler.stop() if dd.rank == 0 else None
+    if dd.rank != 0:
+        return None
+    peaks, pk_src = load_peaks()
+    flops = 6.0 * M * sum(st[k] * st[k + 1] for k in range(len(st) - 1)) * B
+    byt = (16.0 * M * NDnet + 16.0 * NP) * B
+    fp64_peak = an._ctx.fp64_peak_tflops()
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    tf = flops / ms / 1e9
+    gb = byt / ms / 1e6
+    if name == "C4":
+        roof = {"bound": "tensor", "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tf / fp64_peak if fp64_peak else None,
+                "traffic": None, "peak_source": "builder-measured fp64 FMA rate (vab_measure_fp64_peak); fp64 tensor pipe (DMMA) has the same nominal rate",
+                "kernel": "nn_fb_kernel + nn_gw_kernel + nn_fix_kernel (fp64 tensor pipe)", "kernel_ms": ms,
+                "algorithmic_flops_per_launch": flops, "hbm_GBps_algorithmic": gb}
+    else:
+        roof = {"bound": "hbm", "achieved": gb, "peak": hbm, "unit": "GB/s", "frac": gb / hbm, "traffic": None,
+                "peak_source": pk_src, "kernel": "nn_fba_kernel + nn_gw_kernel", "kernel_ms": ms,
+                "algorithmic_bytes_per_launch": byt, "fp64_TFLOPs": tf}
+    metric = "action+gradient evals/sec (%s: va_nnet %s M=%d, %d paths/GPU)" % (name, list(map(int, st)), M, B)
+    line = base_line(metric, UNIT, value, dd, args, ms * K,
+                     {"workload": "%s: va_nnet structure %s, M=%d examples, sigmoid, all weights estimated, RF at beta=100; "
+                                  "one step = %d launches" % (name, list(map(int, st)), M, K),
+                      "paths_per_gpu": B, "global_paths": B * dd.world,
+                      "l2_policy": "XP + grad = %.0f MB per launch vs 126 MB L2" % (2 * B * an._n * 8 / 1e6)})
+    line.update({"roofline": roof, "gpu_launches": int(launches), "clocks": clocks, "ladder": ladder,
+                 "parity_checked": bool(parity and parity["ok"]), "parity": parity,
+                 "e2e": {"value": ladder["evals_per_s_incl_optimizer"] if ladder else None, "unit": UNIT,
+                         "h2d_bytes_per_step": int(X0.nbytes + P0.nbytes), "d2h_bytes_per_step": int(X0.nbytes),
+                         "api": "va_nnet.Annealer.anneal(): host X0/P0 in, host results out (rate incl. optimiser)"}})
+    return line
+
+
+# ------------------------------------------------------------------------------------ GPU arm
+def run_ours(args):
+    dd = Dist(args)
+    leg = {"C2": leg_c2, "C1": leg_c1, "C3": leg_c3,
+           "C4": lambda a, d: leg_nn(a, d, "C4"), "C5": lambda a, d: leg_nn(a, d, "C5")}[args.config]
+    line = leg(args, dd)
+    if dd.rank == 0:
         print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    dd.close()
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--config", default="C2", choices=["C1", "C2", "C3", "C4", "C5"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / CPU oracle legs")
     ap.add_argument("--no-ladder", action="store_true", help="skip the full-ladder leg")
-    ap.add_argument("--no-extra", action="store_true", help="skip the C3 / C4 / C5 evaluation-rate probes")
+    ap.add_argument("--no-extra", action="store_true", help="(kept for compatibility; the other configs are --config legs now)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

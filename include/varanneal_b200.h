@@ -76,6 +76,15 @@ VAB_API int vab_sync(vab_ctx* ctx);
 VAB_API const char* vab_last_error(const vab_ctx* ctx);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 VAB_API long long vab_launch_count(const vab_ctx* ctx);
+/* Number of minimiser cycles (one line-search evaluation of every running path: 11-12 kernels) that
+ * were replayed from the CUDA graph captured by vab_minimize / vab_anneal, as opposed to enqueued
+ * kernel by kernel.  0 means the capture was refused or switched off (VAB_LBFGS_GRAPH=0). */
+VAB_API long long vab_graph_launch_count(const vab_ctx* ctx);
+
+/* Measures the device's double-precision FMA rate on the CUDA cores (TFLOP/s, 2 flops per FMA) with
+ * a register-resident micro-kernel timed by CUDA events: the roofline denominator of the
+ * fp64-bound kernels (rk4, NaKL, neural-network contractions), which MEASURED_PEAKS.json lacks. */
+VAB_API int vab_measure_fp64_peak(vab_ctx* ctx, double* tflops_host);
 
 /* ---- ODE problem -------------------------------------------------------------------------- */
 /* Everything va_ode.Annealer.anneal_init fixes for a run (va_ode.py:531-705). */
@@ -196,6 +205,16 @@ VAB_API int vab_anneal(vab_ctx* ctx, int32_t B, double* XP_dev, int64_t ldxp, do
  * (minpaths, va_ode.py:776) is complete when vab_anneal returns and the transfer costs no wall
  * time.  host_dst may be pageable.  The sink is cleared by the call that used it; NULL clears it. */
 VAB_API int vab_set_path_sink(vab_ctx* ctx, double* host_dst, int64_t host_pitch, int64_t width);
+
+/* Column window of the minimising paths kept by the next vab_anneal call: minpaths_dev then holds
+ * only columns [first, first + width) of every minimiser, as (B, Nbeta, pitch) with
+ * pitch = max(2, width rounded up to even) doubles.  The reference keeps every path of every rung
+ * (minpaths (Nbeta, N*D+NP), va_ode.py:666-667) -- 16 GB per initialisation at
+ * D = 1000, N = 100000, 20 betas -- so a run of that size keeps the per-rung *parameter* estimates
+ * (first = N*D, width = NPest) and only the last rung's path, which vab_anneal leaves in XP_dev.
+ * width < 0 restores whole paths.  Consumed (cleared) by the next vab_anneal / vab_minimize; cannot
+ * be combined with a host sink. */
+VAB_API int vab_set_path_window(vab_ctx* ctx, int64_t first, int64_t width);
 
 /* Strided device -> host copy of `rows` rows of `width` doubles (pitches in doubles), on the
  * context's stream, synchronous for the caller.  Used by the host mirror to lay the device

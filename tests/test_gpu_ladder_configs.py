@@ -1,0 +1,123 @@
+"""Per-beta parity of the device ladder on the *real* configurations against the reference's own
+anneal() + SciPy L-BFGS-B (goldens: tests/golden/make_ladder_golden.py):
+
+  C1  BASELINE.json configs[0] as shipped: 101 betas, gtol = ftol = 1e-8, trapezoid and
+      SimpsonHermite (examples/Lorenz96_D20/Lorenz96_anneal.py).
+  C2  a one-initialisation slice of configs[1] (D=100, N=5001, SimpsonHermite, 20 betas, alpha 2.5).
+
+What "the same per-beta minimum action to 1e-6" can mean here is fixed by two properties of the
+reference itself, both recorded in the goldens:
+
+  * its stopping rule, (f_k - f_{k+1}) <= ftol * max(|f|, 1), resolves A only to ftol * max(|A|, 1)
+    -- 1e-8 absolute, i.e. 1e-4 relative on the early rungs where A ~ 1e-4;
+  * its own reproducibility: the *same* reference code started from X0 * (1 + 2^-52) (one unit in
+    the last place) lands, rung by rung, up to 7e-2 away from itself between beta = 16 and 27 (the
+    multi-modal stretch of the ladder), and 1e-4 away on the saturated rungs beta > 60
+    (``table_ulp1`` / ``table_ulp2`` in the golden).  60 of 101 rungs differ by more than 1e-6.
+
+So the per-rung tolerance asserted is
+    tol_i = max(1e-6, ftol * max(|A_i|, 1) / |A_i|, 10 * band_i)
+with band_i the reference-vs-itself spread in a window of +-2 rungs; and, independently of the
+chaotic drift of a 101-rung chain, a *teacher-forced* check minimises every rung on the device from
+the reference's own minimiser of the previous rung.  The acceptance test of SURVEY.md 7.4(2) --
+SciPy restarted at the device's minimiser must stop at once at the same action -- is applied to
+all rungs and compared with what SciPy does when restarted at *its own* minimisers
+(``self_restart`` in the golden: 20 of 101 rungs need more than 2 iterations there too).
+"""
+import numpy as np
+import pytest
+
+import golden_util
+import ladder_parity as lp
+from oracle.ode_port import OdeProblem
+
+pytestmark = pytest.mark.gpu
+
+
+def _band(z, prefix, tab):
+    keys = [k for k in (prefix + "table_ulp1", prefix + "table_ulp2") if k in z.files]
+    A = tab[:, 1]
+    b = np.zeros(len(A))
+    for k in keys:
+        b = np.maximum(b, np.abs(z[k][:, 1] - A) / np.abs(A))
+    env = np.array([b[max(0, i - 2):i + 3].max() for i in range(len(b))])
+    return b, env
+
+
+def _tolerance(A_ref, env, ftol):
+    return np.maximum(1e-6, np.maximum(ftol * np.maximum(np.abs(A_ref), 1.0) / np.abs(A_ref), 10.0 * env))
+
+
+def _check_chain(s, z, prefix, ftol):
+    tab = z[prefix + "table"]
+    band, env = _band(z, prefix, tab)
+    tol = _tolerance(tab[:, 1], env, ftol)
+    bad = np.where(s["rel"] > tol)[0]
+    assert bad.size == 0, [(int(i), float(s["rel"][i]), float(tol[i])) for i in bad]
+    # where the reference reproduces itself to 1e-6 the device reproduces it too, about as often
+    n_ref = int(np.sum(band <= 1e-6))
+    n_dev = int(np.sum(s["rel"] <= 1e-6))
+    assert n_dev >= 0.7 * n_ref, (n_dev, n_ref)
+    # the device's action at its minimiser is the oracle's action there
+    assert np.max(s["oracle_rel"]) <= 1e-10
+    # acceptance: SciPy restarted at the device minimisers behaves like SciPy restarted at its own
+    sr = z[prefix + "self_restart"]
+    A = np.maximum(np.abs(tab[:, 1]), 1.0)
+    slow_dev, slow_ref = int(np.sum(s["nit"] > 2)), int(np.sum(sr[:, 0] > 2))
+    assert slow_dev <= slow_ref + max(3, len(A) // 10), (slow_dev, slow_ref)
+    quick = s["nit"] <= 2
+    assert np.all(s["drop"][quick] <= 1e-6 * A[quick]), s["drop"][quick].max()
+    assert np.max(s["drop"] / A) <= 10.0 * max(np.max(sr[:, 2] / A), 1e-6), (np.max(s["drop"] / A), np.max(sr[:, 2] / A))
+    return n_dev, n_ref, slow_dev, slow_ref
+
+
+@pytest.mark.parametrize("disc", ["trapezoid", "SimpsonHermite"])
+def test_c1_as_shipped_ladder(disc):
+    an, s, z = lp.run_c1(disc)
+    assert np.all(an.exitflags == 0)
+    n_dev, n_ref, slow_dev, slow_ref = _check_chain(s, z, disc + "/", 1e-8)
+    # evaluations: the device and SciPy take the same route, so the totals are close
+    nfev_ref = int(z[disc + "/counts"][:, 1].sum())
+    assert abs(int(an.nfev_array.sum()) - nfev_ref) <= 0.15 * nfev_ref
+    print("c1/%s: %d rungs within 1e-6 (reference vs itself: %d); restarts > 2 it: %d (reference: %d); nfev %d vs %d"
+          % (disc, n_dev, n_ref, slow_dev, slow_ref, an.nfev_array.sum(), nfev_ref))
+
+
+@pytest.mark.parametrize("disc", ["trapezoid", "SimpsonHermite"])
+def test_c1_teacher_forced_rungs(disc):
+    """Every rung minimised on the device from the reference's minimiser of the rung before: 101
+    independent minimisations from identical starts, compared with the reference's A of that rung."""
+    from varanneal_b200 import va_ode
+    z = golden_util.load("c1_shipped_ladder_golden.npz")
+    data = golden_util.load("l96_ladder_golden.npz")["data"]
+    alpha, RM, RF0, gtol, ftol = z[disc + "/meta"][:5]
+    tab, mp = z[disc + "/table"], z[disc + "/minpaths"]
+    opts = {"gtol": gtol, "ftol": ftol, "maxfun": 1000000, "maxiter": 1000000}
+    an = va_ode.Annealer()
+    an.set_model("lorenz96", 20)
+    an.set_data(data[:, 1:][:, lp.LIDX_C1], t=data[:, 0])
+    rel = np.zeros(len(tab) - 1)
+    for i in range(1, len(tab)):
+        start = mp[i - 1]
+        an.anneal_init(start[:-1].reshape(161, 20).copy(), start[-1:].copy(), alpha, [int(tab[i, 0])], RM, RF0,
+                       lp.LIDX_C1, [0], dt_model=0.025, init_to_data=False, disc=disc, opt_args=opts)
+        _, Amin, status = an.min_lbfgs_scipy(start)
+        assert status == 0
+        rel[i - 1] = abs(Amin - tab[i, 1]) / abs(tab[i, 1])
+    band, env = _band(z, disc + "/", tab)
+    tol = _tolerance(tab[1:, 1], env[1:], ftol)
+    bad = np.where(rel > tol)[0]
+    assert bad.size == 0, [(int(i + 1), float(rel[i]), float(tol[i])) for i in bad]
+    n6 = int(np.sum(rel <= 1e-6))
+    print("c1/%s teacher-forced: %d of %d rungs within 1e-6, median %.1e, max %.1e" % (disc, n6, len(rel), np.median(rel), rel.max()))
+    assert n6 >= 0.6 * len(rel)
+
+
+def test_c2_slice_ladder():
+    an, s, z = lp.run_c2_slice()
+    assert np.all(an.exitflags == 0)
+    n_dev, n_ref, slow_dev, slow_ref = _check_chain(s, z, "", 1e-8)
+    nfev_ref = int(z["counts"][:, 1].sum())
+    assert abs(int(an.nfev_array.sum()) - nfev_ref) <= 0.25 * nfev_ref
+    print("c2 slice: %d rungs within 1e-6 (reference vs itself: %d); restarts > 2 it: %d (reference: %d); nfev %d vs %d"
+          % (n_dev, n_ref, slow_dev, slow_ref, an.nfev_array.sum(), nfev_ref))

@@ -147,6 +147,33 @@ def test_large_linearity_property_full_size():
     assert np.all(np.abs(fd - gd) <= 1e-6 * np.abs(gd))
 
 
+@pytest.mark.parametrize("disc", ["SimpsonHermite", "rk4"])
+def test_headline_c2_shape_against_oracle(disc):
+    """The exact launch bench.py times (BASELINE.json configs[1]: Lorenz96 D=100, N=5001, L=40,
+    SimpsonHermite, RF = RF0 alpha**10, the twin data and initial paths of bench.py, init_to_data)
+    compared with the oracle on two paths of a 64-path batch: A, me, fe and the gradient to
+    1e-10.  rk4 rides along at the same shape."""
+    import bench
+    from varanneal_b200 import va_ode
+    B = 64
+    _, Y = bench.twin_data()
+    X0, P0 = bench.initial_paths(B, 1000)
+    an = va_ode.Annealer()
+    an.set_model("lorenz96", bench.D)
+    an.set_data(Y, t=bench.DT * np.arange(bench.N_MODEL))
+    an.anneal_init(X0, P0, bench.ALPHA, [bench.BETA_EVAL], bench.RM, bench.RF0, bench.LIDX, [0], disc=disc,
+                   init_to_data=True)
+    XP = np.concatenate([X0.reshape(B, -1), P0], axis=1)          # X0 now carries the data (init_to_data)
+    A, G = an.A_gradA(XP)
+    me, fe = an._me.cpu().numpy(), an._fe.cpu().numpy()
+    prob = OdeProblem("lorenz96", bench.D, Y, bench.LIDX, bench.DT, disc, [bench.K_FORCING], [0], bench.RM)
+    for b in (0, B - 1):
+        Ar, mer, fer, gr = prob.action_grad(XP[b], bench.RF0 * bench.ALPHA ** bench.BETA_EVAL, parts=True)
+        assert abs(A[b] - Ar) <= TOL * abs(Ar)
+        assert abs(fe[b] - fer) <= TOL * abs(fer) and abs(me[b] - mer) <= TOL * max(abs(mer), 1e-300)
+        assert np.max(np.abs(G[b] - gr)) <= TOL * np.max(np.abs(gr))
+
+
 @pytest.mark.parametrize("disc", DISCS)
 def test_edge_shapes_minimal_and_unobserved(disc):
     """Smallest legal problems: N_model = 3 (one Simpson pair), a single observed component, and

@@ -41,6 +41,19 @@ class DeviceMin(object):
     bounds = None
     RF0_scalar = None
     verbose = False
+    # ---- extensions for runs that do not fit the reference's "keep everything" layout
+    # keep_paths: which minimising paths anneal() keeps on the host.
+    #   'all'  (reference, va_ode.py:666-667): minpaths (.., Nbeta, n_states + NP)
+    #   'last' : only the final rung's path, minpaths (.., 1, n_states + NP)
+    #   'none' : no paths, minpaths (.., 0, n_states + NP)
+    # The per-rung *parameter* estimates are always kept (``params_array`` (.., Nbeta, NP)), as are
+    # A / me / fe / exitflags.  paths_file: with 'all', back minpaths by a .npy memory map so the
+    # finished rungs stream to disk instead of host RAM.
+    keep_paths = 'all'
+    paths_file = None
+    # wave_size: initialisations resident on the device at once (None: sized from free device memory)
+    wave_size = None
+    _Btot = 1
 
     # ------------------------------------------------------------------ plumbing
     def _open_context(self, device=None):
@@ -283,61 +296,164 @@ class DeviceMin(object):
             lo, hi, ptr(self._A), ptr(self._me), ptr(self._fe), ptr(self._status),
             ptr(self._nit), ptr(self._nfev)), self._ctx.h)
 
-    # ------------------------------------------------------------------ device-resident ladder
-    def _ladder_fits_device(self):
-        """True when the (B, Nbeta, ld) buffer of minimising paths fits next to the minimiser's
-        workspace; otherwise anneal() walks the rungs from the host (anneal_step)."""
+    # ------------------------------------------------------------------ waves
+    def _per_path_extra_bytes(self):
+        """Device bytes per resident path besides the n-vectors (problem-specific workspaces)."""
+        return 0
+
+    def _plan_wave(self, B, n, Nbeta):
+        """How many of the B initialisations are resident at once.  Per path the device holds
+        XP and the gradient, the minimiser's 2m+4 vectors and -- with keep_paths == 'all' -- the
+        Nbeta minimisers of the ladder; a wave is as many paths as fit in 85 % of the free device
+        memory (C3, n = 1e8: 26 vectors x 0.8 GB -> 7 paths of 128 per GPU at a time).
+        ``wave_size`` / VAB_WAVE override."""
+        import os
         torch = _torch()
+        if self.keep_paths not in ('all', 'last', 'none'):
+            raise ValueError("keep_paths must be 'all', 'last' or 'none'")
+        forced = self.wave_size or int(os.environ.get("VAB_WAVE", "0"))
+        if forced:
+            return max(1, min(int(B), int(forced)))
         free, _ = torch.cuda.mem_get_info(self._device)
         m = int((self.opt_args or {}).get("maxcor", 10))
-        work = (2 * m + 4) * self._B * self._ld * 8
-        return self._B * self.Nbeta * self._ld * 8 + work < 0.8 * free
+        ld = round_up(int(n), 16)
+        nvec = 2 + (2 * m + 4) + (Nbeta if self.keep_paths == 'all' else 0)
+        per = nvec * ld * 8 + self._per_path_extra_bytes()
+        fit = int(0.85 * free // per)
+        if fit < 1:
+            raise MemoryError("one path needs %.1f GB on the device (%d vectors of %d doubles); %.1f GB are free"
+                              % (per / 1e9, nvec, ld, free / 1e9))
+        return min(int(B), fit)
+
+    def _ladder_fits_device(self):
+        """anneal() runs the ladder in native calls, wave by wave (waves are sized by _plan_wave
+        to fit); kept for callers of the round-1 name."""
+        return True
+
+    def _wave_rows(self, w0, bw):
+        """(bw, n) rows X0 ++ P0[Pidx] of initialisations [w0, w0 + bw): from the working copy of
+        X0 made by anneal_init, or from the lazy X0 callable."""
+        raise NotImplementedError
+
+    def _set_wave_fixed_params(self, w0, bw):
+        """Fixed (non-estimated) parameter values of the wave's paths -> the device block the
+        kernels read (va_ode.py:178-181: fixed entries come from self.P)."""
+        torch = _torch()
+        P = np.ascontiguousarray(self.P.reshape(self._Btot, self.NP)[w0:w0 + bw], dtype=np.float64)
+        self._pfix_dev[:bw].copy_(torch.from_numpy(P))
+
+    def _load_wave(self, w0, bw):
+        torch = _torch()
+        rows = self._wave_rows(w0, bw)
+        if not isinstance(rows, torch.Tensor):
+            rows = torch.from_numpy(np.ascontiguousarray(rows, dtype=np.float64))
+        self._XP[:bw, :self._n].copy_(rows)
+        self._set_wave_fixed_params(w0, bw)
+        self._dev_paths_current = False
+
+    def _alloc_results(self, B, Nbeta, n_states, batched):
+        """Host result arrays with the reference's layout (va_ode.py:666-699, va_nnet.py:419-452);
+        a batch adds a leading axis; keep_paths shrinks the rung axis of minpaths."""
+        lead = (B,) if batched else ()
+        nkeep = {'all': Nbeta, 'last': 1, 'none': 0}[self.keep_paths]
+        width = n_states + self.NP
+        if self.paths_file is not None and self.keep_paths == 'all':
+            self.minpaths = np.lib.format.open_memmap(self.paths_file, mode='w+', dtype=np.float64,
+                                                      shape=lead + (nkeep, width))
+        else:
+            self.minpaths = np.zeros(lead + (nkeep, width), dtype=np.float64)
+        shape = lead + (Nbeta,)
+        self.A_array = np.zeros(shape, dtype=np.float64)
+        self.me_array = np.zeros(shape, dtype=np.float64)
+        self.fe_array = np.zeros(shape, dtype=np.float64)
+        self.exitflags = np.zeros(shape, dtype=np.int8)
+        self.nit_array = np.zeros(shape, dtype=np.int64)
+        self.nfev_array = np.zeros(shape, dtype=np.int64)
+        self.params_array = np.zeros(shape + (self.NP,), dtype=np.float64)
+        self.params_array[...] = self.P.reshape(lead + (1, self.NP))
+
+    def _require_resident(self, what):
+        if self._Btot != self._B or self.keep_paths != 'all':
+            raise NotImplementedError(
+                "%s drives the device rung by rung and needs every initialisation resident and "
+                "keep_paths='all' (%d of %d fit); use anneal() without track_* / verbose"
+                % (what, self._B, self._Btot))
 
     def _anneal_device(self):
         """The whole beta loop (reference: anneal + anneal_step, va_ode.py:473-490, 707-789;
-        va_nnet.py:281-286, 459-523) in one native call: ``vab_anneal`` runs every path down the
-        ladder on the device (paths advance rung by rung independently of each other), then the
-        result table and the minimising paths are laid out exactly as the stepwise loop does."""
+        va_nnet.py:281-286, 459-523) in native calls: ``vab_anneal`` runs every resident path down
+        the ladder on the device (paths advance rung by rung independently of each other); the
+        initialisations are processed in waves of ``self._B`` resident paths (one wave when they all
+        fit), and the result table and the minimising paths are laid out exactly as the stepwise
+        loop does."""
         torch = _torch()
-        B, nb, n, nX = self._B, self.Nbeta, self._n, self._nX
-        src = self.minpaths[:, 0] if self.batched else self.minpaths[0][None, :]
-        self._upload_paths(self._est_slice(src))
+        Btot, Bw, nb, n, nX = self._Btot, self._B, self.Nbeta, self._n, self._nX
         method = 1 if getattr(self, "method", "L-BFGS-B") == "NCG" else 0     # TNC never gets here (anneal())
         opts = self._lbfgs_opts(method)
         lo = ptr(getattr(self, "_lo_dev", None)) if method == 0 else None
         hi = ptr(getattr(self, "_hi_dev", None)) if method == 0 else None
         dev = self._device
-        table = torch.zeros(B, nb, 5, dtype=torch.float64, device=dev)
-        paths = torch.empty(B, nb, self._ld, dtype=torch.float64, device=dev)
-        stat = torch.zeros(B, nb, dtype=torch.int32, device=dev)
+        keep = self.keep_paths
+        table = torch.zeros(Bw, nb, 5, dtype=torch.float64, device=dev)
+        stat = torch.zeros(Bw, nb, dtype=torch.int32, device=dev)
         nit = torch.zeros_like(stat)
         nfev = torch.zeros_like(stat)
+        npest = self.NPest
+        ppitch = max(2, (npest + 1) // 2 * 2)
+        if keep == 'all':
+            paths = torch.empty(Bw, nb, self._ld, dtype=torch.float64, device=dev)
+        else:
+            paths = torch.zeros(Bw, nb, ppitch, dtype=torch.float64, device=dev)   # parameter window only
         betas = np.asarray(self.beta_array, dtype=np.float64)
         beta_c = (ct.c_double * nb)(*betas)
         lib, h = self._ctx.lib, self._ctx.h
-        # states go home while the ladder runs: finished rungs are copied from the device rows
-        # (pitch ld) straight into the host rows (pitch nX + NP) of self.minpaths
-        mp = self.minpaths.reshape(B * nb, nX + self.NP)
-        _lib.check(lib.vab_set_path_sink(h, ct.c_void_p(mp.ctypes.data), nX + self.NP, nX), h)
-        _lib.check(lib.vab_anneal(h, B, ptr(self._XP), self._ld, float(self.alpha), beta_c, nb,
-                                  ct.byref(opts), lo, hi, ptr(table), ptr(paths), ptr(stat), ptr(nit),
-                                  ptr(nfev)), h)
-        tab = table.cpu().numpy()
-        shape = self.A_array.shape
-        self.A_array[...] = tab[:, :, 1].reshape(shape)
-        self.me_array[...] = tab[:, :, 2].reshape(shape)
-        self.fe_array[...] = tab[:, :, 3].reshape(shape)
-        self.exitflags[...] = stat.cpu().numpy().reshape(shape)
-        self.nit_array[...] = nit.cpu().numpy().reshape(shape)
-        self.nfev_array[...] = nfev.cpu().numpy().reshape(shape)
-        # parameters: the fixed values with the estimates of every rung written in
-        P = np.broadcast_to(self.P.reshape(B, 1, self.NP), (B, nb, self.NP)).copy()
-        if self.NPest > 0:
-            P[:, :, self.Pidx] = paths[:, :, nX:n].cpu().numpy()
-        mp[:, nX:] = P.reshape(B * nb, self.NP)
-        self.P.reshape(B, self.NP)[...] = P[:, -1]
+        nkeep = self.minpaths.shape[-2]
+        mp_all = self.minpaths.reshape(Btot, nkeep, nX + self.NP)
+        shape = (Btot, nb)
+        A_all, me_all, fe_all = (a.reshape(shape) for a in (self.A_array, self.me_array, self.fe_array))
+        ef_all, nit_all, nfev_all = (a.reshape(shape) for a in (self.exitflags, self.nit_array, self.nfev_array))
+        P_all = self.P.reshape(Btot, self.NP)
+        par_all = self.params_array.reshape(Btot, nb, self.NP)
+        self.n_waves = 0
+        for w0 in range(0, Btot, Bw):
+            bw = min(Bw, Btot - w0)
+            self._load_wave(w0, bw)
+            if keep == 'all':
+                # states go home while the ladder runs: finished rungs are copied from the device
+                # rows (pitch ld) straight into the host rows (pitch nX + NP) of self.minpaths
+                mp = mp_all[w0:w0 + bw].reshape(bw * nb, nX + self.NP)
+                _lib.check(lib.vab_set_path_sink(h, ct.c_void_p(mp.ctypes.data), nX + self.NP, nX), h)
+            else:
+                _lib.check(lib.vab_set_path_window(h, nX, npest), h)
+            _lib.check(lib.vab_anneal(h, bw, ptr(self._XP), self._ld, float(self.alpha), beta_c, nb,
+                                      ct.byref(opts), lo, hi, ptr(table), ptr(paths), ptr(stat), ptr(nit),
+                                      ptr(nfev)), h)
+            tab = table[:bw].cpu().numpy()
+            A_all[w0:w0 + bw] = tab[:, :, 1]
+            me_all[w0:w0 + bw] = tab[:, :, 2]
+            fe_all[w0:w0 + bw] = tab[:, :, 3]
+            ef_all[w0:w0 + bw] = stat[:bw].cpu().numpy()
+            nit_all[w0:w0 + bw] = nit[:bw].cpu().numpy()
+            nfev_all[w0:w0 + bw] = nfev[:bw].cpu().numpy()
+            # parameters: the fixed values with the estimates of every rung written in
+            P = np.broadcast_to(P_all[w0:w0 + bw].reshape(bw, 1, self.NP), (bw, nb, self.NP)).copy()
+            if npest > 0:
+                if keep == 'all':
+                    P[:, :, self.Pidx] = paths[:bw, :, nX:n].cpu().numpy()
+                else:
+                    P[:, :, self.Pidx] = paths[:bw, :, :npest].cpu().numpy()
+            par_all[w0:w0 + bw] = P
+            if keep == 'all':
+                mp_all[w0:w0 + bw, :, nX:] = P
+            elif keep == 'last':
+                # vab_anneal leaves the last rung's minimiser in XP
+                _lib.check(lib.vab_copy_rows_to_host(h, ct.c_void_p(mp_all[w0:w0 + bw].ctypes.data), nX + self.NP,
+                                                     ptr(self._XP), self._ld, nX, bw), h)
+                mp_all[w0:w0 + bw, 0, nX:] = P[:, -1]
+            P_all[w0:w0 + bw] = P[:, -1]
+            self.n_waves += 1
         del paths
-        self._dev_paths_current = True
+        self._dev_paths_current = (Btot == Bw)
         self.betaidx = nb - 1
         self.beta = self.beta_array[-1]
         self.RF = self.RF0 * self.alpha ** float(self.beta)

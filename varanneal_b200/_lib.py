@@ -37,6 +37,8 @@ _SIGS = {
     "vab_sync": (ct.c_int, [_VP]),
     "vab_last_error": (ct.c_char_p, [_VP]),
     "vab_launch_count": (ct.c_longlong, [_VP]),
+    "vab_graph_launch_count": (ct.c_longlong, [_VP]),
+    "vab_measure_fp64_peak": (ct.c_int, [_VP, c_double_p]),
     "vab_ode_problem_set": (ct.c_int, [_VP, ct.POINTER(OdeDesc), c_int_p, c_int_p, _VP, _VP]),
     "vab_ode_set_weights": (ct.c_int, [_VP, ct.c_double, _VP, ct.c_double, _VP]),
     "vab_ode_set_fixed_params": (ct.c_int, [_VP, _VP, ct.c_int64]),
@@ -56,6 +58,7 @@ _SIGS = {
                               _VP]),
     "vab_copy_rows_async": (ct.c_int, [_VP, ct.c_int32, _VP, ct.c_int64, _VP, ct.c_int64, ct.c_int64, ct.c_int64, _VP]),
     "vab_set_path_sink": (ct.c_int, [_VP, _VP, ct.c_int64, ct.c_int64]),
+    "vab_set_path_window": (ct.c_int, [_VP, ct.c_int64, ct.c_int64]),
     "vab_copy_rows_to_host": (ct.c_int, [_VP, _VP, ct.c_int64, _VP, ct.c_int64, ct.c_int64, ct.c_int64]),
 }
 EXPORTS = sorted(_SIGS)
@@ -128,3 +131,12 @@ class Context(object):
     @property
     def launches(self):
         return int(self.lib.vab_launch_count(self.h))
+
+    def fp64_peak_tflops(self):
+        v = ct.c_double(0.0)
+        check(self.lib.vab_measure_fp64_peak(self.h, ct.byref(v)), self.h)
+        return float(v.value)
+
+    @property
+    def graph_launches(self):
+        return int(self.lib.vab_graph_launch_count(self.h))

@@ -78,6 +78,13 @@ struct LbPath {
   // Gram blocks over the history slots and the coefficients of the direction
   double SY[MMAX * MMAX];   // SY[i][j] = s_i . y_j
   double YY[MMAX * MMAX];   // y_i . y_j
+  // bounded problems (lbfgsb_bounded.cuh): S'S, the Cauchy search's c = W'(x^c - x) and M c, the
+  // subspace solution, bookkeeping of the projection / backtracking step
+  double SS[MMAX * MMAX];
+  double cvec[2 * MMAX], Mc[2 * MMAX], wv[2 * MMAX];
+  double tsum, alpha_bt, dtd;
+  long long ibd;
+  int nfree, skip_sub, need_bt, abort_dir;
   double gS[MMAX], gY[MMAX], gg;
   double cs[MMAX], cy[MMAX], cg;
 };
@@ -115,6 +122,7 @@ struct LbfgsWork {
   int* prog_host = nullptr;         // pinned [2][B]
   int prog_cap = 0;
   cudaStream_t copy_stream = nullptr;   // device -> host sink of finished rungs
+  cudaStream_t cap_stream = nullptr;    // records the cycle graph when the context runs on the legacy default stream
 };
 
 namespace {
@@ -137,6 +145,7 @@ __device__ __forceinline__ bool frozen(double x, double g, double lo, double hi)
 __device__ void lb_reset(LbPath& s, double ls_ftol, double ls_gtol, double ls_xtol) {
   s.done = 0; s.need_eval = 1; s.accepted = 0; s.do_update = 0; s.redo_dir = 0; s.first = 1;
   s.xt_ready = 0; s.stp_at = 0.0; s.restore = 0.0;
+  s.tsum = 0.0; s.alpha_bt = 1.0; s.dtd = 0.0; s.ibd = -1; s.nfree = 0; s.skip_sub = 1; s.need_bt = 0; s.abort_dir = 0;
   s.iter = 0; s.nfev = 0; s.col = 0; s.head = 0; s.pslot = 0; s.ifun = 0; s.iback = 0; s.nskip = 0;
   s.status = 2;
   s.f = 0.0; s.fold = 0.0; s.me = 0.0; s.fe = 0.0;
@@ -169,7 +178,8 @@ __global__ void lb_clip_kernel(double* X, long long ld, long long n, const doubl
 // along d, from the step it sits at (stp_at) to the new one; the accepted point then needs no copy.
 __global__ void __launch_bounds__(NT) lb_trial_kernel(double* __restrict__ XT, double* __restrict__ X,
                                                       const double* __restrict__ Dv, long long ld, long long n,
-                                                      const LbPath* __restrict__ st, int nchunk, int inplace) {
+                                                      const LbPath* __restrict__ st, int nchunk, int inplace,
+                                                      const double* __restrict__ Zc) {
   const int b = blockIdx.y;
   const LbPath& s = st[b];
   if (s.done || !s.need_eval || s.xt_ready) return;
@@ -197,6 +207,11 @@ __global__ void __launch_bounds__(NT) lb_trial_kernel(double* __restrict__ XT, d
       if (i + 1 < r.i1) *reinterpret_cast<double2*>(xt + i) = *reinterpret_cast<const double2*>(x + i);
       else xt[i] = x[i];
     }
+    return;
+  }
+  if (Zc != nullptr && stp == 1.0) {   // bounded: the full step is the projected point z itself (lnsrlb: x = z)
+    const double* z = Zc + (long long)b * ld;
+    for (long long i = r.i0 + threadIdx.x; i < r.i1; i += NT) xt[i] = z[i];
     return;
   }
   for (long long i = r.i0 + 2LL * threadIdx.x; i < r.i1; i += 2LL * NT) {
@@ -818,12 +833,18 @@ __global__ void __launch_bounds__(HT + 32, 1) lb_direction_tma_kernel(
   if (tid == 0) pout[2] = BIG;
 }
 
+}  // namespace
+#include "lbfgsb_bounded.cuh"
+namespace {
+
 // start of a line search (lnsrlb, task = START)
 __global__ void lb_start_kernel(LbPath* st, int* act_eval, const double* part, int nchunk, LbOpts o,
-                                int bounded, int b0, int xt_fused) {
+                                int bounded, int b0, int xt_fused, const int* boxed_flag) {
   const int b = b0 + blockIdx.x;
   LbPath& s = st[b];
   if (!(s.accepted || s.redo_dir) || s.done) { if (s.done) { s.accepted = 0; s.redo_dir = 0; s.restore = 0.0; } return; }
+  if (s.abort_dir) { s.abort_dir = 0; return; }       // the direction is formed again next cycle (memory dropped)
+  const int boxed = boxed_flag ? *boxed_flag : 0;
   s.restore = 0.0;
   double dd = 0.0, gd = 0.0, stpmx = BIG;
   for (int c = 0; c < nchunk; ++c) {
@@ -835,6 +856,7 @@ __global__ void lb_start_kernel(LbPath* st, int* act_eval, const double* part, i
   s.redo_dir = 0;
   s.do_update = 0;
   s.dnorm = sqrt(dd);
+  s.dtd = dd;
   s.gdold = gd;
   if (!(gd < 0.0) || !(dd > 0.0)) {
     // not a descent direction (info = -4): drop the memory and restart, or give up
@@ -855,7 +877,7 @@ __global__ void lb_start_kernel(LbPath* st, int* act_eval, const double* part, i
     double a1 = (s.iter == 0) ? 1.01 / s.dnorm : 1.01 * 2.0 * (s.f - s.fprev) / gd;
     if (!(a1 > 0.0)) a1 = 1.0;
     s.stp = fmin(fmin(1.0, a1), stpmx);
-  } else if (s.iter == 0 && !bounded) s.stp = fmin(1.0 / s.dnorm, stpmx);
+  } else if (s.iter == 0 && !(bounded && boxed)) s.stp = fmin(1.0 / s.dnorm, stpmx);   // lnsrlb: iter == 0 and not boxed
   else s.stp = fmin(1.0, stpmx);
   s.fold = s.f;
   s.ifun = 1;
@@ -877,7 +899,9 @@ struct LbLadder {
   const double* betas;       // (Nbeta)
   double* rf_path;           // (B) scale of the rung each path is on (read by the action kernels)
   double* table;             // (B, Nbeta, 5) or nullptr
-  double* minpaths;          // (B, Nbeta, ld) or nullptr
+  double* minpaths;          // (B, Nbeta, mp_pitch) or nullptr
+  long long win0, winw;      // columns [win0, win0 + winw) of each minimiser are stored (vab_set_path_window)
+  long long mp_pitch;        // doubles between stored rows (ld for the full path)
   int *status2, *nit2, *nfev2;   // (B, Nbeta) or nullptr
 };
 
@@ -888,7 +912,13 @@ __global__ void __launch_bounds__(NT) lb_save_kernel(const double* __restrict__ 
   if (!s.done || s.finished) return;
   const Range r = chunk_range(n, nchunk, blockIdx.x);
   const double* x = X + (long long)b * ld;
-  double* o = L.minpaths + ((long long)b * L.Nbeta + s.ib) * ld;
+  double* o = L.minpaths + ((long long)b * L.Nbeta + s.ib) * L.mp_pitch;
+  if (L.winw != n) {                  // a column window (e.g. the estimated parameters only)
+    const long long lo = r.i0 > L.win0 ? r.i0 : L.win0;
+    const long long hi = r.i1 < L.win0 + L.winw ? r.i1 : L.win0 + L.winw;
+    for (long long i = lo + threadIdx.x; i < hi; i += NT) o[i - L.win0] = x[i];
+    return;
+  }
   for (long long i = r.i0 + 2LL * threadIdx.x; i < r.i1; i += 2LL * NT) {
     if (i + 1 < r.i1) *reinterpret_cast<double2*>(o + i) = *reinterpret_cast<const double2*>(x + i);
     else o[i] = x[i];
@@ -958,10 +988,13 @@ __global__ void lb_export_kernel(const LbPath* st, int B, double* A, double* me,
     if (e_ != cudaSuccess) return vab_cuda_fail(ctx, e_, #call);              \
   } while (0)
 
-int lb_reserve(vab_ctx* ctx, int B, long long ld, int m, int Nbeta) {
+int lb_reserve(vab_ctx* ctx, int B, long long ld, int m, int Nbeta, bool need_xt, bool gcp) {
   if (!ctx->lb) ctx->lb = new LbfgsWork();
   LbfgsWork* w = ctx->lb;
-  const size_t nvec = (size_t)(2 * m + 4);
+  // GT, G, D, S[m], Y[m] (+ XT: the trial buffer of the bounded / CG paths; the unbounded L-BFGS
+  // path moves x in place and does without it -- one vector per path less at the C3 scale)
+  // (+ Z, T, R: Cauchy point / projected point, breakpoints, subspace residual of the bounded path)
+  const size_t nvec = (size_t)(2 * m + 3 + (need_xt ? 1 : 0) + (gcp ? 3 : 0));
   const size_t need = nvec * (size_t)B * (size_t)ld;
   int rc = vab_reserve(ctx, &w->vec, &w->vec_cap, need);
   if (rc != VAB_OK) return rc;
@@ -976,7 +1009,7 @@ int lb_reserve(vab_ctx* ctx, int B, long long ld, int m, int Nbeta) {
     w->st_cap = B;
   }
   const int nchunk = lb_nchunk(ctx->n_unknowns(), B);
-  rc = vab_reserve(ctx, &w->part, &w->part_cap, (size_t)B * nchunk * NACC_U);
+  rc = vab_reserve(ctx, &w->part, &w->part_cap, (size_t)B * nchunk * (gcp ? NPB : NACC_U));
   if (rc != VAB_OK) return rc;
   rc = vab_reserve(ctx, &w->lad, &w->lad_cap, (size_t)2 * Nbeta + B);
   if (rc != VAB_OK) return rc;
@@ -989,7 +1022,7 @@ int lb_reserve(vab_ctx* ctx, int B, long long ld, int m, int Nbeta) {
     w->prog_cap = B;
   }
   if (!w->copy_stream) LB_CUDA(cudaStreamCreateWithFlags(&w->copy_stream, cudaStreamNonBlocking));
-  if (!w->n_running_dev) LB_CUDA(cudaMalloc((void**)&w->n_running_dev, 2 * sizeof(int)));
+  if (!w->n_running_dev) LB_CUDA(cudaMalloc((void**)&w->n_running_dev, 3 * sizeof(int)));   // [2] = boxed flag
   if (!w->n_running_host) LB_CUDA(cudaMallocHost((void**)&w->n_running_host, 2 * sizeof(int)));
   for (int k = 0; k < 2; ++k)
     if (!w->ev[k]) LB_CUDA(cudaEventCreateWithFlags(&w->ev[k], cudaEventDisableTiming));
@@ -999,14 +1032,31 @@ int lb_reserve(vab_ctx* ctx, int B, long long ld, int m, int Nbeta) {
 
 // Runs every path down the ladder scales_host[0..Nbeta) (Nbeta = 1: a plain minimisation) from XP,
 // in place; leaves the per-path state of the last rung in w->st.
+struct LbSink { double* host = nullptr; long long pitch = 0, width = 0; long long win0 = 0, winw = -1; };
+// the sink armed by vab_set_path_sink belongs to exactly one call: taken (and cleared) before that
+// call validates anything, so no failure path can leave a stale host pointer behind
+LbSink lb_take_sink(vab_ctx* ctx) {
+  LbSink k;
+  k.host = ctx->sink_host; k.pitch = ctx->sink_pitch; k.width = ctx->sink_width;
+  k.win0 = ctx->win0; k.winw = ctx->winw;
+  ctx->sink_host = nullptr; ctx->sink_pitch = 0; ctx->sink_width = 0;
+  ctx->win0 = 0; ctx->winw = -1;
+  return k;
+}
+
 int lb_run(vab_ctx* ctx, int B, double* XP, long long ld, const double* scales_host,
            const double* betas_host, int Nbeta, const vab_lbfgs_opts* uo, const double* lo,
-           const double* hi, double* table, double* minpaths, int* status2, int* nit2, int* nfev2) {
+           const double* hi, double* table, double* minpaths, int* status2, int* nit2, int* nfev2,
+           LbSink sink_req) {
   const long long n = ctx->n_unknowns();
   if (n <= 0) return vab_fail(ctx, VAB_ERR_STATE, "minimize: no problem set on this context");
   if (B < 1 || !XP || ld < n || (ld & 1)) return vab_fail(ctx, VAB_ERR_INVALID, "minimize: bad batch / XP / ldxp");
   if (((uintptr_t)XP & 15) || ((uintptr_t)minpaths & 15))
     return vab_fail(ctx, VAB_ERR_INVALID, "minimize: XP / minpaths must be 16-byte aligned");
+  const bool windowed = sink_req.winw >= 0 && !(sink_req.win0 == 0 && sink_req.winw == n);
+  if (windowed && (sink_req.win0 < 0 || sink_req.win0 + sink_req.winw > n))
+    return vab_fail(ctx, VAB_ERR_INVALID, "anneal: path window outside [0, n)");
+  if (windowed && sink_req.host) return vab_fail(ctx, VAB_ERR_INVALID, "anneal: a path window and a host sink exclude each other");
   if ((lo == nullptr) != (hi == nullptr)) return vab_fail(ctx, VAB_ERR_INVALID, "minimize: give both bounds or none");
   LbOpts o;
   o.m = uo && uo->m > 0 ? uo->m : 10;
@@ -1025,36 +1075,43 @@ int lb_run(vab_ctx* ctx, int B, double* XP, long long ld, const double* scales_h
     if (!(uo && uo->maxls > 0)) o.maxls = 100;
   }
   int poll = uo && uo->poll_every > 0 ? uo->poll_every : 0;
-  int rc = lb_reserve(ctx, B, ld, o.m, Nbeta);
+  const bool bounded = lo != nullptr;
+  // the TMA-fed history passes serve the unbounded L-BFGS case (VAB_LBFGS_TMA=0: plain kernels)
+  bool use_tma = !bounded && o.method == 0;
+  if (const char* e = getenv("VAB_LBFGS_TMA")) use_tma = use_tma && atoi(e) != 0;
+  // bounded L-BFGS-B: generalised Cauchy point + subspace minimisation (lbfgsb_bounded.cuh);
+  // VAB_BOUNDS=projection selects round 1's active-set projection for comparison
+  bool gcp = bounded && o.method == 0;
+  if (const char* e = getenv("VAB_BOUNDS")) gcp = gcp && strcmp(e, "projection") != 0;
+  int rc = lb_reserve(ctx, B, ld, o.m, Nbeta, !use_tma, gcp);
   if (rc != VAB_OK) return rc;
   LbfgsWork* w = ctx->lb;
   cudaStream_t st = ctx->stream;
   const size_t vs = (size_t)B * (size_t)ld;
-  double* XT = w->vec;
-  double* GT = w->vec + vs;
-  double* G = w->vec + 2 * vs;
-  double* Dv = w->vec + 3 * vs;
-  double* S = w->vec + 4 * vs;
-  double* Y = w->vec + (4 + (size_t)o.m) * vs;
+  double* GT = w->vec;
+  double* G = w->vec + vs;
+  double* Dv = w->vec + 2 * vs;
+  double* S = w->vec + 3 * vs;
+  double* Y = w->vec + (3 + (size_t)o.m) * vs;
+  double* XT = use_tma ? XP : w->vec + (3 + 2 * (size_t)o.m) * vs;   // in-place trials: never dereferenced as a separate buffer
+  double* Zc = gcp ? w->vec + (4 + 2 * (size_t)o.m) * vs : nullptr;
+  double* Tb = gcp ? w->vec + (5 + 2 * (size_t)o.m) * vs : nullptr;
+  double* Rs = gcp ? w->vec + (6 + 2 * (size_t)o.m) * vs : nullptr;
+  int* boxed_dev = w->n_running_dev + 2;
   const long long hstride = (long long)vs;
   const int nchunk = lb_nchunk(n, B);
-  const bool bounded = lo != nullptr;
   const dim3 vgrid(nchunk, B);
-  // the TMA-fed history passes serve the unbounded L-BFGS case (VAB_LBFGS_TMA=0: plain kernels)
-  bool use_tma = !bounded && o.method == 0;
-  if (const char* e = getenv("VAB_LBFGS_TMA")) use_tma = use_tma && atoi(e) != 0;
   // ring depth: 2 stages x 2 CTAs per SM (measured best on B200: C2 update 0.93 ms = 6.7 TB/s,
   // direction 0.75 ms) or 4 stages x 1 CTA per SM (VAB_LBFGS_NS=4: 0.99 / 0.78 ms)
   int hns = 2;
   if (const char* e = getenv("VAB_LBFGS_NS")) hns = atoi(e) == 4 ? 4 : 2;
   if (use_tma) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!ctx->attr_lbfgs) {
       LB_CUDA(cudaFuncSetAttribute(lb_update_tma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem(U_NSTR, 4)));
       LB_CUDA(cudaFuncSetAttribute(lb_direction_tma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem(D_NSTR, 4)));
       LB_CUDA(cudaFuncSetAttribute(lb_update_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem(U_NSTR, 2)));
       LB_CUDA(cudaFuncSetAttribute(lb_direction_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem(D_NSTR, 2)));
-      attr_set = true;
+      ctx->attr_lbfgs = true;
     }
   }
 
@@ -1062,6 +1119,10 @@ int lb_run(vab_ctx* ctx, int B, double* XP, long long ld, const double* scales_h
   L.Nbeta = Nbeta;
   L.scales = w->lad; L.betas = w->lad + Nbeta; L.rf_path = w->lad + 2 * (size_t)Nbeta;
   L.table = table; L.minpaths = minpaths; L.status2 = status2; L.nit2 = nit2; L.nfev2 = nfev2;
+  L.win0 = windowed ? sink_req.win0 : 0;
+  L.winw = windowed ? sink_req.winw : n;
+  L.mp_pitch = windowed ? ((sink_req.winw + 1) & ~1LL) : ld;
+  if (L.mp_pitch < 2) L.mp_pitch = 2;
   {
     std::string tmp((size_t)2 * Nbeta * sizeof(double), '\0');
     double* t = reinterpret_cast<double*>(&tmp[0]);
@@ -1072,6 +1133,8 @@ int lb_run(vab_ctx* ctx, int B, double* XP, long long ld, const double* scales_h
   lb_init_kernel<<<(B + 127) / 128, 128, 0, st>>>(w->st, w->act_eval, B, o.ls_ftol, o.ls_gtol, o.ls_xtol,
                                                    L.scales, L.rf_path);
   if (bounded) lb_clip_kernel<<<dim3((unsigned)((n + 255) / 256), B), 256, 0, st>>>(XP, ld, n, lo, hi);
+  if (bounded) lbb_boxed_kernel<<<1, 256, 0, st>>>(lo, hi, n, boxed_dev);
+  else LB_CUDA(cudaMemsetAsync(boxed_dev, 0, sizeof(int), st));
   LB_CUDA(cudaMemsetAsync(Dv, 0, vs * sizeof(double), st));
   LB_CUDA(cudaMemsetAsync(G, 0, vs * sizeof(double), st));
   ctx->launches += 2;
@@ -1080,51 +1143,92 @@ int lb_run(vab_ctx* ctx, int B, double* XP, long long ld, const double* scales_h
     // small problems are launch-bound (a cycle is ~30 us): poll rarely; large ones take ms per cycle
     poll = (n * (long long)B < (1LL << 22)) ? 64 : 8;
   }
-  auto enqueue_cycle = [&]() -> int {
+  auto enqueue_cycle = [&](cudaStream_t st) -> int {
     const int inplace = use_tma ? 1 : 0;       // unbounded L-BFGS: x moves in place, no trial buffer
-    lb_trial_kernel<<<vgrid, NT, 0, st>>>(XT, XP, Dv, ld, n, w->st, nchunk, inplace);
+    lb_trial_kernel<<<vgrid, NT, 0, st>>>(XT, XP, Dv, ld, n, w->st, nchunk, inplace, Zc);
     int r = vab_eval(ctx, B, inplace ? XP : XT, ld, 1.0, L.rf_path, w->act_eval, w->ft, w->met, w->fet, GT, ld);
     if (r != VAB_OK) return r;
     if (bounded) lb_gd_kernel<true><<<vgrid, NT, 0, st>>>(XT, GT, Dv, ld, n, lo, hi, w->st, nchunk, w->part);
     else lb_gd_kernel<false><<<vgrid, NT, 0, st>>>(XT, GT, Dv, ld, n, lo, hi, w->st, nchunk, w->part);
     lb_linesearch_kernel<<<B, 32, 0, st>>>(w->st, w->act_eval, w->ft, w->met, w->fet, w->part, nchunk, o, bounded ? 1 : 0);
+    if (gcp) {
+      // bounded: update, Cauchy point, subspace minimisation, projection, direction d = z - x
+      lbb_update_kernel<<<vgrid, NT, 0, st>>>(XP, G, XT, GT, Dv, S, Y, ld, n, hstride, w->st, o.m, nchunk, w->part);
+      lbb_hist_kernel<<<B, 32, 0, st>>>(w->st, w->part, nchunk, o.m);
+      lbb_cauchy_prep_kernel<<<vgrid, NT, 0, st>>>(XP, G, Dv, Tb, S, Y, ld, n, hstride, lo, hi, w->st, o.m, nchunk, w->part);
+      lbb_cauchy_loop_kernel<<<B, CLT, 0, st>>>(XP, Dv, Tb, S, Y, ld, n, hstride, lo, hi, w->st, o.m, nchunk, w->part);
+      lbb_gram_free_kernel<<<vgrid, NT, 0, st>>>(Tb, S, Y, ld, n, hstride, w->st, o.m, nchunk, w->part);
+      lbb_resid_kernel<<<vgrid, NT, 0, st>>>(XP, G, Dv, Tb, Zc, Rs, S, Y, ld, n, hstride, lo, hi, w->st, o.m, nchunk, w->part);
+      lbb_subsolve_kernel<<<B, 32, 0, st>>>(w->st, w->part, nchunk, o.m);
+      lbb_step_kernel<<<vgrid, NT, 0, st>>>(XP, G, Tb, Zc, Rs, S, Y, ld, n, hstride, lo, hi, w->st, o.m, nchunk, w->part);
+      lbb_decide_kernel<<<B, 32, 0, st>>>(w->st, w->part, nchunk);
+      lbb_backtrack_kernel<<<vgrid, NT, 0, st>>>(XP, Dv, Tb, Zc, Rs, ld, n, lo, hi, w->st, nchunk);
+      lbb_dir_kernel<<<vgrid, NT, 0, st>>>(XP, G, Dv, Zc, ld, n, lo, hi, w->st, nchunk, w->part);
+      ctx->launches += 9;
+    } else
     if (use_tma && hns == 4) lb_update_tma_kernel<4><<<vgrid, HT + 32, hist_smem(U_NSTR, 4), st>>>(XP, G, GT, Dv, S, Y, ld, n, hstride, w->st, o.m, nchunk, w->part);
     else if (use_tma) lb_update_tma_kernel<2><<<vgrid, HT + 32, hist_smem(U_NSTR, 2), st>>>(XP, G, GT, Dv, S, Y, ld, n, hstride, w->st, o.m, nchunk, w->part);
     else if (bounded) lb_update_kernel<true><<<vgrid, NT, 0, st>>>(XP, G, XT, GT, Dv, S, Y, ld, n, hstride, lo, hi, w->st, o.m, nchunk, w->part, 0);
     else lb_update_kernel<false><<<vgrid, NT, 0, st>>>(XP, G, XT, GT, Dv, S, Y, ld, n, hstride, lo, hi, w->st, o.m, nchunk, w->part, 0);
-    lb_gram_kernel<<<B, 64, 0, st>>>(w->st, w->part, nchunk, o.m, 0, o.method);
+    if (!gcp) lb_gram_kernel<<<B, 64, 0, st>>>(w->st, w->part, nchunk, o.m, 0, o.method);
+    if (gcp) { /* direction formed above */ } else
     if (use_tma && hns == 4) lb_direction_tma_kernel<4><<<vgrid, HT + 32, hist_smem(D_NSTR, 4), st>>>(G, Dv, S, Y, XP, ld, n, hstride, w->st, o.m, nchunk, w->part);
     else if (use_tma) lb_direction_tma_kernel<2><<<vgrid, HT + 32, hist_smem(D_NSTR, 2), st>>>(G, Dv, S, Y, XP, ld, n, hstride, w->st, o.m, nchunk, w->part);
     else if (bounded) lb_direction_kernel<true><<<vgrid, NT, 0, st>>>(XP, G, Dv, S, Y, ld, n, hstride, lo, hi, w->st, o.m, nchunk, w->part, 0);
     else lb_direction_kernel<false><<<vgrid, NT, 0, st>>>(XP, G, Dv, S, Y, ld, n, hstride, lo, hi, w->st, o.m, nchunk, w->part, 0);
-    lb_start_kernel<<<B, 1, 0, st>>>(w->st, w->act_eval, w->part, nchunk, o, bounded ? 1 : 0, 0, use_tma ? 1 : 0);
+    lb_start_kernel<<<B, 1, 0, st>>>(w->st, w->act_eval, w->part, nchunk, o, bounded ? 1 : 0, 0, use_tma ? 1 : 0, boxed_dev);
     if (minpaths) { lb_save_kernel<<<vgrid, NT, 0, st>>>(XP, ld, n, w->st, nchunk, L); ctx->launches += 1; }
     lb_advance_kernel<<<(B + 127) / 128, 128, 0, st>>>(w->st, w->act_eval, B, L, o);
     ctx->launches += 8;
     return VAB_OK;
   };
-  // The first cycle runs eagerly (it may allocate workspaces); the steady-state cycle is then
-  // captured once into a CUDA graph and replayed.
-  rc = enqueue_cycle();
+  // Everything this call owns besides the workspaces: the captured graph, and the guarantee that
+  // neither the context's stream nor the sink's copy stream still touches caller memory when the
+  // call returns -- on every exit path.
+  struct Cleanup {
+    cudaStream_t st, copy;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t gexec = nullptr;
+    ~Cleanup() {
+      cudaStreamSynchronize(st);
+      if (copy) cudaStreamSynchronize(copy);
+      if (gexec) cudaGraphExecDestroy(gexec);
+      if (graph) cudaGraphDestroy(graph);
+    }
+  } own{st, w->copy_stream};
+  // The first cycle runs eagerly (it may allocate workspaces and opt kernels in to large shared
+  // memory); the steady-state cycle is then captured once into a CUDA graph and replayed.  Capture
+  // is illegal on the legacy default stream (which is what PyTorch's current stream is unless the
+  // caller set one): the cycle is then recorded on a private capture stream -- recording executes
+  // nothing -- and the instantiated graph is launched into the context's stream like any kernel.
+  rc = enqueue_cycle(st);
   if (rc != VAB_OK) return rc;
   LB_CUDA(cudaGetLastError());
-  cudaGraph_t graph = nullptr;
-  cudaGraphExec_t gexec = nullptr;
   bool use_graph = true;
   if (const char* e = getenv("VAB_LBFGS_GRAPH")) use_graph = atoi(e) != 0;
   long long launches_per_cycle = 0;
   if (use_graph) {
+    cudaStream_t cap = st;
+    if (st == nullptr || st == cudaStreamLegacy || st == cudaStreamPerThread) {
+      if (!w->cap_stream && cudaStreamCreateWithFlags(&w->cap_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        w->cap_stream = nullptr;
+        cudaGetLastError();
+      }
+      cap = w->cap_stream;
+    }
     const long long l0 = ctx->launches;
-    cudaError_t ce = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+    cudaError_t ce = cap ? cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal) : cudaErrorStreamCaptureUnsupported;
     if (ce == cudaSuccess) {
-      rc = enqueue_cycle();
-      cudaError_t ce2 = cudaStreamEndCapture(st, &graph);
+      ctx->stream = cap;                        // vab_eval launches on the context's stream
+      rc = enqueue_cycle(cap);
+      ctx->stream = st;
+      cudaError_t ce2 = cudaStreamEndCapture(cap, &own.graph);
       launches_per_cycle = ctx->launches - l0;
       ctx->launches = l0;
-      if (rc != VAB_OK || ce2 != cudaSuccess || graph == nullptr ||
-          cudaGraphInstantiate(&gexec, graph, 0) != cudaSuccess) {
-        if (graph) cudaGraphDestroy(graph);
-        graph = nullptr; gexec = nullptr;
+      if (rc != VAB_OK || ce2 != cudaSuccess || own.graph == nullptr ||
+          cudaGraphInstantiate(&own.gexec, own.graph, 0) != cudaSuccess) {
+        if (own.graph) cudaGraphDestroy(own.graph);
+        own.graph = nullptr; own.gexec = nullptr;
         cudaGetLastError();
         if (rc != VAB_OK) return rc;
       }
@@ -1136,9 +1240,8 @@ int lb_run(vab_ctx* ctx, int B, double* XP, long long ld, const double* scales_h
   // the counter of the previous group, so the device never idles on the host (the price is at
   // most one group of empty cycles at the end).
   // host sink (vab_set_path_sink): rows of minpaths are sent home as the paths finish their rungs
-  double* sink = (minpaths != nullptr) ? ctx->sink_host : nullptr;
-  const long long sink_pitch = ctx->sink_pitch, sink_width = ctx->sink_width;
-  ctx->sink_host = nullptr; ctx->sink_pitch = 0; ctx->sink_width = 0;
+  double* sink = (minpaths != nullptr) ? sink_req.host : nullptr;
+  const long long sink_pitch = sink_req.pitch, sink_width = sink_req.width;
   if (sink != nullptr && sink_width > ld) return vab_fail(ctx, VAB_ERR_INVALID, "anneal: sink width > ldxp");
   std::vector<int> sent(sink ? B : 0, 0);
   auto send_rows = [&](const int* prog) -> cudaError_t {
@@ -1163,12 +1266,13 @@ int lb_run(vab_ctx* ctx, int B, double* XP, long long ld, const double* scales_h
   while (true) {
     const int k = (int)(groups & 1);
     for (int c = 0; c < gsize; ++c) {
-      if (gexec) {
-        cudaError_t ge = cudaGraphLaunch(gexec, st);
+      if (own.gexec) {
+        cudaError_t ge = cudaGraphLaunch(own.gexec, st);
         if (ge != cudaSuccess) { rc_loop = vab_cuda_fail(ctx, ge, "cudaGraphLaunch"); break; }
         ctx->launches += launches_per_cycle;
+        ctx->graph_launches += 1;
       } else {
-        rc_loop = enqueue_cycle();
+        rc_loop = enqueue_cycle(st);
         if (rc_loop != VAB_OK) break;
       }
     }
@@ -1199,8 +1303,6 @@ int lb_run(vab_ctx* ctx, int B, double* XP, long long ld, const double* scales_h
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(w->copy_stream);
     if (ce != cudaSuccess) rc_loop = vab_cuda_fail(ctx, ce, "anneal: host sink");
   }
-  if (gexec) cudaGraphExecDestroy(gexec);
-  if (graph) cudaGraphDestroy(graph);
   return rc_loop;
 }
 
@@ -1216,6 +1318,7 @@ void lbfgs_destroy(vab_ctx* ctx) {
   cudaFree(w->fet); cudaFree(w->part); cudaFree(w->n_running_dev); cudaFree(w->lad); cudaFree(w->prog_dev);
   if (w->prog_host) cudaFreeHost(w->prog_host);
   if (w->copy_stream) cudaStreamDestroy(w->copy_stream);
+  if (w->cap_stream) cudaStreamDestroy(w->cap_stream);
   if (w->n_running_host) cudaFreeHost(w->n_running_host);
   for (int k = 0; k < 2; ++k)
     if (w->ev[k]) cudaEventDestroy(w->ev[k]);
@@ -1230,13 +1333,14 @@ int vab_minimize(vab_ctx* ctx, int32_t B, double* XP_dev, int64_t ldxp, double r
                  double* A_dev, double* me_dev, double* fe_dev, int32_t* status_dev,
                  int32_t* nit_dev, int32_t* nfev_dev) {
   if (!ctx) return VAB_ERR_INVALID;
+  (void)lb_take_sink(ctx);                            // a sink only serves vab_anneal
   cudaSetDevice(ctx->device);
   if (opts && opts->method == 2) {                    // truncated Newton (min_tnc_scipy), tnc.cu
     if (lo_dev || hi_dev) return vab_fail(ctx, VAB_ERR_INVALID, "minimize: the device truncated Newton takes no bounds");
     return tnc_minimize(ctx, B, XP_dev, ldxp, rf_scale, opts, A_dev, me_dev, fe_dev, status_dev, nit_dev, nfev_dev);
   }
   int rc = lb_run(ctx, B, XP_dev, ldxp, &rf_scale, nullptr, 1, opts, lo_dev, hi_dev, nullptr, nullptr,
-                  nullptr, nullptr, nullptr);
+                  nullptr, nullptr, nullptr, LbSink());
   if (rc != VAB_OK) return rc;
   lb_export_kernel<<<(B + 127) / 128, 128, 0, ctx->stream>>>(ctx->lb->st, B, A_dev, me_dev, fe_dev,
                                                               status_dev, nit_dev, nfev_dev);
@@ -1251,6 +1355,7 @@ int vab_anneal(vab_ctx* ctx, int32_t B, double* XP_dev, int64_t ldxp, double alp
                const double* lo_dev, const double* hi_dev, double* table_dev, double* minpaths_dev,
                int32_t* status_dev, int32_t* nit_dev, int32_t* nfev_dev) {
   if (!ctx) return VAB_ERR_INVALID;
+  const LbSink sink = lb_take_sink(ctx);              // cleared whatever happens below
   if (!beta_host || Nbeta < 1) return vab_fail(ctx, VAB_ERR_INVALID, "anneal: empty beta ladder");
   if (opts && opts->method == 2)
     return vab_fail(ctx, VAB_ERR_INVALID, "anneal: method 2 (truncated Newton) runs rung by rung through vab_minimize");
@@ -1259,7 +1364,7 @@ int vab_anneal(vab_ctx* ctx, int32_t B, double* XP_dev, int64_t ldxp, double alp
   double* scales = reinterpret_cast<double*>(&buf[0]);
   for (int ib = 0; ib < Nbeta; ++ib) scales[ib] = pow(alpha, beta_host[ib]);
   int rc = lb_run(ctx, B, XP_dev, ldxp, scales, beta_host, Nbeta, opts, lo_dev, hi_dev, table_dev,
-                  minpaths_dev, status_dev, nit_dev, nfev_dev);
+                  minpaths_dev, status_dev, nit_dev, nfev_dev, sink);
   if (rc != VAB_OK) return rc;
   cudaError_t e = cudaStreamSynchronize(ctx->stream);
   if (e != cudaSuccess) return vab_cuda_fail(ctx, e, "vab_anneal");

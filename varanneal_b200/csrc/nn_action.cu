@@ -1072,13 +1072,12 @@ int nn_eval(vab_ctx* ctx, int B, const double* XP, long long ldxp, double rf_sca
       if (rc != VAB_OK) return rc;
       P.partials = ctx->partials; P.gwpart = p->gwpart; P.pfull = p->pfull; P.dbuf = p->dbuf; P.lam = p->lam;
       P.me_parts = all_layers ? nullptr : ctx->partials + (size_t)B * P.nparts * 2;
-      static bool attr_split = false;
-      if (!attr_split) {
+      if (!ctx->attr_nn_split) {
         cudaError_t e = cudaFuncSetAttribute(nn_fb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(nn_gw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(nn_fba_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
         if (e != cudaSuccess) return vab_cuda_fail(ctx, e, "nn_action_grad smem opt-in (split)");
-        attr_split = true;
+        ctx->attr_nn_split = true;
       }
       if (smem_gw > 200 * 1024) return vab_fail(ctx, VAB_ERR_INVALID, "nn_action_grad: internal plan error (gw smem)");
       if (p->NP > 0) nn_gather_params_kernel<<<dim3((p->NP + 255) / 256, B), 256, 0, ctx->stream>>>(P);
@@ -1159,11 +1158,10 @@ int nn_eval(vab_ctx* ctx, int B, const double* XP, long long ldxp, double rf_sca
   P.nparts = P.ntiles;
   P.ngw = P.ntiles;
   if (p->NP > 0) nn_gather_params_kernel<<<dim3((p->NP + 255) / 256, B), 256, 0, ctx->stream>>>(P);
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (!ctx->attr_nn_fused) {
     cudaError_t e = cudaFuncSetAttribute(nn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     if (e != cudaSuccess) return vab_cuda_fail(ctx, e, "nn_action_grad smem opt-in");
-    attr_set = true;
+    ctx->attr_nn_fused = true;
   }
   nn_fused_kernel<<<dim3(P.ntiles, B), NT, smem, ctx->stream>>>(P);
   cudaError_t e = cudaGetLastError();
@@ -1190,9 +1188,16 @@ int vab_nn_problem_set(vab_ctx* ctx, int32_t n_layers, const int32_t* structure_
   if ((n_Lin > 0 && (!Lin_host || !data_in_dev)) || (n_Lout > 0 && (!Lout_host || !data_out_dev)))
     return vab_fail(ctx, VAB_ERR_INVALID, "nn_problem_set: Lidx / data missing");
   cudaStreamSynchronize(ctx->stream);
+  // the old problem goes first; until the new one is complete the context holds no NN problem, so a
+  // failure below leaves it in a state where every later call answers VAB_ERR_STATE
+  if (ctx->problem == VAB_PROBLEM_NN) ctx->problem = VAB_PROBLEM_NONE;
   nn_destroy(ctx);
   NnProblem* p = new NnProblem();
   ctx->nn = p;
+  struct Guard {                       // a half-built problem never survives a failed call
+    vab_ctx* c; bool ok = false;
+    ~Guard() { if (!ok) nn_destroy(c); }
+  } guard{ctx};
   p->NL = n_layers; p->M = M; p->act = activation; p->n_Lin = n_Lin; p->n_Lout = n_Lout;
   p->Ltot = n_Lin + n_Lout;
   std::vector<int> st(structure_host, structure_host + n_layers), xoff(n_layers + 1, 0), woff(n_layers - 1),
@@ -1242,6 +1247,7 @@ int vab_nn_problem_set(vab_ctx* ctx, int32_t n_layers, const int32_t* structure_
   p->pmap = p->ints + o_p; p->slot_in = p->ints + o_si; p->slot_out = p->ints + o_so;
   p->data_in = data_in_dev; p->data_out = data_out_dev;
   p->pfix = p->pfix_zero; p->pfix_stride = 0;
+  guard.ok = true;
   ctx->problem = VAB_PROBLEM_NN;
   return VAB_OK;
 }

@@ -2,6 +2,8 @@
 // (register sweep: ode_sweep.cuh; TMA stream: ode_stream.cuh).
 #include <cuda_runtime.h>
 
+#include <mutex>
+
 #include <cstdlib>
 
 #include "ode_action.h"
@@ -180,13 +182,19 @@ SweepKernel stream_kernel(int C, int disc, bool fast, bool perpath, bool window)
   return nullptr;
 }
 
-// resident CTAs per SM of each kernel at a given dynamic shared memory size (queried once)
+// resident CTAs per SM of each kernel at a given dynamic shared memory size (queried once per
+// device: cudaFuncSetAttribute acts on the current device only, so a second context on another
+// GPU of the same process must opt in again)
 int blocks_per_sm(SweepKernel k, size_t smem, cudaError_t* cerr) {
-  struct Entry { SweepKernel k; size_t smem; int nb; };
-  static Entry seen[128];
+  struct Entry { SweepKernel k; size_t smem; int nb; int dev; };
+  static Entry seen[512];
   static int nseen = 0;
+  static std::mutex mu;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(mu);
   for (int i = 0; i < nseen; ++i)
-    if (seen[i].k == k && seen[i].smem == smem) return seen[i].nb;
+    if (seen[i].k == k && seen[i].smem == smem && seen[i].dev == dev) return seen[i].nb;
   // opt in to the largest dynamic shared memory size once per kernel (a later, smaller request
   // must not lower the limit of an earlier one)
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -197,7 +205,7 @@ int blocks_per_sm(SweepKernel k, size_t smem, cudaError_t* cerr) {
     return -1;
   }
   if (nb < 1) return 0;
-  if (nseen < 128) seen[nseen++] = Entry{k, smem, nb};
+  if (nseen < 512) seen[nseen++] = Entry{k, smem, nb, dev};
   return nb;
 }
 

@@ -87,6 +87,8 @@ const char* vab_last_error(const vab_ctx* ctx) {
 
 long long vab_launch_count(const vab_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+long long vab_graph_launch_count(const vab_ctx* ctx) { return ctx ? ctx->graph_launches : 0; }
+
 int vab_ctx_create(int device, void* stream, vab_ctx** out) {
   if (!out) return vab_fail(nullptr, VAB_ERR_INVALID, "vab_ctx_create: out is NULL");
   *out = nullptr;
@@ -177,6 +179,14 @@ int vab_set_path_sink(vab_ctx* ctx, double* host_dst, int64_t host_pitch, int64_
   return VAB_OK;
 }
 
+int vab_set_path_window(vab_ctx* ctx, int64_t first, int64_t width) {
+  if (!ctx) return VAB_ERR_INVALID;
+  if (width >= 0 && first < 0) return vab_fail(ctx, VAB_ERR_INVALID, "set_path_window: negative first column");
+  ctx->win0 = width >= 0 ? first : 0;
+  ctx->winw = width >= 0 ? width : -1;
+  return VAB_OK;
+}
+
 int vab_copy_rows_to_host(vab_ctx* ctx, double* host_dst, int64_t host_pitch, const double* src_dev,
                           int64_t dev_pitch, int64_t width, int64_t rows) {
   if (!ctx) return VAB_ERR_INVALID;
@@ -236,6 +246,9 @@ int vab_ode_problem_set(vab_ctx* ctx, const vab_ode_desc* d, const int32_t* Lidx
     pmap[k] = e;
   }
   cudaStreamSynchronize(ctx->stream);
+  // from here on the old problem is being taken apart: the context holds no ODE problem until the
+  // new one is complete (a failure below leaves later calls answering VAB_ERR_STATE)
+  if (ctx->problem == VAB_PROBLEM_ODE) ctx->problem = VAB_PROBLEM_NONE;
   cudaFree(ctx->pmap_dev);
   cudaFree(ctx->lcomp_dev);
   cudaFree(ctx->wobs_dev);
@@ -261,7 +274,9 @@ int vab_ode_problem_set(vab_ctx* ctx, const vab_ode_desc* d, const int32_t* Lidx
   ctx->pfix_stride = 0;
   ctx->rf0_scalar = 1.0; ctx->rf0_dev = nullptr;
   ctx->problem = VAB_PROBLEM_ODE;
-  return vab_ode_set_weights(ctx, 1.0, nullptr, 1.0, nullptr);
+  const int rcw = vab_ode_set_weights(ctx, 1.0, nullptr, 1.0, nullptr);
+  if (rcw != VAB_OK) ctx->problem = VAB_PROBLEM_NONE;
+  return rcw;
 }
 
 int vab_ode_set_weights(vab_ctx* ctx, double rm_scalar, const double* rm_dev, double rf0_scalar,

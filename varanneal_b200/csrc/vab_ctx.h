@@ -21,6 +21,9 @@ struct vab_ctx {
   int num_sms = 148;
   std::string err;
   long long launches = 0;
+  long long graph_launches = 0;     // cycles replayed from the captured CUDA graph (vab_graph_launch_count)
+  // cudaFuncSetAttribute opt-ins act on the current device: remembered per context, not per process
+  bool attr_lbfgs = false, attr_nn_split = false, attr_nn_fused = false;
   int problem = VAB_PROBLEM_NONE;
 
   // ---- ODE problem (vab_ode_problem_set / set_weights / set_fixed_params)
@@ -49,6 +52,7 @@ struct vab_ctx {
   // ---- host sink of vab_anneal's minimising paths (vab_set_path_sink); consumed by the next call
   double* sink_host = nullptr;
   long long sink_pitch = 0, sink_width = 0;
+  long long win0 = 0, winw = -1;    // vab_set_path_window (winw < 0: whole paths); consumed by the next call too
 
   // ---- workspaces
   double* partials = nullptr;

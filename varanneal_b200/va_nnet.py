@@ -96,9 +96,10 @@ class Annealer(DeviceMin):
         if not self.annealing_initialized:
             self.anneal_init(X0, P0, alpha, beta_array, RM, RF0, Pidx, Lidx, init_to_data, action,
                              disc, method, bounds, opt_args, adolcID)
-        if not self.verbose and self.betaidx == 0 and self.method != 'TNC' and self._ladder_fits_device():
-            self._anneal_device()           # the whole ladder in one native call
+        if not self.verbose and self.betaidx == 0 and self.method != 'TNC':
+            self._anneal_device()           # the whole ladder in native calls, one per wave of paths
             return
+        self._require_resident("anneal() with verbose / method='TNC'")
         for _ in range(self.Nbeta):
             if self.verbose:
                 print('------------------------------')
@@ -168,30 +169,31 @@ class Annealer(DeviceMin):
             self.RF0 = float(RF0)
         self.RF = self.RF0 * self.alpha ** self.beta
 
-        if init_to_data:                      # in the caller's array (va_nnet.py:427-434)
-            Xv = X0.reshape(B, self.M, self.NDnet)
-            Xv[:, :, self.Lidx[0]] = self.data_in
-            Xv[:, :, self.NDnet - st[-1] + self.Lidx[1]] = self.data_out
+        # float64 working copy of the initial states; init_to_data acts on it and is then written
+        # back into the caller's array (the reference mutates X0 in place, va_nnet.py:427-434) --
+        # a strided or integer X0 can no longer lose the clamp on the way to the device
+        Xw = np.array(X0, dtype=np.float64).reshape(B, self.M, self.NDnet)
+        if init_to_data:
+            Xw[:, :, self.Lidx[0]] = self.data_in
+            Xw[:, :, self.NDnet - st[-1] + self.Lidx[1]] = self.data_out
+            if isinstance(X0, np.ndarray) and X0.flags.writeable:
+                X0[...] = Xw.reshape(X0.shape)
+        if method == 'TNC' and bounds is not None:
+            raise NotImplementedError("method='TNC' on the device takes no bounds; use 'L-BFGS-B' for bounded problems")
 
-        shape = (B, self.Nbeta) if self.batched else (self.Nbeta,)
-        self.minpaths = np.zeros(shape + (self.NDens + NP,), dtype=np.float64)
-        XP0 = np.concatenate([np.asarray(X0, dtype=np.float64).reshape(B, self.NDens),
-                              self.P.reshape(B, NP)], axis=1)
-        if self.batched:
-            self.minpaths[:, 0] = XP0
-        else:
-            self.minpaths[0] = XP0[0]
-        self.A_array = np.zeros(shape)
-        self.me_array = np.zeros(shape)
-        self.fe_array = np.zeros(shape)
-        self.exitflags = np.zeros(shape, dtype=np.int8)
-        self.nit_array = np.zeros(shape, dtype=np.int64)
-        self.nfev_array = np.zeros(shape, dtype=np.int64)
         self.adolcID = adolcID
         self._nX = self.NDens
-
         ctx = self._open_context(self._device_arg)
-        self._alloc_paths(B, self.NDens + self.NPest)
+        self._Btot = B
+        Bw = self._plan_wave(B, self.NDens + self.NPest, self.Nbeta)
+        self._alloc_results(B, self.Nbeta, self.NDens, self.batched)
+        self._Xw = None
+        if self.keep_paths == 'all':             # the reference parks XP0 in minpaths[0] (va_nnet.py:419-421)
+            self.minpaths.reshape(B, self.Nbeta, self.NDens + NP)[:, 0] = np.concatenate(
+                [Xw.reshape(B, self.NDens), self.P.reshape(B, NP)], axis=1)
+        else:
+            self._Xw = Xw.reshape(B, self.NDens)
+        self._alloc_paths(Bw, self.NDens + self.NPest)
         self._din_dev = self._to_dev(self.data_in)
         self._dout_dev = self._to_dev(self.data_out)
         _lib.check(ctx.lib.vab_nn_problem_set(
@@ -199,7 +201,7 @@ class Annealer(DeviceMin):
             self.L[0], _lib.int_array(self.Lidx[0]), self.L[1], _lib.int_array(self.Lidx[1]),
             ptr(self._din_dev), ptr(self._dout_dev), self.NPest, _lib.int_array(self.Pidx)), ctx.h)
         _lib.check(ctx.lib.vab_nn_set_weights(ctx.h, rm_in, rm_out, self.RF0), ctx.h)
-        self._pfix_dev = self._to_dev(self.P.reshape(B, NP))
+        self._pfix_dev = self._to_dev(self.P.reshape(B, NP)[:Bw])
         _lib.check(ctx.lib.vab_nn_set_fixed_params(ctx.h, ptr(self._pfix_dev), NP), ctx.h)
         self._lo_dev = self._hi_dev = None
         if bounds is not None:
@@ -233,8 +235,21 @@ class Annealer(DeviceMin):
     def _est_slice(self, full):
         return np.concatenate([full[:, :self.NDens], full[:, self.NDens:][:, self.Pidx]], axis=1)
 
+    def _per_path_extra_bytes(self):
+        # Delta / lambda side buffers of the split kernels: M x sum(d_1..) doubles each per path
+        return 2 * 8 * self.M * int(np.sum(self.structure[1:]))
+
+    def _wave_rows(self, w0, bw):
+        """Initial XP rows of initialisations [w0, w0 + bw) (see DeviceMin._anneal_device)."""
+        if self._Xw is not None:
+            Pw = self.P.reshape(self._Btot, self.NP)[w0:w0 + bw][:, self.Pidx]
+            return np.concatenate([self._Xw[w0:w0 + bw], Pw], axis=1)
+        mp = self.minpaths.reshape(self._Btot, self.Nbeta, self.NDens + self.NP)
+        return self._est_slice(mp[w0:w0 + bw, 0])
+
     def anneal_step(self):
         """va_nnet.py:459-523."""
+        self._require_resident("anneal_step()")
         B, b = self._B, self.betaidx
         prev = max(b - 1, 0)
         if not self._dev_paths_current:
@@ -257,7 +272,9 @@ class Annealer(DeviceMin):
             self.exitflags[:, b], self.nit_array[:, b], self.nfev_array[:, b] = st, nit, nfev
             self.minpaths[:, b, :self.NDens] = XPmin[:, :self.NDens]
             self.minpaths[:, b, self.NDens:] = P
+            self.params_array[:, b] = P
         else:
+            self.params_array[b] = P[0]
             self.A_array[b], self.me_array[b], self.fe_array[b] = A[0], me[0], fe[0]
             self.exitflags[b], self.nit_array[b], self.nfev_array[b] = st[0], nit[0], nfev[0]
             self.minpaths[b, :self.NDens] = XPmin[0, :self.NDens]

@@ -85,10 +85,10 @@ class Annealer(DeviceMin):
             self.anneal_init(X0, P0, alpha, beta_array, RM, RF0, Lidx, Pidx, dt_model,
                              init_to_data, action, disc, method, bounds, opt_args, adolcID)
         tracked = not (track_paths is None and track_params is None and track_action_errors is None)
-        if (not tracked and not self.verbose and self.betaidx == 0 and self.method != 'TNC'
-                and self._ladder_fits_device()):
-            self._anneal_device()           # the whole ladder in one native call
+        if not tracked and not self.verbose and self.betaidx == 0 and self.method != 'TNC':
+            self._anneal_device()           # the whole ladder in native calls, one per wave of paths
             return
+        self._require_resident("anneal() with track_* / verbose / method='TNC'")
         for _ in range(self.Nbeta):
             if self.verbose:
                 print('------------------------------')
@@ -149,11 +149,24 @@ class Annealer(DeviceMin):
         self.opt_args = opt_args
         N, D = self.N_model, self.D
 
-        # batch detection (extension): X0 (B, N, D)
-        X0 = np.asarray(X0) if not isinstance(X0, np.ndarray) else X0
+        # batch detection (extension): X0 (B, N, D), or a callable X0(b0, b1) -> (b1 - b0, N, D)
+        # (NumPy array or CUDA tensor) that produces the initial paths of a block on demand, for
+        # batches whose initial paths do not fit host memory (C3: 0.8 GB each); P0 (B, NP) then
+        # defines the batch size
         P0 = np.asarray(P0, dtype=np.float64) if not isinstance(P0, np.ndarray) else P0
+        lazy = callable(X0)
+        if lazy:
+            if P0.ndim != 2:
+                raise ValueError("a callable X0 needs P0 of shape (B, NP)")
+            self._X0_fn, self._init_to_data = X0, bool(init_to_data)
+            X0 = np.empty((P0.shape[0], 0, 0))
+        else:
+            self._X0_fn = None
+            X0 = np.asarray(X0) if not isinstance(X0, np.ndarray) else X0
         self.batched = (X0.ndim == 3)
-        if self.batched:
+        if lazy:
+            B = P0.shape[0]
+        elif self.batched:
             B = X0.shape[0]
             if X0.shape[1:] != (N, D):
                 raise ValueError("X0 must have shape (B, %d, %d)" % (N, D))
@@ -232,29 +245,28 @@ class Annealer(DeviceMin):
         self.beta = self.beta_array[0]
         self.RF = self.RF0 * self.alpha ** float(self.beta)
 
-        # initialise observed components to the data, in the caller's array (va_ode.py:677-678)
-        if init_to_data:
-            X0[..., ::self.merr_nskip, self.Lidx] = self.Y
-
-        shape = (B, self.Nbeta) if self.batched else (self.Nbeta,)
-        self.minpaths = np.zeros(shape + (nX + self.NP,), dtype=np.float64)
-        XP0 = np.concatenate([np.asarray(X0, dtype=np.float64).reshape(B, nX),
-                              self.P.reshape(B, self.NP)], axis=1)
-        if self.batched:
-            self.minpaths[:, 0] = XP0
-        else:
-            self.minpaths[0] = XP0[0]
-        self.A_array = np.zeros(shape, dtype=np.float64)
-        self.me_array = np.zeros(shape, dtype=np.float64)
-        self.fe_array = np.zeros(shape, dtype=np.float64)
-        self.exitflags = np.zeros(shape, dtype=np.int8)
-        self.nit_array = np.zeros(shape, dtype=np.int64)
-        self.nfev_array = np.zeros(shape, dtype=np.int64)
-        self.adolcID = adolcID               # accepted and ignored: nothing is taped
-
-        # ---- device side
+        # ---- device side: context first (the wave plan needs the free memory of the device)
         ctx = self._open_context(self._device_arg)
-        self._alloc_paths(B, n)
+        self._Btot = B
+        Bw = self._plan_wave(B, n, self.Nbeta)
+        self._alloc_results(B, self.Nbeta, nX, self.batched)
+
+        # initialise observed components to the data (va_ode.py:677-678): on a float64 working
+        # copy, then written back into the caller's array, which the reference mutates in place
+        self._Xw = None
+        if not lazy:
+            Xw = np.array(X0, dtype=np.float64).reshape(B, N, D)
+            if init_to_data:
+                Xw[:, ::self.merr_nskip, self.Lidx] = self.Y
+                if X0.flags.writeable:
+                    X0[...] = Xw.reshape(X0.shape)
+            if self.keep_paths == 'all':         # the reference parks XP0 in minpaths[0] (va_ode.py:667)
+                self.minpaths.reshape(B, self.Nbeta, nX + self.NP)[:, 0] = np.concatenate(
+                    [Xw.reshape(B, nX), self.P.reshape(B, self.NP)], axis=1)
+            else:
+                self._Xw = Xw.reshape(B, nX)
+        self.adolcID = adolcID               # accepted and ignored: nothing is taped
+        self._alloc_paths(Bw, n)
         self._Y_dev = self._to_dev(self.Y)
         self._stim_dev = None
         n_stim = 0
@@ -273,7 +285,7 @@ class Annealer(DeviceMin):
         _lib.check(ctx.lib.vab_ode_set_weights(
             ctx.h, self.RM if np.isscalar(self.RM) else 0.0, ptr(self._rm_dev),
             self.RF0 if np.isscalar(self.RF0) else 1.0, ptr(self._rf0_dev)), ctx.h)
-        self._pfix_dev = self._to_dev(self.P.reshape(B, self.NP))
+        self._pfix_dev = self._to_dev(self.P.reshape(B, self.NP)[:Bw])
         _lib.check(ctx.lib.vab_ode_set_fixed_params(ctx.h, ptr(self._pfix_dev), self.NP), ctx.h)
         self._lo_dev = self._hi_dev = None
         if lo is not None:
@@ -305,6 +317,28 @@ class Annealer(DeviceMin):
             if sub:
                 _lib.check(ctx.lib.vab_ode_set_fixed_params(ctx.h, ptr(self._pfix_dev), self.NP), ctx.h)
 
+    def _wave_rows(self, w0, bw):
+        """Initial XP rows of initialisations [w0, w0 + bw) (see DeviceMin._anneal_device)."""
+        Pw = self.P.reshape(self._Btot, self.NP)[w0:w0 + bw][:, self.Pidx]
+        if self._X0_fn is None:
+            if self._Xw is not None:
+                return np.concatenate([self._Xw[w0:w0 + bw], Pw], axis=1)
+            mp = self.minpaths.reshape(self._Btot, self.Nbeta, self._nX + self.NP)
+            return self._est_slice(mp[w0:w0 + bw, 0])
+        import torch
+        X = self._X0_fn(w0, w0 + bw)
+        N, D = self.N_model, self.D
+        if isinstance(X, torch.Tensor):
+            X = X.to(device=self._device, dtype=torch.float64).reshape(bw, N, D)
+            if self._init_to_data:
+                Li = torch.as_tensor(self.Lidx, device=self._device)
+                X[:, ::self.merr_nskip, Li] = self._Y_dev
+            return torch.cat([X.reshape(bw, N * D), torch.from_numpy(np.ascontiguousarray(Pw)).to(self._device)], dim=1)
+        X = np.array(X, dtype=np.float64).reshape(bw, N, D)
+        if self._init_to_data:
+            X[:, ::self.merr_nskip, self.Lidx] = self.Y
+        return np.concatenate([X.reshape(bw, N * D), Pw], axis=1)
+
     def _est_slice(self, full):
         """(B, nX+NP) rows X ++ full P  ->  (B, nX+NPest) rows X ++ P[Pidx] (va_ode.py:715-732)."""
         return np.concatenate([full[:, :self._nX], full[:, self._nX:][:, self.Pidx]], axis=1)
@@ -312,6 +346,7 @@ class Annealer(DeviceMin):
     def anneal_step(self):
         """One rung of the ladder (va_ode.py:707-789): minimise from the previous minimiser,
         record A / me / fe / path / parameters, then raise RF."""
+        self._require_resident("anneal_step()")
         B, b = self._B, self.betaidx
         prev = max(b - 1, 0)
         if not self._dev_paths_current:
@@ -338,7 +373,9 @@ class Annealer(DeviceMin):
             self.exitflags[:, b], self.nit_array[:, b], self.nfev_array[:, b] = st, nit, nfev
             self.minpaths[:, b, :self._nX] = XPmin[:, :self._nX]
             self.minpaths[:, b, self._nX:] = P
+            self.params_array[:, b] = P
         else:
+            self.params_array[b] = P[0]
             self.A_array[b], self.me_array[b], self.fe_array[b] = A[0], me[0], fe[0]
             self.exitflags[b], self.nit_array[b], self.nfev_array[b] = st[0], nit[0], nfev[0]
             self.minpaths[b, :self._nX] = XPmin[0, :self._nX]
