@@ -86,6 +86,18 @@ VAB_API long long vab_graph_launch_count(const vab_ctx* ctx);
  * fp64-bound kernels (rk4, NaKL, neural-network contractions), which MEASURED_PEAKS.json lacks. */
 VAB_API int vab_measure_fp64_peak(vab_ctx* ctx, double* tflops_host);
 
+/* Measured prototype of the neural-network contraction on the 5th-generation tensor cores
+ * (csrc/ozaki_gemm.cu): P independent products C_p = A_p B_p^T (A_p: M x K, B_p: N x K, fp64, K <= 128)
+ * computed as an Ozaki split -- 7 int8 digit planes per operand, 28 exact int8 x int8 -> int32 plane
+ * products on tcgen05.mma.kind::i8 with TMEM accumulators, operands brought in by TMA tensor maps,
+ * recombined in fp64 -- on generated data with `spread` octaves of dynamic range inside a row, and
+ * compared with an fp64 FMA reference.  out_host[8]: [max |C - Cref| / max |Cref|, ms digit planes,
+ * ms tcgen05 kernel, ms total, fp64-equivalent TFLOP/s (total), the same for the tcgen05 kernel alone,
+ * ms of the fp64 reference kernel, max |Cref|].  Reference math: the layer contractions of
+ * va_nnet.py:210-255. */
+VAB_API int vab_ozaki_gemm_probe(vab_ctx* ctx, int32_t P, int32_t M, int32_t N, int32_t K, int32_t reps,
+                                 double spread, double* out_host);
+
 /* ---- ODE problem -------------------------------------------------------------------------- */
 /* Everything va_ode.Annealer.anneal_init fixes for a run (va_ode.py:531-705). */
 typedef struct {

@@ -39,6 +39,7 @@ _SIGS = {
     "vab_launch_count": (ct.c_longlong, [_VP]),
     "vab_graph_launch_count": (ct.c_longlong, [_VP]),
     "vab_measure_fp64_peak": (ct.c_int, [_VP, c_double_p]),
+    "vab_ozaki_gemm_probe": (ct.c_int, [_VP, ct.c_int32, ct.c_int32, ct.c_int32, ct.c_int32, ct.c_int32, ct.c_double, c_double_p]),
     "vab_ode_problem_set": (ct.c_int, [_VP, ct.POINTER(OdeDesc), c_int_p, c_int_p, _VP, _VP]),
     "vab_ode_set_weights": (ct.c_int, [_VP, ct.c_double, _VP, ct.c_double, _VP]),
     "vab_ode_set_fixed_params": (ct.c_int, [_VP, _VP, ct.c_int64]),
@@ -136,6 +137,13 @@ class Context(object):
         v = ct.c_double(0.0)
         check(self.lib.vab_measure_fp64_peak(self.h, ct.byref(v)), self.h)
         return float(v.value)
+
+    def ozaki_gemm_probe(self, P, M, N, K, reps=5, spread=8.0):
+        out = (ct.c_double * 8)()
+        check(self.lib.vab_ozaki_gemm_probe(self.h, P, M, N, K, reps, float(spread), out), self.h)
+        keys = ("max_rel_err", "ms_planes", "ms_tcgen05", "ms_total", "tflops_equiv_total", "tflops_equiv_tcgen05",
+                "ms_fp64_reference", "max_abs_C")
+        return dict(zip(keys, [float(v) for v in out]))
 
     @property
     def graph_launches(self):

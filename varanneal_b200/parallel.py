@@ -41,20 +41,52 @@ def gather_blocks(local, n_items, group=None):
     return out[:n_items].cpu().numpy()
 
 
-def anneal_sharded(annealer, X0, P0, *args, group=None, **kwargs):
+def anneal_sharded(annealer, X0, P0, *args, group=None, gather_paths='none', **kwargs):
     """Anneal rank-local slices of a batch (X0 (B, N, D), P0 (B, NP)) and gather the
     (B, Nbeta, 5) action tables [beta, A, me, fe, fe/RF] and the (B, Nbeta, NP) parameters.
-    Positional / keyword arguments after P0 are those of ``Annealer.anneal``."""
+    Positional / keyword arguments after P0 are those of ``Annealer.anneal``.
+
+    ``gather_paths``: 'none' (default: the minimising paths stay with the rank that computed them
+    -- at D = 1000, N = 100000 they are 0.8 GB per path and rung and must not be gathered,
+    SURVEY.md 8(e)), 'last' (the last rung's paths, (B, n_states + NP)) or 'all'
+    ((B, Nbeta, n_states + NP); needs keep_paths == 'all').  With 'last' / 'all' a third array is
+    returned."""
     import torch.distributed as dist
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
-    B = X0.shape[0]
+    B = P0.shape[0] if callable(X0) else X0.shape[0]
     lo, hi = shard_bounds(B, world, rank)
+    nb = len(args[1])
     if hi > lo:
-        annealer.anneal(X0[lo:hi], P0[lo:hi], *args, **kwargs)
+        x_loc = (lambda b0, b1: X0(lo + b0, lo + b1)) if callable(X0) else X0[lo:hi]
+        annealer.anneal(x_loc, P0[lo:hi], *args, **kwargs)
         tables = np.stack([annealer.action_errors_table(init=i) for i in range(hi - lo)])
-        params = annealer.minpaths[:, :, annealer._nX:]
+        params = annealer.params_array if hasattr(annealer, "params_array") else annealer.minpaths[:, :, annealer._nX:]
+        paths = annealer.minpaths
     else:
-        tables = np.zeros((0, len(args[1]), 5))
-        params = np.zeros((0, len(args[1]), P0.shape[1]))
-    return gather_blocks(tables, B, group), gather_blocks(params, B, group)
+        tables = np.zeros((0, nb, 5))
+        params = np.zeros((0, nb, P0.shape[1]))
+        paths = None
+    out = (gather_blocks(tables, B, group), gather_blocks(params, B, group))
+    if gather_paths == 'none':
+        return out
+    if gather_paths not in ('last', 'all'):
+        raise ValueError("gather_paths must be 'none', 'last' or 'all'")
+    import torch
+    width = torch.tensor([0 if paths is None else paths.shape[-1]], dtype=torch.int64)
+    if dist.is_initialized():
+        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+        width = width.to(dev)
+        dist.all_reduce(width, op=dist.ReduceOp.MAX, group=group)
+    w = int(width.item())
+    if paths is None:
+        loc = np.zeros((0, w) if gather_paths == 'last' else (0, nb, w))
+    elif gather_paths == 'last':
+        if paths.shape[-2] == 0:
+            raise ValueError("gather_paths='last' needs keep_paths 'all' or 'last'")
+        loc = paths[:, -1]
+    else:
+        if paths.shape[-2] != nb:
+            raise ValueError("gather_paths='all' needs keep_paths='all'")
+        loc = paths
+    return out + (gather_blocks(loc, B, group),)
