@@ -91,9 +91,11 @@ VAB_API int vab_measure_fp64_peak(vab_ctx* ctx, double* tflops_host);
  * computed as an Ozaki split -- 7 int8 digit planes per operand, 28 exact int8 x int8 -> int32 plane
  * products on tcgen05.mma.kind::i8 with TMEM accumulators, operands brought in by TMA tensor maps,
  * recombined in fp64 -- on generated data with `spread` octaves of dynamic range inside a row, and
- * compared with an fp64 FMA reference.  out_host[8]: [max |C - Cref| / max |Cref|, ms digit planes,
+ * compared with an fp64 FMA reference.  out_host[12]: [max |C - Cref| / max |Cref|, ms digit planes,
  * ms tcgen05 kernel, ms total, fp64-equivalent TFLOP/s (total), the same for the tcgen05 kernel alone,
- * ms of the fp64 reference kernel, max |Cref|].  Reference math: the layer contractions of
+ * ms of the fp64 reference kernel, max |Cref|; then for the persistent, pipelined version of the
+ * kernel: max relative error, ms, TFLOP/s-equivalent of the kernel, of kernel + digit planes].
+ * Reference math: the layer contractions of
  * va_nnet.py:210-255. */
 VAB_API int vab_ozaki_gemm_probe(vab_ctx* ctx, int32_t P, int32_t M, int32_t N, int32_t K, int32_t reps,
                                  double spread, double* out_host);

@@ -128,16 +128,18 @@ def test_nn_split_kernels_agree_with_fused_kernel(structure, M, B, monkeypatch):
     XP = np.concatenate([X0, P0[:, Pidx]], axis=1)
     res = {}
     # "1": split design (small networks: the all-layers tile kernel), "L": split design with the
-    # per-layer kernels forced, "0": fused example-tile kernel
-    for flag, split, alll in (("1", "1", "1"), ("L", "1", "0"), ("0", "0", "1")):
+    # per-layer kernels forced, "0": fused example-tile kernel, "S": the register-tiled CUDA-core
+    # kernel for narrow networks (nn_small.cuh; the default where it applies, i.e. widths <= 64)
+    for flag, split, alll, small in (("1", "1", "1", "0"), ("L", "1", "0", "0"), ("0", "0", "1", "0"), ("S", "1", "1", "1")):
         monkeypatch.setenv("VAB_NN_SPLIT", split)
         monkeypatch.setenv("VAB_NN_ALL_LAYERS", alll)
+        monkeypatch.setenv("VAB_NN_SMALL", small)
         an = _annealer(st, data_in, data_out, X0.copy(), P0.copy(), 1.1, [25.0], [2.0, 0.7], 1e-2, Pidx, Lidx=Lidx)
         l0 = an.gpu_launches
         A, G = an.A_gradA(XP)
         res[flag] = (A.copy(), G.copy(), an.gpu_launches - l0, an.me_gaussian(XP), an.fe_gaussian(XP))
     assert res["1"][2] != res["0"][2]                    # really two different launch sequences
-    for k in ("1", "L"):
+    for k in ("1", "L", "S"):
         assert np.max(np.abs(res[k][0] - res["0"][0]) / np.abs(res["0"][0])) <= 1e-13
         assert np.max(np.abs(res[k][1] - res["0"][1])) <= 1e-12 * np.max(np.abs(res["0"][1]))
         assert np.allclose(res[k][3], res["0"][3], rtol=1e-13) and np.allclose(res[k][4], res["0"][4], rtol=1e-13)

@@ -139,10 +139,11 @@ class Context(object):
         return float(v.value)
 
     def ozaki_gemm_probe(self, P, M, N, K, reps=5, spread=8.0):
-        out = (ct.c_double * 8)()
+        out = (ct.c_double * 12)()
         check(self.lib.vab_ozaki_gemm_probe(self.h, P, M, N, K, reps, float(spread), out), self.h)
         keys = ("max_rel_err", "ms_planes", "ms_tcgen05", "ms_total", "tflops_equiv_total", "tflops_equiv_tcgen05",
-                "ms_fp64_reference", "max_abs_C")
+                "ms_fp64_reference", "max_abs_C", "v2_max_rel_err", "v2_ms_tcgen05", "v2_tflops_equiv_tcgen05",
+                "v2_tflops_equiv_total")
         return dict(zip(keys, [float(v) for v in out]))
 
     @property

@@ -886,6 +886,7 @@ __global__ void nn_reduce_kernel(const __grid_constant__ NnParams P, double* A, 
 }
 
 }  // namespace
+#include "nn_small.cuh"
 
 struct NnProblem {
   int NL = 0, M = 0, NDnet = 0, NP = 0, NPest = 0, act = 0, n_Lin = 0, n_Lout = 0, dmax = 0, d0 = 0;
@@ -953,6 +954,42 @@ int nn_eval(vab_ctx* ctx, int B, const double* XP, long long ldxp, double rf_sca
   P.cf2_den = (double)(p->NDnet - p->d0) * p->M;
   P.rf_path = rf_path_dev;
   P.active = active_dev;
+  // ---- small networks (bar-image class): register-tiled CUDA-core kernel, nn_small.cuh
+  {
+    // Opt-in (VAB_NN_SMALL=1): measured on B200 at the bar-image shape (M = 10 000, 32 paths) it only ties
+    // the tensor-pipe tile kernels -- 0.56 ms vs 0.55 ms per evaluation of the batch -- because half of its
+    // shared-memory wavefronts are bank conflicts on the transposed tiles (profiles/r02_nn_small_ncu.json,
+    // DESIGN.md section 4.4); it stays in the tree as the starting point for that work and is covered by
+    // test_nn_split_kernels_agree_with_fused_kernel.
+    const char* env_small = getenv("VAB_NN_SMALL");
+    NnSmallPlan L;
+    size_t smem_small = 0;
+    if (env_small && atoi(env_small) != 0 && nn_small_plan(p->st_host, p->M, B, ctx->num_sms, ldxp, XP, &L, &smem_small)) {
+      int rc = vab_reserve(ctx, &ctx->partials, &ctx->partials_cap, (size_t)B * L.ncta * 2);
+      if (rc != VAB_OK) return rc;
+      rc = vab_reserve(ctx, &p->gwpart, &p->gwpart_cap, (size_t)B * L.ncta * (p->NP > 0 ? p->NP : 1));
+      if (rc != VAB_OK) return rc;
+      rc = vab_reserve(ctx, &p->pfull, &p->pfull_cap, (size_t)B * (p->NP > 0 ? p->NP : 1));
+      if (rc != VAB_OK) return rc;
+      P.partials = ctx->partials; P.gwpart = p->gwpart; P.pfull = p->pfull;
+      P.nparts = L.ncta; P.ngw = L.ncta;
+      if (!ctx->attr_nn_small) {
+        cudaError_t e = cudaFuncSetAttribute(nn_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
+        if (e != cudaSuccess) return vab_cuda_fail(ctx, e, "nn_action_grad smem opt-in (small)");
+        ctx->attr_nn_small = true;
+      }
+      if (p->NP > 0) nn_gather_params_kernel<<<dim3((p->NP + 255) / 256, B), 256, 0, ctx->stream>>>(P);
+      nn_small_kernel<<<dim3(L.ncta, B), SM_NT, smem_small, ctx->stream>>>(P, L);
+      cudaError_t e = cudaGetLastError();
+      if (e != cudaSuccess) return vab_cuda_fail(ctx, e, "nn_small_kernel launch");
+      const int nk = p->NP > 1 ? p->NP : 1;
+      nn_reduce_kernel<<<dim3((nk + 255) / 256, B), 256, 0, ctx->stream>>>(P, A, me, fe);
+      e = cudaGetLastError();
+      if (e != cudaSuccess) return vab_cuda_fail(ctx, e, "nn_reduce_kernel launch");
+      ctx->launches += 3;
+      return VAB_OK;
+    }
+  }
   // ---- split design when every layer's W fits next to the tiles (and a gradient is wanted)
   {
     const char* env_split = getenv("VAB_NN_SPLIT");            // 0: always the fused kernel

@@ -30,6 +30,7 @@
 
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -69,13 +70,24 @@ __global__ void __launch_bounds__(256) ozaki_slice_kernel(const double* __restri
   int e = 0;
   if (amax > 0.0) { (void)frexp(amax, &e); }           // amax = m 2^e, m in [0.5, 1)  ->  |x| / 2^e < 1
   if (lane == 0) expo[orow] = e;
-  for (int k = lane; k < KP; k += 32) {
-    double t = (k < K) ? ldexp(x[k], 6 - e) : 0.0;     // |t| < 64
+  // lane l owns bytes 4 l .. 4 l + 3 of the 128-byte plane row: one 4-byte store per plane, 128 B per warp
+  {
+    const int k0 = 4 * lane;
+    // 2^(6 - e) assembled from its bits (exact scaling; e is within the normal range for finite data)
+    const double sc = __longlong_as_double((long long)(6 - e + 1023) << 52);
+    double t[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) t[c] = (k0 + c < K) ? x[k0 + c] * sc : 0.0;     // |t| < 64
 #pragma unroll
     for (int s = 0; s < NS; ++s) {
-      const double q = rint(t);
-      out[(long long)s * plane_stride + k] = (int8_t)(int)q;
-      t = (t - q) * 128.0;                             // exact: the remainder has fewer significant bits
+      unsigned pack = 0;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const double qd = rint(t[c]);
+        pack |= ((unsigned)(int)qd & 0xFFu) << (8 * c);
+        t[c] = (t[c] - qd) * 128.0;                    // exact: the remainder has fewer significant bits
+      }
+      *reinterpret_cast<unsigned*>(out + (long long)s * plane_stride + k0) = pack;
     }
   }
 }
@@ -230,6 +242,181 @@ __global__ void __launch_bounds__(128, 1) ozaki_mma_kernel(const __grid_constant
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS) : "memory");
 }
 
+
+// ---- version 2: persistent, warp-specialised, pipelined ---------------------------------------
+// 148 CTAs walk the tiles (128 x 32 outputs).  Warp 0 = TMA producer, warp 1 = MMA issuer, warps
+// 2-5 = epilogue.  Operand ring: 3 stages of one K-half each (7 planes of A: 128 rows x 64 B, 7 of B:
+// 32 rows x 64 B, SWIZZLE_64B; 70 KB per stage) with full / empty mbarriers; two accumulator sets in
+// TMEM (2 x 7 x 32 = 448 columns) with tmem_full / tmem_empty mbarriers, so the TMA loads of the
+// next K-half / tile, the MMAs of this one and the fp64 recombination of the previous tile overlap.
+constexpr int TN2 = 32, KH = 64, NSTG = 3;
+constexpr uint32_t A_PLANE2 = TM * KH, B_PLANE2 = TN2 * KH;
+constexpr uint32_t STAGE2 = NS * (A_PLANE2 + B_PLANE2);                 // 71 680 B
+constexpr uint32_t SMEM2_BYTES = NSTG * STAGE2 + 1024 + 64;
+constexpr uint32_t IDESC_S8_N32 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN2 >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+
+// K-major operand in the SWIZZLE_64B layout: stride byte offset = 8 rows x 64 B = 512 >> 4, layout type 4
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;
+  return d;
+}
+__device__ __forceinline__ void umma_s8_n32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(IDESC_S8_N32), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+__global__ void __launch_bounds__(192, 1) ozaki_mma2_kernel(const __grid_constant__ CUtensorMap mapA,
+                                                            const __grid_constant__ CUtensorMap mapB,
+                                                            const OzakiParams q) {
+  extern __shared__ unsigned char smem_raw[];
+  __shared__ __align__(8) unsigned long long bars[2 * NSTG + 4];
+  __shared__ uint32_t tmem_base_sh;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t sbase = (s32(smem_raw) + 1023u) & ~1023u;
+  auto full = [&](int s) { return s32(&bars[s]); };
+  auto empty = [&](int s) { return s32(&bars[NSTG + s]); };
+  auto tfull = [&](int a) { return s32(&bars[2 * NSTG + a]); };
+  auto tempty = [&](int a) { return s32(&bars[2 * NSTG + 2 + a]); };
+  const int ntiles = q.P * q.m_tiles * q.n_tiles;
+
+  if (tid == 0) {
+    for (int s = 0; s < NSTG; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull(a), 1); mbar_init(tempty(a), 4); }   // 4 epilogue warps
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(&tmem_base_sh)), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_base_sh;
+
+  if (warp == 0) {
+    if (lane == 0) {                                 // ---- TMA producer
+      int it = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        int t = tile;
+        const int nt = t % q.n_tiles; t /= q.n_tiles;
+        const int mt = t % q.m_tiles;
+        const int p = t / q.m_tiles;
+        const int rowA = p * q.Mpad + mt * TM, rowB = p * q.Npad + nt * TN2;
+        for (int h = 0; h < 2; ++h, ++it) {
+          const int s = it % NSTG;
+          if (it >= NSTG) mbar_wait(empty(s), (uint32_t)(((it / NSTG) - 1) & 1));
+          mbar_expect_tx(full(s), STAGE2);
+          const uint32_t base = sbase + s * STAGE2;
+          for (int pl = 0; pl < NS; ++pl) {
+            tma_load_3d(base + pl * A_PLANE2, &mapA, full(s), h * KH, rowA, pl);
+            tma_load_3d(base + NS * A_PLANE2 + pl * B_PLANE2, &mapB, full(s), h * KH, rowB, pl);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {                                 // ---- MMA issuer
+      int it = 0, nt_done = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++nt_done) {
+        const int a = nt_done & 1;
+        if (nt_done >= 2) mbar_wait(tempty(a), (uint32_t)(((nt_done >> 1) - 1) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t acc0 = tmem + (uint32_t)(a * NS * TN2);
+        for (int h = 0; h < 2; ++h, ++it) {
+          const int s = it % NSTG;
+          mbar_wait(full(s), (uint32_t)((it / NSTG) & 1));
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t base = sbase + s * STAGE2;
+          for (int t = 0; t < NS; ++t) {
+            for (int i = 0; i <= t; ++i) {
+              const int j = t - i;
+#pragma unroll
+              for (int k = 0; k < KH / 32; ++k) {
+                const uint64_t da = umma_desc_sw64(base + i * A_PLANE2) + (uint64_t)(2 * k);
+                const uint64_t db = umma_desc_sw64(base + NS * A_PLANE2 + j * B_PLANE2) + (uint64_t)(2 * k);
+                umma_s8_n32(acc0 + (uint32_t)(t * TN2), da, db, (h | i | k) ? 1u : 0u);
+              }
+            }
+          }
+          umma_commit(empty(s));                     // the stage may be refilled once these MMAs have read it
+        }
+        umma_commit(tfull(a));                       // accumulators of this tile complete
+      }
+    }
+  } else {                                           // ---- epilogue warps 2..5: TMEM lanes 32 (warp % 4) ..
+    const int lg = warp & 3;
+    int nt_done = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++nt_done) {
+      int t = tile;
+      const int nt = t % q.n_tiles; t /= q.n_tiles;
+      const int mt = t % q.m_tiles;
+      const int p = t / q.m_tiles;
+      const int a = nt_done & 1;
+      mbar_wait(tfull(a), (uint32_t)((nt_done >> 1) & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int row = mt * TM + lg * 32 + lane;
+      const int ea = q.ea[(long long)p * q.Mpad + row];
+      const uint32_t lane_addr = tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)(a * NS * TN2);
+      double acc[TN2];
+#pragma unroll
+      for (int c = 0; c < TN2; ++c) acc[c] = 0.0;
+#pragma unroll
+      for (int tt = NS - 1; tt >= 0; --tt) {
+        uint32_t v[TN2];
+#pragma unroll
+        for (int c0 = 0; c0 < TN2; c0 += 16) {
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+              : "=r"(v[c0 + 0]), "=r"(v[c0 + 1]), "=r"(v[c0 + 2]), "=r"(v[c0 + 3]), "=r"(v[c0 + 4]), "=r"(v[c0 + 5]),
+                "=r"(v[c0 + 6]), "=r"(v[c0 + 7]), "=r"(v[c0 + 8]), "=r"(v[c0 + 9]), "=r"(v[c0 + 10]), "=r"(v[c0 + 11]),
+                "=r"(v[c0 + 12]), "=r"(v[c0 + 13]), "=r"(v[c0 + 14]), "=r"(v[c0 + 15])
+              : "r"(lane_addr + (uint32_t)(tt * TN2 + c0)));
+        }
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int c = 0; c < TN2; ++c) acc[c] = fma(acc[c], 1.0 / 128.0, (double)(int)v[c]);
+      }
+      // the accumulators are in registers: hand the TMEM set back before the global stores
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty(a));
+      if (row < q.M) {
+        double* out = q.C + ((long long)p * q.M + row) * q.N;
+        const int* ebp = q.eb + (long long)p * q.Npad + nt * TN2;
+#pragma unroll
+        for (int c = 0; c < TN2; ++c) {
+          const int col = nt * TN2 + c;
+          if (col < q.N) {
+            // 2^(ea + eb - 12) assembled from its bits: exact scaling, no ldexp call
+            const long long ex = (long long)(ea + ebp[c] - 12 + 1023);
+            const double sc = __longlong_as_double(ex << 52);
+            out[col] = acc[c] * sc;
+          }
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS) : "memory");
+}
+
 // ---- reference + data for the probe ---------------------------------------------------------
 __global__ void ozaki_fill_kernel(double* x, long long n, unsigned long long seed, double spread) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -272,13 +459,14 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-int make_plane_map(vab_ctx* ctx, EncodeTiledFn enc, CUtensorMap* map, void* base, long long rows_total, int box_rows) {
+int make_plane_map(vab_ctx* ctx, EncodeTiledFn enc, CUtensorMap* map, void* base, long long rows_total, int box_rows,
+                   int box_k = KP, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   const cuuint64_t dims[3] = {(cuuint64_t)KP, (cuuint64_t)rows_total, (cuuint64_t)NS};
   const cuuint64_t strides[2] = {(cuuint64_t)KP, (cuuint64_t)rows_total * KP};          // bytes, dims 1 and 2
-  const cuuint32_t box[3] = {(cuuint32_t)KP, (cuuint32_t)box_rows, 1};
+  const cuuint32_t box[3] = {(cuuint32_t)box_k, (cuuint32_t)box_rows, 1};
   const cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return vab_fail(ctx, VAB_ERR_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
   return VAB_OK;
 }
@@ -291,7 +479,7 @@ int make_plane_map(vab_ctx* ctx, EncodeTiledFn enc, CUtensorMap* map, void* base
 
 }  // namespace
 
-// out_host[8]: 0 max |C - Cref| / max |Cref|, 1 ms digit planes (both operands), 2 ms tcgen05 kernel,
+// out_host[12] (8..11: version 2 -- max rel err, ms, TFLOP/s-equivalent of the kernel, of kernel + planes): 0 max |C - Cref| / max |Cref|, 1 ms digit planes (both operands), 2 ms tcgen05 kernel,
 //              3 ms total, 4 fp64-equivalent TFLOP/s of the total, 5 the same for the tcgen05 kernel alone,
 //              6 ms of the fp64 FMA reference kernel, 7 max |Cref|
 extern "C" int vab_ozaki_gemm_probe(vab_ctx* ctx, int32_t P, int32_t M, int32_t N, int32_t K, int32_t reps,
@@ -309,9 +497,11 @@ extern "C" int vab_ozaki_gemm_probe(vab_ctx* ctx, int32_t P, int32_t M, int32_t 
   int *ea = nullptr, *eb = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   EncodeTiledFn enc = nullptr;
-  CUtensorMap mapA, mapB;
-  OzakiParams q;
-  float ms_slice = 0.f, ms_mma = 0.f, ms_ref = 0.f;
+  CUtensorMap mapA, mapB, mapA2, mapB2;
+  OzakiParams q, q2;
+  float ms_slice = 0.f, ms_mma = 0.f, ms_ref = 0.f, ms_mma2 = 0.f;
+  double err2 = 0.0;
+  int grid2 = ctx->num_sms;
   std::vector<double> herr(2 * 256);
   {
     void* fn = nullptr;
@@ -339,6 +529,11 @@ extern "C" int vab_ozaki_gemm_probe(vab_ctx* ctx, int32_t P, int32_t M, int32_t 
   if (rc != VAB_OK) goto done;
   rc = make_plane_map(ctx, enc, &mapB, pb, rowsB, TN);
   if (rc != VAB_OK) goto done;
+  rc = make_plane_map(ctx, enc, &mapA2, pa, rowsA, TM, KH, CU_TENSOR_MAP_SWIZZLE_64B);
+  if (rc != VAB_OK) goto done;
+  rc = make_plane_map(ctx, enc, &mapB2, pb, rowsB, TN2, KH, CU_TENSOR_MAP_SWIZZLE_64B);
+  if (rc != VAB_OK) goto done;
+  OZ_CUDA(cudaFuncSetAttribute(ozaki_mma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM2_BYTES));
   OZ_CUDA(cudaFuncSetAttribute(ozaki_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
   q.M = M; q.N = N; q.P = P; q.m_tiles = m_tiles; q.n_tiles = n_tiles; q.Mpad = Mpad; q.Npad = Npad;
   q.ea = ea; q.eb = eb; q.C = C;
@@ -365,6 +560,30 @@ extern "C" int vab_ozaki_gemm_probe(vab_ctx* ctx, int32_t P, int32_t M, int32_t 
   OZ_CUDA(cudaMemcpyAsync(herr.data(), errbuf, sizeof(double) * 2 * 256, cudaMemcpyDeviceToHost, st));
   OZ_CUDA(cudaStreamSynchronize(st));
   OZ_CUDA(cudaEventElapsedTime(&ms_ref, ev[0], ev[1]));
+  // ---- version 2 (persistent, pipelined) on the same planes; its result replaces C
+  q2 = q; q2.n_tiles = Npad / TN2;
+  if (const char* g = getenv("VAB_OZAKI_GRID")) grid2 = atoi(g) > 0 ? atoi(g) : grid2;
+  if (grid2 > P * m_tiles * q2.n_tiles) grid2 = P * m_tiles * q2.n_tiles;
+  if (getenv("VAB_OZAKI_V2") == nullptr || atoi(getenv("VAB_OZAKI_V2")) != 0) {
+    OZ_CUDA(cudaMemsetAsync(C, 0, sizeof(double) * (size_t)P * M * N, st));
+    for (int rep = 0; rep <= reps; ++rep) {
+      if (rep == 1) OZ_CUDA(cudaEventRecord(ev[2], st));
+      ozaki_mma2_kernel<<<grid2, 192, SMEM2_BYTES, st>>>(mapA2, mapB2, q2);
+      if (rep == reps) OZ_CUDA(cudaEventRecord(ev[3], st));
+    }
+    OZ_CUDA(cudaGetLastError());
+    OZ_CUDA(cudaEventSynchronize(ev[3]));
+    OZ_CUDA(cudaEventElapsedTime(&ms_mma2, ev[2], ev[3]));
+    ms_mma2 /= reps;
+    std::vector<double> herr2(2 * 256);
+    ozaki_err_kernel<<<256, 256, 0, st>>>(C, Cref, (long long)P * M * N, errbuf);
+    OZ_CUDA(cudaMemcpyAsync(herr2.data(), errbuf, sizeof(double) * 2 * 256, cudaMemcpyDeviceToHost, st));
+    OZ_CUDA(cudaStreamSynchronize(st));
+    double e2 = 0.0, m2 = 0.0;
+    for (int k = 0; k < 256; ++k) { e2 = fmax(e2, herr2[2 * k]); m2 = fmax(m2, herr2[2 * k + 1]); }
+    err2 = m2 > 0.0 ? e2 / m2 : 0.0;
+    ctx->launches += reps + 2;
+  }
   ctx->launches += 3 * (reps + 1) + 4;
   {
     double e = 0.0, m = 0.0;
@@ -375,6 +594,9 @@ extern "C" int vab_ozaki_gemm_probe(vab_ctx* ctx, int32_t P, int32_t M, int32_t 
     out_host[4] = flops / ((ms_slice + ms_mma) * 1e-3) / 1e12;
     out_host[5] = flops / (ms_mma * 1e-3) / 1e12;
     out_host[6] = ms_ref; out_host[7] = m;
+    out_host[8] = err2; out_host[9] = ms_mma2;
+    out_host[10] = ms_mma2 > 0.f ? flops / (ms_mma2 * 1e-3) / 1e12 : 0.0;
+    out_host[11] = ms_mma2 > 0.f ? flops / ((ms_slice + ms_mma2) * 1e-3) / 1e12 : 0.0;
   }
 done:
   for (int k = 0; k < 4; ++k) if (ev[k]) cudaEventDestroy(ev[k]);

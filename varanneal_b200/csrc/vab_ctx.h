@@ -23,7 +23,7 @@ struct vab_ctx {
   long long launches = 0;
   long long graph_launches = 0;     // cycles replayed from the captured CUDA graph (vab_graph_launch_count)
   // cudaFuncSetAttribute opt-ins act on the current device: remembered per context, not per process
-  bool attr_lbfgs = false, attr_nn_split = false, attr_nn_fused = false;
+  bool attr_lbfgs = false, attr_nn_split = false, attr_nn_fused = false, attr_nn_small = false;
   int problem = VAB_PROBLEM_NONE;
 
   // ---- ODE problem (vab_ode_problem_set / set_weights / set_fixed_params)
