@@ -150,16 +150,18 @@ def test_nakl_bounded_ladder(disc):
     tolerances (gtol 1e-11, ftol 1e-13).  The device's generalised-Cauchy-point L-BFGS-B against the
     reference + SciPy ladder: every minimiser inside the box, a constrained stationary point of the
     oracle's action, the same active set size at the top rung, per-beta A within
-    max(1e-6, 10 x the reference's own spread) -- measured 1e-6 ... 1e-5 on 13 of 15 rungs, with the
-    two remaining rungs *below* the reference by 3e-3 (a lower local minimum) before re-joining it."""
+    max(1e-6, 10 x the reference's own spread) -- the reference against its ulp-perturbed twin differs
+    by more than 1e-6 on 10 (trapezoid) / 12 (SimpsonHermite) of the 15 rungs, up to 3.3e-3 at
+    beta = 230; the device: 1e-6 ... 1e-5 on 13 of 15 rungs, 3e-3 *below* the reference on the two
+    rungs around beta = 225 (a lower local minimum) before re-joining it to 4e-6 at the top."""
     an, s, z = lp.run_nakl(disc)
     assert np.all(an.exitflags == 0) and s["inside"]
     tab = z[disc + "/table"]
     band, env = _band(z, disc + "/", tab)
-    tol = np.maximum(_tolerance(tab[:, 1], env, 1e-13), 1e-4)
+    tol = _tolerance(tab[:, 1], env, 1e-13)
     bad = _outside(s["rel"], tol, s["A_dev"], tab[:, 1])
     assert bad.size == 0, [(int(i), float(s["rel"][i]), float(tol[i])) for i in bad]
-    assert np.median(s["rel"]) <= 2e-5, s["rel"]
+    assert np.median(s["rel"]) <= 2e-5 and int(np.sum(s["rel"] <= 1e-5)) >= 8, s["rel"]
     assert np.max(s["oracle_rel"]) <= 1e-10
     assert np.max(s["pg"]) <= 5e-3 and np.median(s["pg"]) <= 1e-4          # constrained stationarity
     assert np.max(s["drop"] / np.maximum(np.abs(tab[:, 1]), 1.0)) <= 1e-4     # SciPy gains nothing to speak of
