@@ -181,7 +181,7 @@ typedef struct {
   int32_t poll_every; /* evaluations enqueued between host polls of the done flag (>=1) */
   int32_t method;     /* 0 = L-BFGS-B (min_lbfgs_scipy), 1 = nonlinear CG, Polak-Ribiere+ (min_cg_scipy,
                          _autodiffmin.py:97-119; ftol / m are ignored), 2 = truncated Newton
-                         (min_tnc_scipy, _autodiffmin.py:121-143; vab_minimize only, no bounds;
+                         (min_tnc_scipy, _autodiffmin.py:121-143; vab_minimize only; bounds through an active set;
                          status = SciPy's TNC return code: 0 local minimum, 1 f converged,
                          2 x converged, 3 evaluation limit, 4 line search failed) */
 } vab_lbfgs_opts;

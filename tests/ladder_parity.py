@@ -30,8 +30,15 @@ from oracle import nnet_port                         # noqa: E402
 LIDX_C1 = [0, 2, 4, 6, 8, 10, 14, 16]
 
 
+RESTART_MAXITER = 60      # enough to tell "stops at once" from "keeps going"; keeps the GPU suite short
+
+
 def restart(action_grad, XP, rf, opts, bounds=None):
-    """SciPy L-BFGS-B on the oracle action from XP: (nit, nfev, A_end, A_start, max|proj g| at XP)."""
+    """SciPy L-BFGS-B on the oracle action from XP: (nit, nfev, A_end, A_start, max|proj g| at XP);
+    at most RESTART_MAXITER iterations (a restart that has not stopped by then counts as slow and its
+    gain is what those iterations achieved)."""
+    opts = dict(opts)
+    opts["maxiter"] = min(int(opts.get("maxiter", RESTART_MAXITER)), RESTART_MAXITER)
     A0, g0 = action_grad(XP, rf)
     if bounds is not None:
         lo, hi = bounds

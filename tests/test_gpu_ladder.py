@@ -231,11 +231,42 @@ def test_tnc_method_reaches_scipy_tnc_minimum():
     XPmin, Amin, status = an1.min_tnc_scipy(np.append(X0[0].ravel(), 8.0))
     assert XPmin.shape == (N * D + 1,) and isinstance(Amin, float) and status in (0, 1, 2)
     assert abs(Amin - an.A_array[0, 0]) <= 1e-9 * abs(Amin)
-    an2 = va_ode.Annealer(); an2.set_model("lorenz96", D); an2.set_data(Y, t=t)
-    an2.anneal_init(X0[0].copy(), np.array([8.0]), 2.0, [8], 1.0, 1e-2, Lidx, [0], disc="trapezoid",
-                    method="TNC", bounds=[[-50.0, 50.0]] * (D + 1), init_to_data=False)
-    with pytest.raises(NotImplementedError):
-        an2.anneal_step()
+
+
+def test_tnc_with_bounds_reaches_scipy_tnc_minimum():
+    """method='TNC' with bounds (the reference forwards them, _autodiffmin.py:133-134): the device's
+    active-set truncated Newton and SciPy's bounded TNC on the oracle action reach the same
+    constrained minimum (1e-6 relative on A), with bounds active at the minimiser."""
+    import scipy.optimize as opt
+    from varanneal_b200 import va_ode
+    rng = np.random.RandomState(12)
+    D, N, B = 8, 31, 2
+    Lidx = list(range(D))
+    t = 0.01 * np.arange(N)
+    Y = 2.0 * rng.randn(N, D)
+    X0 = Y[None] + 0.3 * rng.randn(B, N, D)
+    bounds = [[-1.5, 1.5]] * D + [[8.2, 9.0]]
+    lo = np.concatenate([np.tile([-1.5] * D, N), [8.2]])
+    hi = np.concatenate([np.tile([1.5] * D, N), [9.0]])
+    an = va_ode.Annealer()
+    an.set_model("lorenz96", D)
+    an.set_data(Y, t=t)
+    an.anneal(X0.copy(), np.tile([8.5], (B, 1)), 2.0, [8], 1.0, 1e-2, Lidx, [0], disc="trapezoid", method="TNC",
+              bounds=bounds, init_to_data=False, opt_args={"gtol": 1e-8, "maxfun": 200000})
+    prob = OdeProblem("lorenz96", D, Y, Lidx, 0.01, "trapezoid", [8.0], [0], 1.0)
+    rf = 1e-2 * 2.0 ** 8
+    for b in range(B):
+        xp = np.clip(np.append(X0[b].ravel(), 8.5), lo, hi)
+        res = opt.minimize(lambda z: prob.action_grad(z, rf), xp, method="TNC", jac=True, bounds=list(zip(lo, hi)),
+                           options={"gtol": 1e-10, "maxfun": 200000})
+        xmin = an.minpaths[b, 0]
+        assert np.all(xmin >= lo) and np.all(xmin <= hi)
+        assert abs(an.A_array[b, 0] - res.fun) <= 1e-6 * abs(res.fun), (an.A_array[b, 0], res.fun, an.exitflags[b, 0])
+        A, g = prob.action_grad(xmin, rf)
+        pg = np.where(g < 0, np.maximum(xmin - hi, g), np.minimum(xmin - lo, g))
+        assert abs(A - an.A_array[b, 0]) <= 1e-10 * abs(A) and np.max(np.abs(pg)) <= 1e-5
+        assert int(np.sum(xmin <= lo) + np.sum(xmin >= hi)) > 10            # bounds really are active
+    assert np.all(an.exitflags <= 2), an.exitflags
 
 
 def test_vab_anneal_device_resident_ladder_equals_stepwise():

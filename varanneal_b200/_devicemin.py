@@ -287,10 +287,8 @@ class DeviceMin(object):
         if method is None:
             method = {"NCG": 1, "TNC": 2}.get(getattr(self, "method", "L-BFGS-B"), 0)
         opts = self._lbfgs_opts(method)
-        if method == 2 and getattr(self, "_lo_dev", None) is not None:
-            raise NotImplementedError("method='TNC' on the device takes no bounds; use 'L-BFGS-B' for bounded problems")
-        lo = ptr(getattr(self, "_lo_dev", None)) if method == 0 else None     # SciPy's CG ignores bounds
-        hi = ptr(getattr(self, "_hi_dev", None)) if method == 0 else None
+        lo = ptr(getattr(self, "_lo_dev", None)) if method in (0, 2) else None     # SciPy's CG ignores bounds
+        hi = ptr(getattr(self, "_hi_dev", None)) if method in (0, 2) else None
         _lib.check(self._ctx.lib.vab_minimize(
             self._ctx.h, self._B, ptr(self._XP), self._ld, float(rf_scale), ct.byref(opts),
             lo, hi, ptr(self._A), ptr(self._me), ptr(self._fe), ptr(self._status),
@@ -504,7 +502,7 @@ class DeviceMin(object):
         """Same contract as ADmin.min_tnc_scipy (_autodiffmin.py:121-143), on the device: truncated
         Newton (CG inner solve on gradient-difference Hessian-vector products, More'-Thuente
         search); status = SciPy's TNC return code.  See csrc/tnc.cu for what differs from Nash's
-        TNC.  No bounds."""
+        TNC.  Bounds are honoured (active-set version of the same iteration)."""
         XP0 = np.asarray(XP0, dtype=np.float64)
         single = XP0.ndim == 1
         self._upload_paths(XP0)

@@ -1309,7 +1309,8 @@ int lb_run(vab_ctx* ctx, int B, double* XP, long long ld, const double* scales_h
 }  // namespace
 
 int tnc_minimize(vab_ctx* ctx, int B, double* XP, long long ld, double rf_scale, const vab_lbfgs_opts* uo,
-                 double* A, double* me, double* fe, int* status, int* nit, int* nfev);   // tnc.cu
+                 const double* lo, const double* hi, double* A, double* me, double* fe, int* status, int* nit,
+                 int* nfev);   // tnc.cu
 
 void lbfgs_destroy(vab_ctx* ctx) {
   LbfgsWork* w = ctx->lb;
@@ -1336,8 +1337,7 @@ int vab_minimize(vab_ctx* ctx, int32_t B, double* XP_dev, int64_t ldxp, double r
   (void)lb_take_sink(ctx);                            // a sink only serves vab_anneal
   cudaSetDevice(ctx->device);
   if (opts && opts->method == 2) {                    // truncated Newton (min_tnc_scipy), tnc.cu
-    if (lo_dev || hi_dev) return vab_fail(ctx, VAB_ERR_INVALID, "minimize: the device truncated Newton takes no bounds");
-    return tnc_minimize(ctx, B, XP_dev, ldxp, rf_scale, opts, A_dev, me_dev, fe_dev, status_dev, nit_dev, nfev_dev);
+    return tnc_minimize(ctx, B, XP_dev, ldxp, rf_scale, opts, lo_dev, hi_dev, A_dev, me_dev, fe_dev, status_dev, nit_dev, nfev_dev);
   }
   int rc = lb_run(ctx, B, XP_dev, ldxp, &rf_scale, nullptr, 1, opts, lo_dev, hi_dev, nullptr, nullptr,
                   nullptr, nullptr, nullptr, LbSink());

@@ -14,8 +14,15 @@
 // the bounds of the L-BFGS-B driver): the inner solve is plain CG truncated by the
 // Dembo-Steihaug rule ||r|| <= min(0.5, sqrt||g||) ||g|| without Nash's diagonal/BFGS
 // preconditioner and variable rescaling, the line search is More'-Thuente (dcsrch, ftol 1e-4,
-// gtol 0.25 = TNC's eta) instead of Nash's getptc, and there are no bounds.  Same minima on
-// well-conditioned problems (tests/test_gpu_ladder.py), different iterates.
+// gtol 0.25 = TNC's eta) instead of Nash's getptc.  Same minima on well-conditioned problems
+// (tests/test_gpu_ladder.py), different iterates.
+// Bounds (the reference forwards them, _autodiffmin.py:133-134): an active-set version of the same
+// iteration.  At every outer iterate the variables sitting on a bound with the gradient pushing
+// outward are frozen: the inner CG runs in the subspace of the others (r, v, p are zero on the
+// frozen ones), the line search is limited to the largest feasible step (a free variable that
+// would leave the box at once is dropped from the step), trial points are clipped, and the
+// stopping test uses the projected gradient.  Frozen variables are released as soon as their
+// gradient turns inward at a later outer iterate.
 //
 // Per cycle and path (phase 1 = inner CG, phase 2 = line search):
 //   trial     xt = x + delta v  |  x + stp p                                  (3 vector passes)
@@ -78,6 +85,19 @@ struct TncWork {
 
 namespace {
 
+__device__ __forceinline__ bool tn_frozen(double x, double g, double lo, double hi) {
+  return (x <= lo && g > 0.0) || (x >= hi && g < 0.0);
+}
+__device__ __forceinline__ double tn_projg(double x, double g, double lo, double hi) {
+  return g < 0.0 ? fmax(x - hi, g) : fmin(x - lo, g);
+}
+__global__ void tn_clip_kernel(double* X, long long ld, long long n, const double* lo, const double* hi) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double* x = X + (long long)blockIdx.y * ld;
+  x[i] = fmin(fmax(x[i], lo[i]), hi[i]);
+}
+
 __global__ void tn_init_kernel(TnPath* st, int* act_eval, int B) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
@@ -93,7 +113,8 @@ __global__ void tn_init_kernel(TnPath* st, int* act_eval, int B) {
 __global__ void __launch_bounds__(NT) tn_trial_kernel(double* __restrict__ XT, const double* __restrict__ X,
                                                       const double* __restrict__ V, const double* __restrict__ Pv,
                                                       long long ld, long long n, const TnPath* __restrict__ st,
-                                                      int nchunk) {
+                                                      int nchunk, const double* __restrict__ lo,
+                                                      const double* __restrict__ hi) {
   const int b = blockIdx.y;
   const TnPath& s = st[b];
   if (s.phase == PH_DONE) return;
@@ -101,15 +122,21 @@ __global__ void __launch_bounds__(NT) tn_trial_kernel(double* __restrict__ XT, c
   const long long off = (long long)b * ld;
   const double a = (s.phase == PH_CG) ? s.delta : (s.phase == PH_LS ? s.stp : 0.0);
   const double* w = (s.phase == PH_CG) ? V + off : Pv + off;
-  for (long long i = r.i0 + threadIdx.x; i < r.i1; i += NT)
-    XT[off + i] = (s.phase == PH_FIRST) ? X[off + i] : fma(a, w[i], X[off + i]);
+  const bool clip = lo != nullptr && s.phase == PH_LS;      // line-search points stay inside the box
+  for (long long i = r.i0 + threadIdx.x; i < r.i1; i += NT) {
+    double xt = (s.phase == PH_FIRST) ? X[off + i] : fma(a, w[i], X[off + i]);
+    if (clip) xt = fmin(fmax(xt, lo[i]), hi[i]);
+    XT[off + i] = xt;
+  }
 }
 
 // partials per chunk: [0] v.(gt - g)  [1] gt.p  [2] max|gt|  [3] gt.gt
 __global__ void __launch_bounds__(NT) tn_dots_kernel(const double* __restrict__ GT, const double* __restrict__ G,
                                                      const double* __restrict__ V, const double* __restrict__ Pv,
                                                      long long ld, long long n, const TnPath* __restrict__ st,
-                                                     int nchunk, double* __restrict__ part) {
+                                                     int nchunk, double* __restrict__ part,
+                                                     const double* __restrict__ XT, const double* __restrict__ lo,
+                                                     const double* __restrict__ hi) {
   __shared__ double scratch[8 * NT];
   __shared__ double res[4];
   const int b = blockIdx.y;
@@ -123,8 +150,14 @@ __global__ void __launch_bounds__(NT) tn_dots_kernel(const double* __restrict__ 
     const double gt = GT[off + i];
     if (ph == PH_CG) v[0] = fma(V[off + i], gt - G[off + i], v[0]);
     if (ph == PH_LS) v[1] = fma(gt, Pv[off + i], v[1]);
-    v[2] = fmax(v[2], fabs(gt));
-    v[3] = fma(gt, gt, v[3]);
+    if (lo != nullptr) {                              // bounded: projected gradient, |g|^2 over the free variables
+      const double xt = XT[off + i];
+      v[2] = fmax(v[2], fabs(tn_projg(xt, gt, lo[i], hi[i])));
+      if (!tn_frozen(xt, gt, lo[i], hi[i])) v[3] = fma(gt, gt, v[3]);
+    } else {
+      v[2] = fmax(v[2], fabs(gt));
+      v[3] = fma(gt, gt, v[3]);
+    }
   }
   const int op[4] = {RED_SUM, RED_SUM, RED_MAX, RED_SUM};
   block_reduce<4>(v, op, res, scratch);
@@ -197,13 +230,15 @@ __global__ void __launch_bounds__(NT) tn_update_kernel(double* __restrict__ X, c
                                                        double* __restrict__ R, double* __restrict__ V,
                                                        double* __restrict__ Pv, long long ld, long long n,
                                                        const TnPath* __restrict__ st, int nchunk,
-                                                       double* __restrict__ part) {
+                                                       double* __restrict__ part, const double* __restrict__ lo,
+                                                       const double* __restrict__ hi) {
   __shared__ double scratch[8 * NT];
   __shared__ double res[1];
   const int b = blockIdx.y;
   const TnPath& s = st[b];
   const int act = s.act;
   if (act == ACT_NONE || act == ACT_END) return;
+  const bool bnd = lo != nullptr;
   const Range r = chunk_range(n, nchunk, blockIdx.x);
   const long long off = (long long)b * ld;
   double v[1] = {0.0};
@@ -213,8 +248,9 @@ __global__ void __launch_bounds__(NT) tn_update_kernel(double* __restrict__ X, c
       const double g = GT[off + i];
       if (act == ACT_INIT_MOVE) X[off + i] = x;
       G[off + i] = g;
-      R[off + i] = -g;
-      V[off + i] = -g;
+      const double ng = (bnd && tn_frozen(x, g, lo[i], hi[i])) ? 0.0 : -g;   // frozen variables stay out of the inner solve
+      R[off + i] = ng;
+      V[off + i] = ng;
       Pv[off + i] = 0.0;
       v[0] = fma(x, x, v[0]);
     }
@@ -223,7 +259,8 @@ __global__ void __launch_bounds__(NT) tn_update_kernel(double* __restrict__ X, c
     for (long long i = r.i0 + threadIdx.x; i < r.i1; i += NT) {
       const double vi = V[off + i];
       Pv[off + i] = fma(a, vi, Pv[off + i]);
-      const double ri = fma(-ad, GT[off + i] - G[off + i], R[off + i]);
+      double ri = fma(-ad, GT[off + i] - G[off + i], R[off + i]);
+      if (bnd && tn_frozen(X[off + i], G[off + i], lo[i], hi[i])) ri = 0.0;  // Z'(H v): rows of the frozen variables dropped
       R[off + i] = ri;
       v[0] = fma(ri, ri, v[0]);
     }
@@ -274,18 +311,19 @@ __global__ void tn_decide2_kernel(TnPath* st, const double* part, int nchunk, Tn
 
 // partials per chunk: [0] v.v (new CG direction) | g.p (end of CG)   [1] p.p (end of CG)
 __global__ void __launch_bounds__(NT) tn_dir_kernel(const double* __restrict__ G, const double* __restrict__ R,
-                                                    double* __restrict__ V, const double* __restrict__ Pv,
+                                                    double* __restrict__ V, double* __restrict__ Pv,
                                                     long long ld, long long n, const TnPath* __restrict__ st,
-                                                    int nchunk, double* __restrict__ part) {
+                                                    int nchunk, double* __restrict__ part, const double* __restrict__ X,
+                                                    const double* __restrict__ lo, const double* __restrict__ hi) {
   __shared__ double scratch[8 * NT];
-  __shared__ double res[2];
+  __shared__ double res[3];
   const int b = blockIdx.y;
   const TnPath& s = st[b];
   const int act2 = s.act2;
   if (act2 == ACT2_NONE) return;
   const Range r = chunk_range(n, nchunk, blockIdx.x);
   const long long off = (long long)b * ld;
-  double v[2] = {0.0, 0.0};
+  double v[3] = {0.0, 0.0, BIG};
   if (act2 == ACT2_DIR) {
     const double be = s.beta;
     for (long long i = r.i0 + threadIdx.x; i < r.i1; i += NT) {
@@ -295,15 +333,28 @@ __global__ void __launch_bounds__(NT) tn_dir_kernel(const double* __restrict__ G
     }
   } else {
     for (long long i = r.i0 + threadIdx.x; i < r.i1; i += NT) {
-      const double p = Pv[off + i];
+      double p = Pv[off + i];
+      if (lo != nullptr && p != 0.0) {
+        // largest step that keeps x + stp p inside the box; a variable that would leave at once is dropped
+        const double x = X[off + i];
+        if (p < 0.0 && lo[i] > -DBL_MAX) {
+          const double a2 = lo[i] - x;
+          if (a2 >= 0.0) { p = 0.0; Pv[off + i] = 0.0; }
+          else if (p * v[2] < a2) v[2] = a2 / p;
+        } else if (p > 0.0 && hi[i] < DBL_MAX) {
+          const double a2 = hi[i] - x;
+          if (a2 <= 0.0) { p = 0.0; Pv[off + i] = 0.0; }
+          else if (p * v[2] > a2) v[2] = a2 / p;
+        }
+      }
       v[0] = fma(G[off + i], p, v[0]);
       v[1] = fma(p, p, v[1]);
     }
   }
-  const int op[2] = {RED_SUM, RED_SUM};
-  block_reduce<2>(v, op, res, scratch);
+  const int op[3] = {RED_SUM, RED_SUM, RED_MIN};
+  block_reduce<3>(v, op, res, scratch);
   __syncthreads();
-  if (threadIdx.x < 2) part[((long long)b * nchunk + blockIdx.x) * 2 + threadIdx.x] = res[threadIdx.x];
+  if (threadIdx.x < 3) part[((long long)b * nchunk + blockIdx.x) * 3 + threadIdx.x] = res[threadIdx.x];
 }
 
 __global__ void tn_decide3_kernel(TnPath* st, int* act_eval, const double* part, int nchunk, TnOpts o, int B) {
@@ -312,10 +363,11 @@ __global__ void tn_decide3_kernel(TnPath* st, int* act_eval, const double* part,
   TnPath& s = st[b];
   const int act2 = s.act2;
   if (act2 == ACT2_NONE) return;
-  double a0 = 0.0, a1 = 0.0;
+  double a0 = 0.0, a1 = 0.0, smax = BIG;
   for (int c = 0; c < nchunk; ++c) {
-    a0 += part[((long long)b * nchunk + c) * 2 + 0];
-    a1 += part[((long long)b * nchunk + c) * 2 + 1];
+    a0 += part[((long long)b * nchunk + c) * 3 + 0];
+    a1 += part[((long long)b * nchunk + c) * 3 + 1];
+    smax = fmin(smax, part[((long long)b * nchunk + c) * 3 + 2]);
   }
   if (act2 == ACT2_DIR) {
     s.vv = a0;
@@ -328,9 +380,9 @@ __global__ void tn_decide3_kernel(TnPath* st, int* act_eval, const double* part,
     s.phase = PH_DONE; s.status = 4; act_eval[b] = 0;
     return;
   }
-  s.stpmx = BIG;
+  s.stpmx = smax;                                     // BIG without bounds
   s.pp = pp;
-  s.stp = (s.iter == 0) ? fmin(1.0, 1.0 / sqrt(pp)) : 1.0;
+  s.stp = fmin((s.iter == 0) ? fmin(1.0, 1.0 / sqrt(pp)) : 1.0, smax);
   s.fold = s.f;
   s.ifun = 0;
   dcsrch_start(s, s.f, gp, s.stpmx);
@@ -384,8 +436,10 @@ void tnc_destroy(vab_ctx* ctx) {
 }
 
 int tnc_minimize(vab_ctx* ctx, int B, double* XP, long long ld, double rf_scale, const vab_lbfgs_opts* uo,
-                 double* A, double* me, double* fe, int* status, int* nit, int* nfev) {
+                 const double* lo, const double* hi, double* A, double* me, double* fe, int* status, int* nit,
+                 int* nfev) {
   const long long n = ctx->n_unknowns();
+  if ((lo == nullptr) != (hi == nullptr)) return vab_fail(ctx, VAB_ERR_INVALID, "minimize: give both bounds or none");
   if (n <= 0) return vab_fail(ctx, VAB_ERR_STATE, "minimize: no problem set on this context");
   if (B < 1 || !XP || ld < n || (ld & 1)) return vab_fail(ctx, VAB_ERR_INVALID, "minimize: bad batch / XP / ldxp");
   TnOpts o;
@@ -427,20 +481,21 @@ int tnc_minimize(vab_ctx* ctx, int B, double* XP, long long ld, double rf_scale,
   const dim3 vgrid(nchunk, B);
   const int tb = (B + 127) / 128;
   tn_init_kernel<<<tb, 128, 0, st>>>(w->st, w->act_eval, B);
+  if (lo) tn_clip_kernel<<<dim3((unsigned)((n + 255) / 256), B), 256, 0, st>>>(XP, ld, n, lo, hi);
   TN_CUDA(cudaMemsetAsync(w->vec, 0, 6 * vs * sizeof(double), st));
   const int poll = (n * (long long)B < (1LL << 22)) ? 32 : 8;
   long long cycles = 0;
   const long long max_cycles = o.maxfun + 64;
   while (true) {
     for (int c = 0; c < poll; ++c) {
-      tn_trial_kernel<<<vgrid, NT, 0, st>>>(XT, XP, V, Pv, ld, n, w->st, nchunk);
+      tn_trial_kernel<<<vgrid, NT, 0, st>>>(XT, XP, V, Pv, ld, n, w->st, nchunk, lo, hi);
       rc = vab_eval(ctx, B, XT, ld, rf_scale, nullptr, w->act_eval, w->ft, w->met, w->fet, GT, ld);
       if (rc != VAB_OK) return rc;
-      tn_dots_kernel<<<vgrid, NT, 0, st>>>(GT, G, V, Pv, ld, n, w->st, nchunk, w->part);
+      tn_dots_kernel<<<vgrid, NT, 0, st>>>(GT, G, V, Pv, ld, n, w->st, nchunk, w->part, XT, lo, hi);
       tn_decide1_kernel<<<tb, 128, 0, st>>>(w->st, w->act_eval, w->ft, w->met, w->fet, w->part, nchunk, o, B);
-      tn_update_kernel<<<vgrid, NT, 0, st>>>(XP, XT, G, GT, R, V, Pv, ld, n, w->st, nchunk, w->part);
+      tn_update_kernel<<<vgrid, NT, 0, st>>>(XP, XT, G, GT, R, V, Pv, ld, n, w->st, nchunk, w->part, lo, hi);
       tn_decide2_kernel<<<tb, 128, 0, st>>>(w->st, w->part, nchunk, o, B);
-      tn_dir_kernel<<<vgrid, NT, 0, st>>>(G, R, V, Pv, ld, n, w->st, nchunk, w->part);
+      tn_dir_kernel<<<vgrid, NT, 0, st>>>(G, R, V, Pv, ld, n, w->st, nchunk, w->part, XP, lo, hi);
       tn_decide3_kernel<<<tb, 128, 0, st>>>(w->st, w->act_eval, w->part, nchunk, o, B);
       ctx->launches += 7;
     }

@@ -178,8 +178,6 @@ class Annealer(DeviceMin):
             Xw[:, :, self.NDnet - st[-1] + self.Lidx[1]] = self.data_out
             if isinstance(X0, np.ndarray) and X0.flags.writeable:
                 X0[...] = Xw.reshape(X0.shape)
-        if method == 'TNC' and bounds is not None:
-            raise NotImplementedError("method='TNC' on the device takes no bounds; use 'L-BFGS-B' for bounded problems")
 
         self.adolcID = adolcID
         self._nX = self.NDens

@@ -12,7 +12,8 @@ Differences from the reference, all deliberate:
   * errors raise ``ValueError`` instead of ``print`` + ``sys.exit(1)``.
   * ``exitflags`` is filled with the minimiser's status (the reference never writes it, B3).
   * ``set_data_fromfile`` works (the reference's is broken, B5).
-  * ``method``: 'L-BFGS-B', 'NCG' and 'TNC' run on the device ('TNC' rung by rung, no bounds);
+  * ``method``: 'L-BFGS-B', 'NCG' and 'TNC' run on the device ('TNC' rung by rung; bounds honoured by
+    'L-BFGS-B' as SciPy does and by 'TNC' through an active set);
     'LM' is dead code in the reference (B10).
   * batches: ``X0`` of shape (B, N, D) [+ ``P0`` (B, NP) or (NP,)] anneals B independent
     initialisations concurrently; every result array gains a leading B axis.  With the
