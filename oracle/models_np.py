@@ -8,6 +8,9 @@ gradient needs:
 
     jtv(x, v, p, stim)  ->  J_f(x)^T v      row-wise, shape (N', D)
     ptv(x, v, p, stim)  ->  sum_rows (df/dp)^T v, shape (NP,)
+    ptv_rows(x, v, p, stim) -> the same product row by row, shape (N', NP)  (time-dependent
+                            parameters: ``p`` is then (N', NP), one parameter row per time row,
+                            va_ode.py:170-188)
 
 Sources of the model equations:
   * Lorenz96 : examples/Lorenz96_D20/Lorenz96_anneal.py:15-16
@@ -24,10 +27,15 @@ def _split_pstim(p):
     return p, None
 
 
+def _pc(p, k):
+    """Parameter k: a scalar for static parameters, one value per time row for a (rows, NP) series."""
+    return p[k] if np.ndim(p) == 1 else p[:, k]
+
+
 # --------------------------------------------------------------------------- Lorenz 96
 def lorenz96(t, x, p):
     p, _ = _split_pstim(p)
-    k = p[0] if np.ndim(p) >= 1 else p
+    k = p if np.ndim(p) == 0 else (p[0] if np.ndim(p) == 1 else p[:, 0:1])
     return np.roll(x, 1, 1) * (np.roll(x, -1, 1) - np.roll(x, 2, 1)) - x + k
 
 
@@ -39,12 +47,17 @@ def _l96_jtv(x, v, p, stim=None):
             - r(v, -2) * r(x, -1) - v)
 
 
+def _l96_ptv_rows(x, v, p, stim=None):
+    return np.sum(v, axis=1)[:, None]
+
+
 def _l96_ptv(x, v, p, stim=None):
-    return np.array([np.sum(v)])
+    return np.sum(_l96_ptv_rows(x, v, p, stim), axis=0)
 
 
 lorenz96.jtv = _l96_jtv
 lorenz96.ptv = _l96_ptv
+lorenz96.ptv_rows = _l96_ptv_rows
 lorenz96.NP = 1
 lorenz96.model_name = "lorenz96"
 
@@ -52,7 +65,7 @@ lorenz96.model_name = "lorenz96"
 # --------------------------------------------------------------------------- Lorenz 63
 def lorenz63(t, x, p):
     p, _ = _split_pstim(p)
-    s, r, b = p[0], p[1], p[2]
+    s, r, b = _pc(p, 0), _pc(p, 1), _pc(p, 2)
     out = np.zeros_like(x)
     out[:, 0] = s * (x[:, 1] - x[:, 0])
     out[:, 1] = x[:, 0] * (r - x[:, 2]) - x[:, 1]
@@ -61,7 +74,7 @@ def lorenz63(t, x, p):
 
 
 def _l63_jtv(x, v, p, stim=None):
-    s, r, b = p[0], p[1], p[2]
+    s, r, b = _pc(p, 0), _pc(p, 1), _pc(p, 2)
     out = np.zeros_like(v)
     out[:, 0] = -s * v[:, 0] + (r - x[:, 2]) * v[:, 1] + x[:, 1] * v[:, 2]
     out[:, 1] = s * v[:, 0] - v[:, 1] + x[:, 0] * v[:, 2]
@@ -69,14 +82,17 @@ def _l63_jtv(x, v, p, stim=None):
     return out
 
 
+def _l63_ptv_rows(x, v, p, stim=None):
+    return np.stack([(x[:, 1] - x[:, 0]) * v[:, 0], x[:, 0] * v[:, 1], -x[:, 2] * v[:, 2]], axis=1)
+
+
 def _l63_ptv(x, v, p, stim=None):
-    return np.array([np.sum((x[:, 1] - x[:, 0]) * v[:, 0]),
-                     np.sum(x[:, 0] * v[:, 1]),
-                     np.sum(-x[:, 2] * v[:, 2])])
+    return np.sum(_l63_ptv_rows(x, v, p, stim), axis=0)
 
 
 lorenz63.jtv = _l63_jtv
 lorenz63.ptv = _l63_ptv
+lorenz63.ptv_rows = _l63_ptv_rows
 lorenz63.NP = 3
 lorenz63.model_name = "lorenz63"
 
@@ -90,8 +106,14 @@ def _gate(V, z, Vt, Vs, t1, t2):
     return a, T, zinf, tau
 
 
+def _cols(p):
+    """p[k] -> parameter k for both layouts: (NP,) static, (rows, NP) time series."""
+    return p if np.ndim(p) == 1 else np.asarray(p).T
+
+
 def nakl(t, x, pstim):
     p, Iext = _split_pstim(pstim)
+    p = _cols(p)
     if Iext is None:
         Iext = 0.0
     else:
@@ -133,6 +155,7 @@ def _nakl_partials(x, p):
 
 def _nakl_jtv(x, v, pstim, stim=None):
     p, _ = _split_pstim(pstim)
+    p = _cols(p)
     d = _nakl_partials(x, p)
     out = np.zeros_like(v)
     out[:, 0] = d["dV_V"] * v[:, 0]
@@ -146,28 +169,34 @@ def _nakl_jtv(x, v, pstim, stim=None):
     return out
 
 
-def _nakl_ptv(x, v, pstim, stim=None):
+def _nakl_ptv_rows(x, v, pstim, stim=None):
     p, _ = _split_pstim(pstim)
+    p = _cols(p)
     V, m, h, n = x[:, 0], x[:, 1], x[:, 2], x[:, 3]
     d = _nakl_partials(x, p)
-    g = np.zeros(18, dtype=v.dtype)
-    g[0] = np.sum(m ** 3 * h * (p[3] - V) * v[:, 0])
-    g[1] = np.sum(n ** 4 * (p[4] - V) * v[:, 0])
-    g[2] = np.sum((p[5] - V) * v[:, 0])
-    g[3] = np.sum(p[0] * m ** 3 * h * v[:, 0])
-    g[4] = np.sum(p[1] * n ** 4 * v[:, 0])
-    g[5] = p[2] * np.sum(v[:, 0])
+    g = np.zeros((x.shape[0], 18), dtype=v.dtype)
+    g[:, 0] = m ** 3 * h * (p[3] - V) * v[:, 0]
+    g[:, 1] = n ** 4 * (p[4] - V) * v[:, 0]
+    g[:, 2] = (p[5] - V) * v[:, 0]
+    g[:, 3] = p[0] * m ** 3 * h * v[:, 0]
+    g[:, 4] = p[1] * n ** 4 * v[:, 0]
+    g[:, 5] = p[2] * v[:, 0]
     for c in (1, 2, 3):
         a, dz_a, Vs = d[("a", c)]
-        g[2 + 4 * c] = np.sum(dz_a * (-1.0 / Vs) * v[:, c])
-        g[3 + 4 * c] = np.sum(dz_a * (-a / Vs) * v[:, c])
-        g[4 + 4 * c] = np.sum(d[("t1", c)] * v[:, c])
-        g[5 + 4 * c] = np.sum(d[("t2", c)] * v[:, c])
+        g[:, 2 + 4 * c] = dz_a * (-1.0 / Vs) * v[:, c]
+        g[:, 3 + 4 * c] = dz_a * (-a / Vs) * v[:, c]
+        g[:, 4 + 4 * c] = d[("t1", c)] * v[:, c]
+        g[:, 5 + 4 * c] = d[("t2", c)] * v[:, c]
     return g
+
+
+def _nakl_ptv(x, v, pstim, stim=None):
+    return np.sum(_nakl_ptv_rows(x, v, pstim, stim), axis=0)
 
 
 nakl.jtv = _nakl_jtv
 nakl.ptv = _nakl_ptv
+nakl.ptv_rows = _nakl_ptv_rows
 nakl.NP = 18
 nakl.model_name = "nakl"
 

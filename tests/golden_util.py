@@ -29,6 +29,21 @@ def ode_cases():
     return [ode_case(z, str(n)) for n in z["names"]]
 
 
+def ptime_cases():
+    """Cases of ode_ptime_golden.npz (time-dependent parameters; tests/golden/make_ptime_golden.py).
+    `ref` says whether the values come from the verbatim reference (trapezoid / SimpsonHermite) or
+    are extension vectors of the port (euler / forwardmap: the reference's branches do not run)."""
+    z = load("ode_ptime_golden.npz")
+    out = []
+    for n in z["names"]:
+        n = str(n)
+        alpha, beta, dt, ref = z[n + "/meta"]
+        c = ode_case({k: (z[k] if not k.endswith("/meta") else z[k][:3]) for k in z.files if k.startswith(n + "/")}, n)
+        c["dt_model"], c["ref"] = float(dt), bool(ref)
+        out.append(c)
+    return out
+
+
 def nnet_cases():
     z = load("nnet_action_golden.npz")
     out = []

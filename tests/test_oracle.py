@@ -49,6 +49,22 @@ def test_ode_port_matches_reference_golden(c):
     assert np.max(np.abs(g - c["grad"])) <= 1e-12 * np.max(np.abs(c["grad"]))
 
 
+PTIME_CASES = golden_util.ptime_cases()
+
+
+@pytest.mark.parametrize("c", PTIME_CASES, ids=[c["name"] for c in PTIME_CASES])
+def test_ode_port_time_dependent_parameters_match_reference_golden(c):
+    """P0 of shape (N_model, NP): XP = X.flatten() ++ P[:, Pidx].flatten() (va_ode.py:170-188)."""
+    prob = _problem(c)
+    assert prob.ptime and prob.n == c["grad"].size
+    XP = np.append(c["X0"].ravel(), c["P0"][:, c["Pidx"]].ravel())
+    A, me, fe, g = prob.action_grad(XP, _rf(c, prob), parts=True)
+    assert abs(A - c["A"][0]) <= 1e-13 * abs(c["A"][0])
+    assert abs(me - c["A"][1]) <= 1e-13 * abs(c["A"][1])
+    assert abs(fe - c["A"][2]) <= 1e-13 * abs(c["A"][2])
+    assert np.max(np.abs(g - c["grad"])) <= 1e-12 * np.max(np.abs(c["grad"]))
+
+
 @pytest.mark.parametrize("c", NN_CASES, ids=[c["name"] for c in NN_CASES])
 def test_nnet_port_matches_reference_golden(c):
     st = c["structure"]
