@@ -138,6 +138,19 @@ VAB_API int vab_ode_set_weights(vab_ctx* ctx, double rm_scalar, const double* rm
  * all paths (pfix_stride = 0) or (B, NP) (pfix_stride = NP).  Estimated entries are ignored. */
 VAB_API int vab_ode_set_fixed_params(vab_ctx* ctx, const double* pfix_dev, int64_t pfix_stride);
 
+/* Parameter time series: P0 of shape (N_model, NP) (va_ode.py:568-570).  With enabled != 0 every
+ * path is X (N_model, D) ++ P[:, Pidx] (N_model, NPest), both row-major (va_ode.py:170-188, 688-689),
+ * n = N_model * (D + NPest); row n of the parameters enters every evaluation of f at model time n
+ * (trapezoid va_ode.py:368-369, SimpsonHermite :416-418; euler / forwardmap, whose reference branches
+ * do not run, use the same N_model rows and never read the last).  pfix_dev: (N_model, NP) values of
+ * the parameters that are not estimated, shared (pfix_stride = 0) or per path (N_model * NP); may be
+ * NULL when NPest == NP.  The array must stay alive while the problem is set.  Call after
+ * vab_ode_problem_set (which resets to static parameters); rk4 and rows wider than one lane group
+ * (lorenz96 D > 128) are refused.  enabled == 0 returns to static parameters (fixed values zeroed:
+ * call vab_ode_set_fixed_params again). */
+VAB_API int vab_ode_set_time_dependent(vab_ctx* ctx, int32_t enabled, const double* pfix_dev,
+                                       int64_t pfix_stride);
+
 /* Replaces ADmin.A_gradA_taped (_autodiffmin.py:57-58) -- and tape_A (:32-49), which has no
  * analogue -- for B paths at once, with RF = RF0 * rf_scale (rf_scale = alpha**beta,
  * va_ode.py:650,782).  Outputs (any may be NULL): A_dev[B] action, me_dev[B] measurement error

@@ -333,11 +333,17 @@ class DeviceMin(object):
         X0 made by anneal_init, or from the lazy X0 callable."""
         raise NotImplementedError
 
+    def _lay(self):
+        """(NP, Pidx, NPest, block shape) of the parameter block that follows the states in
+        minpaths rows (full block) and in XP (estimated entries).  A parameter time series
+        (va_ode: P0 of shape (N_model, NP)) overrides this with the flattened (N_model, NP) block."""
+        return self.NP, self.Pidx, self.NPest, (self.NP,)
+
     def _set_wave_fixed_params(self, w0, bw):
         """Fixed (non-estimated) parameter values of the wave's paths -> the device block the
         kernels read (va_ode.py:178-181: fixed entries come from self.P)."""
         torch = _torch()
-        P = np.ascontiguousarray(self.P.reshape(self._Btot, self.NP)[w0:w0 + bw], dtype=np.float64)
+        P = np.ascontiguousarray(self.P.reshape(self._Btot, self._lay()[0])[w0:w0 + bw], dtype=np.float64)
         self._pfix_dev[:bw].copy_(torch.from_numpy(P))
 
     def _load_wave(self, w0, bw):
@@ -354,7 +360,8 @@ class DeviceMin(object):
         a batch adds a leading axis; keep_paths shrinks the rung axis of minpaths."""
         lead = (B,) if batched else ()
         nkeep = {'all': Nbeta, 'last': 1, 'none': 0}[self.keep_paths]
-        width = n_states + self.NP
+        NPl, _, _, pshape = self._lay()
+        width = n_states + NPl
         if self.paths_file is not None and self.keep_paths == 'all':
             self.minpaths = np.lib.format.open_memmap(self.paths_file, mode='w+', dtype=np.float64,
                                                       shape=lead + (nkeep, width))
@@ -367,8 +374,9 @@ class DeviceMin(object):
         self.exitflags = np.zeros(shape, dtype=np.int8)
         self.nit_array = np.zeros(shape, dtype=np.int64)
         self.nfev_array = np.zeros(shape, dtype=np.int64)
-        self.params_array = np.zeros(shape + (self.NP,), dtype=np.float64)
-        self.params_array[...] = self.P.reshape(lead + (1, self.NP))
+        self.params_array = np.zeros(shape + (NPl,), dtype=np.float64)
+        self.params_array[...] = self.P.reshape(lead + (1, NPl))
+        self.params_array = self.params_array.reshape(shape + pshape)
 
     def _require_resident(self, what):
         if self._Btot != self._B or self.keep_paths != 'all':
@@ -396,7 +404,7 @@ class DeviceMin(object):
         stat = torch.zeros(Bw, nb, dtype=torch.int32, device=dev)
         nit = torch.zeros_like(stat)
         nfev = torch.zeros_like(stat)
-        npest = self.NPest
+        NPl, Pidxl, npest, _ = self._lay()
         ppitch = max(2, (npest + 1) // 2 * 2)
         if keep == 'all':
             paths = torch.empty(Bw, nb, self._ld, dtype=torch.float64, device=dev)
@@ -406,12 +414,12 @@ class DeviceMin(object):
         beta_c = (ct.c_double * nb)(*betas)
         lib, h = self._ctx.lib, self._ctx.h
         nkeep = self.minpaths.shape[-2]
-        mp_all = self.minpaths.reshape(Btot, nkeep, nX + self.NP)
+        mp_all = self.minpaths.reshape(Btot, nkeep, nX + NPl)
         shape = (Btot, nb)
         A_all, me_all, fe_all = (a.reshape(shape) for a in (self.A_array, self.me_array, self.fe_array))
         ef_all, nit_all, nfev_all = (a.reshape(shape) for a in (self.exitflags, self.nit_array, self.nfev_array))
-        P_all = self.P.reshape(Btot, self.NP)
-        par_all = self.params_array.reshape(Btot, nb, self.NP)
+        P_all = self.P.reshape(Btot, NPl)
+        par_all = self.params_array.reshape(Btot, nb, NPl)
         self.n_waves = 0
         for w0 in range(0, Btot, Bw):
             bw = min(Bw, Btot - w0)
@@ -419,8 +427,8 @@ class DeviceMin(object):
             if keep == 'all':
                 # states go home while the ladder runs: finished rungs are copied from the device
                 # rows (pitch ld) straight into the host rows (pitch nX + NP) of self.minpaths
-                mp = mp_all[w0:w0 + bw].reshape(bw * nb, nX + self.NP)
-                _lib.check(lib.vab_set_path_sink(h, ct.c_void_p(mp.ctypes.data), nX + self.NP, nX), h)
+                mp = mp_all[w0:w0 + bw].reshape(bw * nb, nX + NPl)
+                _lib.check(lib.vab_set_path_sink(h, ct.c_void_p(mp.ctypes.data), nX + NPl, nX), h)
             else:
                 _lib.check(lib.vab_set_path_window(h, nX, npest), h)
             _lib.check(lib.vab_anneal(h, bw, ptr(self._XP), self._ld, float(self.alpha), beta_c, nb,
@@ -434,18 +442,18 @@ class DeviceMin(object):
             nit_all[w0:w0 + bw] = nit[:bw].cpu().numpy()
             nfev_all[w0:w0 + bw] = nfev[:bw].cpu().numpy()
             # parameters: the fixed values with the estimates of every rung written in
-            P = np.broadcast_to(P_all[w0:w0 + bw].reshape(bw, 1, self.NP), (bw, nb, self.NP)).copy()
+            P = np.broadcast_to(P_all[w0:w0 + bw].reshape(bw, 1, NPl), (bw, nb, NPl)).copy()
             if npest > 0:
                 if keep == 'all':
-                    P[:, :, self.Pidx] = paths[:bw, :, nX:n].cpu().numpy()
+                    P[:, :, Pidxl] = paths[:bw, :, nX:n].cpu().numpy()
                 else:
-                    P[:, :, self.Pidx] = paths[:bw, :, :npest].cpu().numpy()
+                    P[:, :, Pidxl] = paths[:bw, :, :npest].cpu().numpy()
             par_all[w0:w0 + bw] = P
             if keep == 'all':
                 mp_all[w0:w0 + bw, :, nX:] = P
             elif keep == 'last':
                 # vab_anneal leaves the last rung's minimiser in XP
-                _lib.check(lib.vab_copy_rows_to_host(h, ct.c_void_p(mp_all[w0:w0 + bw].ctypes.data), nX + self.NP,
+                _lib.check(lib.vab_copy_rows_to_host(h, ct.c_void_p(mp_all[w0:w0 + bw].ctypes.data), nX + NPl,
                                                      ptr(self._XP), self._ld, nX, bw), h)
                 mp_all[w0:w0 + bw, 0, nX:] = P[:, -1]
             P_all[w0:w0 + bw] = P[:, -1]

@@ -29,8 +29,8 @@ __global__ void ode_finalize_kernel(const __grid_constant__ OdeParams P, double*
     if (fe) fe[b] = f;
     if (A) A[b] = m + f;
   }
-  if (k >= 2 && k < P.K && P.G != nullptr) {
-    const int e = P.pmap[k - 2];
+  if (k >= 2 && k < P.K && P.G != nullptr && !P.ptime) {   // (a parameter time series gets its
+    const int e = P.pmap[k - 2];                            //  gradient row by row in the walk kernel)
     if (e >= 0) P.G[(long long)b * P.ldg + (long long)P.N * P.D + e] = v;
   }
 }
@@ -83,7 +83,29 @@ SweepKernel sweep_kernel_for(int disc, bool window) {
   return nullptr;
 }
 
-SweepKernel sweep_kernel(int model, int C, int disc, bool window) {
+// parameter time series (OdeParams::ptime): the PT instantiations of the two register kernels that
+// carry a per-row parameter load and gradient; whole rows inside one lane group only, no rk4
+template <class M, int MINB>
+SweepKernel sweep_kernel_ptime(int disc) {
+  switch (disc) {
+    case DISC_EULER: return sweep_twopoint_kernel<M, DISC_EULER, VAB_SW_PD2, MINB, true>;
+    case DISC_TRAPEZOID: return sweep_twopoint_kernel<M, DISC_TRAPEZOID, VAB_SW_PD2, MINB, true>;
+    case DISC_FORWARDMAP: return sweep_twopoint_kernel<M, DISC_FORWARDMAP, VAB_SW_PD2, MINB, true>;
+    case DISC_SIMPSON: return sweep_simpson_kernel<M, VAB_SW_PDS, MINB, true>;
+  }
+  return nullptr;
+}
+
+SweepKernel sweep_kernel(int model, int C, int disc, bool window, bool ptime = false) {
+  if (ptime) {
+    if (window) return nullptr;
+    if (model == 0 && C == 4) return sweep_kernel_ptime<ModelL96<4>, 3>(disc);   // (spills at 128 registers)
+    if (model == 0 && C == 2) return sweep_kernel_ptime<ModelL96<2>, VAB_SW_MINB>(disc);
+    if (model == 0 && C == 1) return sweep_kernel_ptime<ModelL96<1>, VAB_SW_MINB>(disc);
+    if (model == 1) return sweep_kernel_ptime<ModelL63, VAB_SW_MINB>(disc);
+    if (model == 2) return sweep_kernel_ptime<ModelNaKL, 2>(disc);
+    return nullptr;
+  }
   if (model == 0) {
     if (C == 4) {
       if (disc == DISC_SIMPSON) {                 // tuning variants of the flagship kernel
@@ -223,7 +245,8 @@ int ode_sweep_prepare(int model, int disc, int D, int N, int B, int num_sms, int
   sl->smem = (size_t)128 * K * sizeof(double);
   SweepKernel k = nullptr;
   int nb = 0;
-  if (allow_stream && ode_stream_supported(model, disc, g)) {
+  if (P->ptime && (g.nwin > 1 || disc == DISC_RK4)) return -3;
+  if (allow_stream && !P->ptime && ode_stream_supported(model, disc, g)) {
     const size_t stage_b = (size_t)g.GPW * 4 * (size_t)g.GW * g.C * sizeof(double);
     const bool fast = (P->nskip == 1 && P->rmd == nullptr && P->rf_arr == nullptr && P->L > 0);
     const int ns = stream_ns(g.C, disc, fast);
@@ -237,7 +260,7 @@ int ode_sweep_prepare(int model, int disc, int D, int N, int B, int num_sms, int
     }
   }
   if (!sl->stream) {
-    k = sweep_kernel(model, g.C, disc, g.nwin > 1);
+    k = sweep_kernel(model, g.C, disc, g.nwin > 1, P->ptime != 0);
     if (!k) return -1;
     nb = blocks_per_sm(k, sl->smem, cerr);
     if (nb < 0) return -2;
@@ -275,7 +298,7 @@ int ode_sweep_prepare(int model, int disc, int D, int N, int B, int num_sms, int
 int ode_sweep_launch(const OdeParams& P, const SweepLaunch& sl, int model, int disc,
                      cudaStream_t st, double* A, double* me, double* fe, cudaError_t* cerr, bool pdl) {
   const bool fast = (P.nskip == 1 && P.rmd == nullptr && P.rf_arr == nullptr && P.L > 0);
-  SweepKernel k = sl.stream ? stream_kernel(sl.C, disc, fast, P.rf_path != nullptr, P.nwin > 1) : sweep_kernel(model, sl.C, disc, P.nwin > 1);
+  SweepKernel k = sl.stream ? stream_kernel(sl.C, disc, fast, P.rf_path != nullptr, P.nwin > 1) : sweep_kernel(model, sl.C, disc, P.nwin > 1, P.ptime != 0);
   if (!k) return -1;
   cudaError_t e;
   if (pdl) {

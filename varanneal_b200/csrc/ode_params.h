@@ -5,6 +5,7 @@ enum { DISC_EULER = 0, DISC_TRAPEZOID = 1, DISC_SIMPSON = 2, DISC_FORWARDMAP = 3
 
 struct OdeParams {
   const double* XP;       // (B, ldxp) paths: X (N, D) row-major ++ estimated parameters
+                          // (ptime: ++ (N, NPest) row-major, one parameter row per model time)
   long long ldxp;
   double* G;              // (B, ldg) gradient, same layout; nullptr = value only
   long long ldg;
@@ -25,7 +26,9 @@ struct OdeParams {
   int NP, NPest;
   const int* pmap;        // (NP) -> index among the estimated parameters, or -1
   const double* pfix;     // values of the parameters that are not estimated
-  long long pfix_stride;  // 0 (shared by all paths) or NP
+  long long pfix_stride;  // 0 (shared by all paths) or NP (ptime: N * NP)
+  int ptime;              // 1 = the parameters are a time series (va_ode.py:568-570): pfix is
+                          // (N, NP) per path, row n enters every evaluation of f at time n
   const int* active;      // (B) or nullptr: paths with active[b] == 0 are skipped
   double cm, cf;          // 1/(L N_data), 1/(D (N-1))
   // work decomposition (ode_plan.h)

@@ -106,6 +106,38 @@ struct SLane {
 
   __device__ __forceinline__ bool rowvalid(int r) const { return act && r >= 0 && r < N; }
   __device__ __forceinline__ bool owned(int r) const { return out && r >= r0 && r < r1; }
+  __device__ __forceinline__ bool unit_owns(int r) const { return act && r >= r0 && r < r1; }
+
+  // ---- parameter time series (P.ptime; va_ode.py:170-188) -------------------------------------
+  // parameters of time row `row` (zeros when the row is not needed)
+  __device__ __forceinline__ void loadp(const OdeParams& P, int row, bool need, double* q) const {
+    const long long nX = (long long)N * D;
+#pragma unroll
+    for (int k = 0; k < NPM; ++k) {
+      double v = 0.0;
+      if (need) {
+        const int e = __ldg(P.pmap + k);
+        v = (e >= 0) ? __ldg(xpath + nX + (long long)row * P.NPest + e)
+                     : __ldg(P.pfix + (long long)b * P.pfix_stride + (long long)row * P.NP + k);
+      }
+      q[k] = v;
+    }
+  }
+  // gradient of the parameters of row `row`: minus the sum of the lanes' (df/dp)^T v over the
+  // group, in lane order (bit-reproducible).  Must be executed by all 32 lanes.
+  __device__ __forceinline__ void storep(const OdeParams& P, int row, const double* pl) const {
+    const bool wr = unit_owns(row) && j == 0 && gpath != nullptr;
+    const long long nX = (long long)N * D;
+#pragma unroll
+    for (int k = 0; k < NPM; ++k) {
+      double acc = 0.0;
+      for (int s = 0; s < P.GW; ++s) acc += __shfl_sync(VAB_FULL, pl[k], gbase + s);
+      if (wr) {
+        const int e = __ldg(P.pmap + k);
+        if (e >= 0) gpath[nX + (long long)row * P.NPest + e] = -acc;
+      }
+    }
+  }
 
   // own strip of row `row` (zeros when the row is not needed)
   __device__ __forceinline__ void load(int row, bool need, double* dst) const {
@@ -187,10 +219,13 @@ struct SLane {
 // euler / trapezoid / forwardmap (va_ode.py:341-380, 439-454):
 //   e_m = x_{m+1} - AL x_m - (CA f_m + CB f_{m+1})
 //   g_r = [lam_{r-1} - AL lam_r] + meas_r - J^T(x_r) (CB lam_{r-1} + CA lam_r),  lam = 2 cf w e
-template <class M, int DISC, int PD, int MINB>
+// PT: the parameters are a time series -- row m's parameters are loaded with row m, the adjoint call
+// of a row yields that row's parameter gradient (one call per row: both uses of f(x_r, p_r) share
+// the seed V_r), reduced over the group's lanes and written next to the row's state gradient.
+template <class M, int DISC, int PD, int MINB, bool PT = false>
 __global__ void __launch_bounds__(128, MINB) sweep_twopoint_kernel(const __grid_constant__ OdeParams P) {
   using LN = SLane<M>;
-  constexpr int C = LN::C, H = LN::H, W = LN::W;
+  constexpr int C = LN::C, H = LN::H, W = LN::W, NPM = LN::NPM;
   extern __shared__ double smem[];
   LN L;
   vab_pdl_trigger();
@@ -201,6 +236,11 @@ __global__ void __launch_bounds__(128, MINB) sweep_twopoint_kernel(const __grid_
   const double al = (DISC == DISC_FORWARDMAP) ? 0.0 : 1.0;
   const double cf2 = 2.0 * P.cf;
   double X1[W], F1[C], lamp[C], pf[PD][C];
+  [[maybe_unused]] double P1[NPM];                    // PT: parameters of row m-1
+  if constexpr (PT) {
+#pragma unroll
+    for (int k = 0; k < NPM; ++k) P1[k] = 0.0;
+  }
 #pragma unroll
   for (int c = 0; c < W; ++c) X1[c] = 0.0;
 #pragma unroll
@@ -220,8 +260,11 @@ __global__ void __launch_bounds__(128, MINB) sweep_twopoint_kernel(const __grid_
       L.load(m + PD, need(m + PD), pf[u]);
       L.halo(Xm);
       const bool vm = need(m);
+      [[maybe_unused]] double Pm[NPM];
+      if constexpr (PT) L.loadp(P, m, vm, Pm);
       if (vm) {
-        M::f(Xm, L.p, L.stim_row(P, m), Fm);
+        if constexpr (PT) M::f(Xm, Pm, L.stim_row(P, m), Fm);
+        else M::f(Xm, L.p, L.stim_row(P, m), Fm);
       } else {
 #pragma unroll
         for (int c = 0; c < C; ++c) Fm[c] = 0.0;
@@ -243,11 +286,26 @@ __global__ void __launch_bounds__(128, MINB) sweep_twopoint_kernel(const __grid_
         d[c] = lamp[c] - al * l;
       }
       L.halo(V);
-      if (own) {
-        double jt[C];
-        L.measure(P, m - 1, X1 + H, d);
-        M::adj(X1, V, L.p, jt, L.pacc);
-        L.store(m - 1, d, jt);
+      if constexpr (PT) {
+        double pl[NPM];
+#pragma unroll
+        for (int k = 0; k < NPM; ++k) pl[k] = 0.0;
+        if (own) {
+          double jt[C];
+          L.measure(P, m - 1, X1 + H, d);
+          M::adj(X1, V, P1, jt, pl);
+          L.store(m - 1, d, jt);
+        }
+        L.storep(P, m - 1, pl);
+#pragma unroll
+        for (int k = 0; k < NPM; ++k) P1[k] = Pm[k];
+      } else {
+        if (own) {
+          double jt[C];
+          L.measure(P, m - 1, X1 + H, d);
+          M::adj(X1, V, L.p, jt, L.pacc);
+          L.store(m - 1, d, jt);
+        }
       }
 #pragma unroll
       for (int c = 0; c < W; ++c) X1[c] = Xm[c];
@@ -265,10 +323,10 @@ __global__ void __launch_bounds__(128, MINB) sweep_twopoint_kernel(const __grid_
 // One step per pair; rows a and b get their gradient in the step of their pair, row c's partial
 // seed is carried into the next pair (where it is row a).  Segments start on even rows and the
 // walk begins one pair early so that the c-part of row r0 is available.
-template <class M, int PD, int MINB>
+template <class M, int PD, int MINB, bool PT = false>
 __global__ void __launch_bounds__(128, MINB) sweep_simpson_kernel(const __grid_constant__ OdeParams P) {
   using LN = SLane<M>;
-  constexpr int C = LN::C, H = LN::H, W = LN::W;
+  constexpr int C = LN::C, H = LN::H, W = LN::W, NPM = LN::NPM;
   extern __shared__ double smem[];
   LN L;
   vab_pdl_trigger();
@@ -281,14 +339,17 @@ __global__ void __launch_bounds__(128, MINB) sweep_simpson_kernel(const __grid_c
 #pragma unroll
   for (int c = 0; c < C; ++c) { vcp[c] = 0.0; dcp[c] = 0.0; }
   const int a0 = L.r0 - 2;
+  [[maybe_unused]] double Pa[NPM];                    // PT: parameters of row a
   {
     double own[C];
     L.load(a0, need(a0), own);
 #pragma unroll
     for (int c = 0; c < C; ++c) Xa[H + c] = own[c];
     L.halo(Xa);
+    if constexpr (PT) L.loadp(P, a0, need(a0), Pa);
     if (need(a0)) {
-      M::f(Xa, L.p, L.stim_row(P, a0), Fa);
+      if constexpr (PT) M::f(Xa, Pa, L.stim_row(P, a0), Fa);
+      else M::f(Xa, L.p, L.stim_row(P, a0), Fa);
     } else {
 #pragma unroll
       for (int c = 0; c < C; ++c) Fa[c] = 0.0;
@@ -313,14 +374,21 @@ __global__ void __launch_bounds__(128, MINB) sweep_simpson_kernel(const __grid_c
       L.halo(Xc);
       const bool vc = need(c2);
       const bool vp = need(a) && vc;                 // the pair exists (a >= 0, c <= N-1)
+      [[maybe_unused]] double Pb[NPM], Pc[NPM];
+      if constexpr (PT) {
+        L.loadp(P, bq, vp, Pb);
+        L.loadp(P, c2, vc, Pc);
+      }
       if (vp) {
-        M::f(Xb, L.p, L.stim_row(P, bq), Fb);
+        if constexpr (PT) M::f(Xb, Pb, L.stim_row(P, bq), Fb);
+        else M::f(Xb, L.p, L.stim_row(P, bq), Fb);
       } else {
 #pragma unroll
         for (int c = 0; c < C; ++c) Fb[c] = 0.0;
       }
       if (vc) {
-        M::f(Xc, L.p, L.stim_row(P, c2), Fc);
+        if constexpr (PT) M::f(Xc, Pc, L.stim_row(P, c2), Fc);
+        else M::f(Xc, L.p, L.stim_row(P, c2), Fc);
       } else {
 #pragma unroll
         for (int c = 0; c < C; ++c) Fc[c] = 0.0;
@@ -347,17 +415,41 @@ __global__ void __launch_bounds__(128, MINB) sweep_simpson_kernel(const __grid_c
       }
       L.halo(Va);
       L.halo(Vb);
-      if (L.owned(a)) {
-        double jt[C];
-        L.measure(P, a, Xa + H, da);
-        M::adj(Xa, Va, L.p, jt, L.pacc);
-        L.store(a, da, jt);
-      }
-      if (own_p) {
-        double jt[C];
-        L.measure(P, bq, Xb + H, db);
-        M::adj(Xb, Vb, L.p, jt, L.pacc);
-        L.store(bq, db, jt);
+      if constexpr (PT) {
+        double pl[NPM];
+#pragma unroll
+        for (int k = 0; k < NPM; ++k) pl[k] = 0.0;
+        if (L.owned(a)) {
+          double jt[C];
+          L.measure(P, a, Xa + H, da);
+          M::adj(Xa, Va, Pa, jt, pl);
+          L.store(a, da, jt);
+        }
+        L.storep(P, a, pl);
+#pragma unroll
+        for (int k = 0; k < NPM; ++k) pl[k] = 0.0;
+        if (own_p) {
+          double jt[C];
+          L.measure(P, bq, Xb + H, db);
+          M::adj(Xb, Vb, Pb, jt, pl);
+          L.store(bq, db, jt);
+        }
+        L.storep(P, bq, pl);
+#pragma unroll
+        for (int k = 0; k < NPM; ++k) Pa[k] = Pc[k];
+      } else {
+        if (L.owned(a)) {
+          double jt[C];
+          L.measure(P, a, Xa + H, da);
+          M::adj(Xa, Va, L.p, jt, L.pacc);
+          L.store(a, da, jt);
+        }
+        if (own_p) {
+          double jt[C];
+          L.measure(P, bq, Xb + H, db);
+          M::adj(Xb, Vb, L.p, jt, L.pacc);
+          L.store(bq, db, jt);
+        }
       }
 #pragma unroll
       for (int c = 0; c < W; ++c) Xa[c] = Xc[c];

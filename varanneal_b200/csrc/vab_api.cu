@@ -72,7 +72,7 @@ static int vab_scatter_obs(vab_ctx* ctx, const double* src, long long rows, doub
 }
 
 long long vab_ctx::n_unknowns() const {
-  if (problem == VAB_PROBLEM_ODE) return (long long)od.N_model * od.D + od.NPest;
+  if (problem == VAB_PROBLEM_ODE) return (long long)od.N_model * od.D + (long long)od.NPest * (ptime ? od.N_model : 1);
   if (problem == VAB_PROBLEM_NN) return nn_unknowns(this);
   return 0;
 }
@@ -272,6 +272,7 @@ int vab_ode_problem_set(vab_ctx* ctx, const vab_ode_desc* d, const int32_t* Lidx
   ctx->stim_dev = (d->n_stim > 0) ? stim_dev : nullptr;
   ctx->pfix_dev = ctx->pfix_zero;
   ctx->pfix_stride = 0;
+  ctx->ptime = 0;
   ctx->rf0_scalar = 1.0; ctx->rf0_dev = nullptr;
   ctx->problem = VAB_PROBLEM_ODE;
   const int rcw = vab_ode_set_weights(ctx, 1.0, nullptr, 1.0, nullptr);
@@ -316,10 +317,40 @@ int vab_ode_set_fixed_params(vab_ctx* ctx, const double* pfix_dev, int64_t pfix_
   if (!ctx) return VAB_ERR_INVALID;
   if (ctx->problem != VAB_PROBLEM_ODE) return vab_fail(ctx, VAB_ERR_STATE, "set_fixed_params: no ODE problem set");
   if (!pfix_dev) return vab_fail(ctx, VAB_ERR_INVALID, "set_fixed_params: NULL");
-  if (pfix_stride != 0 && pfix_stride != ctx->od.NP)
-    return vab_fail(ctx, VAB_ERR_INVALID, "set_fixed_params: stride must be 0 or NP");
+  const long long per_path = (long long)ctx->od.NP * (ctx->ptime ? ctx->od.N_model : 1);
+  if (pfix_stride != 0 && pfix_stride != per_path)
+    return vab_fail(ctx, VAB_ERR_INVALID, ctx->ptime ? "set_fixed_params: stride must be 0 or N_model * NP"
+                                                     : "set_fixed_params: stride must be 0 or NP");
   ctx->pfix_dev = pfix_dev;
   ctx->pfix_stride = pfix_stride;
+  return VAB_OK;
+}
+
+int vab_ode_set_time_dependent(vab_ctx* ctx, int32_t enabled, const double* pfix_dev, int64_t pfix_stride) {
+  if (!ctx) return VAB_ERR_INVALID;
+  if (ctx->problem != VAB_PROBLEM_ODE) return vab_fail(ctx, VAB_ERR_STATE, "set_time_dependent: no ODE problem set");
+  const vab_ode_desc& d = ctx->od;
+  if (!enabled) {
+    ctx->ptime = 0;
+    ctx->pfix_dev = ctx->pfix_zero;
+    ctx->pfix_stride = 0;
+    return VAB_OK;
+  }
+  if (d.disc == VAB_DISC_RK4)
+    return vab_fail(ctx, VAB_ERR_INVALID, "set_time_dependent: rk4 (extension) takes static parameters only");
+  OdeGeo geo;
+  if (ode_geometry(d.model, d.disc, d.D, &geo) != 0 || geo.nwin > 1)
+    return vab_fail(ctx, VAB_ERR_INVALID, "set_time_dependent: a parameter time series needs a row that fits "
+                                          "one lane group (D <= 128 for lorenz96)");
+  const long long per_path = (long long)d.NP * d.N_model;
+  if (!pfix_dev && d.NPest < d.NP)
+    return vab_fail(ctx, VAB_ERR_INVALID, "set_time_dependent: the parameters that are not estimated need "
+                                          "their (N_model, NP) values");
+  if (pfix_dev && pfix_stride != 0 && pfix_stride != per_path)
+    return vab_fail(ctx, VAB_ERR_INVALID, "set_time_dependent: stride must be 0 or N_model * NP");
+  ctx->ptime = 1;
+  ctx->pfix_dev = pfix_dev ? pfix_dev : ctx->pfix_zero;   // (never read when every parameter is estimated)
+  ctx->pfix_stride = pfix_dev ? pfix_stride : 0;
   return VAB_OK;
 }
 
@@ -329,7 +360,7 @@ static int ode_eval(vab_ctx* ctx, int B, const double* XP, long long ldxp, doubl
                     const double* rf_path_dev, const int* active_dev, double* A, double* me,
                     double* fe, double* G, long long ldg) {
   const vab_ode_desc& d = ctx->od;
-  const long long n = (long long)d.N_model * d.D + d.NPest;
+  const long long n = ctx->n_unknowns();
   if (B < 1 || !XP) return vab_fail(ctx, VAB_ERR_INVALID, "ode_action_grad: bad batch / XP");
   if (ldxp < n || (ldxp & 1)) return vab_fail(ctx, VAB_ERR_INVALID, "ode_action_grad: ldxp must be even and >= n");
   if (G && (ldg < n || (ldg & 1))) return vab_fail(ctx, VAB_ERR_INVALID, "ode_action_grad: ldg must be even and >= n");
@@ -346,6 +377,7 @@ static int ode_eval(vab_ctx* ctx, int B, const double* XP, long long ldxp, doubl
   P.stim = ctx->stim_dev; P.S = d.n_stim;
   P.NP = d.NP; P.NPest = d.NPest; P.pmap = ctx->pmap_dev;
   P.pfix = ctx->pfix_dev; P.pfix_stride = ctx->pfix_stride;
+  P.ptime = ctx->ptime;
   P.K = 2 + d.NP;
   P.active = active_dev;
   P.cm = d.L > 0 ? 1.0 / ((double)d.L * d.N_data) : 0.0;
@@ -357,6 +389,7 @@ static int ode_eval(vab_ctx* ctx, int B, const double* XP, long long ldxp, doubl
     rc = ode_sweep_prepare(d.model, d.disc, d.D, d.N_model, B, ctx->num_sms, ctx->tseg_override,
                            !ctx->use_sweep, &P, &sl, &cerr);
     if (rc == -1) return vab_fail(ctx, VAB_ERR_INVALID, "ode_action_grad: unsupported shape");
+    if (rc == -3) return vab_fail(ctx, VAB_ERR_INVALID, "ode_action_grad: parameter time series: unsupported discretisation / row width");
     if (rc != 0) return vab_cuda_fail(ctx, cerr, "ode_action_grad occupancy query");
     rc = vab_reserve(ctx, &ctx->partials, &ctx->partials_cap, (size_t)P.nunits * P.K);
     if (rc != VAB_OK) return rc;

@@ -42,6 +42,7 @@ struct vab_ctx {
   const double* rf0_dev = nullptr;
   const double* pfix_dev = nullptr;
   long long pfix_stride = 0;
+  int ptime = 0;                    // parameters are a time series (vab_ode_set_time_dependent)
   double* pfix_zero = nullptr;      // default fixed-parameter block (zeros)
   int tseg_override = 0;            // tuning knob (env VAB_TSEG)
   bool use_sweep = false;           // env VAB_KERNEL=sweep: register sweep kernels even where the stream kernels apply

@@ -18,7 +18,12 @@ Differences from the reference, all deliberate:
   * batches: ``X0`` of shape (B, N, D) [+ ``P0`` (B, NP) or (NP,)] anneals B independent
     initialisations concurrently; every result array gains a leading B axis.  With the
     reference's shapes the results have exactly the reference's shapes.
-  * time-dependent parameters (``P0.ndim == 2`` with a 2-D ``X0``) are a 'next' row (8(f4)).
+  * time-dependent parameters: ``P0`` of shape (N_model, NP) with a 2-D ``X0`` (va_ode.py:568-570),
+    or (B, N_model, NP) with a batch.  ``XP = X.flatten() ++ P[:, Pidx].flatten()`` and row n of P
+    enters f at model time n, as the reference's trapezoid / SimpsonHermite branches do
+    (va_ode.py:170-188, 368-369, 416-418).  euler / forwardmap -- whose reference branches fail on a
+    doubly dropped row -- use the same N_model rows and never read the last one; rk4 and rows wider
+    than one lane group (lorenz96 D > 128) raise.
 """
 import ctypes as ct
 import time
@@ -39,6 +44,7 @@ class Annealer(DeviceMin):
         self._device_arg = device
         self.verbose = verbose
         self.stim = None
+        self._ptime = False                    # parameters are a time series (set by anneal_init)
 
     # ------------------------------------------------------------------ problem definition
     def set_model(self, f, D):
@@ -156,6 +162,7 @@ class Annealer(DeviceMin):
         # defines the batch size
         P0 = np.asarray(P0, dtype=np.float64) if not isinstance(P0, np.ndarray) else P0
         lazy = callable(X0)
+        self._ptime = False
         if lazy:
             if P0.ndim != 2:
                 raise ValueError("a callable X0 needs P0 of shape (B, NP)")
@@ -173,16 +180,27 @@ class Annealer(DeviceMin):
                 raise ValueError("X0 must have shape (B, %d, %d)" % (N, D))
             if P0.ndim == 1:
                 P0 = np.tile(P0, (B, 1))
-            if P0.ndim != 2 or P0.shape[0] != B:
-                raise ValueError("batched anneal: P0 must be (NP,) or (B, NP)")
+            if P0.ndim == 3:
+                self._ptime = True                       # (B, N_model, NP): a time series per path
+                if P0.shape[:2] != (B, N):
+                    raise ValueError("batched anneal with time-dependent parameters: P0 must be "
+                                     "(B, N_model, NP) = (%d, %d, NP)" % (B, N))
+            elif P0.ndim != 2 or P0.shape[0] != B:
+                raise ValueError("batched anneal: P0 must be (NP,), (B, NP) or (B, N_model, NP)")
         else:
             B = 1
             if X0.shape != (N, D):
                 raise ValueError("X0 must have shape (%d, %d)" % (N, D))
-            if P0.ndim != 1:
-                raise NotImplementedError("time-dependent parameters (P0.ndim == 2) are not "
-                                          "built yet (SURVEY.md 8(f4))")
-        self.P = np.array(P0, dtype=np.float64)          # (NP,) or (B, NP); updated per beta
+            if P0.ndim == 2:
+                self._ptime = True                       # va_ode.py:568-570
+                if P0.shape[0] != N:
+                    raise ValueError("time-dependent parameters: P0 must have one row per model time "
+                                     "point, (%d, NP)" % N)
+            elif P0.ndim != 1:
+                raise ValueError("P0 must be (NP,) or (N_model, NP)")
+        if self._ptime and disc == 'rk4':
+            raise ValueError("disc='rk4' (extension) takes static parameters only")
+        self.P = np.array(P0, dtype=np.float64)          # (NP,) / (N, NP) [batch: leading B]; updated per beta
         self.NP = self.P.shape[-1]
         if self.NP != _models.MODEL_NP[self.model_name]:
             raise ValueError("model %s takes %d parameters, P0 has %d"
@@ -195,7 +213,8 @@ class Annealer(DeviceMin):
             raise ValueError("data has %d measured columns but len(Lidx) = %d" % (self.Y.shape[1], self.L))
 
         nX = N * D
-        n = nX + self.NPest
+        NPl, Pidxl, NPestl, _ = self._lay()
+        n = nX + NPestl
         self._nX = nX
 
         # bounds (va_ode.py:582-605): D + NPest [lo, hi] pairs -> one pair per unknown
@@ -205,9 +224,10 @@ class Annealer(DeviceMin):
                 raise ValueError("bounds must hold D + len(Pidx) = %d [lo, hi] pairs" % (D + self.NPest))
             lohi = np.array([[-np.inf if b[0] is None else b[0], np.inf if b[1] is None else b[1]]
                              for b in bounds], dtype=np.float64)
-            self.bounds = [list(b) for b in bounds[:D]] * N + [list(b) for b in bounds[D:]]
-            lo = np.concatenate([np.tile(lohi[:D, 0], N), lohi[D:, 0]])
-            hi = np.concatenate([np.tile(lohi[:D, 1], N), lohi[D:, 1]])
+            nrow = N if self._ptime else 1            # parameter rows (va_ode.py:592-605)
+            self.bounds = [list(b) for b in bounds[:D]] * N + [list(b) for b in bounds[D:]] * nrow
+            lo = np.concatenate([np.tile(lohi[:D, 0], N), np.tile(lohi[D:, 0], nrow)])
+            hi = np.concatenate([np.tile(lohi[:D, 1], N), np.tile(lohi[D:, 1], nrow)])
         else:
             self.bounds = None
             lo = hi = None
@@ -262,8 +282,8 @@ class Annealer(DeviceMin):
                 if X0.flags.writeable:
                     X0[...] = Xw.reshape(X0.shape)
             if self.keep_paths == 'all':         # the reference parks XP0 in minpaths[0] (va_ode.py:667)
-                self.minpaths.reshape(B, self.Nbeta, nX + self.NP)[:, 0] = np.concatenate(
-                    [Xw.reshape(B, nX), self.P.reshape(B, self.NP)], axis=1)
+                self.minpaths.reshape(B, self.Nbeta, nX + NPl)[:, 0] = np.concatenate(
+                    [Xw.reshape(B, nX), self.P.reshape(B, NPl)], axis=1)
             else:
                 self._Xw = Xw.reshape(B, nX)
         self.adolcID = adolcID               # accepted and ignored: nothing is taped
@@ -286,8 +306,11 @@ class Annealer(DeviceMin):
         _lib.check(ctx.lib.vab_ode_set_weights(
             ctx.h, self.RM if np.isscalar(self.RM) else 0.0, ptr(self._rm_dev),
             self.RF0 if np.isscalar(self.RF0) else 1.0, ptr(self._rf0_dev)), ctx.h)
-        self._pfix_dev = self._to_dev(self.P.reshape(B, self.NP)[:Bw])
-        _lib.check(ctx.lib.vab_ode_set_fixed_params(ctx.h, ptr(self._pfix_dev), self.NP), ctx.h)
+        self._pfix_dev = self._to_dev(self.P.reshape(B, NPl)[:Bw])
+        if self._ptime:
+            _lib.check(ctx.lib.vab_ode_set_time_dependent(ctx.h, 1, ptr(self._pfix_dev), NPl), ctx.h)
+        else:
+            _lib.check(ctx.lib.vab_ode_set_fixed_params(ctx.h, ptr(self._pfix_dev), NPl), ctx.h)
         self._lo_dev = self._hi_dev = None
         if lo is not None:
             pad = self._ld - n
@@ -295,6 +318,15 @@ class Annealer(DeviceMin):
             self._hi_dev = self._to_dev(np.concatenate([hi, np.full(pad, np.inf)]))
         self._dev_paths_current = False
         self.initalized = True               # sic (va_ode.py:705)
+
+    def _lay(self):
+        """Parameter block of a path row: (NP,) static, or the flattened (N_model, NP) time series
+        with the estimated entries P[:, Pidx] in row-major order (va_ode.py:688-689)."""
+        if not self._ptime:
+            return self.NP, self.Pidx, self.NPest, (self.NP,)
+        N = self.N_model
+        idx = (np.arange(N)[:, None] * self.NP + self.Pidx[None, :]).reshape(-1)
+        return N * self.NP, idx, N * self.NPest, (N, self.NP)
 
     def _action_grad_native(self, rf_scale, b0=0, nb=None):
         """Evaluates paths [b0, b0 + nb) of the device batch (default: all)."""
@@ -306,9 +338,10 @@ class Annealer(DeviceMin):
         def at(t, per_path):
             return ct.c_void_p(t.data_ptr() + b0 * per_path)
 
+        NPl = self._lay()[0]
         if sub:
             _lib.check(ctx.lib.vab_ode_set_fixed_params(
-                ctx.h, ct.c_void_p(self._pfix_dev.data_ptr() + b0 * self.NP * 8), self.NP), ctx.h)
+                ctx.h, ct.c_void_p(self._pfix_dev.data_ptr() + b0 * NPl * 8), NPl), ctx.h)
         try:
             _lib.check(ctx.lib.vab_ode_action_grad(
                 ctx.h, nb, ct.c_void_p(self._XP.data_ptr() + off), self._ld, float(rf_scale),
@@ -316,15 +349,16 @@ class Annealer(DeviceMin):
                 ct.c_void_p(self._G.data_ptr() + off), self._ld), ctx.h)
         finally:
             if sub:
-                _lib.check(ctx.lib.vab_ode_set_fixed_params(ctx.h, ptr(self._pfix_dev), self.NP), ctx.h)
+                _lib.check(ctx.lib.vab_ode_set_fixed_params(ctx.h, ptr(self._pfix_dev), NPl), ctx.h)
 
     def _wave_rows(self, w0, bw):
         """Initial XP rows of initialisations [w0, w0 + bw) (see DeviceMin._anneal_device)."""
-        Pw = self.P.reshape(self._Btot, self.NP)[w0:w0 + bw][:, self.Pidx]
+        NPl, Pidxl, _, _ = self._lay()
+        Pw = self.P.reshape(self._Btot, NPl)[w0:w0 + bw][:, Pidxl]
         if self._X0_fn is None:
             if self._Xw is not None:
                 return np.concatenate([self._Xw[w0:w0 + bw], Pw], axis=1)
-            mp = self.minpaths.reshape(self._Btot, self.Nbeta, self._nX + self.NP)
+            mp = self.minpaths.reshape(self._Btot, self.Nbeta, self._nX + NPl)
             return self._est_slice(mp[w0:w0 + bw, 0])
         import torch
         X = self._X0_fn(w0, w0 + bw)
@@ -342,7 +376,7 @@ class Annealer(DeviceMin):
 
     def _est_slice(self, full):
         """(B, nX+NP) rows X ++ full P  ->  (B, nX+NPest) rows X ++ P[Pidx] (va_ode.py:715-732)."""
-        return np.concatenate([full[:, :self._nX], full[:, self._nX:][:, self.Pidx]], axis=1)
+        return np.concatenate([full[:, :self._nX], full[:, self._nX:][:, self._lay()[1]]], axis=1)
 
     def anneal_step(self):
         """One rung of the ladder (va_ode.py:707-789): minimise from the previous minimiser,
@@ -366,17 +400,18 @@ class Annealer(DeviceMin):
         if self.verbose:
             print("Optimization complete!  Time = %.3f s" % (time.time() - t0))
             print("Exit flag = %s  Iterations = %s  Obj. function value = %s" % (st, nit, A))
-        P = self.P.reshape(B, self.NP)
+        NPl, Pidxl, _, pshape = self._lay()
+        P = self.P.reshape(B, NPl)                      # a view: self.P is updated (va_ode.py:758-774)
         if self.NPest > 0:
-            P[:, self.Pidx] = XPmin[:, self._nX:]
+            P[:, Pidxl] = XPmin[:, self._nX:]
         if self.batched:
             self.A_array[:, b], self.me_array[:, b], self.fe_array[:, b] = A, me, fe
             self.exitflags[:, b], self.nit_array[:, b], self.nfev_array[:, b] = st, nit, nfev
             self.minpaths[:, b, :self._nX] = XPmin[:, :self._nX]
             self.minpaths[:, b, self._nX:] = P
-            self.params_array[:, b] = P
+            self.params_array[:, b] = P.reshape((B,) + pshape)
         else:
-            self.params_array[b] = P[0]
+            self.params_array[b] = P[0].reshape(pshape)
             self.A_array[b], self.me_array[b], self.fe_array[b] = A[0], me[0], fe[0]
             self.exitflags[b], self.nit_array[b], self.nfev_array[b] = st[0], nit[0], nfev[0]
             self.minpaths[b, :self._nX] = XPmin[0, :self._nX]
@@ -407,8 +442,9 @@ class Annealer(DeviceMin):
         """Measurement error (va_ode.py:138-158); accepts X or XP like the reference."""
         X = np.asarray(X, dtype=np.float64)
         if X.shape[-1] == self._nX:
-            pad = np.zeros(X.shape[:-1] + (self.NPest,))
-            pad[...] = self.P.reshape(self._B, self.NP)[:, self.Pidx] if X.ndim > 1 else self.P.reshape(-1)[self.Pidx]
+            NPl, Pidxl, NPestl, _ = self._lay()
+            pad = np.zeros(X.shape[:-1] + (NPestl,))
+            pad[...] = self.P.reshape(self._B, NPl)[:, Pidxl] if X.ndim > 1 else self.P.reshape(-1)[Pidxl]
             X = np.concatenate([X, pad], axis=-1)
         me = self._eval_parts(X)[1]
         return float(me[0]) if X.ndim == 1 else me
@@ -438,13 +474,16 @@ class Annealer(DeviceMin):
             np.savetxt(filename, out.reshape(self.Nbeta * self.N_model, 1 + self.D), fmt=fmt)
 
     def save_params(self, filename, dtype=np.float64, fmt="%.8e", init=None):
-        """(Nbeta, NP): fixed values with the per-beta estimates written in (va_ode.py:811-845)."""
+        """(Nbeta, NP) -- time-dependent parameters: (Nbeta, N_model, NP) -- fixed values with the
+        per-beta estimates written in (va_ode.py:811-845).  As text a time series is written as
+        Nbeta * N_model rows (the reference's np.savetxt call fails on the 3-D array)."""
         mp = self._per_init(self.minpaths, init)
-        out = np.array(mp[:, self._nX:], dtype=np.float64)
+        pshape = (self.N_model, self.NP) if self._ptime else (self.NP,)
+        out = np.array(mp[:, self._nX:], dtype=np.float64).reshape((self.Nbeta,) + pshape)
         if filename.endswith('.npy'):
             np.save(filename, out.astype(dtype))
         else:
-            np.savetxt(filename, out, fmt=fmt)
+            np.savetxt(filename, out.reshape(-1, self.NP), fmt=fmt)
 
     def action_errors_table(self, cmpt=0, init=None):
         """(Nbeta, 5) rows [beta, A, me, fe, fe / (RF0 alpha**beta)] (va_ode.py:847-873)."""
