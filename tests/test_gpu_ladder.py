@@ -405,3 +405,26 @@ def test_tma_history_kernels_match_plain_kernels(monkeypatch):
         assert np.max(np.abs(a.A_array - b.A_array) / np.abs(b.A_array)) <= 1e-9
         assert np.max(np.abs(a.minpaths - b.minpaths)) <= 1e-5
         assert np.all(np.abs(a.nit_array - b.nit_array) <= np.maximum(5, 0.2 * b.nit_array)), (a.nit_array, b.nit_array)
+
+
+def test_fused_cycle_kernel_is_bit_identical():
+    """Small problems: the one-cluster-per-path cycle kernel (lb_fused_kernel) and the per-phase
+    kernels do the same arithmetic in the same order -- which of the two runs is a scheduling
+    decision (it depends on the batch size) and must not change a single bit of the result."""
+    import os
+    z = golden_util.load("l96_ladder_golden.npz")
+    runs = []
+    old = os.environ.get("VAB_LBFGS_FUSED")
+    try:
+        for mode in ("1", "0"):
+            os.environ["VAB_LBFGS_FUSED"] = mode
+            runs.append(_run("SimpsonHermite", z, B=3))
+    finally:
+        if old is None:
+            os.environ.pop("VAB_LBFGS_FUSED", None)
+        else:
+            os.environ["VAB_LBFGS_FUSED"] = old
+    a, b = runs
+    for name in ("A_array", "me_array", "fe_array", "exitflags", "nit_array", "nfev_array", "minpaths", "params_array"):
+        assert np.array_equal(getattr(a, name), getattr(b, name)), name
+    assert a._ctx.graph_launches > 0 and b._ctx.graph_launches > 0

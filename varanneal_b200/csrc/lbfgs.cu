@@ -40,8 +40,10 @@
 // Per-path arithmetic does not depend on what the other paths do, so the results are identical
 // to running the rungs one after the other.
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
 
 #include <cfloat>
+#include <cstdio>
 #include <chrono>
 #include <cstdint>
 #include <cmath>
@@ -255,32 +257,20 @@ __global__ void __launch_bounds__(NT) lb_gd_kernel(const double* __restrict__ XT
   if (threadIdx.x < 2) part[((long long)b * nchunk + blockIdx.x) * 2 + threadIdx.x] = res[threadIdx.x];
 }
 
-// line-search state machine + stopping tests; one warp per path
-__global__ void lb_linesearch_kernel(LbPath* st, int* act_eval, const double* ft, const double* met,
-                                     const double* fet, const double* part, int nchunk, LbOpts o,
-                                     int bounded) {
-  const int b = blockIdx.x;
-  LbPath& s = st[b];
-  if (s.done || !s.need_eval) return;
-  double gd = 0.0, sbg = 0.0;
-  if (threadIdx.x == 0) {
-    for (int c = 0; c < nchunk; ++c) {
-      gd += part[((long long)b * nchunk + c) * 2 + 0];
-      sbg = fmax(sbg, part[((long long)b * nchunk + c) * 2 + 1]);
-    }
-  } else {
-    return;
-  }
+// line-search state machine + stopping tests of one path (one thread); gd = g.d and sbg = max |proj g|
+// of the trial point, fb / meb / feb its action, act = the path's entry of the evaluation mask
+__device__ void lb_linesearch_body(LbPath& s, int* act, double fb, double meb, double feb, double gd, double sbg,
+                                   const LbOpts& o) {
   s.nfev += 1;
   s.xt_ready = 0;                  // any further trial of this search goes through lb_trial_kernel
-  const double f = ft[b];
+  const double f = fb;
   if (s.first) {
     s.first = 0;
-    s.f = f; s.me = met[b]; s.fe = fet[b];
+    s.f = f; s.me = meb; s.fe = feb;
     s.sbgnrm = sbg;
     s.need_eval = 0;
     s.accepted = 1; s.do_update = 0;
-    if (sbg <= o.pgtol) { s.done = 1; s.status = 0; act_eval[b] = 0; }
+    if (sbg <= o.pgtol) { s.done = 1; s.status = 0; *act = 0; }
     return;
   }
   // an evaluation that produced a NaN / Inf cannot be used by the search: treat as a failed step
@@ -291,7 +281,7 @@ __global__ void lb_linesearch_kernel(LbPath* st, int* act_eval, const double* ft
   else s.iback = o.maxls;      // force the restart branch below
   if (finite && conv) {
     // NEW_X
-    s.f = f; s.me = met[b]; s.fe = fet[b];
+    s.f = f; s.me = meb; s.fe = feb;
     s.gd = gd;
     s.iter += 1;
     s.sbgnrm = sbg;
@@ -321,7 +311,7 @@ __global__ void lb_linesearch_kernel(LbPath* st, int* act_eval, const double* ft
         s.pslot = (s.col < o.m) ? (s.head + s.col) % o.m : s.head;
       }
     }
-    if (s.done) act_eval[b] = 0;
+    if (s.done) *act = 0;
     return;
   }
   s.stp_at = stp_eval;                                 // in-place trials: where x sits now
@@ -335,14 +325,137 @@ __global__ void lb_linesearch_kernel(LbPath* st, int* act_eval, const double* ft
     s.need_eval = 0;
     s.restore = stp_eval;
     if (s.col == 0) {
-      s.done = 1; s.status = 2; act_eval[b] = 0;      // ABNORMAL_TERMINATION_IN_LNSRCH
+      s.done = 1; s.status = 2; *act = 0;      // ABNORMAL_TERMINATION_IN_LNSRCH
     } else {
       s.col = 0; s.head = 0; s.theta = 1.0;
       s.redo_dir = 1;                                  // RESTART_FROM_LNSRCH
     }
   }
+}
+
+// one warp per path
+__global__ void lb_linesearch_kernel(LbPath* st, int* act_eval, const double* ft, const double* met,
+                                     const double* fet, const double* part, int nchunk, LbOpts o,
+                                     int bounded) {
+  const int b = blockIdx.x;
+  LbPath& s = st[b];
+  if (s.done || !s.need_eval) return;
+  if (threadIdx.x != 0) return;
+  double gd = 0.0, sbg = 0.0;
+  for (int c = 0; c < nchunk; ++c) {
+    gd += part[((long long)b * nchunk + c) * 2 + 0];
+    sbg = fmax(sbg, part[((long long)b * nchunk + c) * 2 + 1]);
+  }
+  lb_linesearch_body(s, act_eval + b, ft[b], met[b], fet[b], gd, sbg, o);
   (void)bounded;
 }
+
+// sum over the 16 lanes of a half warp (MMAX <= 16 columns, one per lane), fixed butterfly order
+__device__ __forceinline__ double half_sum(double v) {
+#pragma unroll
+  for (int sft = 8; sft > 0; sft >>= 1) v += __shfl_xor_sync(0xffffffffu, v, sft);
+  return v;
+}
+
+// lb_gram_body for L-BFGS executed by one warp: lane j owns column j of the coefficient vectors, the
+// inner products of the two-loop recursion are half-warp reductions instead of a serial chain of
+// dependent multiply-adds (same algebra; the sums associate differently).  s, SYs, YYs, sum in
+// shared memory.  All 32 lanes must call.
+__device__ void lb_gram_warp(LbPath& s, const double* sum, double* SYs, double* YYs, int m) {
+  const int j = threadIdx.x & 31;
+  const bool on = j < m;
+  int col = s.col, head = s.head;
+  double theta = s.theta;
+  double gSj = on ? s.gS[j] : 0.0, gYj = on ? s.gY[j] : 0.0;
+  const bool accepted = s.accepted != 0, upd = s.do_update != 0;
+  const int p = s.pslot;
+  const double dr = s.dr;
+  __syncwarp();
+  if (accepted) {
+    if (upd) {
+      if (on && j != p) {
+        SYs[p * MMAX + j] = sum[2 * MMAX + j];      // s_p . y_j
+        SYs[j * MMAX + p] = sum[3 * MMAX + j];      // s_j . y_p
+        YYs[p * MMAX + j] = sum[4 * MMAX + j];
+        YYs[j * MMAX + p] = sum[4 * MMAX + j];
+      }
+      if (j == p) {
+        SYs[p * MMAX + p] = dr;                     // s'y from the line search, as L-BFGS-B does
+        YYs[p * MMAX + p] = sum[5 * MMAX];
+      }
+      theta = sum[5 * MMAX] / dr;
+      if (col < m) col += 1;
+      else head = (head + 1) % m;
+      if (on) { gSj = (j == p) ? sum[5 * MMAX + 1] : sum[j]; gYj = (j == p) ? sum[5 * MMAX + 2] : sum[MMAX + j]; }
+      __syncwarp();
+      if (on) {                                     // write back the row / column that changed
+        s.SY[p * MMAX + j] = SYs[p * MMAX + j]; s.SY[j * MMAX + p] = SYs[j * MMAX + p];
+        s.YY[p * MMAX + j] = YYs[p * MMAX + j]; s.YY[j * MMAX + p] = YYs[j * MMAX + p];
+      }
+      if (j == 0) { s.theta = theta; s.col = col; s.head = head; }
+    } else if (on) {
+      gSj = sum[j]; gYj = sum[MMAX + j];
+    }
+    if (on) { s.gS[j] = gSj; s.gY[j] = gYj; }
+    if (j == 0) s.gg = sum[5 * MMAX + 3];
+  }
+  __syncwarp();
+  // r = H ghat  as  cg * ghat + sum_j cs_j s_j + cy_j y_j   (d = -r)
+  double cg = 1.0, csj = 0.0, cyj = 0.0, alphaj = 0.0;
+  for (int k = col - 1; k >= 0; --k) {               // newest -> oldest
+    const int i = (head + k) % m;
+    const double gi = __shfl_sync(0xffffffffu, gSj, i);
+    const double sq = gi * cg + half_sum(on ? cyj * SYs[i * MMAX + j] : 0.0);
+    const double a = sq / SYs[i * MMAX + i];
+    if (j == i) { alphaj = a; cyj -= a; }
+  }
+  const double gamma = (col > 0) ? 1.0 / theta : 1.0;
+  cg *= gamma;
+  cyj *= gamma;
+  for (int k = 0; k < col; ++k) {                    // oldest -> newest
+    const int i = (head + k) % m;
+    const double gi = __shfl_sync(0xffffffffu, gYj, i);
+    const double yr = gi * cg + half_sum(on ? cyj * YYs[i * MMAX + j] + csj * SYs[j * MMAX + i] : 0.0);
+    const double beta = yr / SYs[i * MMAX + i];
+    if (j == i) csj += alphaj - beta;
+  }
+  if (j == 0) s.cg = cg;
+  if (j < MMAX) { s.cs[j] = csj; s.cy[j] = cyj; }
+}
+
+// Reduction of NV <= 64 per-thread sums over the CTA without NV rounds through shared memory: a
+// halving butterfly inside each warp (at every step a lane hands half of its values to its partner
+// and adds the half it receives: 62 exchanges instead of 5 NV; lane l ends up with the warp sums of
+// entries 2l and 2l + 1), then the warps in order.  wred: (NT / 32) * 64 doubles.  Fixed order.
+template <int NV>
+__device__ void cta_reduce_sum(const double* acc, double* out, double* wred) {
+  static_assert(NV <= 64, "halving butterfly over 64 slots");
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double v[64];
+#pragma unroll
+  for (int k = 0; k < 64; ++k) v[k] = (k < NV) ? acc[k] : 0.0;
+#pragma unroll
+  for (int half = 32, mask = 16; half >= 2; half >>= 1, mask >>= 1) {
+    const bool up = (lane & mask) != 0;
+#pragma unroll
+    for (int k = 0; k < half; ++k) {
+      const double send = up ? v[k] : v[k + half];
+      const double keep = up ? v[k + half] : v[k];
+      v[k] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
+    }
+  }
+  // one more step (mask 1 handled above when half == 2 -> values 0, 1 remain)
+  wred[warp * 64 + 2 * lane] = v[0];
+  wred[warp * 64 + 2 * lane + 1] = v[1];
+  __syncthreads();
+  for (int k = threadIdx.x; k < NV; k += NT) {
+    double a = wred[k];
+#pragma unroll
+    for (int w = 1; w < NT / 32; ++w) a += wred[w * 64 + k];
+    out[k] = a;
+  }
+}
+
 
 // accepted step: x <- xt, g <- gt; if the pair is kept, s = stp d and y = gt - g go to slot p;
 // partial dot products (NACC_U per chunk):
@@ -406,33 +519,16 @@ __global__ void __launch_bounds__(NT, 1) lb_update_kernel(
       Y[(long long)p * hstride + off + i] = yv;
     }
   }
-  __shared__ int op[NACC_U];
-  for (int k = threadIdx.x; k < NACC_U; k += NT) op[k] = RED_SUM;
-  block_reduce<NACC_U>(acc, op, res, scratch);
+  cta_reduce_sum<NACC_U>(acc, res, scratch);
   __syncthreads();
   for (int k = threadIdx.x; k < NACC_U; k += NT)
     part[((long long)b * nchunk + blockIdx.x) * NACC_U + k] = res[k];
 }
 
-// history bookkeeping + the two-loop recursion in coefficient space; one thread per path
-__global__ void lb_gram_kernel(LbPath* st, const double* part, int nchunk, int m, int b0, int method) {
-  const int b = b0 + blockIdx.x;
-  LbPath& s = st[b];
-  if (!(s.accepted || s.redo_dir) || s.done) return;
-  __shared__ double sum[NACC_U];
-  if (s.accepted) {
-    for (int k = threadIdx.x; k < NACC_U; k += blockDim.x) {
-      double a = 0.0;
-      for (int c = 0; c < nchunk; ++c) a += part[((long long)b * nchunk + c) * NACC_U + k];
-      sum[k] = a;
-    }
-  }
-  // the Gram blocks are walked by one thread: stage them in shared memory (global latency would
-  // dominate the ~m^2 dependent loads of the two-loop recursion)
-  __shared__ double SYs[MMAX * MMAX], YYs[MMAX * MMAX];
-  for (int k = threadIdx.x; k < MMAX * MMAX; k += blockDim.x) { SYs[k] = s.SY[k]; YYs[k] = s.YY[k]; }
-  __syncthreads();
-  if (threadIdx.x != 0) return;
+// history bookkeeping + the two-loop recursion in coefficient space of one path (one thread).
+// sum: the NACC_U dot products of the update pass (read when s.accepted); SYs / YYs: the path's
+// Gram blocks staged in shared memory (updated in place and written back to s)
+__device__ void lb_gram_body(LbPath& s, const double* sum, double* SYs, double* YYs, int m, int method) {
   if (method == 1) {
     // Polak-Ribiere+:  d = -g + max(0, g_new.(g_new - g_old) / g_old.g_old) d_old
     double beta = 0.0;
@@ -498,6 +594,28 @@ __global__ void lb_gram_kernel(LbPath* st, const double* part, int nchunk, int m
   }
   s.cg = cg;
   for (int j = 0; j < MMAX; ++j) { s.cs[j] = cs[j]; s.cy[j] = cy[j]; }
+}
+
+// history bookkeeping + the two-loop recursion in coefficient space; one thread per path
+__global__ void lb_gram_kernel(LbPath* st, const double* part, int nchunk, int m, int b0, int method) {
+  const int b = b0 + blockIdx.x;
+  LbPath& s = st[b];
+  if (!(s.accepted || s.redo_dir) || s.done) return;
+  __shared__ double sum[NACC_U];
+  if (s.accepted) {
+    for (int k = threadIdx.x; k < NACC_U; k += blockDim.x) {
+      double a = 0.0;
+      for (int c = 0; c < nchunk; ++c) a += part[((long long)b * nchunk + c) * NACC_U + k];
+      sum[k] = a;
+    }
+  }
+  // the Gram blocks are walked by one thread: stage them in shared memory (global latency would
+  // dominate the ~m^2 dependent loads of the two-loop recursion)
+  __shared__ double SYs[MMAX * MMAX], YYs[MMAX * MMAX];
+  for (int k = threadIdx.x; k < MMAX * MMAX; k += blockDim.x) { SYs[k] = s.SY[k]; YYs[k] = s.YY[k]; }
+  __syncthreads();
+  if (method == 1) { if (threadIdx.x == 0) lb_gram_body(s, sum, SYs, YYs, m, method); }
+  else if (threadIdx.x < 32) lb_gram_warp(s, sum, SYs, YYs, m);
 }
 
 // d = -(cg ghat + sum_j cs_j S_j + cy_j Y_j), frozen components zero; partials [d.d, g.d, stpmx]
@@ -838,20 +956,10 @@ __global__ void __launch_bounds__(HT + 32, 1) lb_direction_tma_kernel(
 namespace {
 
 // start of a line search (lnsrlb, task = START)
-__global__ void lb_start_kernel(LbPath* st, int* act_eval, const double* part, int nchunk, LbOpts o,
-                                int bounded, int b0, int xt_fused, const int* boxed_flag) {
-  const int b = b0 + blockIdx.x;
-  LbPath& s = st[b];
-  if (!(s.accepted || s.redo_dir) || s.done) { if (s.done) { s.accepted = 0; s.redo_dir = 0; s.restore = 0.0; } return; }
-  if (s.abort_dir) { s.abort_dir = 0; return; }       // the direction is formed again next cycle (memory dropped)
-  const int boxed = boxed_flag ? *boxed_flag : 0;
+// (dd = d.d, gd = g.d, stpmx = largest feasible step of the direction just formed; one thread)
+__device__ void lb_start_body(LbPath& s, int* act, double dd, double gd, double stpmx, const LbOpts& o,
+                              int bounded, int xt_fused, int boxed) {
   s.restore = 0.0;
-  double dd = 0.0, gd = 0.0, stpmx = BIG;
-  for (int c = 0; c < nchunk; ++c) {
-    dd += part[((long long)b * nchunk + c) * 3 + 0];
-    gd += part[((long long)b * nchunk + c) * 3 + 1];
-    stpmx = fmin(stpmx, part[((long long)b * nchunk + c) * 3 + 2]);
-  }
   s.accepted = 0;
   s.redo_dir = 0;
   s.do_update = 0;
@@ -860,7 +968,7 @@ __global__ void lb_start_kernel(LbPath* st, int* act_eval, const double* part, i
   s.gdold = gd;
   if (!(gd < 0.0) || !(dd > 0.0)) {
     // not a descent direction (info = -4): drop the memory and restart, or give up
-    if (s.col == 0) { s.done = 1; s.status = (dd == 0.0) ? 0 : 2; act_eval[b] = 0; }
+    if (s.col == 0) { s.done = 1; s.status = (dd == 0.0) ? 0 : 2; *act = 0; }
     else {
       s.col = 0; s.head = 0; s.theta = 1.0; s.redo_dir = 1;
       // in-place trials: the direction pass has already moved x by this (rejected) direction;
@@ -870,7 +978,7 @@ __global__ void lb_start_kernel(LbPath* st, int* act_eval, const double* part, i
     return;
   }
   if (bounded && s.iter == 0) stpmx = fmin(stpmx, 1.0);
-  if (!(stpmx > 0.0)) { s.done = 1; s.status = 2; act_eval[b] = 0; return; }
+  if (!(stpmx > 0.0)) { s.done = 1; s.status = 2; *act = 0; return; }
   s.stpmx = stpmx;
   if (o.method == 1) {
     // SciPy's CG: alpha_1 = min(1, 1.01 * 2 (f_k - f_{k-1}) / g.d), with f_{-1} = f_0 + |g|/2
@@ -886,7 +994,23 @@ __global__ void lb_start_kernel(LbPath* st, int* act_eval, const double* part, i
   s.need_eval = 1;
   s.xt_ready = (xt_fused && s.iter > 0 && s.stp == 1.0) ? 1 : 0;   // lb_direction_tma_kernel wrote xt = x + d
   s.stp_at = s.xt_ready ? 1.0 : 0.0;
-  act_eval[b] = 1;
+  *act = 1;
+}
+
+__global__ void lb_start_kernel(LbPath* st, int* act_eval, const double* part, int nchunk, LbOpts o,
+                                int bounded, int b0, int xt_fused, const int* boxed_flag) {
+  const int b = b0 + blockIdx.x;
+  LbPath& s = st[b];
+  if (!(s.accepted || s.redo_dir) || s.done) { if (s.done) { s.accepted = 0; s.redo_dir = 0; s.restore = 0.0; } return; }
+  if (s.abort_dir) { s.abort_dir = 0; return; }       // the direction is formed again next cycle (memory dropped)
+  const int boxed = boxed_flag ? *boxed_flag : 0;
+  double dd = 0.0, gd = 0.0, stpmx = BIG;
+  for (int c = 0; c < nchunk; ++c) {
+    dd += part[((long long)b * nchunk + c) * 3 + 0];
+    gd += part[((long long)b * nchunk + c) * 3 + 1];
+    stpmx = fmin(stpmx, part[((long long)b * nchunk + c) * 3 + 2]);
+  }
+  lb_start_body(s, act_eval + b, dd, gd, stpmx, o, bounded, xt_fused, boxed);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -925,10 +1049,7 @@ __global__ void __launch_bounds__(NT) lb_save_kernel(const double* __restrict__ 
   }
 }
 
-__global__ void lb_advance_kernel(LbPath* st, int* act_eval, int B, LbLadder L, LbOpts o) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
-  LbPath& s = st[b];
+__device__ void lb_advance_body(LbPath& s, int* act_eval, int b, const LbLadder& L, const LbOpts& o) {
   if (!s.done || s.finished) return;
   const int ib = s.ib;
   if (L.table) {
@@ -947,6 +1068,266 @@ __global__ void lb_advance_kernel(LbPath* st, int* act_eval, int B, LbLadder L, 
     s.finished = 1;
     s.accepted = 0; s.redo_dir = 0;
     act_eval[b] = 0;
+  }
+}
+
+__global__ void lb_advance_kernel(LbPath* st, int* act_eval, int B, LbLadder L, LbOpts o) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  lb_advance_body(st[b], act_eval, b, L, o);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Small problems (the shipped Lorenz96 example: n = 3221): a cycle of eleven dependent launches
+// costs ~60 us of launch latency for a few microseconds of work.  Everything that follows the
+// evaluation -- g.d, the line-search decision, the history update, the two-loop recursion, the new
+// direction, the start of the next search, the end-of-rung bookkeeping and the next trial point --
+// is done here by ONE thread-block cluster per path: FCS CTAs, each owning one chunk of the
+// vectors (read from L2; a CTA only ever touches its own chunk), partial dot products exchanged
+// through distributed shared memory, phases separated by cluster barriers, decisions taken by
+// thread 0 of CTA 0 with the same code (lb_*_body) as the per-phase kernels and published to the
+// other CTAs through CTA 0's shared memory.  A cycle is then three launches (walk, finalize, this).
+// Unbounded L-BFGS and CG; separate trial buffer XT.  What it buys is modest -- replayed from a CUDA
+// graph the eleven small kernels cost ~1.7 us each, not the 5 us of an eager launch: the fused
+// kernel itself takes ~20 us (the update pass and the coefficient-space recursion dominate), the
+// walk ~12 us -- so it is used only while every cluster gets its own SMs (B * FCS <= SM count).
+constexpr int FCS = 8;                  // CTAs per path (cluster size)
+
+struct FusedFlags {
+  int finished, done, need_eval, first, accepted, do_update, redo_dir, pslot, col, ib;
+  double stp, cg, cd;
+  double cs[MMAX], cy[MMAX];
+};
+__device__ void fused_publish(FusedFlags& F, const LbPath& s) {
+  F.finished = s.finished; F.done = s.done; F.need_eval = s.need_eval; F.first = s.first;
+  F.accepted = s.accepted; F.do_update = s.do_update; F.redo_dir = s.redo_dir; F.pslot = s.pslot;
+  F.col = s.col; F.ib = s.ib;
+  F.stp = s.stp; F.cg = s.cg; F.cd = s.cd;
+  for (int j = 0; j < MMAX; ++j) { F.cs[j] = s.cs[j]; F.cy[j] = s.cy[j]; }
+}
+
+__global__ void __cluster_dims__(FCS, 1, 1) __launch_bounds__(NT, 1) lb_fused_kernel(
+    double* X, double* G, double* XT, const double* GT, double* Dv, double* S, double* Y, long long ld,
+    long long n, long long hstride, LbPath* st, int* act_eval, const double* ft, const double* met,
+    const double* fet, LbOpts o, LbLadder L, long long* dbg) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cl = cg::this_cluster();
+  __shared__ double scratch[8 * NT];
+  __shared__ double res[NACC_U];
+  __shared__ double sum[NACC_U];
+  __shared__ double SYs[MMAX * MMAX], YYs[MMAX * MMAX];
+  __shared__ int ops[NACC_U];
+  __shared__ FusedFlags F;
+  const int rank = (int)cl.block_rank(), tid = threadIdx.x;
+  const int b = blockIdx.x / FCS;
+  const bool lead = (rank == 0 && tid == 0);
+  // development aid (VAB_FUSED_TIMING=1): SM cycles spent up to each phase boundary, summed over calls
+  long long t_prev = 0;
+  int t_slot = 0;
+  auto stamp = [&]() {
+    if (dbg != nullptr && lead && blockIdx.x == 0) {
+      const long long t = clock64();
+      if (t_slot > 0) dbg[t_slot] += t - t_prev;
+      t_prev = t;
+      ++t_slot;
+    }
+  };
+  stamp();
+  // the path's state lives in CTA 0's shared memory for the duration of the kernel: the decision
+  // code is a single thread chasing a few hundred dependent loads and stores, which costs tens of
+  // microseconds against global memory and next to nothing here
+  __shared__ LbPath sp;
+  static_assert(sizeof(LbPath) % 8 == 0, "LbPath is copied as 8-byte words");
+  LbPath& s = sp;                                     // touched by CTA 0 only
+  if (rank == 0) {
+    const unsigned long long* src = reinterpret_cast<const unsigned long long*>(st + b);
+    unsigned long long* dst = reinterpret_cast<unsigned long long*>(&sp);
+    for (int k = tid; k < (int)(sizeof(LbPath) / 8); k += NT) dst[k] = src[k];
+    __syncthreads();
+  }
+  const FusedFlags* F0 = cl.map_shared_rank(&F, 0);
+  const long long off = (long long)b * ld;
+  const Range r = chunk_range(n, FCS, rank);
+  const int m = o.m;
+  // sum over the CTAs' res[k], in rank order (fixed order: bit-reproducible)
+  auto gather = [&](int k, int op) {
+    double a = 0.0;
+    for (int q = 0; q < FCS; ++q) {
+      const double u = *cl.map_shared_rank(&res[k], q);
+      a = (q == 0) ? u : ((op == RED_SUM) ? a + u : (op == RED_MAX ? fmax(a, u) : fmin(a, u)));
+    }
+    return a;
+  };
+
+  if (lead) fused_publish(F, s);
+  cl.sync();
+  stamp();
+  const bool fin = F0->finished != 0;
+  cl.sync();                                          // (CTA 0 must not leave before the others have read the flag)
+  stamp();
+  if (fin) return;                                    // uniform over the cluster (nothing to write back)
+
+  // ---- g.d and max |g| of the trial point (lb_gd_kernel), then the line-search decision
+  const bool ph1 = !F0->done && F0->need_eval;
+  if (ph1) {
+    const bool first = F0->first != 0;
+    double v[2] = {0.0, 0.0};
+    for (long long i = r.i0 + tid; i < r.i1; i += NT) {
+      const double gi = GT[off + i];
+      if (!first) v[0] = fma(gi, Dv[off + i], v[0]);
+      v[1] = fmax(v[1], fabs(gi));
+    }
+    const int op2[2] = {RED_SUM, RED_MAX};
+    block_reduce<2>(v, op2, res, scratch);
+  }
+  cl.sync();
+  stamp();
+  if (lead) {
+    if (ph1) lb_linesearch_body(s, act_eval + b, ft[b], met[b], fet[b], gather(0, RED_SUM), gather(1, RED_MAX), o);
+    fused_publish(F, s);
+  }
+  cl.sync();
+  stamp();
+
+  // ---- accepted step: x <- xt, g <- gt, new pair into slot p, dot products (lb_update_kernel)
+  const bool ph2 = F0->accepted != 0;
+  const bool ph3 = (F0->accepted || F0->redo_dir) && !F0->done;
+  const bool done_now = F0->done != 0;
+  if (ph2) {
+    const bool upd = F0->do_update != 0;
+    const int p = F0->pslot, col = F0->col;
+    const double stp = F0->stp;
+    double acc[NACC_U];
+#pragma unroll
+    for (int k = 0; k < NACC_U; ++k) acc[k] = 0.0;
+    for (long long i = r.i0 + tid; i < r.i1; i += NT) {
+      const double xt = XT[off + i], gt = GT[off + i];
+      const double gold = G[off + i];
+      double sv = 0.0, yv = 0.0;
+      if (upd) {
+        sv = stp * Dv[off + i];
+        yv = gt - gold;
+      }
+      const double gh = gt;
+#pragma unroll
+      for (int j = 0; j < MMAX; ++j) {
+        if (j < m && (j < col || col == m) && !(upd && j == p)) {
+          const double sj = S[(long long)j * hstride + off + i];
+          const double yj = Y[(long long)j * hstride + off + i];
+          acc[j] = fma(gh, sj, acc[j]);
+          acc[MMAX + j] = fma(gh, yj, acc[MMAX + j]);
+          acc[2 * MMAX + j] = fma(sv, yj, acc[2 * MMAX + j]);
+          acc[3 * MMAX + j] = fma(yv, sj, acc[3 * MMAX + j]);
+          acc[4 * MMAX + j] = fma(yv, yj, acc[4 * MMAX + j]);
+        }
+      }
+      acc[5 * MMAX] = fma(yv, yv, acc[5 * MMAX]);
+      acc[5 * MMAX + 1] = fma(gh, sv, acc[5 * MMAX + 1]);
+      acc[5 * MMAX + 2] = fma(gh, yv, acc[5 * MMAX + 2]);
+      acc[5 * MMAX + 3] = fma(gh, gh, acc[5 * MMAX + 3]);
+      X[off + i] = xt;
+      G[off + i] = gt;
+      if (upd) {
+        S[(long long)p * hstride + off + i] = sv;
+        Y[(long long)p * hstride + off + i] = yv;
+      }
+    }
+    cta_reduce_sum<NACC_U>(acc, res, scratch);
+  }
+  cl.sync();
+  stamp();
+  // ---- history bookkeeping and two-loop recursion (lb_gram_kernel), CTA 0
+  if (rank == 0) {
+    if (ph3) {
+      if (ph2)
+        for (int k = tid; k < NACC_U; k += NT) sum[k] = gather(k, RED_SUM);
+      for (int k = tid; k < MMAX * MMAX; k += NT) { SYs[k] = s.SY[k]; YYs[k] = s.YY[k]; }
+      __syncthreads();
+      if (o.method == 1) { if (tid == 0) lb_gram_body(s, sum, SYs, YYs, m, o.method); }
+      else if (tid < 32) lb_gram_warp(s, sum, SYs, YYs, m);
+      __syncthreads();
+    }
+    if (tid == 0) fused_publish(F, s);
+  }
+  cl.sync();
+  stamp();
+
+  // ---- d = -(cg g + sum_j cs_j S_j + cy_j Y_j) [+ cd d_old]; d.d, g.d (lb_direction_kernel)
+  if (ph3) {
+    const int col = F0->col;
+    double cs[MMAX], cy[MMAX];
+#pragma unroll
+    for (int j = 0; j < MMAX; ++j) { cs[j] = F0->cs[j]; cy[j] = F0->cy[j]; }
+    const double cgc = F0->cg, cd = F0->cd;
+    double v[3] = {0.0, 0.0, BIG};
+    for (long long i = r.i0 + tid; i < r.i1; i += NT) {
+      const double g = G[off + i];
+      double rr = cgc * g;
+#pragma unroll
+      for (int j = 0; j < MMAX; ++j) {
+        if (j < m && (j < col || col == m)) {
+          rr = fma(cs[j], S[(long long)j * hstride + off + i], rr);
+          rr = fma(cy[j], Y[(long long)j * hstride + off + i], rr);
+        }
+      }
+      double d = -rr;
+      if (cd != 0.0) d = fma(cd, Dv[off + i], d);
+      Dv[off + i] = d;
+      v[0] = fma(d, d, v[0]);
+      v[1] = fma(g, d, v[1]);
+    }
+    const int op3[3] = {RED_SUM, RED_SUM, RED_MIN};
+    block_reduce<3>(v, op3, res, scratch);
+  }
+  cl.sync();
+  stamp();
+  // ---- start of the next line search (lb_start_kernel)
+  if (lead) {
+    if (!ph3) { if (done_now) { s.accepted = 0; s.redo_dir = 0; s.restore = 0.0; } }
+    else if (s.abort_dir) s.abort_dir = 0;
+    else lb_start_body(s, act_eval + b, gather(0, RED_SUM), gather(1, RED_SUM), gather(2, RED_MIN), o, 0, 0, 0);
+    fused_publish(F, s);
+  }
+  cl.sync();
+  stamp();
+
+  // ---- end of a rung: minimiser to minpaths, table row, next rung (lb_save_kernel + lb_advance_kernel)
+  const bool ph5 = F0->done && !F0->finished;
+  const int ib = F0->ib;
+  cl.sync();                                          // everyone has read the flags of this phase
+  stamp();
+  if (ph5) {
+    if (L.minpaths != nullptr) {
+      double* out = L.minpaths + ((long long)b * L.Nbeta + ib) * L.mp_pitch;
+      if (L.winw != n) {
+        const long long w0 = r.i0 > L.win0 ? r.i0 : L.win0;
+        const long long w1 = r.i1 < L.win0 + L.winw ? r.i1 : L.win0 + L.winw;
+        for (long long i = w0 + tid; i < w1; i += NT) out[i - L.win0] = X[off + i];
+      } else {
+        for (long long i = r.i0 + tid; i < r.i1; i += NT) out[i] = X[off + i];
+      }
+    }
+    if (lead) { lb_advance_body(s, act_eval, b, L, o); fused_publish(F, s); }
+  }
+  cl.sync();
+  stamp();
+
+  // ---- trial point of the next evaluation (lb_trial_kernel)
+  if (!F0->done && F0->need_eval) {
+    if (F0->first) {
+      for (long long i = r.i0 + tid; i < r.i1; i += NT) XT[off + i] = X[off + i];
+    } else {
+      const double stp = F0->stp;
+      for (long long i = r.i0 + tid; i < r.i1; i += NT) XT[off + i] = fma(stp, Dv[off + i], X[off + i]);
+    }
+  }
+  cl.sync();                                          // no CTA leaves while its shared memory may still be read
+  stamp();
+  if (dbg != nullptr && lead && blockIdx.x == 0) dbg[0] += 1;
+  if (rank == 0) {                                    // state back to global memory
+    const unsigned long long* src = reinterpret_cast<const unsigned long long*>(&sp);
+    unsigned long long* dst = reinterpret_cast<unsigned long long*>(st + b);
+    for (int k = tid; k < (int)(sizeof(LbPath) / 8); k += NT) dst[k] = src[k];
   }
 }
 
@@ -1008,7 +1389,8 @@ int lb_reserve(vab_ctx* ctx, int B, long long ld, int m, int Nbeta, bool need_xt
     LB_CUDA(cudaMalloc((void**)&w->fet, sizeof(double) * B));
     w->st_cap = B;
   }
-  const int nchunk = lb_nchunk(ctx->n_unknowns(), B);
+  int nchunk = lb_nchunk(ctx->n_unknowns(), B);
+  if (nchunk < FCS) nchunk = FCS;                 // small problems use FCS fixed chunks (lb_run)
   rc = vab_reserve(ctx, &w->part, &w->part_cap, (size_t)B * nchunk * (gcp ? NPB : NACC_U));
   if (rc != VAB_OK) return rc;
   rc = vab_reserve(ctx, &w->lad, &w->lad_cap, (size_t)2 * Nbeta + B);
@@ -1079,6 +1461,18 @@ int lb_run(vab_ctx* ctx, int B, double* XP, long long ld, const double* scales_h
   // the TMA-fed history passes serve the unbounded L-BFGS case (VAB_LBFGS_TMA=0: plain kernels)
   bool use_tma = !bounded && o.method == 0;
   if (const char* e = getenv("VAB_LBFGS_TMA")) use_tma = use_tma && atoi(e) != 0;
+  // small unbounded problems are launch-latency bound: one cluster per path does everything
+  // behind the evaluation in a single launch (lb_fused_kernel); VAB_LBFGS_FUSED=0/1 overrides
+  // (measured on the shipped Lorenz96 example, n = 3221: 37 us per cycle against 50 us for one path,
+  // 50 against 58 us for 16; with more clusters than SMs the per-phase kernels win again)
+  // Small problems (n <= 32768) run the plain kernels on FCS fixed chunks per path; the fused kernel
+  // does exactly the same arithmetic in the same order (chunks, reduction trees, recursion), so the
+  // choice between the two is pure scheduling and the results are bit-identical
+  // (tests/test_gpu_ladder.py::test_fused_cycle_kernel_is_bit_identical).
+  const bool small = !bounded && n <= 32768;
+  bool fused = small && (long long)B * FCS <= ctx->num_sms;
+  if (const char* e = getenv("VAB_LBFGS_FUSED")) fused = small && atoi(e) != 0;
+  if (small) use_tma = false;
   // bounded L-BFGS-B: generalised Cauchy point + subspace minimisation (lbfgsb_bounded.cuh);
   // VAB_BOUNDS=projection selects round 1's active-set projection for comparison
   bool gcp = bounded && o.method == 0;
@@ -1099,7 +1493,7 @@ int lb_run(vab_ctx* ctx, int B, double* XP, long long ld, const double* scales_h
   double* Rs = gcp ? w->vec + (6 + 2 * (size_t)o.m) * vs : nullptr;
   int* boxed_dev = w->n_running_dev + 2;
   const long long hstride = (long long)vs;
-  const int nchunk = lb_nchunk(n, B);
+  const int nchunk = small ? FCS : lb_nchunk(n, B);
   const dim3 vgrid(nchunk, B);
   // ring depth: 2 stages x 2 CTAs per SM (measured best on B200: C2 update 0.93 ms = 6.7 TB/s,
   // direction 0.75 ms) or 4 stages x 1 CTA per SM (VAB_LBFGS_NS=4: 0.99 / 0.78 ms)
@@ -1143,7 +1537,24 @@ int lb_run(vab_ctx* ctx, int B, double* XP, long long ld, const double* scales_h
     // small problems are launch-bound (a cycle is ~30 us): poll rarely; large ones take ms per cycle
     poll = (n * (long long)B < (1LL << 22)) ? 64 : 8;
   }
+  long long* fused_dbg = nullptr;
+  if (fused && getenv("VAB_FUSED_TIMING")) {
+    if (cudaMalloc((void**)&fused_dbg, 32 * sizeof(long long)) == cudaSuccess) cudaMemset(fused_dbg, 0, 32 * sizeof(long long));
+    else fused_dbg = nullptr;
+  }
+  if (fused) {                                 // the first trial point (x itself); later ones come from lb_fused_kernel
+    lb_trial_kernel<<<vgrid, NT, 0, st>>>(XT, XP, Dv, ld, n, w->st, nchunk, 0, nullptr);
+    ctx->launches += 1;
+  }
   auto enqueue_cycle = [&](cudaStream_t st) -> int {
+    if (fused) {
+      int r = vab_eval(ctx, B, XT, ld, 1.0, L.rf_path, w->act_eval, w->ft, w->met, w->fet, GT, ld);
+      if (r != VAB_OK) return r;
+      lb_fused_kernel<<<B * FCS, NT, 0, st>>>(XP, G, XT, GT, Dv, S, Y, ld, n, hstride, w->st, w->act_eval,
+                                              w->ft, w->met, w->fet, o, L, fused_dbg);
+      ctx->launches += 1;
+      return VAB_OK;
+    }
     const int inplace = use_tma ? 1 : 0;       // unbounded L-BFGS: x moves in place, no trial buffer
     lb_trial_kernel<<<vgrid, NT, 0, st>>>(XT, XP, Dv, ld, n, w->st, nchunk, inplace, Zc);
     int r = vab_eval(ctx, B, inplace ? XP : XT, ld, 1.0, L.rf_path, w->act_eval, w->ft, w->met, w->fet, GT, ld);
@@ -1298,6 +1709,15 @@ int lb_run(vab_ctx* ctx, int B, double* XP, long long ld, const double* scales_h
     }
   }
   cudaStreamSynchronize(st);
+  if (fused_dbg) {
+    long long h[32];
+    if (cudaMemcpy(h, fused_dbg, sizeof(h), cudaMemcpyDeviceToHost) == cudaSuccess && h[0] > 0) {
+      fprintf(stderr, "lb_fused_kernel: %lld calls; mean SM cycles per phase:", h[0]);
+      for (int q = 1; q < 16; ++q) fprintf(stderr, " %.0f", (double)h[q] / (double)h[0]);
+      fprintf(stderr, "\n");
+    }
+    cudaFree(fused_dbg);
+  }
   if (sink && rc_loop == VAB_OK) {
     cudaError_t ce = send_rows(nullptr);
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(w->copy_stream);
