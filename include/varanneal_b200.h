@@ -134,6 +134,14 @@ VAB_API int vab_ode_problem_set(vab_ctx* ctx, const vab_ode_desc* desc,
 VAB_API int vab_ode_set_weights(vab_ctx* ctx, double rm_scalar, const double* rm_dev,
                         double rf0_scalar, const double* rf0_dev);
 
+/* Matrix form of RM: rm_dev is (N_data, L, L) row-major -- an (L, L) matrix is repeated over time by
+ * the caller, as va_ode.py:616-617 does -- and the measurement error is
+ * sum_i diff_i . (RM_i diff_i) / (L N_data) (va_ode.py:149-152; the matrix need not be symmetric).
+ * Replaces the scalar / per-entry RM of vab_ode_set_weights (which in turn clears the matrix); RF0 is
+ * left as it is.  The array must stay alive while it is set.  The term costs L^2 work per observed
+ * entry in a kernel of its own behind the fused action kernels. */
+VAB_API int vab_ode_set_rm_matrix(vab_ctx* ctx, const double* rm_dev);
+
 /* Values of the parameters that are NOT estimated (va_ode.py:178-181): pfix_dev is (NP) shared by
  * all paths (pfix_stride = 0) or (B, NP) (pfix_stride = NP).  Estimated entries are ignored. */
 VAB_API int vab_ode_set_fixed_params(vab_ctx* ctx, const double* pfix_dev, int64_t pfix_stride);

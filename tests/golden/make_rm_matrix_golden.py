@@ -1,0 +1,85 @@
+"""Golden fixtures for the matrix form of RM -- (L, L) or (N_data, L, L), va_ode.py:149-152, 612-621 --
+generated from the reference itself.  Run in the build container (needs /root/reference):
+
+    python tests/golden/make_rm_matrix_golden.py
+
+Action values are the verbatim reference's (A_gaussian / me_gaussian / fe_gaussian through
+oracle.ref_shim), gradients are complex-step differentiation through it.  The matrices are
+deliberately *not* symmetric -- the gradient of diff.(RM diff) is (RM + RM') diff -- but their
+symmetric part is positive definite, so the action can be minimised.
+"""
+import contextlib
+import io
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_shim                      # noqa: E402
+from oracle.models_np import MODELS              # noqa: E402
+from oracle.ode_port import OdeProblem           # noqa: E402
+
+REF = ref_shim.REFERENCE_ROOT
+L96_FILE = os.path.join(REF, "examples", "Lorenz96_D20", "l96_D20_dt0p025_N161_sm0p5_sec1_mem1.npy")
+ShimOde, _ = ref_shim.make_shim_classes()
+LIDX = [0, 2, 4, 6, 8, 10, 14, 16]
+
+
+def main():
+    data = np.load(L96_FILE)
+    t, Yall = data[:, 0], data[:, 1:]
+    rng = np.random.RandomState(2024)
+    L = len(LIDX)
+    out, names = {}, []
+    for name, disc, nd, dt_model, per_time in (("LL_trapezoid", "trapezoid", 41, None, False),
+                                               ("NLL_simpson", "SimpsonHermite", 41, None, True),
+                                               ("NLL_nskip2_euler", "euler", 21, 0.0125, True),
+                                               ("LL_lorenz63", "trapezoid", 31, None, False)):
+        if "lorenz63" in name:
+            model, D, Lidx, P0, Pidx = "lorenz63", 3, [0, 2], np.array([10.0, 28.0, 8.0 / 3.0]), [1]
+            tt = 0.01 * np.arange(nd)
+            Y = rng.randn(nd, 2) * 5.0
+        else:
+            model, D, Lidx, P0, Pidx = "lorenz96", 20, LIDX, np.array([8.17]), [0]
+            tt, Y = t[:nd], Yall[:nd][:, LIDX]
+        Lc = len(Lidx)
+        def mat():          # positive definite symmetric part (the action stays bounded below) + a skew part
+            G, H = rng.randn(Lc, Lc), rng.randn(Lc, Lc)
+            return 3.0 * np.eye(Lc) + G.dot(G.T) / Lc + 0.8 * (H - H.T)
+        RM = np.array([mat() for _ in range(nd)]) if per_time else mat()
+        an = ShimOde()
+        an.set_model(MODELS[model], D)
+        an.set_data(Y, t=tt)
+        nskip = 1 if dt_model is None else int(round((tt[1] - tt[0]) / dt_model))
+        N = (nd - 1) * nskip + 1
+        X0 = 20.0 * rng.rand(N, D) - 10.0
+        alpha, beta, RF0 = 1.5, 14, 4e-6
+        with contextlib.redirect_stdout(io.StringIO()):
+            an.anneal_init(X0.copy(), P0.copy(), alpha, [beta], RM.copy(), RF0, np.array(Lidx), Pidx,
+                           dt_model=dt_model, init_to_data=False, disc=disc)
+        XP = np.append(X0.ravel(), P0[Pidx])
+        A = float(an.A(XP))
+        me = float(an.me_gaussian(XP[:N * D]))
+        fe = float(an.fe_gaussian(XP))
+        g = ref_shim.complex_step_grad(an.A, XP)
+        RMfull = RM if RM.ndim == 3 else np.resize(RM, (nd, Lc, Lc))
+        prob = OdeProblem(model, D, Y, Lidx, an.dt_model, disc, P0, Pidx, RMfull, nskip=nskip)
+        Ap, mep, fep, gp = prob.action_grad(XP, RF0 * alpha ** beta, parts=True)
+        print("%-18s A=%.16e me=%.6e port rel %.1e / %.1e grad rel %.1e" % (
+            name, A, me, abs(Ap - A) / abs(A), abs(mep - me) / abs(me), np.max(np.abs(gp - g)) / np.max(np.abs(g))))
+        names.append(name)
+        for k, v in (("X0", X0), ("P0", P0), ("t", tt), ("Y", Y), ("Lidx", np.asarray(Lidx, dtype=np.int64)),
+                     ("Pidx", np.asarray(Pidx, dtype=np.int64)), ("RM", RM),
+                     ("meta", np.array([alpha, beta, RF0, -1.0 if dt_model is None else dt_model])),
+                     ("model_disc", np.array([model, disc])), ("A", np.array([A, me, fe])), ("grad", g)):
+            out[name + "/" + k] = np.asarray(v)
+    out["names"] = np.array(names)
+    np.savez_compressed(os.path.join(HERE, "ode_rm_matrix_golden.npz"), **out)
+
+
+if __name__ == "__main__":
+    main()

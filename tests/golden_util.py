@@ -44,6 +44,21 @@ def ptime_cases():
     return out
 
 
+def rm_matrix_cases():
+    """Cases of ode_rm_matrix_golden.npz (matrix RM, tests/golden/make_rm_matrix_golden.py)."""
+    z = load("ode_rm_matrix_golden.npz")
+    out = []
+    for n in z["names"]:
+        n = str(n)
+        alpha, beta, RF0, dtm = z[n + "/meta"]
+        model, disc = [str(s) for s in z[n + "/model_disc"]]
+        out.append(dict(name=n, model=model, disc=disc, X0=z[n + "/X0"], P0=z[n + "/P0"], t=z[n + "/t"], Y=z[n + "/Y"],
+                        stim=None, Lidx=z[n + "/Lidx"], Pidx=z[n + "/Pidx"], RM=z[n + "/RM"], RF0=float(RF0),
+                        alpha=float(alpha), beta=int(beta), dt_model=None if dtm < 0 else float(dtm),
+                        A=z[n + "/A"], grad=z[n + "/grad"]))
+    return out
+
+
 def nnet_cases():
     z = load("nnet_action_golden.npz")
     out = []

@@ -50,6 +50,22 @@ def test_ode_port_matches_reference_golden(c):
 
 
 PTIME_CASES = golden_util.ptime_cases()
+RM_CASES = golden_util.rm_matrix_cases()
+
+
+@pytest.mark.parametrize("c", RM_CASES, ids=[c["name"] for c in RM_CASES])
+def test_ode_port_matrix_rm_matches_reference_golden(c):
+    """RM of shape (L, L) / (N_data, L, L): sum_i diff_i . (RM_i diff_i) (va_ode.py:149-152)."""
+    nd = c["Y"].shape[0]
+    L = len(c["Lidx"])
+    cc = dict(c, RM=c["RM"] if c["RM"].ndim == 3 else np.resize(c["RM"], (nd, L, L)))
+    prob = _problem(cc)
+    XP = np.append(c["X0"].ravel(), c["P0"][c["Pidx"]])
+    A, me, fe, g = prob.action_grad(XP, _rf(c, prob), parts=True)
+    assert abs(A - c["A"][0]) <= 1e-13 * abs(c["A"][0])
+    assert abs(me - c["A"][1]) <= 1e-13 * abs(c["A"][1])
+    assert abs(fe - c["A"][2]) <= 1e-12 * abs(c["A"][2])
+    assert np.max(np.abs(g - c["grad"])) <= 1e-12 * np.max(np.abs(c["grad"]))
 
 
 @pytest.mark.parametrize("c", PTIME_CASES, ids=[c["name"] for c in PTIME_CASES])

@@ -43,6 +43,7 @@ _SIGS = {
     "vab_ode_problem_set": (ct.c_int, [_VP, ct.POINTER(OdeDesc), c_int_p, c_int_p, _VP, _VP]),
     "vab_ode_set_weights": (ct.c_int, [_VP, ct.c_double, _VP, ct.c_double, _VP]),
     "vab_ode_set_fixed_params": (ct.c_int, [_VP, _VP, ct.c_int64]),
+    "vab_ode_set_rm_matrix": (ct.c_int, [_VP, _VP]),
     "vab_ode_set_time_dependent": (ct.c_int, [_VP, ct.c_int32, _VP, ct.c_int64]),
     "vab_ode_action_grad": (ct.c_int, [_VP, ct.c_int32, _VP, ct.c_int64, ct.c_double,
                                        _VP, _VP, _VP, _VP, ct.c_int64]),

@@ -51,6 +51,52 @@ __global__ void vab_scatter_obs_kernel(const double* __restrict__ src, double* _
   dst[r * D + comp[l]] = scale * src[i];
 }
 
+// Matrix RM (va_ode.py:149-152): me = cm sum_i diff_i . (RM_i diff_i), gradient cm (RM_i + RM_i') diff_i.
+// The quadratic form couples the observed components of a row, which the walk kernels spread over
+// lanes; it is added here, after the walk + finalize kernels (which run with zero measurement
+// weights): one CTA per path, thread per (data row, observed column), fixed-order reduction.
+// rm: (N_data, L, L) row-major.  Meant for the small problems this form of RM is used on (L^2 work
+// per observed entry).
+__global__ void __launch_bounds__(256) ode_me_matrix_kernel(const double* XP, long long ldxp, double* G,
+                                                            long long ldg, const double* Yd, const int* lcomp,
+                                                            const double* rm, int N_data, int L, int D, int nskip,
+                                                            double cm, const int* active, double* A, double* me) {
+  const int b = blockIdx.x;
+  if (active != nullptr && active[b] == 0) return;
+  const double* x = XP + (long long)b * ldxp;
+  double* g = G ? G + (long long)b * ldg : nullptr;
+  double acc = 0.0;
+  for (long long t = threadIdx.x; t < (long long)N_data * L; t += 256) {
+    const long long i = t / L;
+    const int l = (int)(t - i * L);
+    const long long xrow = i * nskip * D, yrow = i * D;
+    const double* R = rm + i * L * L;
+    double w = 0.0, wt = 0.0;
+    for (int k = 0; k < L; ++k) {
+      const int c = lcomp[k];
+      const double dk = x[xrow + c] - Yd[yrow + c];
+      w = fma(R[(long long)l * L + k], dk, w);
+      wt = fma(R[(long long)k * L + l], dk, wt);
+    }
+    const int cl = lcomp[l];
+    const double dl = x[xrow + cl] - Yd[yrow + cl];
+    acc = fma(dl, w, acc);
+    if (g) g[xrow + cl] += cm * (w + wt);
+  }
+  __shared__ double red[256];
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int sft = 128; sft > 0; sft >>= 1) {
+    if ((int)threadIdx.x < sft) red[threadIdx.x] += red[threadIdx.x + sft];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double v = cm * red[0];
+    if (A) A[b] += v;
+    if (me) me[b] += v;
+  }
+}
+
 // src == nullptr: fill one row with `scale` at the observed components (the scalar-RM weights)
 static int vab_scatter_obs(vab_ctx* ctx, const double* src, long long rows, double scale,
                            double** dst, size_t* cap) {
@@ -273,6 +319,7 @@ int vab_ode_problem_set(vab_ctx* ctx, const vab_ode_desc* d, const int32_t* Lidx
   ctx->pfix_dev = ctx->pfix_zero;
   ctx->pfix_stride = 0;
   ctx->ptime = 0;
+  ctx->rm_matrix = nullptr;
   ctx->rf0_scalar = 1.0; ctx->rf0_dev = nullptr;
   ctx->problem = VAB_PROBLEM_ODE;
   const int rcw = vab_ode_set_weights(ctx, 1.0, nullptr, 1.0, nullptr);
@@ -288,6 +335,7 @@ int vab_ode_set_weights(vab_ctx* ctx, double rm_scalar, const double* rm_dev, do
   const vab_ode_desc& d = ctx->od;
   const double cm2 = d.L > 0 ? 2.0 / ((double)d.L * d.N_data) : 0.0;
   ctx->rm_scalar = rm_scalar; ctx->rm_dev = nullptr;
+  ctx->rm_matrix = nullptr;
   {  // weights of the measurement term in the dense layout: 2 cm RM at the observed components
     size_t cap = (size_t)d.D + 2;
     int rc = vab_scatter_obs(ctx, nullptr, 1, 0.0, &ctx->wobs_dev, &cap);   // zero fill
@@ -323,6 +371,20 @@ int vab_ode_set_fixed_params(vab_ctx* ctx, const double* pfix_dev, int64_t pfix_
                                                      : "set_fixed_params: stride must be 0 or NP");
   ctx->pfix_dev = pfix_dev;
   ctx->pfix_stride = pfix_stride;
+  return VAB_OK;
+}
+
+int vab_ode_set_rm_matrix(vab_ctx* ctx, const double* rm_dev) {
+  if (!ctx) return VAB_ERR_INVALID;
+  if (ctx->problem != VAB_PROBLEM_ODE) return vab_fail(ctx, VAB_ERR_STATE, "set_rm_matrix: no ODE problem set");
+  if (!rm_dev) return vab_fail(ctx, VAB_ERR_INVALID, "set_rm_matrix: NULL");
+  if (ctx->od.L < 1) return vab_fail(ctx, VAB_ERR_INVALID, "set_rm_matrix: nothing is observed");
+  // the walk kernels carry no measurement term any more; RF0 stays what it was
+  const double rf0 = ctx->rf0_scalar;
+  const double* rf0d = ctx->rf0_dev;
+  const int rc = vab_ode_set_weights(ctx, 0.0, nullptr, rf0, rf0d);
+  if (rc != VAB_OK) return rc;
+  ctx->rm_matrix = rm_dev;
   return VAB_OK;
 }
 
@@ -407,6 +469,13 @@ static int ode_eval(vab_ctx* ctx, int B, const double* XP, long long ldxp, doubl
   if (rc == -1) return vab_fail(ctx, VAB_ERR_INVALID, "ode_action_grad: no kernel for this model/disc");
   if (rc != 0) return vab_cuda_fail(ctx, cerr, "ode_action_grad launch");
   ctx->launches += 2;
+  if (ctx->rm_matrix != nullptr) {
+    ode_me_matrix_kernel<<<B, 256, 0, ctx->stream>>>(XP, ldxp, G, ldg, ctx->Y_dense, ctx->lcomp_dev, ctx->rm_matrix,
+                                                     d.N_data, d.L, d.D, d.nskip, P.cm, active_dev, A, me);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return vab_cuda_fail(ctx, e, "ode_me_matrix_kernel");
+    ctx->launches += 1;
+  }
   return VAB_OK;
 }
 

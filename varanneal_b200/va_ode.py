@@ -238,11 +238,12 @@ class Annealer(DeviceMin):
         if isinstance(RM, np.ndarray) and RM.ndim > 0:
             if RM.shape == (self.L,):
                 self.RM = np.resize(RM, (self.N_data, self.L)).astype(np.float64)
-            elif RM.shape == (self.N_data, self.L):
+            elif RM.shape == (self.L, self.L):
+                self.RM = np.resize(RM, (self.N_data, self.L, self.L)).astype(np.float64)   # va_ode.py:616-617
+            elif RM.shape in ((self.N_data, self.L), (self.N_data, self.L, self.L)):
                 self.RM = RM.astype(np.float64)
             else:
-                raise ValueError("RM must be a scalar, (L,) or (N_data, L); the matrix forms "
-                                 "(va_ode.py:149-152) are not supported")
+                raise ValueError("RM must be a scalar, (L,), (N_data, L), (L, L) or (N_data, L, L)")
         else:
             self.RM = float(RM)
         if isinstance(RF0, list):
@@ -301,11 +302,14 @@ class Annealer(DeviceMin):
         _lib.check(ctx.lib.vab_ode_problem_set(
             ctx.h, desc, _lib.int_array(self.Lidx), _lib.int_array(self.Pidx),
             ptr(self._Y_dev), ptr(self._stim_dev)), ctx.h)
+        rm_matrix = (not np.isscalar(self.RM)) and self.RM.ndim == 3          # va_ode.py:149-152
         self._rm_dev = None if np.isscalar(self.RM) else self._to_dev(self.RM)
         self._rf0_dev = None if np.isscalar(self.RF0) else self._to_dev(self.RF0)
         _lib.check(ctx.lib.vab_ode_set_weights(
-            ctx.h, self.RM if np.isscalar(self.RM) else 0.0, ptr(self._rm_dev),
+            ctx.h, self.RM if np.isscalar(self.RM) else 0.0, None if rm_matrix else ptr(self._rm_dev),
             self.RF0 if np.isscalar(self.RF0) else 1.0, ptr(self._rf0_dev)), ctx.h)
+        if rm_matrix:
+            _lib.check(ctx.lib.vab_ode_set_rm_matrix(ctx.h, ptr(self._rm_dev)), ctx.h)
         self._pfix_dev = self._to_dev(self.P.reshape(B, NPl)[:Bw])
         if self._ptime:
             _lib.check(ctx.lib.vab_ode_set_time_dependent(ctx.h, 1, ptr(self._pfix_dev), NPl), ctx.h)
