@@ -13,7 +13,7 @@ Follows (file:line under /root/reference/varanneal):
 The reference loops over examples m and layers n in Python; this port batches the examples
 into one (M x d_n)(d_n x d_{n+1}) product per layer, which is the same arithmetic in a
 different summation order (pinned against the verbatim reference to ~1e-15 relative by
-tests/test_oracle_vs_reference.py; gradient pinned by complex-step through the reference).
+tests/test_oracle.py; gradient pinned by complex-step through the reference).
 """
 import numpy as np
 
