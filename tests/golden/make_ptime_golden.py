@@ -125,6 +125,15 @@ def main():
     print("ptime ladder: %.1f s; A %s" % (time.time() - t0, an.A_array))
     out["ladder/beta"] = beta
     out["ladder/table"] = np.column_stack([an.beta_array, an.A_array, an.me_array, an.fe_array])
+    # the reference's own reproducibility: the same run from X0 * (1 + 2^-52) (one unit in the last place)
+    an2 = ShimOde()
+    an2.set_model(MODELS["lorenz96"], c["D"])
+    an2.set_data(Y, t=t)
+    an2.grad_fn = lambda XP, an=an2, prob=prob: prob.action_grad(XP, an.RF)[1]
+    an2.anneal_quiet(X0 * (1.0 + 2.0 ** -52), P0.copy(), c["alpha"], beta, c["RM"], c["RF0"], np.array(c["Lidx"]), [0],
+                     dt_model=c["dt"], init_to_data=True, disc="trapezoid", method="L-BFGS-B", opt_args=opts)
+    out["ladder/table_ulp1"] = np.column_stack([an2.beta_array, an2.A_array, an2.me_array, an2.fe_array])
+    print("ptime ladder twin: rel %s" % (np.abs(an2.A_array - an.A_array) / an.A_array))
     out["ladder/minpaths"] = an.minpaths
     out["ladder/P_final"] = np.array(an.P)
     out["ladder/meta"] = np.array([c["alpha"], c["RM"], c["RF0"], opts["gtol"], opts["ftol"]])

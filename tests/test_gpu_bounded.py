@@ -146,8 +146,14 @@ def test_nakl_tutorial_box_single_rung_vs_scipy():
         assert an.exitflags[0] == 0 and r.status == 0
         A, g = prob.action_grad(xmin, rf)
         assert abs(A - an.A_array[0]) <= 1e-10 * abs(A)
-        # ~1500 iterations in a shallow valley, both stop on the relative-reduction test: the device
-        # must not end *above* SciPy by more than 1e-6 (measured: 2e-5 below it) and within 1e-3 of it
-        assert an.A_array[0] - r.fun <= 1e-6 * abs(r.fun), (disc, an.A_array[0], r.fun, an.nit_array[0], r.nit)
-        assert abs(an.A_array[0] - r.fun) <= 1e-3 * abs(r.fun)
+        # ~1500 iterations in a shallow valley, both stop on the relative-reduction test; which of the
+        # two ends lower is decided by rounding (measured: 2e-5 below SciPy with one build of the action
+        # kernel, 3e-5 above with the next; the reference's own ulp-perturbed twin runs of this problem
+        # differ by 4.6e-5 / 3.3e-3, tests/golden/nakl_bounded_ladder_golden.npz).  Asserted: within
+        # 1e-4 / 1e-3 of SciPy, and SciPy restarted at the device's point gains next to nothing.
+        assert abs(an.A_array[0] - r.fun) <= (1e-4 if disc == "SimpsonHermite" else 1e-3) * abs(r.fun), \
+            (disc, an.A_array[0], r.fun, an.nit_array[0], r.nit)
+        r2 = opt.minimize(lambda z: prob.action_grad(z, rf), xmin, method="L-BFGS-B", jac=True,
+                          bounds=list(zip(lo, hi)), options=dict(opts, maxiter=60))
+        assert A - r2.fun <= 1e-4 * abs(A), (disc, A, r2.fun, r2.nit)
         assert int(np.sum(xmin <= lo) + np.sum(xmin >= hi)) > 0

@@ -1600,13 +1600,16 @@ int lb_run(vab_ctx* ctx, int B, double* XP, long long ld, const double* scales_h
     cudaStream_t st, copy;
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t gexec = nullptr;
+    long long* dbg = nullptr;
     ~Cleanup() {
       cudaStreamSynchronize(st);
       if (copy) cudaStreamSynchronize(copy);
+      if (dbg) cudaFree(dbg);
       if (gexec) cudaGraphExecDestroy(gexec);
       if (graph) cudaGraphDestroy(graph);
     }
   } own{st, w->copy_stream};
+  own.dbg = fused_dbg;
   // The first cycle runs eagerly (it may allocate workspaces and opt kernels in to large shared
   // memory); the steady-state cycle is then captured once into a CUDA graph and replayed.  Capture
   // is illegal on the legacy default stream (which is what PyTorch's current stream is unless the
@@ -1716,7 +1719,6 @@ int lb_run(vab_ctx* ctx, int B, double* XP, long long ld, const double* scales_h
       for (int q = 1; q < 16; ++q) fprintf(stderr, " %.0f", (double)h[q] / (double)h[0]);
       fprintf(stderr, "\n");
     }
-    cudaFree(fused_dbg);
   }
   if (sink && rc_loop == VAB_OK) {
     cudaError_t ce = send_rows(nullptr);
