@@ -788,8 +788,10 @@ def leg_nn(args, dd, name):
     tf = flops / ms / 1e9
     gb = byt / ms / 1e6
     if name == "C4":
-        roof = {"bound": "tensor", "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tf / fp64_peak if fp64_peak else None,
-                "traffic": None, "peak_source": "builder-measured fp64 FMA rate (vab_measure_fp64_peak); fp64 tensor pipe (DMMA) has the same nominal rate",
+        dmma_peak = an._ctx.fp64_dmma_peak_tflops()
+        roof = {"bound": "tensor", "achieved": tf, "peak": dmma_peak, "unit": "TFLOP/s", "frac": tf / dmma_peak if dmma_peak else None,
+                "traffic": None, "peak_source": "builder-measured rate of mma.sync.m8n8k4.f64 (vab_measure_fp64_dmma_peak), the instruction the "
+                                                "contractions issue; fp64 FMA rate on the CUDA cores: %.1f TFLOP/s" % fp64_peak,
                 "kernel": "nn_fb_kernel + nn_gw_kernel + nn_fix_kernel (fp64 tensor pipe)", "kernel_ms": ms,
                 "algorithmic_flops_per_launch": flops, "hbm_GBps_algorithmic": gb}
     else:

@@ -85,6 +85,9 @@ VAB_API long long vab_graph_launch_count(const vab_ctx* ctx);
  * a register-resident micro-kernel timed by CUDA events: the roofline denominator of the
  * fp64-bound kernels (rk4, NaKL, neural-network contractions), which MEASURED_PEAKS.json lacks. */
 VAB_API int vab_measure_fp64_peak(vab_ctx* ctx, double* tflops_host);
+/* The same for the fp64 tensor pipe: sustained rate of mma.sync.m8n8k4.f64 (DMMA), the instruction
+ * the neural-network contractions issue -- their roofline denominator. */
+VAB_API int vab_measure_fp64_dmma_peak(vab_ctx* ctx, double* tflops_host);
 
 /* Measured prototype of the neural-network contraction on the 5th-generation tensor cores
  * (csrc/ozaki_gemm.cu): P independent products C_p = A_p B_p^T (A_p: M x K, B_p: N x K, fp64, K <= 128)

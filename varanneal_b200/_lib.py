@@ -39,6 +39,7 @@ _SIGS = {
     "vab_launch_count": (ct.c_longlong, [_VP]),
     "vab_graph_launch_count": (ct.c_longlong, [_VP]),
     "vab_measure_fp64_peak": (ct.c_int, [_VP, c_double_p]),
+    "vab_measure_fp64_dmma_peak": (ct.c_int, [_VP, c_double_p]),
     "vab_ozaki_gemm_probe": (ct.c_int, [_VP, ct.c_int32, ct.c_int32, ct.c_int32, ct.c_int32, ct.c_int32, ct.c_double, c_double_p]),
     "vab_ode_problem_set": (ct.c_int, [_VP, ct.POINTER(OdeDesc), c_int_p, c_int_p, _VP, _VP]),
     "vab_ode_set_weights": (ct.c_int, [_VP, ct.c_double, _VP, ct.c_double, _VP]),
@@ -138,6 +139,11 @@ class Context(object):
     def fp64_peak_tflops(self):
         v = ct.c_double(0.0)
         check(self.lib.vab_measure_fp64_peak(self.h, ct.byref(v)), self.h)
+        return float(v.value)
+
+    def fp64_dmma_peak_tflops(self):
+        v = ct.c_double(0.0)
+        check(self.lib.vab_measure_fp64_dmma_peak(self.h, ct.byref(v)), self.h)
         return float(v.value)
 
     def ozaki_gemm_probe(self, P, M, N, K, reps=5, spread=8.0):

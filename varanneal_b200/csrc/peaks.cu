@@ -24,9 +24,35 @@ __global__ void __launch_bounds__(256) fp64_fma_kernel(double* out, int iters, d
   if (s == 123.456) out[blockIdx.x * blockDim.x + threadIdx.x] = s;     // never true: keeps the loop alive
 }
 
+// the same for the fp64 tensor pipe: 8 independent DMMA.8x8x4 accumulator chains per warp (the
+// instruction the neural-network kernels issue, nn_action.cu)
+__global__ void __launch_bounds__(256) fp64_dmma_kernel(double* out, int iters, double a, double b) {
+  double c[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) c[k] = (double)(threadIdx.x + k) * 1e-3;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                   : "+d"(c[2 * k]), "+d"(c[2 * k + 1])
+                   : "d"(a), "d"(b));
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) s += c[k];
+  if (s == 123.456) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 }  // namespace
 
-extern "C" int vab_measure_fp64_peak(vab_ctx* ctx, double* tflops_host) {
+// which: 0 = DFMA on the CUDA cores, 1 = DMMA.8x8x4 on the tensor pipe
+static int measure_peak(vab_ctx* ctx, int which, double* tflops_host);
+
+extern "C" int vab_measure_fp64_dmma_peak(vab_ctx* ctx, double* tflops_host) { return measure_peak(ctx, 1, tflops_host); }
+
+extern "C" int vab_measure_fp64_peak(vab_ctx* ctx, double* tflops_host) { return measure_peak(ctx, 0, tflops_host); }
+
+static int measure_peak(vab_ctx* ctx, int which, double* tflops_host) {
   if (!ctx || !tflops_host) return VAB_ERR_INVALID;
   cudaSetDevice(ctx->device);
   double* out = nullptr;
@@ -39,13 +65,16 @@ extern "C" int vab_measure_fp64_peak(vab_ctx* ctx, double* tflops_host) {
   double best = 0.0;
   for (int rep = 0; rep < 6; ++rep) {
     cudaEventRecord(e0, ctx->stream);
-    fp64_fma_kernel<<<blocks, threads, 0, ctx->stream>>>(out, iters, 0.999999, 1e-9);
+    if (which == 1) fp64_dmma_kernel<<<blocks, threads, 0, ctx->stream>>>(out, iters, 0.999999, 1e-9);
+    else fp64_fma_kernel<<<blocks, threads, 0, ctx->stream>>>(out, iters, 0.999999, 1e-9);
     cudaEventRecord(e1, ctx->stream);
     e = cudaEventSynchronize(e1);
     if (e != cudaSuccess) break;
     float ms = 0.f;
     cudaEventElapsedTime(&ms, e0, e1);
-    const double flops = 2.0 * 16.0 * iters * (double)blocks * threads;
+    // DFMA: 16 FMAs per thread and iteration; DMMA: 8 instructions per warp and iteration, 8x8x4 MACs each
+    const double flops = which == 1 ? 2.0 * 8.0 * 256.0 * iters * (double)blocks * (threads / 32)
+                                    : 2.0 * 16.0 * iters * (double)blocks * threads;
     if (rep > 0 && ms > 0.f) best = fmax(best, flops / (ms * 1e-3) / 1e12);   // first launch = warm-up
   }
   ctx->launches += 6;
