@@ -42,8 +42,9 @@ def gather_blocks(local, n_items, group=None):
 
 
 def anneal_sharded(annealer, X0, P0, *args, group=None, gather_paths='none', **kwargs):
-    """Anneal rank-local slices of a batch (X0 (B, N, D), P0 (B, NP)) and gather the
-    (B, Nbeta, 5) action tables [beta, A, me, fe, fe/RF] and the (B, Nbeta, NP) parameters.
+    """Anneal rank-local slices of a batch (X0 (B, N, D), P0 (B, NP) -- or (B, N, NP) for parameter
+    time series) and gather the (B, Nbeta, 5) action tables [beta, A, me, fe, fe/RF] and the
+    (B, Nbeta, NP) [(B, Nbeta, N, NP)] parameters.
     Positional / keyword arguments after P0 are those of ``Annealer.anneal``.
 
     ``gather_paths``: 'none' (default: the minimising paths stay with the rank that computed them
@@ -65,7 +66,7 @@ def anneal_sharded(annealer, X0, P0, *args, group=None, gather_paths='none', **k
         paths = annealer.minpaths
     else:
         tables = np.zeros((0, nb, 5))
-        params = np.zeros((0, nb, P0.shape[1]))
+        params = np.zeros((0, nb) + tuple(P0.shape[1:]))       # (NP,) or, for parameter time series, (N_model, NP)
         paths = None
     out = (gather_blocks(tables, B, group), gather_blocks(params, B, group))
     if gather_paths == 'none':
