@@ -1470,7 +1470,9 @@ int lb_run(vab_ctx* ctx, int B, double* XP, long long ld, const double* scales_h
   // choice between the two is pure scheduling and the results are bit-identical
   // (tests/test_gpu_ladder.py::test_fused_cycle_kernel_is_bit_identical).
   const bool small = !bounded && n <= 32768;
-  bool fused = small && (long long)B * FCS <= ctx->num_sms;
+  // (a cluster needs its FCS SMs inside one GPC -- 18 SMs on B200, i.e. two clusters per GPC: stay a
+  //  little below SM count / FCS so that every cluster is resident at once)
+  bool fused = small && B <= ctx->num_sms / FCS - 2;
   if (const char* e = getenv("VAB_LBFGS_FUSED")) fused = small && atoi(e) != 0;
   if (small) use_tma = false;
   // bounded L-BFGS-B: generalised Cauchy point + subspace minimisation (lbfgsb_bounded.cuh);
