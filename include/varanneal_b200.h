@@ -185,6 +185,11 @@ VAB_API int vab_nn_problem_set(vab_ctx* ctx, int32_t n_layers, const int32_t* st
                        int32_t NPest, const int32_t* Pidx_host);
 /* RM scalar or (2,) (va_nnet.py:131-144): pass rm_in == rm_out for the scalar form. RF0 scalar. */
 VAB_API int vab_nn_set_weights(vab_ctx* ctx, double rm_in, double rm_out, double rf0);
+/* Matrix form of RM for the network (va_nnet.py:135-139): rm_in_dev (n_Lin, n_Lin), rm_out_dev
+ * (n_Lout, n_Lout), row-major, not necessarily symmetric; me = sum_m [din_m . (RM_in din_m) +
+ * dout_m . (RM_out dout_m)] / (Ltot M).  Replaces the scalar weights of vab_nn_set_weights (which in
+ * turn clears the matrices; RF0 is kept).  The arrays must stay alive while they are set. */
+VAB_API int vab_nn_set_rm_matrices(vab_ctx* ctx, const double* rm_in_dev, const double* rm_out_dev);
 VAB_API int vab_nn_set_fixed_params(vab_ctx* ctx, const double* pfix_dev, int64_t pfix_stride);
 /* Replaces A_gradA_taped for va_nnet.A_gaussian (va_nnet.py:111-255). Same conventions. */
 VAB_API int vab_nn_action_grad(vab_ctx* ctx, int32_t B, const double* XP_dev, int64_t ldxp,

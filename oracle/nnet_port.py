@@ -3,7 +3,7 @@ action (va_nnet) and its analytic adjoint.  Checker for the CUDA path; never imp
 product.
 
 Follows (file:line under /root/reference/varanneal):
-  measurement error   va_nnet.py:117-173   ``me_gaussian`` (scalar RM, or RM.shape == (2,))
+  measurement error   va_nnet.py:117-173   ``me_gaussian`` (scalar RM, RM.shape == (2,), or two matrices)
   model error         va_nnet.py:175-255   ``fe_gaussian`` + ``disc_forwardmap`` :260-264
   parameter layout    va_nnet.py:194-207   P = [W_0 (d_1 x d_0 row-major), b_0, W_1, b_1, ...]
   state layout        va_nnet.py:149-152,212   X.reshape(M, NDnet), layers concatenated
@@ -53,13 +53,19 @@ class NnetProblem(object):
         self.NP = self.P.size
         self.Pidx = np.asarray(Pidx, dtype=np.int64)
         self.NPest = self.Pidx.size
+        # RM: scalar, shape (2,), or a pair of matrices [RM_in (Lin, Lin), RM_out (Lout, Lout)]
+        # (va_nnet.py:131-140); everything is carried as one matrix per side
         if np.isscalar(RM):
-            self.RMin = self.RMout = float(RM)
+            rin, rout = float(RM) * np.eye(self.Lin.size), float(RM) * np.eye(self.Lout.size)
+        elif np.ndim(RM[0]) == 0:
+            if len(RM) != 2:
+                raise ValueError("RM must be scalar, shape (2,) or a pair of matrices")
+            rin, rout = float(RM[0]) * np.eye(self.Lin.size), float(RM[1]) * np.eye(self.Lout.size)
         else:
-            RM = np.asarray(RM, dtype=np.float64)
-            if RM.shape != (2,):
-                raise ValueError("RM must be scalar or shape (2,)")
-            self.RMin, self.RMout = float(RM[0]), float(RM[1])
+            rin, rout = np.asarray(RM[0], dtype=np.float64), np.asarray(RM[1], dtype=np.float64)
+            if rin.shape != (self.Lin.size,) * 2 or rout.shape != (self.Lout.size,) * 2:
+                raise ValueError("RM matrices must be (Lin, Lin) and (Lout, Lout)")
+        self.RMin, self.RMout = rin, rout
         self.act, self.dact = ACTIVATIONS[act]
         self.xoff = np.concatenate([[0], np.cumsum(self.structure)])
         d = self.structure
@@ -95,7 +101,8 @@ class NnetProblem(object):
         X, _ = self.unpack(XP)
         din = self.layer(X, 0)[:, self.Lin] - self.data_in
         dout = self.layer(X, self.NL - 1)[:, self.Lout] - self.data_out
-        return (self.RMin * np.sum(din * din) + self.RMout * np.sum(dout * dout)) / (self.Ltot * self.M)
+        q = np.einsum("ml,lk,mk->", din, self.RMin, din) + np.einsum("ml,lk,mk->", dout, self.RMout, dout)
+        return q / (self.Ltot * self.M)
 
     def fe(self, XP, RF):
         X, p = self.unpack(XP)
@@ -117,12 +124,12 @@ class NnetProblem(object):
         cm = 1.0 / (self.Ltot * self.M)
         din = self.layer(X, 0)[:, self.Lin] - self.data_in
         dout = self.layer(X, self.NL - 1)[:, self.Lout] - self.data_out
-        me = cm * (self.RMin * np.sum(din * din) + self.RMout * np.sum(dout * dout))
+        me = cm * (np.einsum("ml,lk,mk->", din, self.RMin, din) + np.einsum("ml,lk,mk->", dout, self.RMout, dout))
         g0 = np.zeros((self.M, self.structure[0]))
-        g0[:, self.Lin] = 2.0 * cm * self.RMin * din
+        g0[:, self.Lin] = cm * din @ (self.RMin + self.RMin.T)
         GX[:, self.xoff[0]:self.xoff[1]] += g0
         gl = np.zeros((self.M, self.structure[-1]))
-        gl[:, self.Lout] = 2.0 * cm * self.RMout * dout
+        gl[:, self.Lout] = cm * dout @ (self.RMout + self.RMout.T)
         GX[:, self.xoff[self.NL - 1]:self.xoff[self.NL]] += gl
 
         cf = RF / ((self.NDnet - self.structure[0]) * self.M)

@@ -81,5 +81,57 @@ def main():
     np.savez_compressed(os.path.join(HERE, "ode_rm_matrix_golden.npz"), **out)
 
 
+def main_nnet():
+    """va_nnet: RM = [RM_in, RM_out] as one (2, L, L) array (va_nnet.py:135-139; reachable in the
+    reference only when as many input as output components are measured)."""
+    from oracle import nnet_port
+    _, ShimNnet = ref_shim.make_shim_classes()
+    rng = np.random.RandomState(77)
+    out, names = {}, []
+    for name, structure, M, Lidx in (("nn_8_12_8_full", [8, 12, 8], 7, [np.arange(8), np.arange(8)]),
+                                     ("nn_7_10_9_partial", [7, 10, 9], 5, [np.array([0, 2, 5]), np.array([1, 4, 8])])):
+        structure = np.array(structure)
+        NDnet = int(structure.sum())
+        L = len(Lidx[0])
+        data_in, data_out = rng.rand(M, L), rng.rand(M, L)
+        NP = int(sum(structure[n] * structure[n + 1] + structure[n + 1] for n in range(len(structure) - 1)))
+        X0 = rng.rand(M * NDnet)
+        P0 = 0.4 * rng.randn(NP)
+        Pidx = np.arange(NP)
+
+        def mat():
+            G, H = rng.randn(L, L), rng.randn(L, L)
+            return 2.0 * np.eye(L) + G.dot(G.T) / L + 0.5 * (H - H.T)
+        RM = np.array([mat(), mat()])
+        RF0, alpha, beta = 1e-3, 1.1, 30
+        an = ShimNnet()
+        an.set_structure(structure)
+        an.set_activation(nnet_port.sigmoid)
+        an.set_input_data(data_in)
+        an.set_output_data(data_out)
+        with contextlib.redirect_stdout(io.StringIO()):
+            an.anneal_init(X0.copy(), P0.copy(), alpha, [beta], RM.copy(), RF0, Pidx, Lidx=Lidx, init_to_data=False)
+        XP = np.append(X0, P0[Pidx])
+        A = float(an.A(XP))
+        me = float(an.me_gaussian(XP[:M * NDnet]))
+        fe = float(an.fe_gaussian(XP))
+        g = ref_shim.complex_step_grad(an.A, XP)
+        prob = nnet_port.NnetProblem(structure, data_in, data_out, Lidx, P0, Pidx, RM)
+        Ap, gp = prob.action_grad(XP, RF0 * alpha ** beta)
+        print("%-20s A=%.16e me=%.6e port rel %.1e grad rel %.1e" % (
+            name, A, me, abs(Ap - A) / abs(A), np.max(np.abs(gp - g)) / np.max(np.abs(g))))
+        names.append(name)
+        for k, v in (("structure", structure), ("data_in", data_in), ("data_out", data_out), ("X0", X0), ("P0", P0),
+                     ("Pidx", Pidx), ("Lin", Lidx[0]), ("Lout", Lidx[1]), ("RM", RM),
+                     ("meta", np.array([RF0, alpha, beta])), ("A", np.array([A, me, fe])), ("grad", g)):
+            out[name + "/" + k] = np.asarray(v)
+    out["names"] = np.array(names)
+    np.savez_compressed(os.path.join(HERE, "nnet_rm_matrix_golden.npz"), **out)
+
+
 if __name__ == "__main__":
-    main()
+    what = sys.argv[1:] or ["ode", "nnet"]
+    if "ode" in what:
+        main()
+    if "nnet" in what:
+        main_nnet()

@@ -70,3 +70,17 @@ def nnet_cases():
                         RM=float(RM), RF0=float(RF0), alpha=float(alpha), beta=float(beta),
                         A=z[n + "/A"], grad=z[n + "/grad"]))
     return out
+
+
+def nnet_rm_matrix_cases():
+    """Cases of nnet_rm_matrix_golden.npz (va_nnet with RM = [RM_in, RM_out], make_rm_matrix_golden.py)."""
+    z = load("nnet_rm_matrix_golden.npz")
+    out = []
+    for n in z["names"]:
+        n = str(n)
+        RF0, alpha, beta = z[n + "/meta"]
+        out.append(dict(name=n, structure=z[n + "/structure"], data_in=z[n + "/data_in"], data_out=z[n + "/data_out"],
+                        X0=z[n + "/X0"], P0=z[n + "/P0"], Pidx=z[n + "/Pidx"], Lidx=[z[n + "/Lin"], z[n + "/Lout"]],
+                        RM=z[n + "/RM"], RF0=float(RF0), alpha=float(alpha), beta=float(beta), A=z[n + "/A"],
+                        grad=z[n + "/grad"]))
+    return out

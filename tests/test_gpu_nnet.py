@@ -39,6 +39,43 @@ def test_nn_action_grad_vs_reference_golden(c):
     assert abs(an.fe_gaussian(XP) - c["A"][2]) <= TOL * abs(c["A"][2])
 
 
+NN_RM_CASES = golden_util.nnet_rm_matrix_cases()
+
+
+@pytest.mark.parametrize("c", NN_RM_CASES, ids=[c["name"] for c in NN_RM_CASES])
+@pytest.mark.parametrize("flags", ["", "F", "S"])
+def test_nn_matrix_rm_vs_reference_golden(c, flags, monkeypatch):
+    """RM = [RM_in, RM_out] (va_nnet.py:135-139), not symmetric, through every kernel family (split
+    kernels, fused kernel, register-tiled small-network kernel) and for a batch with unequal paths."""
+    if "F" in flags:
+        monkeypatch.setenv("VAB_NN_SPLIT", "0")
+    if "S" in flags:
+        monkeypatch.setenv("VAB_NN_SMALL", "1")
+    an = _annealer(c["structure"], c["data_in"], c["data_out"], c["X0"].copy(), c["P0"].copy(), c["alpha"],
+                   [c["beta"]], c["RM"].copy(), c["RF0"], c["Pidx"], Lidx=c["Lidx"])
+    XP = np.append(c["X0"], c["P0"][c["Pidx"]])
+    A, g = an.A_gradA_taped(XP)
+    assert abs(A - c["A"][0]) <= TOL * abs(c["A"][0])
+    assert np.max(np.abs(g - c["grad"])) <= TOL * np.max(np.abs(c["grad"]))
+    assert abs(an.me_gaussian(XP) - c["A"][1]) <= TOL * abs(c["A"][1])
+    # a batch of three different paths, differently sized matrices on the two sides (extension)
+    rng = np.random.default_rng(2)
+    B = 3
+    X0 = np.tile(c["X0"], (B, 1)) + 0.1 * rng.standard_normal((B, c["X0"].size))
+    P0 = np.tile(c["P0"], (B, 1)) + 0.05 * rng.standard_normal((B, c["P0"].size))
+    Lidx = [c["Lidx"][0], c["Lidx"][1][:-1]]
+    RM = [c["RM"][0], c["RM"][1][:-1, :-1]]
+    anb = _annealer(c["structure"], c["data_in"], c["data_out"][:, :-1], X0.copy(), P0.copy(), c["alpha"], [c["beta"]], RM,
+                    c["RF0"], c["Pidx"], Lidx=Lidx)
+    XPb = np.concatenate([X0, P0[:, c["Pidx"]]], axis=1)
+    Ab, gb = anb.A_gradA_taped(XPb)
+    for b in range(B):
+        prob = nnet_port.NnetProblem(c["structure"], c["data_in"], c["data_out"][:, :-1], Lidx, P0[b], c["Pidx"], RM)
+        Ao, go = prob.action_grad(XPb[b], c["RF0"] * c["alpha"] ** c["beta"])
+        assert abs(Ab[b] - Ao) <= TOL * abs(Ao)
+        assert np.max(np.abs(gb[b] - go)) <= TOL * np.max(np.abs(go))
+
+
 @pytest.mark.parametrize("structure,M,act,RM,partial,B", [
     ([25, 30, 4], 1000, "sigmoid", 1.0, False, 2),          # bar-images shape, many example tiles
     ([100, 100, 100, 100], 130, "sigmoid", [3.0, 0.5], False, 2),   # nnet_twin widths ~100, RM (2,)

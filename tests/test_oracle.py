@@ -81,6 +81,20 @@ def test_ode_port_time_dependent_parameters_match_reference_golden(c):
     assert np.max(np.abs(g - c["grad"])) <= 1e-12 * np.max(np.abs(c["grad"]))
 
 
+NN_RM_CASES = golden_util.nnet_rm_matrix_cases()
+
+
+@pytest.mark.parametrize("c", NN_RM_CASES, ids=[c["name"] for c in NN_RM_CASES])
+def test_nnet_port_matrix_rm_matches_reference_golden(c):
+    """va_nnet with RM = [RM_in, RM_out] (va_nnet.py:135-139)."""
+    prob = nnet_port.NnetProblem(c["structure"], c["data_in"], c["data_out"], c["Lidx"], c["P0"], c["Pidx"], c["RM"])
+    XP = np.append(c["X0"], c["P0"][c["Pidx"]])
+    A, g = prob.action_grad(XP, c["RF0"] * c["alpha"] ** c["beta"])
+    assert abs(A - c["A"][0]) <= 1e-13 * abs(c["A"][0])
+    assert abs(prob.me(XP) - c["A"][1]) <= 1e-13 * abs(c["A"][1])
+    assert np.max(np.abs(g - c["grad"])) <= 1e-12 * np.max(np.abs(c["grad"]))
+
+
 @pytest.mark.parametrize("c", NN_CASES, ids=[c["name"] for c in NN_CASES])
 def test_nnet_port_matches_reference_golden(c):
     st = c["structure"]

@@ -52,6 +52,7 @@ _SIGS = {
                                       ct.c_int32, c_int_p, ct.c_int32, c_int_p, _VP, _VP,
                                       ct.c_int32, c_int_p]),
     "vab_nn_set_weights": (ct.c_int, [_VP, ct.c_double, ct.c_double, ct.c_double]),
+    "vab_nn_set_rm_matrices": (ct.c_int, [_VP, _VP, _VP]),
     "vab_nn_set_fixed_params": (ct.c_int, [_VP, _VP, ct.c_int64]),
     "vab_nn_action_grad": (ct.c_int, [_VP, ct.c_int32, _VP, ct.c_int64, ct.c_double,
                                       _VP, _VP, _VP, _VP, ct.c_int64]),

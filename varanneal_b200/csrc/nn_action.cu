@@ -898,6 +898,8 @@ struct NnProblem {
   const double* data_in = nullptr;
   const double* data_out = nullptr;
   double rm_in = 1.0, rm_out = 1.0, rf0 = 1.0;
+  const double* rm_in_mat = nullptr;   // (n_Lin, n_Lin) / (n_Lout, n_Lout) matrix form of RM (vab_nn_set_rm_matrices),
+  const double* rm_out_mat = nullptr;  // caller-owned; rm_in = rm_out = 0 while set
   const double* pfix = nullptr;
   long long pfix_stride = 0;
   double* pfix_zero = nullptr;
@@ -929,9 +931,87 @@ void nn_destroy(vab_ctx* ctx) {
 
 long long nn_unknowns(const vab_ctx* ctx) { return ctx->nn ? ctx->nn->NDens + ctx->nn->NPest : 0; }
 
+// Matrix RM (va_nnet.py:135-139): me = cm sum_m [din_m . (RM_in din_m) + dout_m . (RM_out dout_m)], added
+// behind the action kernels (which then run with zero measurement weights): one CTA per path, thread
+// per (example, measured component), fixed-order reduction.  cin / cout: state column of each measured
+// input / output component, rebuilt from the slot tables.
+__global__ void __launch_bounds__(256) nn_me_matrix_kernel(const __grid_constant__ NnParams P, const double* rm_in,
+                                                           const double* rm_out, double cm, double* A, double* me) {
+  extern __shared__ int cols[];
+  const int b = blockIdx.x;
+  if (P.active != nullptr && P.active[b] == 0) return;
+  const int d0 = P.structure[0], dl = P.structure[P.NL - 1], ND = P.NDnet, clast = ND - dl;
+  int* cin = cols;
+  int* cout = cols + P.n_Lin;
+  for (int c = threadIdx.x; c < d0; c += 256) { const int sl = P.slot_in[c]; if (sl >= 0) cin[sl] = c; }
+  for (int c = threadIdx.x; c < dl; c += 256) { const int sl = P.slot_out[c]; if (sl >= 0) cout[sl] = clast + c; }
+  __syncthreads();
+  const double* x = P.XP + (long long)b * P.ldxp;
+  double* g = P.G ? P.G + (long long)b * P.ldg : nullptr;
+  const int Lt = P.n_Lin + P.n_Lout;
+  double acc = 0.0;
+  for (long long t = threadIdx.x; t < (long long)P.M * Lt; t += 256) {
+    const long long m = t / Lt;
+    int l = (int)(t - m * Lt);
+    const bool in = l < P.n_Lin;
+    if (!in) l -= P.n_Lin;
+    const int L = in ? P.n_Lin : P.n_Lout;
+    const int* col = in ? cin : cout;
+    const double* dat = in ? P.data_in + m * P.n_Lin : P.data_out + m * P.n_Lout;
+    const double* R = in ? rm_in : rm_out;
+    const long long base = m * ND;
+    double w = 0.0, wt = 0.0;
+    for (int k = 0; k < L; ++k) {
+      const double dk = x[base + col[k]] - dat[k];
+      w = fma(R[(long long)l * L + k], dk, w);
+      wt = fma(R[(long long)k * L + l], dk, wt);
+    }
+    const double dv = x[base + col[l]] - dat[l];
+    acc = fma(dv, w, acc);
+    if (g) g[base + col[l]] += cm * (w + wt);
+  }
+  __shared__ double red[256];
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int sft = 128; sft > 0; sft >>= 1) {
+    if ((int)threadIdx.x < sft) red[threadIdx.x] += red[threadIdx.x + sft];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double v = cm * red[0];
+    if (A) A[b] += v;
+    if (me) me[b] += v;
+  }
+}
+
+static int nn_eval_core(vab_ctx* ctx, int B, const double* XP, long long ldxp, double rf_scale,
+                        const double* rf_path_dev, const int* active_dev, double* A, double* me, double* fe,
+                        double* G, long long ldg);
+
 int nn_eval(vab_ctx* ctx, int B, const double* XP, long long ldxp, double rf_scale,
             const double* rf_path_dev, const int* active_dev, double* A, double* me, double* fe,
             double* G, long long ldg) {
+  int rc = nn_eval_core(ctx, B, XP, ldxp, rf_scale, rf_path_dev, active_dev, A, me, fe, G, ldg);
+  if (rc != VAB_OK) return rc;
+  NnProblem* p = ctx->nn;
+  if (p->rm_in_mat != nullptr) {
+    NnParams P;
+    memset(&P, 0, sizeof(P));
+    P.XP = XP; P.ldxp = ldxp; P.G = G; P.ldg = ldg; P.B = B; P.M = p->M; P.NL = p->NL; P.NDnet = p->NDnet;
+    P.structure = p->structure; P.slot_in = p->slot_in; P.slot_out = p->slot_out; P.n_Lin = p->n_Lin; P.n_Lout = p->n_Lout;
+    P.data_in = p->data_in; P.data_out = p->data_out; P.active = active_dev;
+    const double cm = p->Ltot > 0 ? 1.0 / ((double)p->Ltot * p->M) : 0.0;
+    nn_me_matrix_kernel<<<B, 256, (size_t)(p->n_Lin + p->n_Lout + 1) * sizeof(int), ctx->stream>>>(P, p->rm_in_mat, p->rm_out_mat, cm, A, me);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return vab_cuda_fail(ctx, e, "nn_me_matrix_kernel launch");
+    ctx->launches += 1;
+  }
+  return VAB_OK;
+}
+
+static int nn_eval_core(vab_ctx* ctx, int B, const double* XP, long long ldxp, double rf_scale,
+                        const double* rf_path_dev, const int* active_dev, double* A, double* me, double* fe,
+                        double* G, long long ldg) {
   NnProblem* p = ctx->nn;
   if (!p) return vab_fail(ctx, VAB_ERR_STATE, "nn_action_grad: no NN problem set");
   const long long n = p->NDens + p->NPest;
@@ -1293,6 +1373,16 @@ int vab_nn_set_weights(vab_ctx* ctx, double rm_in, double rm_out, double rf0) {
   if (!ctx) return VAB_ERR_INVALID;
   if (!ctx->nn) return vab_fail(ctx, VAB_ERR_STATE, "nn_set_weights: no NN problem set");
   ctx->nn->rm_in = rm_in; ctx->nn->rm_out = rm_out; ctx->nn->rf0 = rf0;
+  ctx->nn->rm_in_mat = nullptr; ctx->nn->rm_out_mat = nullptr;
+  return VAB_OK;
+}
+
+int vab_nn_set_rm_matrices(vab_ctx* ctx, const double* rm_in_dev, const double* rm_out_dev) {
+  if (!ctx) return VAB_ERR_INVALID;
+  if (!ctx->nn) return vab_fail(ctx, VAB_ERR_STATE, "nn_set_rm_matrices: no NN problem set");
+  if (!rm_in_dev || !rm_out_dev) return vab_fail(ctx, VAB_ERR_INVALID, "nn_set_rm_matrices: NULL");
+  ctx->nn->rm_in = 0.0; ctx->nn->rm_out = 0.0;       // the action kernels carry no measurement term any more
+  ctx->nn->rm_in_mat = rm_in_dev; ctx->nn->rm_out_mat = rm_out_dev;
   return VAB_OK;
 }
 

@@ -11,7 +11,8 @@ Deliberate differences:
     ``varanneal_b200.va_nnet.sigmoid`` ...): arbitrary Python callables cannot run in a kernel.
   * the default ``Lidx=None`` observes every input and output neuron with integer indices (the
     reference builds float ``np.linspace`` indices that no longer index under modern NumPy).
-  * ``RM`` scalar or shape (2,) (input / output weights, va_nnet.py:131-144); matrix forms raise.
+  * ``RM`` scalar, shape (2,) (input / output weights, va_nnet.py:131-144) or a pair of matrices
+    [RM_in, RM_out] (va_nnet.py:135-139).
   * ``exitflags`` is filled; errors raise.
   * batches: ``X0`` (B, M*NDnet) + ``P0`` (B, NP) anneal B initialisations at once.
 """
@@ -145,13 +146,23 @@ class Annealer(DeviceMin):
         self.Ltot = self.L[0] + self.L[1]
         if self.data_in.shape != (self.M, self.L[0]) or self.data_out.shape != (self.M, self.L[1]):
             raise ValueError("data_in / data_out must be (M, len(Lidx[0])) / (M, len(Lidx[1]))")
-        if np.ndim(RM) == 0:
+        rm_mats = None
+        if np.isscalar(RM) or (isinstance(RM, np.ndarray) and RM.ndim == 0):
             self.RM = float(RM)
             rm_in = rm_out = self.RM
+        elif len(RM) == 2 and np.ndim(RM[0]) == 2 and np.ndim(RM[1]) == 2:
+            # [RM_in, RM_out] matrices (va_nnet.py:135-139; the reference reaches this branch only
+            # with a (2, L, L) array, i.e. as many measured inputs as outputs -- a pair of
+            # differently sized matrices is accepted here as well)
+            rm_mats = (np.ascontiguousarray(RM[0], dtype=np.float64), np.ascontiguousarray(RM[1], dtype=np.float64))
+            if rm_mats[0].shape != (self.L[0],) * 2 or rm_mats[1].shape != (self.L[1],) * 2:
+                raise ValueError("RM matrices must be (len(Lidx[0]),)*2 and (len(Lidx[1]),)*2")
+            self.RM = RM
+            rm_in = rm_out = 0.0
         else:
             RM = np.asarray(RM, dtype=np.float64)
             if RM.shape != (2,):
-                raise ValueError("RM must be a scalar or of shape (2,) (va_nnet.py:131-144)")
+                raise ValueError("RM must be a scalar, of shape (2,), or a pair of matrices (va_nnet.py:131-144)")
             self.RM = RM
             rm_in, rm_out = float(RM[0]), float(RM[1])
         if bounds is not None:
@@ -199,6 +210,9 @@ class Annealer(DeviceMin):
             self.L[0], _lib.int_array(self.Lidx[0]), self.L[1], _lib.int_array(self.Lidx[1]),
             ptr(self._din_dev), ptr(self._dout_dev), self.NPest, _lib.int_array(self.Pidx)), ctx.h)
         _lib.check(ctx.lib.vab_nn_set_weights(ctx.h, rm_in, rm_out, self.RF0), ctx.h)
+        if rm_mats is not None:
+            self._rm_mats_dev = (self._to_dev(rm_mats[0]), self._to_dev(rm_mats[1]))
+            _lib.check(ctx.lib.vab_nn_set_rm_matrices(ctx.h, ptr(self._rm_mats_dev[0]), ptr(self._rm_mats_dev[1])), ctx.h)
         self._pfix_dev = self._to_dev(self.P.reshape(B, NP)[:Bw])
         _lib.check(ctx.lib.vab_nn_set_fixed_params(ctx.h, ptr(self._pfix_dev), NP), ctx.h)
         self._lo_dev = self._hi_dev = None
