@@ -137,6 +137,14 @@ VAB_API int vab_ode_problem_set(vab_ctx* ctx, const vab_ode_desc* desc,
 VAB_API int vab_ode_set_weights(vab_ctx* ctx, double rm_scalar, const double* rm_dev,
                         double rf0_scalar, const double* rf0_dev);
 
+/* Matrix form of RF0: rf0_mat_dev is (N_model-1, D, D) row-major -- a (D, D) matrix is repeated over
+ * time by the caller, as va_ode.py:631-632 does; model error sum over the Simpson pairs of
+ * e1_i . (RF[2i] e1_i) + e2_i . (RF[2i+1] e2_i), RF = RF0 * scale (va_ode.py:211-218).  SimpsonHermite
+ * only (the reference's branch for the other discretisations does not run), rows inside one lane
+ * group, static parameters.  Replaces the RF0 of vab_ode_set_weights (which clears it).  The array
+ * must stay alive while it is set. */
+VAB_API int vab_ode_set_rf_matrix(vab_ctx* ctx, const double* rf0_mat_dev);
+
 /* Matrix form of RM: rm_dev is (N_data, L, L) row-major -- an (L, L) matrix is repeated over time by
  * the caller, as va_ode.py:616-617 does -- and the measurement error is
  * sum_i diff_i . (RM_i diff_i) / (L N_data) (va_ode.py:149-152; the matrix need not be symmetric).

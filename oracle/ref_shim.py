@@ -3,7 +3,8 @@
 The reference (paulrozdeba/varanneal) is Python 2 and imports ``adolc``; neither exists in
 this image.  This module reads the three reference files as text from ``/root/reference``
 (never copied into this repo), applies the purely syntactic py2->py3 substitutions listed in
-SURVEY.md App. C, and ``exec``s them into fresh module objects with a stub ``adolc`` module.
+SURVEY.md App. C (plus ``/`` -> ``//`` in the one loop bound that relies on Python 2's integer
+division, ``va_ode.py:215``), and ``exec``s them into fresh module objects with a stub ``adolc`` module.
 The reference's own ``Annealer.anneal_init / A_gaussian / me_gaussian / fe_gaussian /
 disc_* / anneal_step / save_*`` then run verbatim under NumPy 2.x.
 
@@ -56,6 +57,7 @@ _EXEC_RE = re.compile(r"exec '(self\.\w+) = self\.(\w*)%s'%\((\w+),?\)")
 def _py3(src):
     src = _EXEC_RE.sub(r"exec('\1 = self.\2%s'%(\3,))", src)
     src = src.replace(".im_func.", ".__func__.")
+    src = src.replace("xrange((self.N_model - 1) / 2)", "xrange((self.N_model - 1) // 2)")   # py2 integer division (va_ode.py:215)
     src = src.replace("xrange", "range")
     return src
 

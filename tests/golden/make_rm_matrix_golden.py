@@ -129,8 +129,60 @@ def main_nnet():
     np.savez_compressed(os.path.join(HERE, "nnet_rm_matrix_golden.npz"), **out)
 
 
+def main_rf():
+    """Matrix RF0 -- (D, D) or (N_model-1, D, D), va_ode.py:211-223, 629-636 -- with SimpsonHermite,
+    the only discretisation for which the reference's branch runs (:222 contracts the whole residual
+    array for the others).  RF = RF0 * alpha**beta scales the matrices (va_ode.py:650)."""
+    data = np.load(L96_FILE)
+    t, Yall = data[:, 0], data[:, 1:]
+    rng = np.random.RandomState(909)
+    out, names = {}, []
+    for name, model, per_time in (("rf_DD_l96", "lorenz96", False), ("rf_NDD_l96", "lorenz96", True),
+                                  ("rf_NDD_l63", "lorenz63", True)):
+        nd = 41 if model == "lorenz96" else 31
+        if model == "lorenz63":
+            D, Lidx, P0, Pidx = 3, [0, 2], np.array([10.0, 28.0, 8.0 / 3.0]), [1]
+            tt = 0.01 * np.arange(nd)
+            Y = rng.randn(nd, 2) * 5.0
+        else:
+            D, Lidx, P0, Pidx = 20, LIDX, np.array([8.17]), [0]
+            tt, Y = t[:nd], Yall[:nd][:, LIDX]
+
+        def mat():
+            G, H = rng.randn(D, D), rng.randn(D, D)
+            return 1e-3 * (2.0 * np.eye(D) + G.dot(G.T) / D + 0.6 * (H - H.T))
+        RF0 = np.array([mat() for _ in range(nd - 1)]) if per_time else mat()
+        an = ShimOde()
+        an.set_model(MODELS[model], D)
+        an.set_data(Y, t=tt)
+        X0 = 20.0 * rng.rand(nd, D) - 10.0
+        alpha, beta, RM = 1.5, 9, 4.0
+        with contextlib.redirect_stdout(io.StringIO()):
+            an.anneal_init(X0.copy(), P0.copy(), alpha, [beta], RM, RF0.copy(), np.array(Lidx), Pidx,
+                           dt_model=None, init_to_data=False, disc="SimpsonHermite")
+        XP = np.append(X0.ravel(), P0[Pidx])
+        A = float(an.A(XP))
+        me = float(an.me_gaussian(XP[:nd * D]))
+        fe = float(an.fe_gaussian(XP))
+        g = ref_shim.complex_step_grad(an.A, XP)
+        RFfull = RF0 if RF0.ndim == 3 else np.resize(RF0, (nd - 1, D, D))
+        prob = OdeProblem(model, D, Y, Lidx, an.dt_model, "SimpsonHermite", P0, Pidx, RM)
+        Ap, mep, fep, gp = prob.action_grad(XP, RFfull * alpha ** beta, parts=True)
+        print("%-12s A=%.16e fe=%.6e port rel %.1e / %.1e grad rel %.1e" % (
+            name, A, fe, abs(Ap - A) / abs(A), abs(fep - fe) / abs(fe), np.max(np.abs(gp - g)) / np.max(np.abs(g))))
+        names.append(name)
+        for k, v in (("X0", X0), ("P0", P0), ("t", tt), ("Y", Y), ("Lidx", np.asarray(Lidx, dtype=np.int64)),
+                     ("Pidx", np.asarray(Pidx, dtype=np.int64)), ("RF0", RF0), ("meta", np.array([alpha, beta, RM])),
+                     ("model", np.array([model])), ("A", np.array([A, me, fe])), ("grad", g)):
+            out[name + "/" + k] = np.asarray(v)
+    out["names"] = np.array(names)
+    np.savez_compressed(os.path.join(HERE, "ode_rf_matrix_golden.npz"), **out)
+
+
 if __name__ == "__main__":
-    what = sys.argv[1:] or ["ode", "nnet"]
+    what = sys.argv[1:] or ["ode", "nnet", "rf"]
+    if "rf" in what:
+        main_rf()
     if "ode" in what:
         main()
     if "nnet" in what:

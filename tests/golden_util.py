@@ -84,3 +84,17 @@ def nnet_rm_matrix_cases():
                         RM=z[n + "/RM"], RF0=float(RF0), alpha=float(alpha), beta=float(beta), A=z[n + "/A"],
                         grad=z[n + "/grad"]))
     return out
+
+
+def rf_matrix_cases():
+    """Cases of ode_rf_matrix_golden.npz (matrix RF0 with SimpsonHermite, make_rm_matrix_golden.py)."""
+    z = load("ode_rf_matrix_golden.npz")
+    out = []
+    for n in z["names"]:
+        n = str(n)
+        alpha, beta, RM = z[n + "/meta"]
+        out.append(dict(name=n, model=str(z[n + "/model"][0]), disc="SimpsonHermite", X0=z[n + "/X0"], P0=z[n + "/P0"],
+                        t=z[n + "/t"], Y=z[n + "/Y"], stim=None, Lidx=z[n + "/Lidx"], Pidx=z[n + "/Pidx"], RM=float(RM),
+                        RF0=z[n + "/RF0"], alpha=float(alpha), beta=int(beta), dt_model=None, A=z[n + "/A"],
+                        grad=z[n + "/grad"]))
+    return out

@@ -79,6 +79,53 @@ def test_matrix_rm_vs_reference_golden(c):
         assert A0 - r.fun <= 1e-4 * abs(A0), (b, A0, r.fun, r.nit, float(np.max(np.abs(g0))), an.exitflags[b], an.nit_array[b])
 
 
+RF_CASES = golden_util.rf_matrix_cases()
+
+
+@pytest.mark.parametrize("c", RF_CASES, ids=[c["name"] for c in RF_CASES])
+def test_matrix_rf_vs_reference_golden(c):
+    """RF0 as a (D, D) or (N-1, D, D) matrix with SimpsonHermite (va_ode.py:211-218, 629-636)."""
+    import scipy.optimize as opt
+    from oracle.ode_port import OdeProblem
+    from varanneal_b200 import va_ode
+    N, D = c["X0"].shape
+
+    def annealer():
+        an = va_ode.Annealer()
+        an.set_model(c["model"], D)
+        an.set_data(c["Y"], t=c["t"])
+        return an
+    an = annealer()
+    an.anneal_init(c["X0"].copy(), c["P0"].copy(), c["alpha"], [c["beta"]], c["RM"], c["RF0"].copy(), c["Lidx"],
+                   c["Pidx"], init_to_data=False, disc="SimpsonHermite")
+    XP = np.append(c["X0"].ravel(), c["P0"][c["Pidx"]])
+    A, g = an.A_gradA_taped(XP)
+    assert abs(A - c["A"][0]) <= TOL * abs(c["A"][0])
+    assert np.max(np.abs(g - c["grad"])) <= TOL * np.max(np.abs(c["grad"]))
+    assert abs(an.fe_gaussian(XP) - c["A"][2]) <= TOL * abs(c["A"][2])
+    assert abs(an.me_gaussian(XP[:N * D]) - c["A"][1]) <= TOL * abs(c["A"][1])
+    with pytest.raises(ValueError, match="SimpsonHermite"):
+        annealer().anneal_init(c["X0"].copy(), c["P0"].copy(), c["alpha"], [c["beta"]], c["RM"], c["RF0"].copy(),
+                               c["Lidx"], c["Pidx"], init_to_data=False, disc="trapezoid")
+    # a two-rung ladder of a small batch ends at stationary points of the oracle action
+    B = 2
+    rng = np.random.default_rng(9)
+    X0 = c["X0"][None] + 0.2 * rng.standard_normal((B, N, D))
+    beta = [c["beta"], c["beta"] + 2]
+    an = annealer()
+    an.anneal(X0, np.tile(c["P0"], (B, 1)), c["alpha"], beta, c["RM"], c["RF0"].copy(), c["Lidx"], c["Pidx"],
+              init_to_data=True, disc="SimpsonHermite", opt_args={"gtol": 1e-9, "ftol": 1e-13})
+    prob = OdeProblem(c["model"], D, c["Y"], c["Lidx"], an.dt_model, "SimpsonHermite", c["P0"], c["Pidx"], c["RM"])
+    RF = (c["RF0"] if c["RF0"].ndim == 3 else np.resize(c["RF0"], (N - 1, D, D))) * c["alpha"] ** beta[-1]
+    for b in range(B):
+        xp = an._est_slice(an.minpaths[b, -1][None])[0]
+        A0, g0 = prob.action_grad(xp, RF)
+        assert abs(A0 - an.A_array[b, -1]) <= TOL * abs(A0)
+        r = opt.minimize(lambda v: prob.action_grad(v, RF), xp, jac=True, method="L-BFGS-B",
+                         options=dict(gtol=1e-9, ftol=1e-13, maxiter=200))
+        assert A0 - r.fun <= 1e-4 * abs(A0), (b, A0, r.fun, r.nit)
+
+
 def test_kernel_families_agree_bitwise_contract():
     """The TMA stream kernels and the register sweep kernels implement the same arithmetic with
     different data movement; on the shipped Lorenz96 case they must agree to rounding."""

@@ -51,6 +51,22 @@ def test_ode_port_matches_reference_golden(c):
 
 PTIME_CASES = golden_util.ptime_cases()
 RM_CASES = golden_util.rm_matrix_cases()
+RF_CASES = golden_util.rf_matrix_cases()
+
+
+@pytest.mark.parametrize("c", RF_CASES, ids=[c["name"] for c in RF_CASES])
+def test_ode_port_matrix_rf_matches_reference_golden(c):
+    """RF0 of shape (D, D) / (N-1, D, D) with SimpsonHermite (va_ode.py:211-218)."""
+    N, D = c["X0"].shape
+    prob = _problem(c)
+    RF = (c["RF0"] if c["RF0"].ndim == 3 else np.resize(c["RF0"], (N - 1, D, D))) * c["alpha"] ** c["beta"]
+    XP = np.append(c["X0"].ravel(), c["P0"][c["Pidx"]])
+    A, me, fe, g = prob.action_grad(XP, RF, parts=True)
+    assert abs(A - c["A"][0]) <= 1e-13 * abs(c["A"][0])
+    assert abs(fe - c["A"][2]) <= 1e-13 * abs(c["A"][2])
+    assert np.max(np.abs(g - c["grad"])) <= 1e-12 * np.max(np.abs(c["grad"]))
+    with pytest.raises(ValueError):
+        OdeProblem(c["model"], D, c["Y"], c["Lidx"], 0.01, "trapezoid", c["P0"], c["Pidx"], 1.0).fe(XP, RF)
 
 
 @pytest.mark.parametrize("c", RM_CASES, ids=[c["name"] for c in RM_CASES])

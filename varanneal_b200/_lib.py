@@ -45,6 +45,7 @@ _SIGS = {
     "vab_ode_set_weights": (ct.c_int, [_VP, ct.c_double, _VP, ct.c_double, _VP]),
     "vab_ode_set_fixed_params": (ct.c_int, [_VP, _VP, ct.c_int64]),
     "vab_ode_set_rm_matrix": (ct.c_int, [_VP, _VP]),
+    "vab_ode_set_rf_matrix": (ct.c_int, [_VP, _VP]),
     "vab_ode_set_time_dependent": (ct.c_int, [_VP, ct.c_int32, _VP, ct.c_int64]),
     "vab_ode_action_grad": (ct.c_int, [_VP, ct.c_int32, _VP, ct.c_int64, ct.c_double,
                                        _VP, _VP, _VP, _VP, ct.c_int64]),

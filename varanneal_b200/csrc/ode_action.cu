@@ -96,7 +96,16 @@ SweepKernel sweep_kernel_ptime(int disc) {
   return nullptr;
 }
 
-SweepKernel sweep_kernel(int model, int C, int disc, bool window, bool ptime = false) {
+SweepKernel sweep_kernel(int model, int C, int disc, bool window, bool ptime = false, bool mrf = false) {
+  if (mrf) {                                  // matrix RF: SimpsonHermite, whole rows in one lane group
+    if (window || ptime || disc != DISC_SIMPSON) return nullptr;
+    if (model == 0 && C == 4) return sweep_simpson_kernel<ModelL96<4>, VAB_SW_PDS, 3, false, true>;
+    if (model == 0 && C == 2) return sweep_simpson_kernel<ModelL96<2>, VAB_SW_PDS, VAB_SW_MINB, false, true>;
+    if (model == 0 && C == 1) return sweep_simpson_kernel<ModelL96<1>, VAB_SW_PDS, VAB_SW_MINB, false, true>;
+    if (model == 1) return sweep_simpson_kernel<ModelL63, VAB_SW_PDS, VAB_SW_MINB, false, true>;
+    if (model == 2) return sweep_simpson_kernel<ModelNaKL, VAB_SW_PDS, 2, false, true>;
+    return nullptr;
+  }
   if (ptime) {
     if (window) return nullptr;
     if (model == 0 && C == 4) return sweep_kernel_ptime<ModelL96<4>, 3>(disc);   // (spills at 128 registers)
@@ -246,7 +255,8 @@ int ode_sweep_prepare(int model, int disc, int D, int N, int B, int num_sms, int
   SweepKernel k = nullptr;
   int nb = 0;
   if (P->ptime && (g.nwin > 1 || disc == DISC_RK4)) return -3;
-  if (allow_stream && !P->ptime && ode_stream_supported(model, disc, g)) {
+  if (P->rf_mat && (g.nwin > 1 || disc != DISC_SIMPSON || P->ptime)) return -3;
+  if (allow_stream && !P->ptime && !P->rf_mat && ode_stream_supported(model, disc, g)) {
     const size_t stage_b = (size_t)g.GPW * 4 * (size_t)g.GW * g.C * sizeof(double);
     const bool fast = (P->nskip == 1 && P->rmd == nullptr && P->rf_arr == nullptr && P->L > 0);
     const int ns = stream_ns(g.C, disc, fast);
@@ -260,7 +270,7 @@ int ode_sweep_prepare(int model, int disc, int D, int N, int B, int num_sms, int
     }
   }
   if (!sl->stream) {
-    k = sweep_kernel(model, g.C, disc, g.nwin > 1, P->ptime != 0);
+    k = sweep_kernel(model, g.C, disc, g.nwin > 1, P->ptime != 0, P->rf_mat != nullptr);
     if (!k) return -1;
     nb = blocks_per_sm(k, sl->smem, cerr);
     if (nb < 0) return -2;
@@ -298,7 +308,7 @@ int ode_sweep_prepare(int model, int disc, int D, int N, int B, int num_sms, int
 int ode_sweep_launch(const OdeParams& P, const SweepLaunch& sl, int model, int disc,
                      cudaStream_t st, double* A, double* me, double* fe, cudaError_t* cerr, bool pdl) {
   const bool fast = (P.nskip == 1 && P.rmd == nullptr && P.rf_arr == nullptr && P.L > 0);
-  SweepKernel k = sl.stream ? stream_kernel(sl.C, disc, fast, P.rf_path != nullptr, P.nwin > 1) : sweep_kernel(model, sl.C, disc, P.nwin > 1, P.ptime != 0);
+  SweepKernel k = sl.stream ? stream_kernel(sl.C, disc, fast, P.rf_path != nullptr, P.nwin > 1) : sweep_kernel(model, sl.C, disc, P.nwin > 1, P.ptime != 0, P.rf_mat != nullptr);
   if (!k) return -1;
   cudaError_t e;
   if (pdl) {

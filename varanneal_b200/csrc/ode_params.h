@@ -17,6 +17,7 @@ struct OdeParams {
   const double* rmd;      // (N_data, D): 2 cm RM[n, l] at observed components, else 0; or nullptr
   double rf_scalar;       // RF0 * scale when rf_arr == nullptr
   const double* rf_arr;   // RF0 (N-1, D) or nullptr
+  const double* rf_mat;   // RF0 (N-1, D, D), matrix form (va_ode.py:211-223; SimpsonHermite only), or nullptr
   double rf_scale;
   double rf0;             // RF0 when it is a scalar (rf_scalar = rf0 * rf_scale)
   const double* rf_path;  // (B) or nullptr: per-path scale replacing rf_scale (asynchronous ladder:

@@ -171,6 +171,33 @@ struct SLane {
   __device__ __forceinline__ double wgt(const OdeParams& P, int row, int c) const {
     return P.rf_arr ? __ldg(P.rf_arr + (long long)row * D + i0 + c) * rsc : rfs;
   }
+  // matrix RF (P.rf_mat, va_ode.py:211-223): out = scale (R_row + R_row') e for the own components;
+  // e is exchanged over the group's lanes strip by strip.  e' R e = 1/2 e . out.  Whole rows inside
+  // one lane group only.  Must be executed by all 32 lanes.
+  __device__ __forceinline__ void matrf(const OdeParams& P, int row, bool valid, const double* e, double* res) const {
+#pragma unroll
+    for (int c = 0; c < C; ++c) res[c] = 0.0;
+    const double* R = P.rf_mat + (long long)row * D * D;
+    const bool ld = valid && out;
+    for (int s = 0; s < P.TPR; ++s) {
+      double es[C];
+#pragma unroll
+      for (int k = 0; k < C; ++k) es[k] = __shfl_sync(VAB_FULL, e[k], gbase + s);
+      if (ld) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          const long long i = i0 + c;
+#pragma unroll
+          for (int k = 0; k < C; ++k) {
+            const long long jj = (long long)s * C + k;
+            if (i < D && jj < D) res[c] = fma(__ldg(R + i * D + jj) + __ldg(R + jj * D + i), es[k], res[c]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) res[c] *= rsc;
+  }
   // measurement term of row r (va_ode.py:138-158): adds to the direct gradient and to me_acc
   // (me_acc collects sum 2 cm RM diff^2 = 2 me)
   __device__ __forceinline__ void measure(const OdeParams& P, int r, const double* xown, double* dir) {
@@ -323,7 +350,8 @@ __global__ void __launch_bounds__(128, MINB) sweep_twopoint_kernel(const __grid_
 // One step per pair; rows a and b get their gradient in the step of their pair, row c's partial
 // seed is carried into the next pair (where it is row a).  Segments start on even rows and the
 // walk begins one pair early so that the c-part of row r0 is available.
-template <class M, int PD, int MINB, bool PT = false>
+// MRF: RF is one (D, D) matrix per residual row (P.rf_mat): the seeds are (R + R') e instead of 2 w e.
+template <class M, int PD, int MINB, bool PT = false, bool MRF = false>
 __global__ void __launch_bounds__(128, MINB) sweep_simpson_kernel(const __grid_constant__ OdeParams P) {
   using LN = SLane<M>;
   constexpr int C = LN::C, H = LN::H, W = LN::W, NPM = LN::NPM;
@@ -395,10 +423,28 @@ __global__ void __launch_bounds__(128, MINB) sweep_simpson_kernel(const __grid_c
       }
       const bool own_p = L.owned(bq);
       double Va[W], Vb[W], da[C], db[C], vcn[C], dcn[C];
+      [[maybe_unused]] double m1[C], m2[C];
+      if constexpr (MRF) {
+        double e1[C], e2[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          e1[c] = vp ? Xc[H + c] - Xa[H + c] - dt3 * (Fa[c] + 4.0 * Fb[c] + Fc[c]) : 0.0;
+          e2[c] = vp ? Xb[H + c] - 0.5 * (Xa[H + c] + Xc[H + c]) - dt4 * (Fa[c] - Fc[c]) : 0.0;
+        }
+        L.matrf(P, a, vp, e1, m1);
+        L.matrf(P, bq, vp, e2, m2);
+        if (vp && own_p) {
+#pragma unroll
+          for (int c = 0; c < C; ++c) L.fe_acc = fma(0.5 * e1[c], m1[c], fma(0.5 * e2[c], m2[c], L.fe_acc));
+        }
+      }
 #pragma unroll
       for (int c = 0; c < C; ++c) {
         double l1 = 0.0, l2 = 0.0;
-        if (vp) {
+        if constexpr (MRF) {
+          l1 = 0.5 * cf2 * m1[c];
+          l2 = 0.5 * cf2 * m2[c];
+        } else if (vp) {
           const double w1 = L.wgt(P, a, c), w2 = L.wgt(P, bq, c);
           const double e1 = Xc[H + c] - Xa[H + c] - dt3 * (Fa[c] + 4.0 * Fb[c] + Fc[c]);
           const double e2 = Xb[H + c] - 0.5 * (Xa[H + c] + Xc[H + c]) - dt4 * (Fa[c] - Fc[c]);

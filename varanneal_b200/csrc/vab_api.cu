@@ -320,6 +320,7 @@ int vab_ode_problem_set(vab_ctx* ctx, const vab_ode_desc* d, const int32_t* Lidx
   ctx->pfix_stride = 0;
   ctx->ptime = 0;
   ctx->rm_matrix = nullptr;
+  ctx->rf0_mat = nullptr;
   ctx->rf0_scalar = 1.0; ctx->rf0_dev = nullptr;
   ctx->problem = VAB_PROBLEM_ODE;
   const int rcw = vab_ode_set_weights(ctx, 1.0, nullptr, 1.0, nullptr);
@@ -358,6 +359,24 @@ int vab_ode_set_weights(vab_ctx* ctx, double rm_scalar, const double* rm_dev, do
     ctx->rm_dev = ctx->rm_dense;
   }
   ctx->rf0_scalar = rf0_scalar; ctx->rf0_dev = rf0_dev;
+  ctx->rf0_mat = nullptr;
+  return VAB_OK;
+}
+
+int vab_ode_set_rf_matrix(vab_ctx* ctx, const double* rf0_mat_dev) {
+  if (!ctx) return VAB_ERR_INVALID;
+  if (ctx->problem != VAB_PROBLEM_ODE) return vab_fail(ctx, VAB_ERR_STATE, "set_rf_matrix: no ODE problem set");
+  if (!rf0_mat_dev) return vab_fail(ctx, VAB_ERR_INVALID, "set_rf_matrix: NULL");
+  const vab_ode_desc& d = ctx->od;
+  if (d.disc != VAB_DISC_SIMPSON_HERMITE)
+    return vab_fail(ctx, VAB_ERR_INVALID, "set_rf_matrix: the matrix form of RF exists for SimpsonHermite only "
+                                          "(the reference's branch for the other discretisations does not run, va_ode.py:222)");
+  OdeGeo geo;
+  if (ode_geometry(d.model, d.disc, d.D, &geo) != 0 || geo.nwin > 1)
+    return vab_fail(ctx, VAB_ERR_INVALID, "set_rf_matrix: needs a row that fits one lane group (D <= 128 for lorenz96)");
+  if (ctx->ptime) return vab_fail(ctx, VAB_ERR_INVALID, "set_rf_matrix: not together with a parameter time series");
+  ctx->rf0_mat = rf0_mat_dev;
+  ctx->rf0_scalar = 1.0; ctx->rf0_dev = nullptr;
   return VAB_OK;
 }
 
@@ -382,8 +401,10 @@ int vab_ode_set_rm_matrix(vab_ctx* ctx, const double* rm_dev) {
   // the walk kernels carry no measurement term any more; RF0 stays what it was
   const double rf0 = ctx->rf0_scalar;
   const double* rf0d = ctx->rf0_dev;
+  const double* rf0m = ctx->rf0_mat;
   const int rc = vab_ode_set_weights(ctx, 0.0, nullptr, rf0, rf0d);
   if (rc != VAB_OK) return rc;
+  ctx->rf0_mat = rf0m;
   ctx->rm_matrix = rm_dev;
   return VAB_OK;
 }
@@ -400,6 +421,7 @@ int vab_ode_set_time_dependent(vab_ctx* ctx, int32_t enabled, const double* pfix
   }
   if (d.disc == VAB_DISC_RK4)
     return vab_fail(ctx, VAB_ERR_INVALID, "set_time_dependent: rk4 (extension) takes static parameters only");
+  if (ctx->rf0_mat) return vab_fail(ctx, VAB_ERR_INVALID, "set_time_dependent: not together with a matrix RF");
   OdeGeo geo;
   if (ode_geometry(d.model, d.disc, d.D, &geo) != 0 || geo.nwin > 1)
     return vab_fail(ctx, VAB_ERR_INVALID, "set_time_dependent: a parameter time series needs a row that fits "
@@ -436,6 +458,7 @@ static int ode_eval(vab_ctx* ctx, int B, const double* XP, long long ldxp, doubl
   P.Y = ctx->Y_dense; P.wobs = ctx->wobs_dev; P.rmd = ctx->rm_dev;
   P.rf_scalar = ctx->rf0_scalar * rf_scale; P.rf_arr = ctx->rf0_dev; P.rf_scale = rf_scale;
   P.rf0 = ctx->rf0_scalar; P.rf_path = rf_path_dev;
+  P.rf_mat = ctx->rf0_mat;
   P.stim = ctx->stim_dev; P.S = d.n_stim;
   P.NP = d.NP; P.NPest = d.NPest; P.pmap = ctx->pmap_dev;
   P.pfix = ctx->pfix_dev; P.pfix_stride = ctx->pfix_stride;

@@ -38,6 +38,7 @@ struct vab_ctx {
   const double* stim_dev = nullptr;
   double rm_scalar = 1.0;
   const double* rm_dev = nullptr;   // = rm_dense when RM is an array
+  const double* rf0_mat = nullptr;    // (N_model-1, D, D) matrix form of RF0 (vab_ode_set_rf_matrix), caller-owned
   const double* rm_matrix = nullptr;  // (N_data, L, L) matrix form of RM (vab_ode_set_rm_matrix), caller-owned
   double rf0_scalar = 1.0;
   const double* rf0_dev = nullptr;

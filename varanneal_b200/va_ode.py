@@ -251,11 +251,18 @@ class Annealer(DeviceMin):
         if isinstance(RF0, np.ndarray) and RF0.ndim > 0:
             if RF0.shape == (D,):
                 self.RF0 = np.resize(RF0, (N - 1, D)).astype(np.float64)
-            elif RF0.shape == (N - 1, D):
+            elif RF0.shape == (D, D):
+                self.RF0 = np.resize(RF0, (N - 1, D, D)).astype(np.float64)          # va_ode.py:631-632
+            elif RF0.shape in ((N - 1, D), (N - 1, D, D)):
                 self.RF0 = RF0.astype(np.float64)
             else:
-                raise ValueError("RF0 must be a scalar, (D,) or (N_model-1, D); the matrix forms "
-                                 "are broken in the reference (va_ode.py:222) and not supported")
+                raise ValueError("RF0 must be a scalar, (D,), (N_model-1, D), (D, D) or (N_model-1, D, D)")
+            if self.RF0.ndim == 3:
+                if disc != 'SimpsonHermite':
+                    raise ValueError("a matrix RF0 works with disc='SimpsonHermite' only: the reference's branch "
+                                     "for the other discretisations does not run (va_ode.py:222)")
+                if self._ptime:
+                    raise ValueError("a matrix RF0 cannot be combined with time-dependent parameters")
         else:
             self.RF0 = float(RF0)
 
@@ -305,11 +312,14 @@ class Annealer(DeviceMin):
         rm_matrix = (not np.isscalar(self.RM)) and self.RM.ndim == 3          # va_ode.py:149-152
         self._rm_dev = None if np.isscalar(self.RM) else self._to_dev(self.RM)
         self._rf0_dev = None if np.isscalar(self.RF0) else self._to_dev(self.RF0)
+        rf_matrix = (not np.isscalar(self.RF0)) and self.RF0.ndim == 3         # va_ode.py:211-218
         _lib.check(ctx.lib.vab_ode_set_weights(
             ctx.h, self.RM if np.isscalar(self.RM) else 0.0, None if rm_matrix else ptr(self._rm_dev),
-            self.RF0 if np.isscalar(self.RF0) else 1.0, ptr(self._rf0_dev)), ctx.h)
+            self.RF0 if np.isscalar(self.RF0) else 1.0, None if rf_matrix else ptr(self._rf0_dev)), ctx.h)
         if rm_matrix:
             _lib.check(ctx.lib.vab_ode_set_rm_matrix(ctx.h, ptr(self._rm_dev)), ctx.h)
+        if rf_matrix:
+            _lib.check(ctx.lib.vab_ode_set_rf_matrix(ctx.h, ptr(self._rf0_dev)), ctx.h)
         self._pfix_dev = self._to_dev(self.P.reshape(B, NPl)[:Bw])
         if self._ptime:
             _lib.check(ctx.lib.vab_ode_set_time_dependent(ctx.h, 1, ptr(self._pfix_dev), NPl), ctx.h)
@@ -496,7 +506,8 @@ class Annealer(DeviceMin):
         out[:, 1] = self._per_init(self.A_array, init)
         out[:, 2] = self._per_init(self.me_array, init)
         out[:, 3] = self._per_init(self.fe_array, init)
-        rf0 = self.RF0 if np.isscalar(self.RF0) else self.RF0[0, cmpt]
+        # (va_ode.py:859-866: RF0[0, 0] for an array, RF0[0, 0, 0] for the matrix form; cmpt picks the column)
+        rf0 = self.RF0 if np.isscalar(self.RF0) else (self.RF0[0, cmpt] if self.RF0.ndim == 2 else self.RF0[0, cmpt, cmpt])
         out[:, 4] = out[:, 3] / (rf0 * float(self.alpha) ** self.beta_array.astype(np.float64))
         return out
 
