@@ -150,9 +150,10 @@ def test_nakl_tutorial_box_single_rung_vs_scipy():
         # two ends lower is decided by rounding (measured: 2e-5 below SciPy with one build of the action
         # kernel, 3e-5 above with the next; the reference's own ulp-perturbed twin runs of this problem
         # differ by 4.6e-5 / 3.3e-3, tests/golden/nakl_bounded_ladder_golden.npz).  Asserted: within
-        # 1e-4 / 1e-3 of SciPy, and SciPy restarted at the device's point gains next to nothing.
-        assert abs(an.A_array[0] - r.fun) <= (1e-4 if disc == "SimpsonHermite" else 1e-3) * abs(r.fun), \
-            (disc, an.A_array[0], r.fun, an.nit_array[0], r.nit)
+        # 1e-3 of SciPy, and SciPy restarted at the device's point gains next to nothing.
+        # (SciPy on the oracle is just as sensitive: re-associating one product in the oracle's Simpson
+        # adjoint moved *its* end point from 0.03824563 after 1342 iterations to 0.03823652 after 3786.)
+        assert abs(an.A_array[0] - r.fun) <= 1e-3 * abs(r.fun), (disc, an.A_array[0], r.fun, an.nit_array[0], r.nit)
         r2 = opt.minimize(lambda z: prob.action_grad(z, rf), xmin, method="L-BFGS-B", jac=True,
                           bounds=list(zip(lo, hi)), options=dict(opts, maxiter=60))
         assert A - r2.fun <= 1e-4 * abs(A), (disc, A, r2.fun, r2.nit)
