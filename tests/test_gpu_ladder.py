@@ -415,16 +415,98 @@ def test_fused_cycle_kernel_is_bit_identical():
     z = golden_util.load("l96_ladder_golden.npz")
     runs = []
     old = os.environ.get("VAB_LBFGS_FUSED")
+    old_res = os.environ.get("VAB_LBFGS_RESIDENT")
+    os.environ["VAB_LBFGS_RESIDENT"] = "0"           # the resident ladder kernel would serve this problem
     try:
         for mode in ("1", "0"):
             os.environ["VAB_LBFGS_FUSED"] = mode
             runs.append(_run("SimpsonHermite", z, B=3))
     finally:
-        if old is None:
-            os.environ.pop("VAB_LBFGS_FUSED", None)
-        else:
-            os.environ["VAB_LBFGS_FUSED"] = old
+        for k, v in (("VAB_LBFGS_FUSED", old), ("VAB_LBFGS_RESIDENT", old_res)):
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
     a, b = runs
     for name in ("A_array", "me_array", "fe_array", "exitflags", "nit_array", "nfev_array", "minpaths", "params_array"):
         assert np.array_equal(getattr(a, name), getattr(b, name)), name
     assert a._ctx.graph_launches > 0 and b._ctx.graph_launches > 0
+
+
+def _resident_run(mode, disc, Pidx, B, N_data, nskip, nbeta, maxiter):
+    """Short ladder on the shipped data with the shared-memory-resident ladder kernel forced on
+    (mode '8' / '4': CTAs per path) or off ('0')."""
+    import os
+    from varanneal_b200 import va_ode
+    data = golden_util.load("l96_ladder_golden.npz")["data"]
+    old = os.environ.get("VAB_LBFGS_RESIDENT")
+    os.environ["VAB_LBFGS_RESIDENT"] = mode
+    try:
+        rng = np.random.RandomState(3)
+        an = va_ode.Annealer()
+        an.set_model("lorenz96", 20)
+        Y = data[:N_data * nskip:nskip, 1:][:, LIDX]
+        an.set_data(Y, t=data[:N_data * nskip:nskip, 0])
+        N = nskip * (len(Y) - 1) + 1
+        X0 = 20.0 * rng.rand(B, N, 20) - 10.0
+        P0 = 8.0 + 0.5 * rng.randn(B, 1)
+        an.anneal(X0, P0, 2.0, np.arange(0, 3 * nbeta, 3), 4.0, 4e-6, LIDX, Pidx, dt_model=0.025, init_to_data=True,
+                  disc=disc, opt_args={"gtol": 1e-11, "ftol": 1e-15, "maxfun": 1000000, "maxiter": maxiter})
+    finally:
+        if old is None:
+            os.environ.pop("VAB_LBFGS_RESIDENT", None)
+        else:
+            os.environ["VAB_LBFGS_RESIDENT"] = old
+    return an, Y, P0
+
+
+@pytest.mark.parametrize("disc", ["trapezoid", "SimpsonHermite", "euler", "forwardmap"])
+@pytest.mark.parametrize("Pidx", [[0], []])
+def test_resident_ladder_kernel_agrees_with_per_phase_kernels(disc, Pidx):
+    """lb_resident_kernel (small Lorenz96 problems: the whole ladder of a path in one launch, vectors in
+    distributed shared memory, the action evaluated by a second implementation) against the per-phase
+    kernels.  One iteration per rung leaves rounding differences no room to grow: the two agree to
+    1e-12; over six iterations per rung they take the same numbers of iterations and evaluations and
+    stay within 1e-4 (measured <= 5e-6); and the action the kernel reports at its minimisers is the
+    oracle's action there to 1e-10 -- for clusters of 8 and of 4 CTAs, with and without an estimated
+    forcing, with measurements at every and at every second model time."""
+    for (B, N_data, nskip) in ((2, 161, 1), (3, 21, 2)):
+        ref1, Y, P0 = _resident_run("0", disc, Pidx, B, N_data, nskip, 2, 1)
+        ref6, _, _ = _resident_run("0", disc, Pidx, B, N_data, nskip, 3, 6)
+        for mode in ("8", "4"):
+            a1, _, _ = _resident_run(mode, disc, Pidx, B, N_data, nskip, 2, 1)
+            assert np.max(np.abs(a1.A_array - ref1.A_array) / np.abs(ref1.A_array)) <= 1e-12
+            assert np.max(np.abs(a1.minpaths - ref1.minpaths)) <= 1e-11
+            a6, _, _ = _resident_run(mode, disc, Pidx, B, N_data, nskip, 3, 6)
+            assert np.array_equal(a6.nit_array, ref6.nit_array) and np.array_equal(a6.nfev_array, ref6.nfev_array)
+            assert np.array_equal(a6.exitflags, ref6.exitflags)
+            assert np.max(np.abs(a6.A_array - ref6.A_array) / np.abs(ref6.A_array)) <= 1e-4
+            assert np.allclose(a6.me_array + a6.fe_array, a6.A_array, rtol=1e-13)
+            for b in range(B):
+                pfix = P0[b] if not Pidx else a6.minpaths[b, -1, -1:]
+                prob = OdeProblem("lorenz96", 20, Y, LIDX, 0.025, disc, pfix, Pidx, 4.0, nskip=nskip)
+                for i in range(3):
+                    A, _ = prob.action_grad(a6.minpaths[b, i], 4e-6 * 2.0 ** (3.0 * i))
+                    assert abs(A - a6.A_array[b, i]) <= 1e-10 * abs(A), (mode, b, i)
+
+
+def test_resident_ladder_kernel_c1_batch_matches_single():
+    """A path's result does not depend on how many other paths share the launch, nor on the round of
+    clusters it runs in (64 paths of the shipped example need two rounds of 4-CTA clusters)."""
+    z = golden_util.load("l96_ladder_golden.npz")
+    zz = {k: z[k] for k in z.files}
+    zz["trapezoid/beta"] = z["trapezoid/beta"][:4]
+    import os
+    old = os.environ.get("VAB_LBFGS_RESIDENT")
+    os.environ["VAB_LBFGS_RESIDENT"] = "4"
+    try:
+        single = _run("trapezoid", zz)
+        batch = _run("trapezoid", zz, B=70)
+    finally:
+        if old is None:
+            os.environ.pop("VAB_LBFGS_RESIDENT", None)
+        else:
+            os.environ["VAB_LBFGS_RESIDENT"] = old
+    for b in (0, 35, 69):
+        assert np.array_equal(batch.A_array[b], single.A_array)
+        assert np.array_equal(batch.minpaths[b], single.minpaths)

@@ -53,6 +53,7 @@
 #include <vector>
 
 #include "lb_common.cuh"
+#include "ode_params.h"
 #include "vab_ctx.h"
 #include "vab_tma.cuh"
 
@@ -1331,6 +1332,10 @@ __global__ void __cluster_dims__(FCS, 1, 1) __launch_bounds__(NT, 1) lb_fused_ke
   }
 }
 
+}  // namespace
+#include "lb_resident.cuh"
+namespace {
+
 __global__ void lb_count_kernel(const LbPath* st, int B, int* n_running, int* prog, int Nbeta) {
   int c = 0;
   for (int b = threadIdx.x; b < B; b += blockDim.x) {
@@ -1475,6 +1480,56 @@ int lb_run(vab_ctx* ctx, int B, double* XP, long long ld, const double* scales_h
   bool fused = small && B <= ctx->num_sms / FCS - 2;
   if (const char* e = getenv("VAB_LBFGS_FUSED")) fused = small && atoi(e) != 0;
   if (small) use_tma = false;
+  // Lorenz96 problems small enough for an 8-CTA cluster's shared memory run their whole ladder inside
+  // one launch (lb_resident.cuh) while every cluster is resident at once (two per GPC);
+  // VAB_LBFGS_RESIDENT=0/1 overrides.  The action is evaluated by a second implementation there, so
+  // its results agree with the other paths to rounding, not bit for bit.
+  bool resident = false;
+  int res_rpc = 0, res_cs = 0;
+  size_t res_smem = 0;
+  ResKernel res_kernel = nullptr;
+  if (small && o.method == 0 && ctx->problem == VAB_PROBLEM_ODE) {
+    const vab_ode_desc& d = ctx->od;
+    if (d.model == 0 && d.NP == 1 && d.n_stim == 0 && !ctx->ptime && !ctx->rm_dev && !ctx->rm_matrix &&
+        !ctx->rf0_dev && !ctx->rf0_mat && d.disc != VAB_DISC_RK4) {
+      // clusters of 8 CTAs give the shortest cycle; clusters of 4 let twice as many paths be resident
+      // at once.  A batch that needs more than two rounds of clusters takes the general path, whose
+      // cost per cycle grows slowly with the batch.
+      int want = -1;                                  // -1: decide here, 0: off, 1: on (size decided here), 4 / 8: that size
+      if (const char* e = getenv("VAB_LBFGS_RESIDENT")) want = atoi(e);
+      const int sizes[2] = {8, 4};
+      bool fits[2] = {false, false};
+      int cap[2] = {0, 0}, rpc[2] = {0, 0};
+      size_t smem[2] = {0, 0};
+      ResKernel kern[2] = {lb_resident_pick<8>(d.disc), lb_resident_pick<4>(d.disc)};
+      for (int q = 0; q < 2 && want != 0; ++q) {
+        const int cs = sizes[q];
+        rpc[q] = lb_resident_rows(d.N_model, cs);
+        smem[q] = lb_resident_smem(rpc[q], d.D);
+        if (smem[q] > (size_t)226000 || (long long)rpc[q] * cs < d.N_model) continue;
+        if (cudaFuncSetAttribute(kern[q], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem[q]) != cudaSuccess) { cudaGetLastError(); continue; }
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.gridDim = dim3(B * cs); cfg.blockDim = dim3(RNT); cfg.dynamicSmemBytes = smem[q]; cfg.attrs = at; cfg.numAttrs = 1;
+        if (cudaOccupancyMaxActiveClusters(&cap[q], kern[q], &cfg) != cudaSuccess) { cudaGetLastError(); cap[q] = 0; }
+        fits[q] = cap[q] >= 1;
+      }
+      int pick = -1;
+      if (want == 8 || want == 4) pick = fits[want == 8 ? 0 : 1] ? (want == 8 ? 0 : 1) : -1;
+      else if (want != 0) {
+        if (fits[0] && B <= cap[0]) pick = 0;
+        else if (fits[1] && B <= 2 * cap[1]) pick = 1;
+        else if (want == 1) pick = fits[1] ? 1 : (fits[0] ? 0 : -1);
+      }
+      if (pick >= 0) {
+        resident = true; res_cs = sizes[pick]; res_rpc = rpc[pick]; res_smem = smem[pick]; res_kernel = kern[pick];
+      }
+    }
+  }
+  if (resident) fused = false;
   // bounded L-BFGS-B: generalised Cauchy point + subspace minimisation (lbfgsb_bounded.cuh);
   // VAB_BOUNDS=projection selects round 1's active-set projection for comparison
   bool gcp = bounded && o.method == 0;
@@ -1540,7 +1595,7 @@ int lb_run(vab_ctx* ctx, int B, double* XP, long long ld, const double* scales_h
     poll = (n * (long long)B < (1LL << 22)) ? 64 : 8;
   }
   long long* fused_dbg = nullptr;
-  if (fused && getenv("VAB_FUSED_TIMING")) {
+  if ((fused && getenv("VAB_FUSED_TIMING")) || (resident && getenv("VAB_RESIDENT_TIMING"))) {
     if (cudaMalloc((void**)&fused_dbg, 32 * sizeof(long long)) == cudaSuccess) cudaMemset(fused_dbg, 0, 32 * sizeof(long long));
     else fused_dbg = nullptr;
   }
@@ -1617,11 +1672,37 @@ int lb_run(vab_ctx* ctx, int B, double* XP, long long ld, const double* scales_h
   // is illegal on the legacy default stream (which is what PyTorch's current stream is unless the
   // caller set one): the cycle is then recorded on a private capture stream -- recording executes
   // nothing -- and the instantiated graph is launched into the context's stream like any kernel.
-  rc = enqueue_cycle(st);
-  if (rc != VAB_OK) return rc;
-  LB_CUDA(cudaGetLastError());
-  bool use_graph = true;
-  if (const char* e = getenv("VAB_LBFGS_GRAPH")) use_graph = atoi(e) != 0;
+  if (resident) {
+    const vab_ode_desc& d = ctx->od;
+    ResArgs ra;
+    memset(&ra, 0, sizeof(ra));
+    ra.XP = XP; ra.ld = ld; ra.N = d.N_model; ra.D = d.D; ra.nskip = d.nskip; ra.nobs = d.L; ra.RPC = res_rpc; ra.disc = d.disc;
+    ra.dt = d.dt_model; ra.cf = 1.0 / ((double)d.D * (d.N_model - 1)); ra.rf0 = ctx->rf0_scalar;
+    ra.Y = ctx->Y_dense; ra.wobs = ctx->wobs_dev; ra.k_est = d.NPest == 1 ? 1 : 0;
+    ra.pfix = ctx->pfix_dev; ra.pfix_stride = ctx->pfix_stride;
+    ra.st = w->st; ra.o = o; ra.L = L;
+    {
+      double mc0 = (double)Nbeta * ((double)o.maxfun + (double)o.maxiter + 64.0);
+      ra.max_cycles = mc0 < 9.0e18 ? (long long)mc0 : (long long)9.0e18;
+    }
+    ra.dbg = fused_dbg;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = res_cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.gridDim = dim3(B * res_cs); cfg.blockDim = dim3(RNT); cfg.dynamicSmemBytes = res_smem; cfg.stream = st;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    LB_CUDA(cudaLaunchKernelEx(&cfg, res_kernel, ra));
+    LB_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+  } else {
+    rc = enqueue_cycle(st);
+    if (rc != VAB_OK) return rc;
+    LB_CUDA(cudaGetLastError());
+  }
+  bool use_graph = !resident;
+  if (const char* e = getenv("VAB_LBFGS_GRAPH")) use_graph = use_graph && atoi(e) != 0;
   long long launches_per_cycle = 0;
   if (use_graph) {
     cudaStream_t cap = st;
@@ -1679,7 +1760,7 @@ int lb_run(vab_ctx* ctx, int B, double* XP, long long ld, const double* scales_h
   const double t_limit = getenv("VAB_LBFGS_MAX_SECONDS") ? atof(getenv("VAB_LBFGS_MAX_SECONDS")) : 0.0;
   const auto t0 = std::chrono::steady_clock::now();
   int gsize = poll < 4 ? poll : 4;              // groups grow 4, 8, ... poll: short runs waste little
-  while (true) {
+  while (!resident) {
     const int k = (int)(groups & 1);
     for (int c = 0; c < gsize; ++c) {
       if (own.gexec) {
@@ -1717,7 +1798,7 @@ int lb_run(vab_ctx* ctx, int B, double* XP, long long ld, const double* scales_h
   if (fused_dbg) {
     long long h[32];
     if (cudaMemcpy(h, fused_dbg, sizeof(h), cudaMemcpyDeviceToHost) == cudaSuccess && h[0] > 0) {
-      fprintf(stderr, "lb_fused_kernel: %lld calls; mean SM cycles per phase:", h[0]);
+      fprintf(stderr, "%s: %lld cycles; mean SM clocks per phase:", resident ? "lb_resident_kernel" : "lb_fused_kernel", h[0]);
       for (int q = 1; q < 16; ++q) fprintf(stderr, " %.0f", (double)h[q] / (double)h[0]);
       fprintf(stderr, "\n");
     }
