@@ -53,7 +53,7 @@ else:
     for disc in (("trapezoid",) if quick else ("trapezoid", "SimpsonHermite")):
         alpha, RM, RF0, gtol, ftol = z[disc + "/meta"][:5]
         beta = z[disc + "/table"][:, 0]
-        plan = ((1, "8"), (1, "4"), (16, "8"), (16, "4"), (32, "4"), (64, "4"), (64, "-1")) if quick else \
+        plan = ((1, "8"), (1, "4")) if quick else \
             ((1, "8"), (1, "4"), (1, "0"), (16, "8"), (16, "4"), (16, "0"), (64, "4"), (64, "0"))
         for (B, mode) in plan:
             if True:

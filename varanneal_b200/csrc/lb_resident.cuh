@@ -258,12 +258,15 @@ __global__ void __launch_bounds__(RNT, 1) lb_resident_kernel(const ResArgs A) {
   };
   auto f_at = [&](int r, int i) -> double { return F[(r - (R0 - 2)) * D + i]; };
 
+  __shared__ long long tacc[16];                        // phase clocks (development aid), flushed at the end
+  if (tid < 16) tacc[tid] = 0;
+  const bool timing = A.dbg != nullptr && blockIdx.x == 0 && tid == 0;
   long long t_prev = 0;
   int t_slot = 0;
   auto stamp = [&]() {
-    if (A.dbg != nullptr && blockIdx.x == 0 && tid == 0) {
+    if (timing) {
       const long long t = clock64();
-      if (t_slot > 0) A.dbg[t_slot] += t - t_prev;
+      if (t_slot > 0) tacc[t_slot] += t - t_prev;
       t_prev = t;
       ++t_slot;
     }
@@ -589,8 +592,10 @@ __global__ void __launch_bounds__(RNT, 1) lb_resident_kernel(const ResArgs A) {
       __syncthreads();
     }
     stamp();                                            // 9: end of rung
-    if (A.dbg != nullptr && blockIdx.x == 0 && tid == 0) A.dbg[0] += 1;
+    if (timing) tacc[0] += 1;
   }
+  if (timing)
+    for (int k = 0; k < 16; ++k) A.dbg[k] += tacc[k];
   // ---- results back to global memory
   for (int e = tid; e < nloc; e += RNT) xg[(long long)R0 * D + e] = X[e];
   if (A.k_est && last && tid == 0) xg[nX] = pk[0];
