@@ -80,6 +80,12 @@ VAB_API long long vab_launch_count(const vab_ctx* ctx);
  * were replayed from the CUDA graph captured by vab_minimize / vab_anneal, as opposed to enqueued
  * kernel by kernel.  0 means the capture was refused or switched off (VAB_LBFGS_GRAPH=0). */
 VAB_API long long vab_graph_launch_count(const vab_ctx* ctx);
+/* Which kernels evaluated the last neural-network action on this context: 0 none yet, 1 fused
+ * example-tile kernel, 2 per-layer fp64 tensor-pipe (DMMA) kernels, 3 all-layer DMMA tile kernel,
+ * 4 CUDA-core register-tiled kernel (VAB_NN_SMALL=1), 5 tcgen05 / TMEM / TMA Ozaki-split contractions
+ * (VAB_NN_TCGEN05=1; layers up to 128 wide).  No reference counterpart: a diagnostic the parity tests
+ * use to assert that the path they mean to check is the one that ran. */
+VAB_API int vab_nn_kernel_family(const vab_ctx* ctx);
 
 /* Measures the device's double-precision FMA rate on the CUDA cores (TFLOP/s, 2 flops per FMA) with
  * a register-resident micro-kernel timed by CUDA events: the roofline denominator of the

@@ -217,3 +217,60 @@ def test_nn_tnc_method_minimises_the_oracle_action():
         assert abs(an.A_array[i] - res.fun) <= 1e-6 * abs(res.fun), (i, an.A_array[i], res.fun)
         A, g = prob.action_grad(an.minpaths[i][:M * NDnet], rf)
         assert abs(A - an.A_array[i]) <= 1e-10 * abs(A) and np.max(np.abs(g)) <= 1e-5 * max(1.0, abs(A))
+
+
+# ---------------------------------------------------------------------------------------------
+# tcgen05 / TMEM / TMA path (VAB_NN_TCGEN05=1): the forward and the backward-to-states contractions of
+# every layer as Ozaki-split int8 GEMMs on the 5th-generation tensor cores (csrc/ozaki_gemm.cu), the
+# same 1e-10 bar as the fp64 tensor-pipe kernels.
+@pytest.mark.parametrize("c", [c for c in NN_CASES if max(c["structure"]) <= 128], ids=lambda c: c["name"])
+def test_nn_tcgen05_path_vs_reference_golden(c, monkeypatch):
+    monkeypatch.setenv("VAB_NN_TCGEN05", "1")
+    an = _annealer(c["structure"], c["data_in"], c["data_out"], c["X0"].copy(), c["P0"].copy(), c["alpha"],
+                   [c["beta"]], c["RM"], c["RF0"], c["Pidx"])
+    XP = np.append(c["X0"], c["P0"][c["Pidx"]])
+    A, g = an.A_gradA_taped(XP)
+    assert an._ctx.nn_kernel_family == 5, "the tcgen05 kernels did not run"
+    assert abs(A - c["A"][0]) <= TOL * abs(c["A"][0])
+    assert np.max(np.abs(g - c["grad"])) <= TOL * np.max(np.abs(c["grad"]))
+    assert abs(an.fe_gaussian(XP) - c["A"][2]) <= TOL * abs(c["A"][2])
+
+
+@pytest.mark.parametrize("structure,M,act,RM,partial,B", [
+    ([25, 30, 4], 1000, "sigmoid", 1.0, False, 2),                  # bar-images shape
+    ([100, 100, 100, 100], 130, "sigmoid", [3.0, 0.5], False, 2),   # nnet_twin widths
+    ([100, 100, 100, 100, 100], 1000, "sigmoid", 1.0, False, 3),    # C4: 5 x 100, M = 1000
+    ([128, 17, 5], 300, "tanh", 2.0, True, 3),                      # the widest layer the planes hold
+    ([6, 9, 9, 3], 40, "linear", 1.5, True, 1),
+])
+def test_nn_tcgen05_path_vs_oracle(structure, M, act, RM, partial, B, monkeypatch):
+    monkeypatch.setenv("VAB_NN_TCGEN05", "1")
+    rng = np.random.RandomState(3)
+    st = np.array(structure)
+    NDnet = int(st.sum())
+    NP = int(sum(st[n] * st[n + 1] + st[n + 1] for n in range(len(st) - 1)))
+    Lidx = [np.arange(st[0])[::2], np.arange(st[-1])]
+    data_in = rng.rand(M, len(Lidx[0]))
+    data_out = rng.rand(M, len(Lidx[1]))
+    # states and weights with three decades of spread inside a row: the digit planes are scaled by
+    # the row maximum, so small entries next to large ones are what they resolve least well
+    X0 = rng.rand(B, M * NDnet) * 10.0 ** rng.uniform(-3, 0, size=(B, M * NDnet))
+    P0 = 0.3 * rng.randn(B, NP) * 10.0 ** rng.uniform(-3, 0, size=(B, NP))
+    Pidx = np.arange(0, NP, 3) if partial else np.arange(NP)
+    alpha, beta, RF0 = 1.1, 30.0, 1e-2
+    an = _annealer(st, data_in, data_out, X0.copy(), P0.copy(), alpha, [beta], RM, RF0, Pidx, act=act, Lidx=Lidx)
+    XP = np.concatenate([X0, P0[:, Pidx]], axis=1)
+    A, G = an.A_gradA(XP)
+    assert an._ctx.nn_kernel_family == 5, "the tcgen05 kernels did not run"
+    for b in range(B):
+        prob = nnet_port.NnetProblem(st, data_in, data_out, Lidx, P0[b], Pidx, RM, act=act)
+        Ar, gr = prob.action_grad(XP[b], RF0 * alpha ** beta)
+        assert abs(A[b] - Ar) <= TOL * abs(Ar)
+        assert np.max(np.abs(G[b] - gr)) <= TOL * np.max(np.abs(gr))
+    # and the default (fp64 tensor-pipe) kernels on the same input agree with it to the same bar
+    monkeypatch.delenv("VAB_NN_TCGEN05")
+    an2 = _annealer(st, data_in, data_out, X0.copy(), P0.copy(), alpha, [beta], RM, RF0, Pidx, act=act, Lidx=Lidx)
+    A2, G2 = an2.A_gradA(XP)
+    assert an2._ctx.nn_kernel_family in (2, 3)
+    assert np.max(np.abs(A - A2) / np.abs(A2)) <= TOL
+    assert np.max(np.abs(G - G2)) <= TOL * np.max(np.abs(G2))

@@ -38,6 +38,7 @@ _SIGS = {
     "vab_last_error": (ct.c_char_p, [_VP]),
     "vab_launch_count": (ct.c_longlong, [_VP]),
     "vab_graph_launch_count": (ct.c_longlong, [_VP]),
+    "vab_nn_kernel_family": (ct.c_int, [_VP]),
     "vab_measure_fp64_peak": (ct.c_int, [_VP, c_double_p]),
     "vab_measure_fp64_dmma_peak": (ct.c_int, [_VP, c_double_p]),
     "vab_ozaki_gemm_probe": (ct.c_int, [_VP, ct.c_int32, ct.c_int32, ct.c_int32, ct.c_int32, ct.c_int32, ct.c_double, c_double_p]),
@@ -159,3 +160,8 @@ class Context(object):
     @property
     def graph_launches(self):
         return int(self.lib.vab_graph_launch_count(self.h))
+
+    @property
+    def nn_kernel_family(self):
+        """1 fused, 2 per-layer DMMA, 3 all-layer DMMA, 4 CUDA cores, 5 tcgen05 (include/varanneal_b200.h)."""
+        return int(self.lib.vab_nn_kernel_family(self.h))

@@ -713,6 +713,52 @@ __global__ void __launch_bounds__(NT, 2) nn_fba_kernel(const __grid_constant__ N
 // Elementwise pass over the gradient rows after nn_fb_kernel: columns of the middle layers
 // += lambda of the layer below; observed components of the input / output layer += the
 // measurement term (va_nnet.py:117-173), whose per-block sums are the me partials.
+// tcgen05 path (VAB_NN_TCGEN05=1): the contractions Z = X_n W_n^T and Delta W_n of nn_fb_kernel run as
+// Ozaki-split int8 GEMMs on the 5th-generation tensor cores (ozaki_gemm.cu: TMA tensor maps, TMEM
+// accumulators); this kernel is the epilogue between the two -- the same arithmetic as the
+// accumulator epilogue of nn_fb_kernel (va_nnet.py:210-255: activation, residual, lambda, Delta), one
+// block per tile of TMF examples so that the fe partials keep the layout nn_reduce_kernel sums.
+__global__ void __launch_bounds__(256) nn_tc_epilogue_kernel(const __grid_constant__ NnParams P, int n,
+                                                             const double* __restrict__ Z) {
+  const int mtb = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+  if (P.active != nullptr && P.active[b] == 0) return;
+  const int dn1 = P.structure[n + 1], d0 = P.structure[0];
+  const int xo1 = P.xoff[n + 1];
+  const int ND1 = P.NDnet - d0;
+  const bool lastl = (n + 1 == P.NL - 1);
+  const double* xp = P.XP + (long long)b * P.ldxp;
+  double* gp = P.G + (long long)b * P.ldg;
+  double* dbuf = P.dbuf + (long long)b * P.M * ND1;
+  double* lam = P.lam + (long long)b * P.M * ND1;
+  const double* bias = P.pfull + (long long)b * P.NP + P.boff[n];
+  const double* z = Z + (long long)b * P.M * dn1;
+  const double cf2 = (P.rf_path != nullptr) ? P.cf2_num * __ldg(P.rf_path + b) / P.cf2_den : P.cf2;
+  const int m0 = mtb * P.TMF, rows = min(P.TMF, P.M - m0);
+  double fe_acc = 0.0;
+  for (int e = tid; e < rows * dn1; e += 256) {
+    const int m = e / dn1, j = e - m * dn1;
+    const long long grow = (long long)(m0 + m);
+    const double sv = act_f(P.act, z[grow * dn1 + j] + bias[j]);
+    const double ev = xp[grow * P.NDnet + xo1 + j] - sv;
+    const double lm = cf2 * ev;
+    fe_acc = fma(lm, ev, fe_acc);
+    if (lastl) gp[grow * P.NDnet + xo1 + j] = lm;
+    else lam[grow * ND1 + (xo1 - d0) + j] = lm;
+    dbuf[grow * ND1 + (xo1 - d0) + j] = -lm * act_d(P.act, sv);
+  }
+  __shared__ double red[8];
+  for (int sft = 16; sft > 0; sft >>= 1) fe_acc += __shfl_down_sync(0xffffffffu, fe_acc, sft);
+  if ((tid & 31) == 0) red[tid >> 5] = fe_acc;
+  __syncthreads();
+  if (tid == 0) {
+    double c = 0.0;
+    for (int w = 0; w < 8; ++w) c += red[w];
+    const long long item = ((long long)b * (P.NL - 1) + n) * P.nmt + mtb;
+    P.partials[item * 2 + 0] = 0.0;
+    P.partials[item * 2 + 1] = 0.5 * c;
+  }
+}
+
 constexpr int FIX_NT = 256;
 __global__ void __launch_bounds__(FIX_NT) nn_fix_kernel(const __grid_constant__ NnParams P) {
   const int b = blockIdx.y;
@@ -911,6 +957,8 @@ struct NnProblem {
   size_t dbuf_cap = 0;
   double* lam = nullptr;
   size_t lam_cap = 0;
+  double* zbuf = nullptr;          // tcgen05 path: Z = X_n W_n^T of the layer in flight (B, M, d_{n+1})
+  size_t zbuf_cap = 0;
   double* one_dev = nullptr;       // device constant 1.0
   std::vector<int> st_host;        // layer widths (host copy, for launch planning)
 };
@@ -924,6 +972,7 @@ void nn_destroy(vab_ctx* ctx) {
   cudaFree(p->pfull);
   cudaFree(p->dbuf);
   cudaFree(p->lam);
+  cudaFree(p->zbuf);
   cudaFree(p->one_dev);
   delete p;
   ctx->nn = nullptr;
@@ -1059,6 +1108,7 @@ static int nn_eval_core(vab_ctx* ctx, int B, const double* XP, long long ldxp, d
         ctx->attr_nn_small = true;
       }
       if (p->NP > 0) nn_gather_params_kernel<<<dim3((p->NP + 255) / 256, B), 256, 0, ctx->stream>>>(P);
+      ctx->nn_family = 4;
       nn_small_kernel<<<dim3(L.ncta, B), SM_NT, smem_small, ctx->stream>>>(P, L);
       cudaError_t e = cudaGetLastError();
       if (e != cudaSuccess) return vab_cuda_fail(ctx, e, "nn_small_kernel launch");
@@ -1078,11 +1128,19 @@ static int nn_eval_core(vab_ctx* ctx, int B, const double* XP, long long ldxp, d
     int TMF = 0;
     size_t smem_fb = 0, smem_gw = 0;
     bool fits = use_split && G != nullptr && p->NL >= 2;
+    // VAB_NN_TCGEN05=1: the forward and backward-to-states contractions on tcgen05 / TMEM / TMA
+    // (Ozaki-split, ozaki_gemm.cu) instead of the fp64 tensor pipe; layers up to 128 wide
+    bool use_tc = false;
+    if (const char* env_tc = getenv("VAB_NN_TCGEN05")) {
+      use_tc = fits && atoi(env_tc) != 0;
+      for (int n = 0; n < p->NL && use_tc; ++n)
+        if (p->st_host[n] > 128) use_tc = false;
+    }
     // small networks: all layers of an example tile + every W resident (nn_fba_kernel)
     bool all_layers = false;
     int fba_pxn = 0, fba_pd = 0;
     size_t smem_fba = 0;
-    if (fits && p->NL - 1 <= 64) {
+    if (fits && p->NL - 1 <= 64 && !use_tc) {
       const char* env_fba = getenv("VAB_NN_ALL_LAYERS");      // 0: per-layer kernels even for small networks
       if (!(env_fba && atoi(env_fba) == 0)) {
         fba_pxn = ((p->NDnet + 7) & ~7) + 4;
@@ -1200,10 +1258,39 @@ static int nn_eval_core(vab_ctx* ctx, int B, const double* XP, long long ldxp, d
       if (p->NP > 0) nn_gather_params_kernel<<<dim3((p->NP + 255) / 256, B), 256, 0, ctx->stream>>>(P);
       int nl = 3;
       cudaError_t e = cudaSuccess;
+      ctx->nn_family = all_layers ? 3 : (use_tc ? 5 : 2);
       if (all_layers) {
         nn_fba_kernel<<<dim3(P.nmt, B), NT, smem_fba, ctx->stream>>>(P);
         e = cudaGetLastError();
         if (e != cudaSuccess) return vab_cuda_fail(ctx, e, "nn_fba_kernel launch");
+        nl = 2;
+      } else if (use_tc) {
+        int d1max = 0;
+        for (int n = 1; n < p->NL; ++n) d1max = p->st_host[n] > d1max ? p->st_host[n] : d1max;
+        rc = vab_reserve(ctx, &p->zbuf, &p->zbuf_cap, (size_t)B * p->M * d1max);
+        if (rc != VAB_OK) return rc;
+        const int d0 = p->d0;
+        const long long ND1 = p->NDnet - d0;
+        int xo = 0, wo = 0;
+        for (int n = 0; n + 1 < p->NL; ++n) {
+          const int dn = p->st_host[n], dn1 = p->st_host[n + 1];
+          const int xo1 = xo + dn;
+          // Z[b] = X_n[b] W_n[b]^T
+          rc = ozaki_gemm(ctx, B, p->M, dn1, dn, XP + xo, p->NDnet, 1, ldxp, p->pfull + wo, dn, 1, p->NP,
+                          p->zbuf, dn1, (long long)p->M * dn1, active_dev);
+          if (rc != VAB_OK) return rc;
+          nn_tc_epilogue_kernel<<<dim3(P.nmt, B), 256, 0, ctx->stream>>>(P, n, p->zbuf);
+          e = cudaGetLastError();
+          if (e != cudaSuccess) return vab_cuda_fail(ctx, e, "nn_tc_epilogue_kernel launch");
+          // back term of layer n's gradient rows: G[b][:, xo : xo + dn] = Delta[b] W_n[b]
+          rc = ozaki_gemm(ctx, B, p->M, dn, dn1, p->dbuf + (xo1 - d0), ND1, 1, (long long)p->M * ND1,
+                          p->pfull + wo, 1, dn, p->NP, G + xo, p->NDnet, ldg, active_dev);
+          if (rc != VAB_OK) return rc;
+          ctx->launches += 1;
+          xo = xo1;
+          wo += dn * dn1 + dn1;
+        }
+        nn_fix_kernel<<<dim3((unsigned)nfix, B), FIX_NT, 0, ctx->stream>>>(P);
         nl = 2;
       } else {
         // 16 warps when every warp still gets a (row tile, column group) task of the smallest layer pair
@@ -1280,6 +1367,7 @@ static int nn_eval_core(vab_ctx* ctx, int B, const double* XP, long long ldxp, d
     if (e != cudaSuccess) return vab_cuda_fail(ctx, e, "nn_action_grad smem opt-in");
     ctx->attr_nn_fused = true;
   }
+  ctx->nn_family = 1;
   nn_fused_kernel<<<dim3(P.ntiles, B), NT, smem, ctx->stream>>>(P);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return vab_cuda_fail(ctx, e, "nn_fused_kernel launch");

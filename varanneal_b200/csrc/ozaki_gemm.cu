@@ -49,12 +49,15 @@ __device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta
 
 // ---- digit planes ---------------------------------------------------------------------------
 // one warp per row: row max -> exponent, then the digits of every element
+// (element k of row r of problem p = src[p pstride + r ld + k kstride]: kstride != 1 slices a transposed operand)
 __global__ void __launch_bounds__(256) ozaki_slice_kernel(const double* __restrict__ src, long long ld, long long pstride,
                                                           int rows, int K, int rows_pad, int8_t* __restrict__ planes,
-                                                          long long plane_stride, int* __restrict__ expo) {
+                                                          long long plane_stride, int* __restrict__ expo,
+                                                          long long kstride = 1, const int* __restrict__ active = nullptr) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int p = blockIdx.y;
   if (warp >= rows_pad) return;
+  if (active != nullptr && active[p] == 0) return;
   const long long orow = (long long)p * rows_pad + warp;
   int8_t* out = planes + orow * KP;
   if (warp >= rows) {                                  // padding rows: zeros
@@ -65,7 +68,7 @@ __global__ void __launch_bounds__(256) ozaki_slice_kernel(const double* __restri
   }
   const double* x = src + (long long)p * pstride + (long long)warp * ld;
   double amax = 0.0;
-  for (int k = lane; k < K; k += 32) amax = fmax(amax, fabs(x[k]));
+  for (int k = lane; k < K; k += 32) amax = fmax(amax, fabs(x[(long long)k * kstride]));
   for (int sft = 16; sft > 0; sft >>= 1) amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, sft));
   int e = 0;
   if (amax > 0.0) { (void)frexp(amax, &e); }           // amax = m 2^e, m in [0.5, 1)  ->  |x| / 2^e < 1
@@ -77,7 +80,7 @@ __global__ void __launch_bounds__(256) ozaki_slice_kernel(const double* __restri
     const double sc = __longlong_as_double((long long)(6 - e + 1023) << 52);
     double t[4];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) t[c] = (k0 + c < K) ? x[k0 + c] * sc : 0.0;     // |t| < 64
+    for (int c = 0; c < 4; ++c) t[c] = (k0 + c < K) ? x[(long long)(k0 + c) * kstride] * sc : 0.0;     // |t| < 64
 #pragma unroll
     for (int s = 0; s < NS; ++s) {
       unsigned pack = 0;
@@ -143,7 +146,9 @@ struct OzakiParams {
   int Mpad, Npad;
   const int* ea;             // (P * Mpad) row exponents of A
   const int* eb;             // (P * Npad)
-  double* C;                 // (P, M, N)
+  double* C;                 // element (p, r, c) at C[p cps + r ldc + c]
+  long long ldc, cps;
+  const int* active;         // (P) or nullptr: problems to skip
 };
 
 __global__ void __launch_bounds__(128, 1) ozaki_mma_kernel(const __grid_constant__ CUtensorMap mapA,
@@ -160,6 +165,7 @@ __global__ void __launch_bounds__(128, 1) ozaki_mma_kernel(const __grid_constant
   const int nt = tile % q.n_tiles; tile /= q.n_tiles;
   const int mt = tile % q.m_tiles;
   const int p = tile / q.m_tiles;
+  if (q.active != nullptr && q.active[p] == 0) return;
 
   if (tid == 0) {
     mbar_init(bar_tma, 1);
@@ -228,7 +234,7 @@ __global__ void __launch_bounds__(128, 1) ozaki_mma_kernel(const __grid_constant
       for (int c = 0; c < 16; ++c) acc[c] = fma(acc[c], 1.0 / 128.0, (double)(int)v[c]);
     }
     if (row < q.M) {
-      double* out = q.C + ((long long)p * q.M + row) * q.N;
+      double* out = q.C + (long long)p * q.cps + (long long)row * q.ldc;
 #pragma unroll
       for (int c = 0; c < 16; ++c) {
         const int col = nt * TN + c0 + c;
@@ -396,7 +402,7 @@ __global__ void __launch_bounds__(192, 1) ozaki_mma2_kernel(const __grid_constan
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty(a));
       if (row < q.M) {
-        double* out = q.C + ((long long)p * q.M + row) * q.N;
+        double* out = q.C + (long long)p * q.cps + (long long)row * q.ldc;
         const int* ebp = q.eb + (long long)p * q.Npad + nt * TN2;
 #pragma unroll
         for (int c = 0; c < TN2; ++c) {
@@ -479,6 +485,83 @@ int make_plane_map(vab_ctx* ctx, EncodeTiledFn enc, CUtensorMap* map, void* base
 
 }  // namespace
 
+// ---- product entry point (nn_action.cu, VAB_NN_TCGEN05=1) -----------------------------------------
+// C[p][r][c] = sum_k A[p][r][k] B[p][c][k] for P problems with K <= 128, operands addressed by
+// (problem stride, row stride, element stride), the output by (problem stride, row pitch):
+// digit planes of both operands (ozaki_slice_kernel), then one tcgen05 tile per CTA
+// (ozaki_mma_kernel).  The plane / exponent workspaces belong to the context and only grow.
+struct OzakiWork {
+  int8_t *pa = nullptr, *pb = nullptr;
+  int *ea = nullptr, *eb = nullptr;
+  size_t pa_cap = 0, pb_cap = 0, ea_cap = 0, eb_cap = 0;      // bytes / ints
+  EncodeTiledFn enc = nullptr;
+  bool attr = false;
+};
+
+void ozaki_destroy(vab_ctx* ctx) {
+  OzakiWork* w = ctx->oz;
+  if (!w) return;
+  cudaFree(w->pa); cudaFree(w->pb); cudaFree(w->ea); cudaFree(w->eb);
+  delete w;
+  ctx->oz = nullptr;
+}
+
+template <typename T>
+static int oz_reserve(vab_ctx* ctx, T** buf, size_t* cap, size_t need) {
+  if (*cap >= need) return VAB_OK;
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(*buf);
+  *buf = nullptr; *cap = 0;
+  cudaError_t e = cudaMalloc((void**)buf, need * sizeof(T));
+  if (e != cudaSuccess) return vab_cuda_fail(ctx, e, "ozaki workspace");
+  *cap = need;
+  return VAB_OK;
+}
+
+int ozaki_gemm(vab_ctx* ctx, int P, int M, int N, int K,
+               const double* A, long long lda, long long aks, long long aps,
+               const double* B, long long ldb, long long bks, long long bps,
+               double* C, long long ldc, long long cps, const int* active_dev) {
+  if (P < 1 || M < 1 || N < 1 || K < 1 || K > KP) return vab_fail(ctx, VAB_ERR_INVALID, "ozaki_gemm: bad sizes (K <= 128)");
+  if (!ctx->oz) ctx->oz = new OzakiWork();
+  OzakiWork* w = ctx->oz;
+  if (!w->enc) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || !fn || qres != cudaDriverEntryPointSuccess) return vab_fail(ctx, VAB_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+    w->enc = (EncodeTiledFn)fn;
+  }
+  if (!w->attr) {
+    cudaError_t e = cudaFuncSetAttribute(ozaki_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    if (e != cudaSuccess) return vab_cuda_fail(ctx, e, "ozaki_gemm smem opt-in");
+    w->attr = true;
+  }
+  const int m_tiles = (M + TM - 1) / TM, n_tiles = (N + TN - 1) / TN;
+  const int Mpad = m_tiles * TM, Npad = n_tiles * TN;
+  const long long rowsA = (long long)P * Mpad, rowsB = (long long)P * Npad;
+  int rc = oz_reserve(ctx, &w->pa, &w->pa_cap, (size_t)NS * rowsA * KP);
+  if (rc == VAB_OK) rc = oz_reserve(ctx, &w->pb, &w->pb_cap, (size_t)NS * rowsB * KP);
+  if (rc == VAB_OK) rc = oz_reserve(ctx, &w->ea, &w->ea_cap, (size_t)rowsA);
+  if (rc == VAB_OK) rc = oz_reserve(ctx, &w->eb, &w->eb_cap, (size_t)rowsB);
+  if (rc != VAB_OK) return rc;
+  CUtensorMap mapA, mapB;
+  rc = make_plane_map(ctx, w->enc, &mapA, w->pa, rowsA, TM);
+  if (rc == VAB_OK) rc = make_plane_map(ctx, w->enc, &mapB, w->pb, rowsB, TN);
+  if (rc != VAB_OK) return rc;
+  cudaStream_t st = ctx->stream;
+  ozaki_slice_kernel<<<dim3((Mpad * 32 + 255) / 256, P), 256, 0, st>>>(A, lda, aps, M, K, Mpad, w->pa, rowsA * KP, w->ea, aks, active_dev);
+  ozaki_slice_kernel<<<dim3((Npad * 32 + 255) / 256, P), 256, 0, st>>>(B, ldb, bps, N, K, Npad, w->pb, rowsB * KP, w->eb, bks, active_dev);
+  OzakiParams q;
+  q.M = M; q.N = N; q.P = P; q.m_tiles = m_tiles; q.n_tiles = n_tiles; q.Mpad = Mpad; q.Npad = Npad;
+  q.ea = w->ea; q.eb = w->eb; q.C = C; q.ldc = ldc; q.cps = cps; q.active = active_dev;
+  ozaki_mma_kernel<<<P * m_tiles * n_tiles, 128, SMEM_BYTES, st>>>(mapA, mapB, q);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return vab_cuda_fail(ctx, e, "ozaki_gemm launch");
+  ctx->launches += 3;
+  return VAB_OK;
+}
+
 // out_host[12] (8..11: version 2 -- max rel err, ms, TFLOP/s-equivalent of the kernel, of kernel + planes): 0 max |C - Cref| / max |Cref|, 1 ms digit planes (both operands), 2 ms tcgen05 kernel,
 //              3 ms total, 4 fp64-equivalent TFLOP/s of the total, 5 the same for the tcgen05 kernel alone,
 //              6 ms of the fp64 FMA reference kernel, 7 max |Cref|
@@ -536,7 +619,7 @@ extern "C" int vab_ozaki_gemm_probe(vab_ctx* ctx, int32_t P, int32_t M, int32_t 
   OZ_CUDA(cudaFuncSetAttribute(ozaki_mma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM2_BYTES));
   OZ_CUDA(cudaFuncSetAttribute(ozaki_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
   q.M = M; q.N = N; q.P = P; q.m_tiles = m_tiles; q.n_tiles = n_tiles; q.Mpad = Mpad; q.Npad = Npad;
-  q.ea = ea; q.eb = eb; q.C = C;
+  q.ea = ea; q.eb = eb; q.C = C; q.ldc = N; q.cps = (long long)M * N; q.active = nullptr;
   for (int rep = 0; rep <= reps; ++rep) {            // rep 0 = warm-up
     if (rep == 1) OZ_CUDA(cudaEventRecord(ev[0], st));
     ozaki_slice_kernel<<<dim3((Mpad * 32 + 255) / 256, P), 256, 0, st>>>(A, K, (long long)M * K, M, K, Mpad, pa, rowsA * KP, ea);

@@ -135,6 +135,8 @@ long long vab_launch_count(const vab_ctx* ctx) { return ctx ? ctx->launches : 0;
 
 long long vab_graph_launch_count(const vab_ctx* ctx) { return ctx ? ctx->graph_launches : 0; }
 
+int vab_nn_kernel_family(const vab_ctx* ctx) { return ctx ? ctx->nn_family : 0; }
+
 int vab_ctx_create(int device, void* stream, vab_ctx** out) {
   if (!out) return vab_fail(nullptr, VAB_ERR_INVALID, "vab_ctx_create: out is NULL");
   *out = nullptr;
@@ -177,6 +179,7 @@ int vab_ctx_destroy(vab_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   nn_destroy(ctx);
   lbfgs_destroy(ctx);
+  ozaki_destroy(ctx);
   tnc_destroy(ctx);
   cudaFree(ctx->pmap_dev);
   cudaFree(ctx->lcomp_dev);

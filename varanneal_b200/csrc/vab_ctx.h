@@ -12,6 +12,7 @@
 struct NnProblem;   // nn_action.h
 struct LbfgsWork;   // lbfgs.cu
 struct TncWork;     // tnc.cu
+struct OzakiWork;   // ozaki_gemm.cu
 
 enum { VAB_PROBLEM_NONE = 0, VAB_PROBLEM_ODE = 1, VAB_PROBLEM_NN = 2 };
 
@@ -62,6 +63,8 @@ struct vab_ctx {
   size_t partials_cap = 0;          // doubles
   LbfgsWork* lb = nullptr;
   TncWork* tn = nullptr;
+  OzakiWork* oz = nullptr;          // digit planes of the tcgen05 contraction path (VAB_NN_TCGEN05=1)
+  int nn_family = 0;                // kernels of the last NN evaluation: 1 fused, 2 per-layer DMMA, 3 all-layer DMMA, 4 CUDA cores, 5 tcgen05
 
   long long n_unknowns() const;     // per path, for the problem currently set
 };
@@ -74,6 +77,13 @@ int vab_reserve(vab_ctx* ctx, double** buf, size_t* cap, size_t need);
 // objective evaluation for the problem currently set (ODE or NN); used by the minimiser.
 // active_dev: (B) int mask or nullptr.  rf_path_dev: (B) per-path scale of RF0 (replaces rf_scale)
 // or nullptr.
+// fp64 contraction on tcgen05 / TMEM / TMA (ozaki_gemm.cu): C[p][r][c] = sum_k A[p][r][k] B[p][c][k], K <= 128
+int ozaki_gemm(vab_ctx* ctx, int P, int M, int N, int K,
+               const double* A, long long lda, long long aks, long long aps,
+               const double* B, long long ldb, long long bks, long long bps,
+               double* C, long long ldc, long long cps, const int* active_dev);
+void ozaki_destroy(vab_ctx* ctx);
+
 int vab_eval(vab_ctx* ctx, int B, const double* XP, long long ldxp, double rf_scale,
              const double* rf_path_dev, const int* active_dev, double* A, double* me, double* fe,
              double* G, long long ldg);
