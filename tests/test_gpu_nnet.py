@@ -104,7 +104,8 @@ def test_nn_action_grad_vs_oracle(structure, M, act, RM, partial, B):
         assert np.max(np.abs(G[b] - gr)) <= TOL * np.max(np.abs(gr))
 
 
-def test_nn_ladder_vs_scipy():
+@pytest.mark.parametrize("tcgen05", [False, True], ids=["dmma", "tcgen05"])
+def test_nn_ladder_vs_scipy(tcgen05, monkeypatch):
     """Short annealing ladder over the neuron states of a small twin network with the weights held
     at (perturbed) teacher values, at RF values where the model error shapes the minimum.  (With
     the weights free, or at small RF, the net fits anything: A -> 0 along a flat valley, SciPy
@@ -112,6 +113,8 @@ def test_nn_ladder_vs_scipy():
     it -- measured while writing this test.)  Per-beta minimum action vs SciPy L-BFGS-B on the
     oracle action to 1e-6 relative; and SciPy started at the device's minimiser has nothing left
     to do."""
+    if tcgen05:                            # the same ladder with every contraction on tcgen05 (graph-replayed cycles)
+        monkeypatch.setenv("VAB_NN_TCGEN05", "1")
     rng = np.random.RandomState(8)
     st = np.array([4, 6, 3])
     M = 12
@@ -145,6 +148,7 @@ def test_nn_ladder_vs_scipy():
         assert res2.nit <= 2 and abs(res2.fun - an.A_array[i]) <= 1e-9 * abs(res2.fun)
     assert an.minpaths.shape == (len(betas), M * NDnet + NP)
     assert np.all(an.exitflags == 0)
+    assert an._ctx.nn_kernel_family == (5 if tcgen05 else 3)
 
 
 @pytest.mark.parametrize("structure,M,B", [([25, 30, 4], 333, 2), ([100, 100, 100], 129, 2), ([12, 40], 70, 3)])
@@ -188,6 +192,8 @@ def test_nn_tnc_method_minimises_the_oracle_action():
     of the ladder test above (weights held at perturbed teacher values, RF large enough for the
     model error to shape the minimum; with free weights the valley is flat and SciPy's own
     L-BFGS-B runs 1e5 iterations without converging)."""
+    if tcgen05:                            # the same ladder with every contraction on tcgen05 (graph-replayed cycles)
+        monkeypatch.setenv("VAB_NN_TCGEN05", "1")
     rng = np.random.RandomState(8)
     st = np.array([4, 6, 3])
     M = 12

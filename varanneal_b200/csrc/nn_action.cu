@@ -759,6 +759,22 @@ __global__ void __launch_bounds__(256) nn_tc_epilogue_kernel(const __grid_consta
   }
 }
 
+// tcgen05 path: bias gradient of layer n, Gb_n[j] = sum_m Delta[m][j], per chunk of TC_KC examples (the
+// chunks of the split-K weight-gradient GEMM), summed in chunk order by nn_reduce_kernel.
+constexpr int TC_KC = 128;
+__global__ void __launch_bounds__(128) nn_tc_bias_kernel(const __grid_constant__ NnParams P, int n) {
+  const int c = blockIdx.x, b = blockIdx.y, j = threadIdx.x;
+  if (P.active != nullptr && P.active[b] == 0) return;
+  const int dn1 = P.structure[n + 1], d0 = P.structure[0];
+  if (j >= dn1) return;
+  const int ND1 = P.NDnet - d0;
+  const double* d = P.dbuf + (long long)b * P.M * ND1 + (P.xoff[n + 1] - d0) + j;
+  const int m1 = min(P.M, (c + 1) * TC_KC);
+  double acc = 0.0;
+  for (int m = c * TC_KC; m < m1; ++m) acc += d[(long long)m * ND1];
+  P.gwpart[((long long)b * P.ngw + c) * P.NP + P.boff[n] + j] = acc;
+}
+
 constexpr int FIX_NT = 256;
 __global__ void __launch_bounds__(FIX_NT) nn_fix_kernel(const __grid_constant__ NnParams P) {
   const int b = blockIdx.y;
@@ -1227,7 +1243,7 @@ static int nn_eval_core(vab_ctx* ctx, int B, const double* XP, long long ldxp, d
       P.gw_klen = klen;
       P.gw_nsplit = (p->M + klen - 1) / klen;
       P.nparts = all_layers ? P.nmt : (p->NL - 1) * P.nmt;
-      P.ngw = P.gw_nsplit;
+      P.ngw = use_tc ? (p->M + TC_KC - 1) / TC_KC : P.gw_nsplit;
       P.fba_pxn = fba_pxn; P.fba_pd = fba_pd;
       P.fb_T = fb_T; P.fb_nbuf = fb_nbuf;
       const size_t nd1 = (size_t)(p->NDnet - p->d0);
@@ -1291,7 +1307,30 @@ static int nn_eval_core(vab_ctx* ctx, int B, const double* XP, long long ldxp, d
           wo += dn * dn1 + dn1;
         }
         nn_fix_kernel<<<dim3((unsigned)nfix, B), FIX_NT, 0, ctx->stream>>>(P);
-        nl = 2;
+        // weight gradients GW_n = Delta_n^T X_n: split-K over chunks of TC_KC examples, one tcgen05
+        // problem per (path, chunk), partial blocks to gwpart (summed in chunk order by nn_reduce_kernel)
+        xo = 0; wo = 0;
+        for (int n = 0; n + 1 < p->NL; ++n) {
+          const int dn = p->st_host[n], dn1 = p->st_host[n + 1];
+          const int xo1 = xo + dn;
+          rc = ozaki_gemm_chunked(ctx, B, P.ngw, dn1, dn, TC_KC, p->M,
+                                  p->dbuf + (xo1 - d0), 1, ND1, (long long)p->M * ND1, (long long)TC_KC * ND1,
+                                  XP + xo, 1, p->NDnet, ldxp, (long long)TC_KC * p->NDnet,
+                                  p->gwpart + wo, dn, p->NP, active_dev);
+          if (rc != VAB_OK) return rc;
+          nn_tc_bias_kernel<<<dim3(P.ngw, B), 128, 0, ctx->stream>>>(P, n);
+          ctx->launches += 1;
+          xo = xo1;
+          wo += dn * dn1 + dn1;
+        }
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return vab_cuda_fail(ctx, e, "nn tcgen05 weight-gradient launch");
+        const int nk = p->NP > 1 ? p->NP : 1;
+        nn_reduce_kernel<<<dim3((nk + 255) / 256, B), 256, 0, ctx->stream>>>(P, A, me, fe);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return vab_cuda_fail(ctx, e, "nn_reduce_kernel launch");
+        ctx->launches += 4;
+        return VAB_OK;
       } else {
         // 16 warps when every warp still gets a (row tile, column group) task of the smallest layer pair
         int min_tasks = 1 << 30;

@@ -53,11 +53,16 @@ __device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta
 __global__ void __launch_bounds__(256) ozaki_slice_kernel(const double* __restrict__ src, long long ld, long long pstride,
                                                           int rows, int K, int rows_pad, int8_t* __restrict__ planes,
                                                           long long plane_stride, int* __restrict__ expo,
-                                                          long long kstride = 1, const int* __restrict__ active = nullptr) {
+                                                          long long kstride = 1, const int* __restrict__ active = nullptr,
+                                                          int pdiv = 1, long long cstride = 0, int ktotal = 0) {
+  // problem p = (path p / pdiv, chunk p % pdiv of the contraction axis): chunk c starts cstride doubles
+  // further and holds min(K, ktotal - c K) elements (the split-K form of a contraction longer than 128)
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int p = blockIdx.y;
   if (warp >= rows_pad) return;
-  if (active != nullptr && active[p] == 0) return;
+  const int po = p / pdiv, pc = p - po * pdiv;
+  if (active != nullptr && active[po] == 0) return;
+  if (ktotal > 0) K = min(K, ktotal - pc * K);
   const long long orow = (long long)p * rows_pad + warp;
   int8_t* out = planes + orow * KP;
   if (warp >= rows) {                                  // padding rows: zeros
@@ -66,7 +71,7 @@ __global__ void __launch_bounds__(256) ozaki_slice_kernel(const double* __restri
     if (lane == 0) expo[orow] = 0;
     return;
   }
-  const double* x = src + (long long)p * pstride + (long long)warp * ld;
+  const double* x = src + (long long)po * pstride + (long long)pc * cstride + (long long)warp * ld;
   double amax = 0.0;
   for (int k = lane; k < K; k += 32) amax = fmax(amax, fabs(x[(long long)k * kstride]));
   for (int sft = 16; sft > 0; sft >>= 1) amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, sft));
@@ -148,7 +153,8 @@ struct OzakiParams {
   const int* eb;             // (P * Npad)
   double* C;                 // element (p, r, c) at C[p cps + r ldc + c]
   long long ldc, cps;
-  const int* active;         // (P) or nullptr: problems to skip
+  const int* active;         // (P / pdiv) or nullptr: paths to skip
+  int pdiv;                  // problems per path (chunks of a split contraction)
 };
 
 __global__ void __launch_bounds__(128, 1) ozaki_mma_kernel(const __grid_constant__ CUtensorMap mapA,
@@ -165,7 +171,7 @@ __global__ void __launch_bounds__(128, 1) ozaki_mma_kernel(const __grid_constant
   const int nt = tile % q.n_tiles; tile /= q.n_tiles;
   const int mt = tile % q.m_tiles;
   const int p = tile / q.m_tiles;
-  if (q.active != nullptr && q.active[p] == 0) return;
+  if (q.active != nullptr && q.active[p / q.pdiv] == 0) return;
 
   if (tid == 0) {
     mbar_init(bar_tma, 1);
@@ -518,11 +524,16 @@ static int oz_reserve(vab_ctx* ctx, T** buf, size_t* cap, size_t need) {
   return VAB_OK;
 }
 
-int ozaki_gemm(vab_ctx* ctx, int P, int M, int N, int K,
-               const double* A, long long lda, long long aks, long long aps,
-               const double* B, long long ldb, long long bks, long long bps,
-               double* C, long long ldc, long long cps, const int* active_dev) {
-  if (P < 1 || M < 1 || N < 1 || K < 1 || K > KP) return vab_fail(ctx, VAB_ERR_INVALID, "ozaki_gemm: bad sizes (K <= 128)");
+// Split-K form: every path holds nchunk problems, chunk c contracting over elements
+// [c K, min((c + 1) K, Ktotal)) of an axis of length Ktotal (apc / bpc: doubles between chunks);
+// problem (path b, chunk c) writes C[(b nchunk + c) cps + r ldc + col] -- partial products summed by
+// the caller in chunk order.
+int ozaki_gemm_chunked(vab_ctx* ctx, int paths, int nchunk, int M, int N, int K, int Ktotal,
+                       const double* A, long long lda, long long aks, long long aps, long long apc,
+                       const double* B, long long ldb, long long bks, long long bps, long long bpc,
+                       double* C, long long ldc, long long cps, const int* active_dev) {
+  const int P = paths * nchunk;
+  if (paths < 1 || nchunk < 1 || M < 1 || N < 1 || K < 1 || K > KP) return vab_fail(ctx, VAB_ERR_INVALID, "ozaki_gemm: bad sizes (K <= 128)");
   if (!ctx->oz) ctx->oz = new OzakiWork();
   OzakiWork* w = ctx->oz;
   if (!w->enc) {
@@ -550,16 +561,24 @@ int ozaki_gemm(vab_ctx* ctx, int P, int M, int N, int K,
   if (rc == VAB_OK) rc = make_plane_map(ctx, w->enc, &mapB, w->pb, rowsB, TN);
   if (rc != VAB_OK) return rc;
   cudaStream_t st = ctx->stream;
-  ozaki_slice_kernel<<<dim3((Mpad * 32 + 255) / 256, P), 256, 0, st>>>(A, lda, aps, M, K, Mpad, w->pa, rowsA * KP, w->ea, aks, active_dev);
-  ozaki_slice_kernel<<<dim3((Npad * 32 + 255) / 256, P), 256, 0, st>>>(B, ldb, bps, N, K, Npad, w->pb, rowsB * KP, w->eb, bks, active_dev);
+  const int kt = Ktotal;
+  ozaki_slice_kernel<<<dim3((Mpad * 32 + 255) / 256, P), 256, 0, st>>>(A, lda, aps, M, K, Mpad, w->pa, rowsA * KP, w->ea, aks, active_dev, nchunk, apc, kt);
+  ozaki_slice_kernel<<<dim3((Npad * 32 + 255) / 256, P), 256, 0, st>>>(B, ldb, bps, N, K, Npad, w->pb, rowsB * KP, w->eb, bks, active_dev, nchunk, bpc, kt);
   OzakiParams q;
   q.M = M; q.N = N; q.P = P; q.m_tiles = m_tiles; q.n_tiles = n_tiles; q.Mpad = Mpad; q.Npad = Npad;
-  q.ea = w->ea; q.eb = w->eb; q.C = C; q.ldc = ldc; q.cps = cps; q.active = active_dev;
+  q.ea = w->ea; q.eb = w->eb; q.C = C; q.ldc = ldc; q.cps = cps; q.active = active_dev; q.pdiv = nchunk;
   ozaki_mma_kernel<<<P * m_tiles * n_tiles, 128, SMEM_BYTES, st>>>(mapA, mapB, q);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return vab_cuda_fail(ctx, e, "ozaki_gemm launch");
   ctx->launches += 3;
   return VAB_OK;
+}
+
+int ozaki_gemm(vab_ctx* ctx, int P, int M, int N, int K,
+               const double* A, long long lda, long long aks, long long aps,
+               const double* B, long long ldb, long long bks, long long bps,
+               double* C, long long ldc, long long cps, const int* active_dev) {
+  return ozaki_gemm_chunked(ctx, P, 1, M, N, K, K, A, lda, aks, aps, 0, B, ldb, bks, bps, 0, C, ldc, cps, active_dev);
 }
 
 // out_host[12] (8..11: version 2 -- max rel err, ms, TFLOP/s-equivalent of the kernel, of kernel + planes): 0 max |C - Cref| / max |Cref|, 1 ms digit planes (both operands), 2 ms tcgen05 kernel,
@@ -619,7 +638,7 @@ extern "C" int vab_ozaki_gemm_probe(vab_ctx* ctx, int32_t P, int32_t M, int32_t 
   OZ_CUDA(cudaFuncSetAttribute(ozaki_mma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM2_BYTES));
   OZ_CUDA(cudaFuncSetAttribute(ozaki_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
   q.M = M; q.N = N; q.P = P; q.m_tiles = m_tiles; q.n_tiles = n_tiles; q.Mpad = Mpad; q.Npad = Npad;
-  q.ea = ea; q.eb = eb; q.C = C; q.ldc = N; q.cps = (long long)M * N; q.active = nullptr;
+  q.ea = ea; q.eb = eb; q.C = C; q.ldc = N; q.cps = (long long)M * N; q.active = nullptr; q.pdiv = 1;
   for (int rep = 0; rep <= reps; ++rep) {            // rep 0 = warm-up
     if (rep == 1) OZ_CUDA(cudaEventRecord(ev[0], st));
     ozaki_slice_kernel<<<dim3((Mpad * 32 + 255) / 256, P), 256, 0, st>>>(A, K, (long long)M * K, M, K, Mpad, pa, rowsA * KP, ea);

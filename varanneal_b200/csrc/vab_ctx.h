@@ -82,6 +82,10 @@ int ozaki_gemm(vab_ctx* ctx, int P, int M, int N, int K,
                const double* A, long long lda, long long aks, long long aps,
                const double* B, long long ldb, long long bks, long long bps,
                double* C, long long ldc, long long cps, const int* active_dev);
+int ozaki_gemm_chunked(vab_ctx* ctx, int paths, int nchunk, int M, int N, int K, int Ktotal,
+                       const double* A, long long lda, long long aks, long long aps, long long apc,
+                       const double* B, long long ldb, long long bks, long long bps, long long bpc,
+                       double* C, long long ldc, long long cps, const int* active_dev);
 void ozaki_destroy(vab_ctx* ctx);
 
 int vab_eval(vab_ctx* ctx, int B, const double* XP, long long ldxp, double rf_scale,
