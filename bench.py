@@ -531,7 +531,7 @@ def leg_c1(args, dd):
     sampler = ClockSampler(dd.local)
     if dd.rank == 0:
         sampler.start()
-    for B1 in (1, 64):
+    for B1 in (1, 32, 64):
         rng = np.random.RandomState(12345 + dd.rank)
         X0 = 20.0 * rng.rand(B1, 161, 20) - 10.0
         P0 = 4.0 * rng.rand(B1, 1) + 6.0
@@ -572,7 +572,7 @@ def leg_c1(args, dd):
     line.update({"steps": 1, "warmup": 0, "roofline": None, "e2e": {"value": v["evals_per_s_incl_optimizer"], "unit": UNIT,
                  "h2d_bytes_per_step": 64 * 3221 * 8, "d2h_bytes_per_step": 64 * 101 * 3221 * 8,
                  "api": "va_ode.Annealer.anneal(): host X0/P0 in, host minpaths out"},
-                 "gpu_launches": v["launches"], "clocks": clocks, "one_path": out[1], "batch": out[64]})
+                 "gpu_launches": v["launches"], "clocks": clocks, "one_path": out[1], "batch32": out[32], "batch": out[64]})
     return line
 
 
@@ -758,6 +758,30 @@ def leg_nn(args, dd, name):
         parity["what"] = "path 0 of the timed launch vs oracle.nnet_port"
         if not parity["ok"]:
             raise SystemExit("bench: the timed %s launch disagrees with the oracle: %r" % (name, parity))
+    # the same launches with every contraction on tcgen05 / TMEM / TMA (VAB_NN_TCGEN05=1: Ozaki-split
+    # int8 GEMMs, csrc/ozaki_gemm.cu) -- the opt-in path, timed and oracle-checked beside the default one
+    tc = None
+    if dd.rank == 0 and int(st.max()) <= 128:
+        os.environ["VAB_NN_TCGEN05"] = "1"
+        try:
+            for _ in range(3):
+                an._action_grad_native(scale)
+            t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0e.record()
+            for _ in range(K):
+                an._action_grad_native(scale)
+            t1e.record()
+            torch.cuda.synchronize()
+            ms_tc = t0e.elapsed_time(t1e) / K
+            ptc = oracle_check(an._A[0].item(), an._G[0, :an._n].cpu().numpy(), Ar, gr)
+            tc = {"kernel_ms": ms_tc, "evals_per_s": B / ms_tc * 1e3, "kernel_family": an._ctx.nn_kernel_family,
+                  "parity": ptc, "kernels": "ozaki_slice_kernel + ozaki_mma_kernel (tcgen05.mma.kind::i8, TMEM accumulators, "
+                                            "cp.async.bulk.tensor operands) + nn_tc_epilogue_kernel + nn_fix_kernel",
+                  "note": "opt-in (VAB_NN_TCGEN05=1); the default path stays on the fp64 tensor pipe, which is faster at these widths"}
+            if not ptc["ok"] or tc["kernel_family"] != 5:
+                raise SystemExit("bench: the tcgen05 %s launch disagrees with the oracle: %r" % (name, tc))
+        finally:
+            os.environ.pop("VAB_NN_TCGEN05", None)
     ladder = None
     if not args.no_ladder:
         anl = va_nnet.Annealer(device=dd.local)
@@ -804,7 +828,9 @@ def leg_nn(args, dd, name):
                                   "one step = %d launches" % (name, list(map(int, st)), M, K),
                       "paths_per_gpu": B, "global_paths": B * dd.world,
                       "l2_policy": "XP + grad = %.0f MB per launch vs 126 MB L2" % (2 * B * an._n * 8 / 1e6)})
-    line.update({"roofline": roof, "gpu_launches": int(launches), "clocks": clocks, "ladder": ladder,
+    if tc is not None:
+        tc["fp64_equiv_TFLOPs"] = flops / tc["kernel_ms"] / 1e9
+    line.update({"roofline": roof, "tcgen05": tc, "gpu_launches": int(launches), "clocks": clocks, "ladder": ladder,
                  "parity_checked": bool(parity and parity["ok"]), "parity": parity,
                  "e2e": {"value": ladder["evals_per_s_incl_optimizer"] if ladder else None, "unit": UNIT,
                          "h2d_bytes_per_step": int(X0.nbytes + P0.nbytes), "d2h_bytes_per_step": int(X0.nbytes),
