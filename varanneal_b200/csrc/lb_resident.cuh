@@ -49,7 +49,8 @@ struct ResArgs {
 };
 
 // vector slots of the per-CTA store
-enum { RV_X = 0, RV_G = 1, RV_D = 2, RV_XT = 3, RV_GT = 4, RV_S = 5, RV_Y = 5 + MMAX, RV_N = 5 + 2 * MMAX };
+// (the trial point lives apart from them, between its halo rows: XTH)
+enum { RV_X = 0, RV_G = 1, RV_D = 2, RV_GT = 3, RV_S = 4, RV_Y = 4 + MMAX, RV_N = 4 + 2 * MMAX };
 
 // History bookkeeping of an accepted step and the two-loop recursion r = H g in coefficient space
 // (r = cg g + sum_j cs_j s_j + cy_j y_j, d = -r) by one warp, on the path state in shared memory.
@@ -157,6 +158,41 @@ __device__ __forceinline__ double warp_sum16(double (&v)[16]) {
   return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
 }
 
+// NV per-thread values over the CTA: butterflies inside the warps, then the warps in order by NV
+// threads.  wred: (RNT / 32) * NV doubles that no other reduction in flight uses.  One block barrier
+// inside; out[] is complete behind the *next* barrier of the caller.  Fixed order.
+template <int NV>
+__device__ __forceinline__ void res_reduce(double (&v)[NV], const int (&op)[NV], double* out, double* wred) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int sft = 16; sft > 0; sft >>= 1) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const double u = __shfl_xor_sync(0xffffffffu, v[k], sft);
+      v[k] = (op[k] == RED_SUM) ? v[k] + u : (op[k] == RED_MAX ? fmax(v[k], u) : fmin(v[k], u));
+    }
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) wred[warp * NV + k] = v[k];
+  }
+  __syncthreads();
+  if (threadIdx.x < NV) {
+    const int k = threadIdx.x;
+    int o = op[0];
+#pragma unroll
+    for (int kk = 1; kk < NV; ++kk)
+      if (kk == k) o = op[kk];
+    double a = wred[k];
+#pragma unroll
+    for (int w = 1; w < RNT / 32; ++w) {
+      const double u = wred[w * NV + k];
+      a = (o == RED_SUM) ? a + u : (o == RED_MAX ? fmax(a, u) : fmin(a, u));
+    }
+    out[k] = a;
+  }
+}
+
 template <int DISC, int RCS>
 __global__ void __launch_bounds__(RNT, 1) lb_resident_kernel(const ResArgs A) {
   namespace cg = cooperative_groups;
@@ -170,8 +206,8 @@ __global__ void __launch_bounds__(RNT, 1) lb_resident_kernel(const ResArgs A) {
   const int VS = RPC * D;                               // doubles per vector slice
   const int nloc = nrow * D;                            // own elements
   double* vec = rs;                                     // RV_N slices
-  double* XH = vec + (size_t)RV_N * VS;                 // halo rows of the trial point: rows R0-2, R0-1, R1
-  double* F = XH + 3 * D;                               // f of rows R0-2 .. R1           [(RPC + 3)][D]
+  double* XTH = vec + (size_t)RV_N * VS;                // trial point with its halo rows: rows R0-2 .. R0+RPC  [(RPC + 3)][D]
+  double* F = XTH + (size_t)(RPC + 3) * D;              // f of rows R0-2 .. R1           [(RPC + 3)][D]
   double* E1 = F + (size_t)(RPC + 3) * D;               // seeds per residual row / pair
   double* E2 = E1 + (size_t)(RPC + 3) * D;
   double* scratch = E2 + (size_t)(RPC + 3) * D;         // 8 * NT (block_reduce / cta_reduce_sum)
@@ -190,7 +226,7 @@ __global__ void __launch_bounds__(RNT, 1) lb_resident_kernel(const ResArgs A) {
   double* X = vec + RV_X * VS;
   double* G = vec + RV_G * VS;
   double* Dv = vec + RV_D * VS;
-  double* XT = vec + RV_XT * VS;
+  double* XT = XTH + 2 * D;                             // own rows of the trial point
   double* GT = vec + RV_GT * VS;
   const long long nX = (long long)N * D;
   const long long n = nX + (A.k_est ? 1 : 0);
@@ -214,6 +250,7 @@ __global__ void __launch_bounds__(RNT, 1) lb_resident_kernel(const ResArgs A) {
     pk[0] = A.k_est ? xg[nX] : A.pfix[(long long)b * A.pfix_stride];
     dummy_act = 1;
   }
+  for (int e = tid; e < (RPC + 3) * D; e += RNT) XTH[e] = 0.0;
   for (int e = tid; e < VS; e += RNT) {
     G[e] = 0.0; Dv[e] = 0.0;
     double w = 0.0, y = 0.0;
@@ -229,6 +266,14 @@ __global__ void __launch_bounds__(RNT, 1) lb_resident_kernel(const ResArgs A) {
   __syncthreads();
   if (tid == 0) rf_cur = A.rf0 * A.L.scales[s.ib];
   __syncthreads();
+  // Halo rows are *pushed*: whoever writes a row of the trial point that a neighbour's stencil needs
+  // stores it into that neighbour's XTH as well (remote shared-memory stores, visible behind the
+  // cluster barrier that follows the trial point anyway).  rank - 1 needs my first row (its row R1),
+  // rank + 1 my last two (its rows R0-2, R0-1).
+  double* prevH = (rank > 0 && nrow > 0) ? cl.map_shared_rank(XTH, rank - 1) + (size_t)(RPC + 2) * D : nullptr;
+  double* nextH = (R0 + RPC < N) ? cl.map_shared_rank(XTH, rank + 1) - (size_t)(RPC - 2) * D : nullptr;
+  const int e_next = (RPC - 2) * D;                     // first element of the last two rows of a full slice
+  cl.sync();                                            // every XTH is zeroed before the first push arrives
 
   // sum / max over the CTAs' partial k, in rank order
   auto gather_sum = [&](double* part, int k) {
@@ -250,11 +295,9 @@ __global__ void __launch_bounds__(RNT, 1) lb_resident_kernel(const ResArgs A) {
     return a;
   };
   // trial-point row r, component i (periodic): own slice or halo
-  auto xt_at = [&](int r, int i) -> double {
+  auto xt_at = [&](int r, int i) -> double {            // R0 - 2 <= r <= R0 + RPC
     if (i < 0) i += D; else if (i >= D) i -= D;
-    if (r >= R0 && r < R1) return XT[(r - R0) * D + i];
-    if (r == R1) return XH[2 * D + i];
-    return XH[(r - (R0 - 2)) * D + i];                  // R0 - 2, R0 - 1
+    return XTH[(r - (R0 - 2)) * D + i];
   };
   auto f_at = [&](int r, int i) -> double { return F[(r - (R0 - 2)) * D + i]; };
 
@@ -280,27 +323,18 @@ __global__ void __launch_bounds__(RNT, 1) lb_resident_kernel(const ResArgs A) {
     const double cf2 = 2.0 * A.cf;
     const double fk = s.first ? pk[0] : fma(s.stp, pk[2], pk[0]);       // trial forcing
     // ---- trial point (lb_trial_kernel)
-    if (s.first) {
-      for (int e = tid; e < nloc; e += RNT) XT[e] = X[e];
-    } else {
+    {
+      const bool fst = s.first != 0;
       const double stp = s.stp;
-      for (int e = tid; e < nloc; e += RNT) XT[e] = fma(stp, Dv[e], X[e]);
+      for (int e = tid; e < nloc; e += RNT) {
+        const double v = fst ? X[e] : fma(stp, Dv[e], X[e]);
+        XT[e] = v;
+        if (prevH != nullptr && e < D) prevH[e] = v;
+        if (nextH != nullptr && e >= e_next) nextH[e] = v;
+      }
     }
     cl.sync();
-    stamp();                                            // 1: trial point + barrier
-    // ---- halo rows of the trial point from the neighbour CTAs
-    for (int e = tid; e < 3 * D; e += RNT) {
-      const int h = e / D, i = e - h * D;
-      const int r = (h == 2) ? R1 : R0 - 2 + h;
-      double v = 0.0;
-      if (r >= 0 && r < N && nrow > 0) {
-        const int q = r / RPC;
-        const double* rem = cl.map_shared_rank(XT, q);
-        v = rem[(r - q * RPC) * D + i];
-      }
-      XH[e] = v;
-    }
-    __syncthreads();
+    stamp();                                            // 1: trial point, halo rows pushed, barrier
     // ---- f of the rows R0-2 .. R1 (the rows beside the slice are recomputed, not exchanged)
     for (int e = tid; e < (RPC + 3) * D; e += RNT) {
       const int lr = e / D, i = e - lr * D;
@@ -401,7 +435,7 @@ __global__ void __launch_bounds__(RNT, 1) lb_resident_kernel(const ResArgs A) {
       double v[5] = {acc_fe, acc_me, acc_pk, acc_gd, acc_mx};
       const int op5[5] = {RED_SUM, RED_SUM, RED_SUM, RED_SUM, RED_MAX};
       stamp();                                          // 2: evaluation (halo, f, seeds, gradient rows)
-      block_reduce<5>(v, op5, partA, scratch);
+      res_reduce<5>(v, op5, partA, scratch);
     }
     cl.sync();
     stamp();                                            // 3: partial sums + barrier
@@ -510,15 +544,15 @@ __global__ void __launch_bounds__(RNT, 1) lb_resident_kernel(const ResArgs A) {
       double v[3] = {0.0, 0.0, BIG};
       for (int e = tid; e < nloc; e += RNT) {
         const double g = G[e];
-        double rr = cgc * g;
+        double rr = cgc * g, ry = 0.0;                  // two chains: the S and the Y terms
 #pragma unroll
         for (int j = 0; j < MMAX; ++j) {
           if (j < m && (j < col || col == m)) {
             rr = fma(cs[j], vec[(size_t)(RV_S + j) * VS + e], rr);
-            rr = fma(cy[j], vec[(size_t)(RV_Y + j) * VS + e], rr);
+            ry = fma(cy[j], vec[(size_t)(RV_Y + j) * VS + e], ry);
           }
         }
-        double d = -rr;
+        double d = -(rr + ry);
         if (cd != 0.0) d = fma(cd, Dv[e], d);
         Dv[e] = d;
         v[0] = fma(d, d, v[0]);
@@ -540,7 +574,7 @@ __global__ void __launch_bounds__(RNT, 1) lb_resident_kernel(const ResArgs A) {
         if (last && tid == 0) { v[0] = fma(dkk, dkk, v[0]); v[1] = fma(gkk, dkk, v[1]); }
       }
       const int op3[3] = {RED_SUM, RED_SUM, RED_MIN};
-      block_reduce<3>(v, op3, partC, scratch);
+      res_reduce<3>(v, op3, partC, scratch + 64);
       __syncthreads();
       if (A.k_est && tid == 0) pk[2] = dkk;
     }
@@ -627,7 +661,7 @@ inline int lb_resident_rows(int N, int cs) {            // rows per CTA: even, a
 }
 
 inline size_t lb_resident_smem(int RPC, int D) {
-  return ((size_t)RV_N * RPC * D + 3 * (size_t)D + 3 * (size_t)(RPC + 3) * D + 8 * NT + 2 * NACC_U + 2 * (size_t)RPC * D) * sizeof(double);
+  return ((size_t)RV_N * RPC * D + 4 * (size_t)(RPC + 3) * D + 8 * NT + 2 * NACC_U + 2 * (size_t)RPC * D) * sizeof(double);
 }
 
 }  // namespace
