@@ -500,6 +500,7 @@ __global__ void __launch_bounds__(RNT, 1) lb_resident_kernel(const ResArgs A) {
         one(GT[e], G[e], Dv[e], u0 ? S0[e] : 0.0, u0 ? Y0[e] : 0.0, u1 ? S1[e] : 0.0, u1 ? Y1[e] : 0.0);
       if (A.k_est && last && lane == 0)                 // the forcing's terms are counted once, by the last CTA
         one(pk[4], pk[1], pk[2], pk[8 + j0], pk[8 + MMAX + j0], j1 < MMAX ? pk[8 + j1] : 0.0, j1 < MMAX ? pk[8 + MMAX + j1] : 0.0);
+      stamp();                                          // 5a: dot products
       const double tsum = warp_sum16(a);
       if (!(lane & 1)) {
         const int q = lane >> 1;                        // entry 0..15 of this warp
@@ -508,6 +509,7 @@ __global__ void __launch_bounds__(RNT, 1) lb_resident_kernel(const ResArgs A) {
         else if (q < 14 && warp == 7) partB[5 * MMAX + (q - 10)] = tsum;
       }
       __syncthreads();                                  // every warp has read g and the history
+      stamp();                                          // 5b: butterfly + block barrier
       for (int e = tid; e < nloc; e += RNT) {
         const double gt = GT[e];
         if (upd) {
@@ -529,6 +531,7 @@ __global__ void __launch_bounds__(RNT, 1) lb_resident_kernel(const ResArgs A) {
       if (ph2)
         for (int k = tid; k < NACC_U; k += RNT) tot[k] = gather_sum(partB, k);
       __syncthreads();
+      stamp();                                          // 6a: totals gathered
       if (tid < 32) res_gram_warp(s, tot, m);
       __syncthreads();
     }
