@@ -62,15 +62,40 @@ enum { RV_X = 0, RV_G = 1, RV_D = 2, RV_GT = 3, RV_S = 4, RV_Y = 4 + MMAX, RV_N 
 //   first loop   a_c = rho_c (s_c.g - sum_{k newer} a_k s_c.y_k)
 //   second loop  b_c = rho_c (gamma (y_c.g - sum_k a_k y_c.y_k) + sum_{k older} (a_k - b_k) s_k.y_c)
 //   cg = gamma, cy_k = -gamma a_k, cs_k = a_k - b_k.                          All 32 lanes must call.
-__device__ void res_gram_warp(LbPath& s, const double* sum, int m) {
+__device__ void res_gram_warp(LbPath& s, const double* sum, int m, long long* tacc = nullptr) {
   const unsigned full = 0xffffffffu;
   const int j = threadIdx.x & 31;
+  long long tq = tacc ? clock64() : 0;
+  auto lap = [&](int slot) {                            // development aid: clocks per section (lane 0)
+    if (tacc != nullptr && j == 0) { const long long t = clock64(); tacc[slot] += t - tq; tq = t; }
+  };
   const bool on = j < m;
   int col = s.col, head = s.head;
-  double theta = s.theta;
   const bool accepted = s.accepted != 0, upd = s.do_update != 0;
+  const bool newpair = accepted && upd;
   const int p = s.pslot;
-  const double dr = s.dr;
+  const double dr = s.dr, yy = sum[5 * MMAX];
+  const double theta_old = s.theta;
+  if (newpair) {
+    if (col < m) col += 1;
+    else head = (head + 1 == m) ? 0 : head + 1;
+  }
+  const int k = j;                                   // age of this lane's pair
+  const bool act = k < col;
+  int ik = head + k;
+  if (ik >= m) ik -= m;
+  if (!act) ik = 0;
+  // The divisions of the phase -- rho_k = 1 / s_k.y_k per lane, theta = y.y / s.y, gamma = 1 / theta --
+  // as ONE division instruction: lanes MMAX and MMAX + 1 carry the operands of theta and gamma (a
+  // dependent fp64 division costs ~500 clocks here; three in a row were a third of the phase)
+  const double diag = (newpair && ik == p) ? dr : s.SY[ik * MMAX + ik];
+  double num = 1.0, den = act ? diag : 1.0;
+  if (j == MMAX) { num = newpair ? yy : theta_old; den = newpair ? dr : 1.0; }
+  if (j == MMAX + 1) { num = newpair ? dr : 1.0; den = newpair ? yy : theta_old; }
+  const double quo = num / den;
+  const double rho = act ? quo : 0.0;
+  const double theta = __shfl_sync(full, quo, MMAX);
+  const double gamma = (col > 0) ? __shfl_sync(full, quo, MMAX + 1) : 1.0;
   __syncwarp();
   if (accepted) {
     if (upd) {
@@ -82,11 +107,8 @@ __device__ void res_gram_warp(LbPath& s, const double* sum, int m) {
       }
       if (j == p) {
         s.SY[p * MMAX + p] = dr;                     // s'y from the line search, as L-BFGS-B does
-        s.YY[p * MMAX + p] = sum[5 * MMAX];
+        s.YY[p * MMAX + p] = yy;
       }
-      theta = sum[5 * MMAX] / dr;
-      if (col < m) col += 1;
-      else head = (head + 1) % m;
       if (on) { s.gS[j] = (j == p) ? sum[5 * MMAX + 1] : sum[j]; s.gY[j] = (j == p) ? sum[5 * MMAX + 2] : sum[MMAX + j]; }
       if (j == 0) { s.theta = theta; s.col = col; s.head = head; }
     } else if (on) {
@@ -95,46 +117,53 @@ __device__ void res_gram_warp(LbPath& s, const double* sum, int m) {
     if (j == 0) s.gg = sum[5 * MMAX + 3];
   }
   __syncwarp();
-  const int k = j;                                   // age of this lane's pair
-  const bool act = k < col;
-  int ik = head + k;
-  if (ik >= m) ik -= m;
-  if (!act) ik = 0;
-  const double rho = act ? 1.0 / s.SY[ik * MMAX + ik] : 0.0;
+  lap(10);
   // this lane's row / column of the Gram blocks in age order, in registers before the chains start
+  // (entries of pairs that do not exist yet are loaded too -- always inside the arrays -- and never
+  // used); the row of the first loop is pre-scaled by rho_k, which takes the multiply out of its chain
   double syr[MMAX], syc[MMAX], yyr[MMAX];
+  {
+    const double* syrow = s.SY + ik * MMAX;
+    const double* yyrow = s.YY + ik * MMAX;
+    const double* sycol = s.SY + ik;
+    int ic = head < m ? head : 0;
 #pragma unroll
-  for (int c = 0; c < MMAX; ++c) {
-    int ic = head + c;
-    if (ic >= m) ic -= m;
-    const bool v = act && c < col;
-    syr[c] = v ? s.SY[ik * MMAX + ic] : 0.0;         // s_k . y_c
-    syc[c] = v ? s.SY[ic * MMAX + ik] : 0.0;         // s_c . y_k
-    yyr[c] = v ? s.YY[ik * MMAX + ic] : 0.0;
+    for (int c = 0; c < MMAX; ++c) {
+      // masked here, off the chains: the first loop updates only older pairs (k < c), the second
+      // only newer ones (k > c); pairs that do not exist contribute nothing
+      // (pairs that do not exist are skipped by the loops; lanes without a pair compute garbage
+      // nobody reads)
+      syr[c] = (k < c) ? rho * syrow[ic] : 0.0;      // rho_k s_k . y_c
+      syc[c] = (k > c) ? sycol[ic * MMAX] : 0.0;     // s_c . y_k
+      yyr[c] = yyrow[ic];
+      ic = (ic + 1 >= m) ? 0 : ic + 1;
+    }
   }
-  double t = act ? s.gS[ik] : 0.0;
+  double t = act ? rho * s.gS[ik] : 0.0;             // rho_k s_k . q
   double u = act ? s.gY[ik] : 0.0;
-  const double gamma = (col > 0) ? 1.0 / theta : 1.0;
+  lap(11);
   double a = 0.0;
 #pragma unroll
   for (int c = MMAX - 1; c >= 0; --c) {              // newest -> oldest
     if (c < col) {
-      const double ac = __shfl_sync(full, t * rho, c);
+      const double ac = __shfl_sync(full, t, c);
+      t = fma(-ac, syr[c], t);                       // the chain: shuffle, multiply-add
       if (k == c) a = ac;
-      if (k < c) t = fma(-ac, syr[c], t);
       u = fma(-ac, yyr[c], u);                       // y_k . (g - sum_c a_c y_c), off the chain
     }
   }
   u *= gamma;
+  lap(12);
   double cs = 0.0;
 #pragma unroll
   for (int c = 0; c < MMAX; ++c) {                   // oldest -> newest
     if (c < col) {
       const double cc = __shfl_sync(full, fma(-rho, u, a), c);
+      u = fma(cc, syc[c], u);                        // the chain: multiply-add, shuffle, multiply-add
       if (k == c) cs = cc;
-      if (k > c) u = fma(cc, syc[c], u);
     }
   }
+  lap(13);
   if (j == 0) s.cg = gamma;
   if (j < MMAX) { s.cs[j] = 0.0; s.cy[j] = 0.0; }
   __syncwarp();
@@ -314,6 +343,10 @@ __global__ void __launch_bounds__(RNT, 1) lb_resident_kernel(const ResArgs A) {
       ++t_slot;
     }
   };
+  // The first trial point of a search is x + d (stp = 1) except in the first iteration of a rung: the
+  // direction pass writes it (and pushes its halo rows) in the same sweep, its barrier serves as the
+  // trial point's, and the next cycle skips the trial phase if the search did start with stp = 1.
+  bool spec = false;
   long long cycles = 0;
   while (!s.finished && cycles < A.max_cycles) {
     ++cycles;
@@ -323,7 +356,7 @@ __global__ void __launch_bounds__(RNT, 1) lb_resident_kernel(const ResArgs A) {
     const double cf2 = 2.0 * A.cf;
     const double fk = s.first ? pk[0] : fma(s.stp, pk[2], pk[0]);       // trial forcing
     // ---- trial point (lb_trial_kernel)
-    {
+    if (!(spec && !s.first && s.stp == 1.0)) {
       const bool fst = s.first != 0;
       const double stp = s.stp;
       for (int e = tid; e < nloc; e += RNT) {
@@ -332,8 +365,9 @@ __global__ void __launch_bounds__(RNT, 1) lb_resident_kernel(const ResArgs A) {
         if (prevH != nullptr && e < D) prevH[e] = v;
         if (nextH != nullptr && e >= e_next) nextH[e] = v;
       }
+      cl.sync();
     }
-    cl.sync();
+    spec = false;
     stamp();                                            // 1: trial point, halo rows pushed, barrier
     // ---- f of the rows R0-2 .. R1 (the rows beside the slice are recomputed, not exchanged)
     for (int e = tid; e < (RPC + 3) * D; e += RNT) {
@@ -462,10 +496,11 @@ __global__ void __launch_bounds__(RNT, 1) lb_resident_kernel(const ResArgs A) {
     // ---- accepted step: x <- xt, g <- gt, new pair, dot products (lb_update_kernel)
     const bool ph2 = s.accepted != 0;
     const bool ph3 = (s.accepted || s.redo_dir) && !s.done;
+    const bool upd = s.do_update != 0;
+    const int p = s.pslot;
+    const double stp = s.stp;
     if (ph2) {
-      const bool upd = s.do_update != 0;
-      const int p = s.pslot, col = s.col;
-      const double stp = s.stp;
+      const int col = s.col;
       // Dot products by warp: warp w owns the history slots w and w + 8 (five products each: g.s_j,
       // g.y_j, s.y_j, y.s_j, y.y_j), warp 7 also y.y, g.s, g.y, g.g; a lane walks the own elements with
       // stride 32 and the 16 sums of a warp are reduced by one halving butterfly -- no pass through
@@ -496,11 +531,11 @@ __global__ void __launch_bounds__(RNT, 1) lb_resident_kernel(const ResArgs A) {
           a[10] = fma(yv, yv, a[10]); a[11] = fma(gt, sv, a[11]); a[12] = fma(gt, yv, a[12]); a[13] = fma(gt, gt, a[13]);
         }
       };
+#pragma unroll 4
       for (int e = lane; e < nloc; e += 32)
         one(GT[e], G[e], Dv[e], u0 ? S0[e] : 0.0, u0 ? Y0[e] : 0.0, u1 ? S1[e] : 0.0, u1 ? Y1[e] : 0.0);
       if (A.k_est && last && lane == 0)                 // the forcing's terms are counted once, by the last CTA
         one(pk[4], pk[1], pk[2], pk[8 + j0], pk[8 + MMAX + j0], j1 < MMAX ? pk[8 + j1] : 0.0, j1 < MMAX ? pk[8 + MMAX + j1] : 0.0);
-      stamp();                                          // 5a: dot products
       const double tsum = warp_sum16(a);
       if (!(lane & 1)) {
         const int q = lane >> 1;                        // entry 0..15 of this warp
@@ -508,34 +543,37 @@ __global__ void __launch_bounds__(RNT, 1) lb_resident_kernel(const ResArgs A) {
         else if (q < 10) { if (j1 < MMAX) partB[(q - 5) * MMAX + j1] = tsum; }
         else if (q < 14 && warp == 7) partB[5 * MMAX + (q - 10)] = tsum;
       }
-      __syncthreads();                                  // every warp has read g and the history
-      stamp();                                          // 5b: butterfly + block barrier
-      for (int e = tid; e < nloc; e += RNT) {
-        const double gt = GT[e];
-        if (upd) {
-          vec[(size_t)(RV_S + p) * VS + e] = stp * Dv[e];
-          vec[(size_t)(RV_Y + p) * VS + e] = gt - G[e];
+    }
+    cl.sync();                                          // (also: every warp has read g and the history)
+    stamp();                                            // 5: dot products + barrier
+    // warps 0-1 gather the totals, then warp 0 runs the recursion while warps 1-7 commit the step
+    // (x <- xt, g <- gt, the new pair into slot p): neither touches what the other reads
+    {
+      const int warp = tid >> 5;
+      if (warp < 2) {
+        if (ph3 && ph2 && tid < NACC_U) tot[tid] = gather_sum(partB, tid);
+        asm volatile("bar.sync 1, 64;" ::: "memory");
+        if (warp == 0 && ph3) res_gram_warp(s, tot, m, timing ? tacc : nullptr);
+      }
+      if (ph2 && warp >= 1) {
+        for (int e = tid - 32; e < nloc; e += RNT - 32) {
+          const double gt = GT[e];
+          if (upd) {
+            vec[(size_t)(RV_S + p) * VS + e] = stp * Dv[e];
+            vec[(size_t)(RV_Y + p) * VS + e] = gt - G[e];
+          }
+          X[e] = XT[e];
+          G[e] = gt;
         }
-        X[e] = XT[e];
-        G[e] = gt;
+        if (A.k_est && tid == 32) {                     // every CTA updates its replica of the forcing
+          if (upd) { pk[8 + p] = stp * pk[2]; pk[8 + MMAX + p] = pk[4] - pk[1]; }
+          pk[0] = pk[3];
+          pk[1] = pk[4];
+        }
       }
-      if (A.k_est && tid == 0) {                        // every CTA updates its replica of the forcing
-        if (upd) { pk[8 + p] = stp * pk[2]; pk[8 + MMAX + p] = pk[4] - pk[1]; }
-        pk[0] = pk[3];
-        pk[1] = pk[4];
-      }
-    }
-    cl.sync();
-    stamp();                                            // 5: update pass + barrier
-    if (ph3) {
-      if (ph2)
-        for (int k = tid; k < NACC_U; k += RNT) tot[k] = gather_sum(partB, k);
-      __syncthreads();
-      stamp();                                          // 6a: totals gathered
-      if (tid < 32) res_gram_warp(s, tot, m);
       __syncthreads();
     }
-    stamp();                                            // 6: totals + two-loop recursion
+    stamp();                                            // 6: totals, two-loop recursion | commit
 
     // ---- direction (lb_direction_kernel) and the start of the next search
     if (ph3) {
@@ -558,6 +596,12 @@ __global__ void __launch_bounds__(RNT, 1) lb_resident_kernel(const ResArgs A) {
         double d = -(rr + ry);
         if (cd != 0.0) d = fma(cd, Dv[e], d);
         Dv[e] = d;
+        {                                               // the trial point x + d of the next cycle
+          const double v = fma(1.0, d, X[e]);
+          XT[e] = v;
+          if (prevH != nullptr && e < D) prevH[e] = v;
+          if (nextH != nullptr && e >= e_next) nextH[e] = v;
+        }
         v[0] = fma(d, d, v[0]);
         v[1] = fma(g, d, v[1]);
       }
@@ -581,6 +625,7 @@ __global__ void __launch_bounds__(RNT, 1) lb_resident_kernel(const ResArgs A) {
       __syncthreads();
       if (A.k_est && tid == 0) pk[2] = dkk;
     }
+    spec = ph3 && !s.abort_dir;                         // x + d is in place (thread 0 clears abort_dir behind the barrier)
     cl.sync();
     stamp();                                            // 7: direction pass + barrier
     if (tid == 0) {
