@@ -1493,8 +1493,9 @@ int lb_run(vab_ctx* ctx, int B, double* XP, long long ld, const double* scales_h
     if (d.model == 0 && d.NP == 1 && d.n_stim == 0 && !ctx->ptime && !ctx->rm_dev && !ctx->rm_matrix &&
         !ctx->rf0_dev && !ctx->rf0_mat && d.disc != VAB_DISC_RK4) {
       // clusters of 8 CTAs give the shortest cycle; clusters of 4 let twice as many paths be resident
-      // at once.  A batch that needs more than two rounds of clusters takes the general path, whose
-      // cost per cycle grows slowly with the batch.
+      // at once.  Larger batches run in rounds of clusters, scheduled as clusters finish; measured on C1
+      // that stays ahead of the general path at every batch size tried (128 paths: 3.5 s against 8.6 s;
+      // the general path costs ~70 ms per path-ladder at 256 paths, a round of 32 resident clusters 0.87 s).
       int want = -1;                                  // -1: decide here, 0: off, 1: on (size decided here), 4 / 8: that size
       if (const char* e = getenv("VAB_LBFGS_RESIDENT")) want = atoi(e);
       const int sizes[2] = {8, 4};
@@ -1521,8 +1522,8 @@ int lb_run(vab_ctx* ctx, int B, double* XP, long long ld, const double* scales_h
       if (want == 8 || want == 4) pick = fits[want == 8 ? 0 : 1] ? (want == 8 ? 0 : 1) : -1;
       else if (want != 0) {
         if (fits[0] && B <= cap[0]) pick = 0;
-        else if (fits[1] && B <= 2 * cap[1]) pick = 1;
-        else if (want == 1) pick = fits[1] ? 1 : (fits[0] ? 0 : -1);
+        else if (fits[1]) pick = 1;
+        else if (fits[0]) pick = 0;
       }
       if (pick >= 0) {
         resident = true; res_cs = sizes[pick]; res_rpc = rpc[pick]; res_smem = smem[pick]; res_kernel = kern[pick];
