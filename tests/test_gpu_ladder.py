@@ -433,7 +433,7 @@ def test_fused_cycle_kernel_is_bit_identical():
     assert a._ctx.graph_launches > 0 and b._ctx.graph_launches > 0
 
 
-def _resident_run(mode, disc, Pidx, B, N_data, nskip, nbeta, maxiter):
+def _resident_run(mode, disc, Pidx, B, N_data, nskip, nbeta, maxiter, dt_div=1):
     """Short ladder on the shipped data with the shared-memory-resident ladder kernel forced on
     (mode '8' / '4': CTAs per path) or off ('0')."""
     import os
@@ -447,10 +447,10 @@ def _resident_run(mode, disc, Pidx, B, N_data, nskip, nbeta, maxiter):
         an.set_model("lorenz96", 20)
         Y = data[:N_data * nskip:nskip, 1:][:, LIDX]
         an.set_data(Y, t=data[:N_data * nskip:nskip, 0])
-        N = nskip * (len(Y) - 1) + 1
+        N = nskip * dt_div * (len(Y) - 1) + 1
         X0 = 20.0 * rng.rand(B, N, 20) - 10.0
         P0 = 8.0 + 0.5 * rng.randn(B, 1)
-        an.anneal(X0, P0, 2.0, np.arange(0, 3 * nbeta, 3), 4.0, 4e-6, LIDX, Pidx, dt_model=0.025, init_to_data=True,
+        an.anneal(X0, P0, 2.0, np.arange(0, 3 * nbeta, 3), 4.0, 4e-6, LIDX, Pidx, dt_model=0.025 / dt_div, init_to_data=True,
                   disc=disc, opt_args={"gtol": 1e-11, "ftol": 1e-15, "maxfun": 1000000, "maxiter": maxiter})
     finally:
         if old is None:
@@ -510,3 +510,25 @@ def test_resident_ladder_kernel_c1_batch_matches_single():
     for b in (0, 35, 69):
         assert np.array_equal(batch.A_array[b], single.A_array)
         assert np.array_equal(batch.minpaths[b], single.minpaths)
+
+
+@pytest.mark.parametrize("disc", ["trapezoid", "SimpsonHermite"])
+def test_resident_ladder_kernel_sixteen_cta_clusters(disc):
+    """Paths too long for the shared memory of 8 CTAs (here N_model = 481: three model steps per
+    measurement interval) run in clusters of 16 (a non-portable cluster size): same checks as for the
+    other cluster sizes."""
+    ref1, Y, P0 = _resident_run("0", disc, [0], 2, 161, 1, 2, 1, dt_div=3)
+    a1, _, _ = _resident_run("16", disc, [0], 2, 161, 1, 2, 1, dt_div=3)
+    assert a1.minpaths.shape[-1] == 481 * 20 + 1
+    assert np.max(np.abs(a1.A_array - ref1.A_array) / np.abs(ref1.A_array)) <= 1e-12
+    assert np.max(np.abs(a1.minpaths - ref1.minpaths)) <= 1e-11
+    ref6, _, _ = _resident_run("0", disc, [0], 2, 161, 1, 3, 6, dt_div=3)
+    a6, _, _ = _resident_run("-1", disc, [0], 2, 161, 1, 3, 6, dt_div=3)        # chosen by the library: 16 is all that fits
+    assert np.array_equal(a6.nit_array, ref6.nit_array) and np.array_equal(a6.nfev_array, ref6.nfev_array)
+    assert np.max(np.abs(a6.A_array - ref6.A_array) / np.abs(ref6.A_array)) <= 1e-4
+    assert a6._ctx.graph_launches == 0 and ref6._ctx.graph_launches > 0       # one launch, no replayed cycles
+    for b in range(2):
+        prob = OdeProblem("lorenz96", 20, Y, LIDX, 0.025 / 3, disc, a6.minpaths[b, -1, -1:], [0], 4.0, nskip=3)
+        for i in range(3):
+            A, _ = prob.action_grad(a6.minpaths[b, i], 4e-6 * 2.0 ** (3.0 * i))
+            assert abs(A - a6.A_array[b, i]) <= 1e-10 * abs(A), (b, i)

@@ -1496,19 +1496,21 @@ int lb_run(vab_ctx* ctx, int B, double* XP, long long ld, const double* scales_h
       // at once.  Larger batches run in rounds of clusters, scheduled as clusters finish; measured on C1
       // that stays ahead of the general path at every batch size tried (128 paths: 3.5 s against 8.6 s;
       // the general path costs ~70 ms per path-ladder at 256 paths, a round of 32 resident clusters 0.87 s).
-      int want = -1;                                  // -1: decide here, 0: off, 1: on (size decided here), 4 / 8: that size
+      int want = -1;                                  // -1: decide here, 0: off, 1: on (size decided here), 4 / 8 / 16: that size
       if (const char* e = getenv("VAB_LBFGS_RESIDENT")) want = atoi(e);
-      const int sizes[2] = {8, 4};
-      bool fits[2] = {false, false};
-      int cap[2] = {0, 0}, rpc[2] = {0, 0};
-      size_t smem[2] = {0, 0};
-      ResKernel kern[2] = {lb_resident_pick<8>(d.disc), lb_resident_pick<4>(d.disc)};
-      for (int q = 0; q < 2 && want != 0; ++q) {
+      // (16 CTAs: a non-portable cluster size, for paths too long for 8 CTAs' shared memory)
+      const int sizes[3] = {8, 4, 16};
+      bool fits[3] = {false, false, false};
+      int cap[3] = {0, 0, 0}, rpc[3] = {0, 0, 0};
+      size_t smem[3] = {0, 0, 0};
+      ResKernel kern[3] = {lb_resident_pick<8>(d.disc), lb_resident_pick<4>(d.disc), lb_resident_pick<16>(d.disc)};
+      for (int q = 0; q < 3 && want != 0; ++q) {
         const int cs = sizes[q];
         rpc[q] = lb_resident_rows(d.N_model, cs);
         smem[q] = lb_resident_smem(rpc[q], d.D);
         if (smem[q] > (size_t)226000 || (long long)rpc[q] * cs < d.N_model) continue;
         if (cudaFuncSetAttribute(kern[q], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem[q]) != cudaSuccess) { cudaGetLastError(); continue; }
+        if (cs > 8 && cudaFuncSetAttribute(kern[q], cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { cudaGetLastError(); continue; }
         cudaLaunchConfig_t cfg;
         memset(&cfg, 0, sizeof(cfg));
         cudaLaunchAttribute at[1];
@@ -1519,11 +1521,14 @@ int lb_run(vab_ctx* ctx, int B, double* XP, long long ld, const double* scales_h
         fits[q] = cap[q] >= 1;
       }
       int pick = -1;
-      if (want == 8 || want == 4) pick = fits[want == 8 ? 0 : 1] ? (want == 8 ? 0 : 1) : -1;
-      else if (want != 0) {
+      if (want == 8 || want == 4 || want == 16) {
+        const int q = want == 8 ? 0 : (want == 4 ? 1 : 2);
+        pick = fits[q] ? q : -1;
+      } else if (want != 0) {
         if (fits[0] && B <= cap[0]) pick = 0;
         else if (fits[1]) pick = 1;
         else if (fits[0]) pick = 0;
+        else if (fits[2]) pick = 2;
       }
       if (pick >= 0) {
         resident = true; res_cs = sizes[pick]; res_rpc = rpc[pick]; res_smem = smem[pick]; res_kernel = kern[pick];
