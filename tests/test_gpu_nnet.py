@@ -147,7 +147,13 @@ def test_nn_ladder_vs_scipy(tcgen05, monkeypatch):
                             options={"gtol": 1e-9, "ftol": 1e-13})
         assert res2.nit <= 2 and abs(res2.fun - an.A_array[i]) <= 1e-9 * abs(res2.fun)
     assert an.minpaths.shape == (len(betas), M * NDnet + NP)
-    assert np.all(an.exitflags == 0)
+    if tcgen05:
+        # the split contractions carry rounding noise of ~1e-14 of the row maxima: with ftol = 1e-15 the
+        # last line search of a rung may find no decrease left and end "abnormally" (status 2) *at* the
+        # minimum -- the two checks above hold on every rung either way
+        assert np.all(np.isin(an.exitflags, (0, 2))), an.exitflags
+    else:
+        assert np.all(an.exitflags == 0)
     assert an._ctx.nn_kernel_family == (5 if tcgen05 else 3)
 
 
@@ -192,8 +198,6 @@ def test_nn_tnc_method_minimises_the_oracle_action():
     of the ladder test above (weights held at perturbed teacher values, RF large enough for the
     model error to shape the minimum; with free weights the valley is flat and SciPy's own
     L-BFGS-B runs 1e5 iterations without converging)."""
-    if tcgen05:                            # the same ladder with every contraction on tcgen05 (graph-replayed cycles)
-        monkeypatch.setenv("VAB_NN_TCGEN05", "1")
     rng = np.random.RandomState(8)
     st = np.array([4, 6, 3])
     M = 12
