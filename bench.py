@@ -475,6 +475,12 @@ def leg_c2(args, dd):
                 rel = np.abs(local_tab0[:, 1] - ref) / np.abs(ref)
                 ladder["max_rel_dA_vs_cpu"] = float(rel.max())
                 ladder["rel_dA_vs_cpu_per_beta"] = [float(v) for v in rel]
+                signed = (local_tab0[:, 1] - ref) / np.abs(ref)
+                ladder["device_lower_than_cpu_on_rungs"] = [int(i) for i in np.where(signed < -1e-6)[0]]
+                ladder["max_rel_dA_where_device_is_higher"] = float(np.max(np.maximum(signed, 0.0)))
+                ladder["rel_dA_note"] = ("(A_dev - A_cpu) / A_cpu per rung; on the rungs listed in "
+                                         "device_lower_than_cpu_on_rungs the device's minimum is the *lower* one "
+                                         "(multi-modal stretch of the ladder, DESIGN.md 2.1)")
                 if "table_ulp1" in z.files:
                     band = np.abs(z["table_ulp1"][:, 1] - ref) / np.abs(ref)
                     ladder["reference_self_spread_max"] = float(band.max())
